@@ -1,0 +1,45 @@
+"""Build libaqml_b200.so in-tree with nvcc for sm_100a:  python -m aqml_b200.build"""
+from __future__ import annotations
+
+import os
+import shutil
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+SRC = [os.path.join(HERE, "csrc", f) for f in ("kernels.cu", "slatm.cu")]
+HDR = [os.path.join(HERE, "csrc", f) for f in ("common.cuh", "pairtile.cuh", "packing.cuh")] + \
+      [os.path.join(os.path.dirname(HERE), "include", "aqml_b200.h")]
+OUT = os.path.join(HERE, "lib", "libaqml_b200.so")
+
+
+def nvcc_path():
+    for c in (os.environ.get("NVCC"), shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
+        if c and os.path.exists(c):
+            return c
+    raise RuntimeError("nvcc not found")
+
+
+def up_to_date():
+    if not os.path.exists(OUT):
+        return False
+    t = os.path.getmtime(OUT)
+    return all(os.path.getmtime(f) <= t for f in SRC + HDR)
+
+
+def build(force=False, verbose=False):
+    if not force and up_to_date():
+        return OUT
+    os.makedirs(os.path.dirname(OUT), exist_ok=True)
+    cmd = [nvcc_path(), "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
+           "-ccbin", "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++",
+           "-shared", "-Xcompiler", "-fPIC", "-o", OUT] + SRC
+    if verbose:
+        cmd.insert(1, "-Xptxas=-v")
+        print(" ".join(cmd))
+    subprocess.check_call(cmd)
+    return OUT
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

@@ -1,0 +1,655 @@
+// Kernel-matrix assembly: host orchestration + C ABI (see include/aqml_b200.h for the reference
+// interfaces each entry point replaces: fkernels.f90, fdistance.f90, algo/aqml.py:204-255).
+#include "pairtile.cuh"
+#include "packing.cuh"
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <numeric>
+
+namespace aqml {
+
+std::string &last_error_ref() {
+    static thread_local std::string s;
+    return s;
+}
+std::atomic<long long> g_launches{0};
+
+void require_device() {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n <= 0) {
+        cudaGetLastError();
+        fail(AQML_ECUDA, "no CUDA device available (aqml_b200 has no CPU fallback): %s",
+             e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+    }
+}
+
+// =============================================================================================
+// device kernels: packing
+// =============================================================================================
+// One block per packed row: gather (optional row map / column map), subtract an optional mean,
+// zero-pad to the 16-column pitch, and produce |row|^2.
+__global__ void __launch_bounds__(256) pack_rows_kernel(PackJob J) {
+    const int r = blockIdx.x;
+    int src = J.rowmap ? J.rowmap[r] : (r < J.nvalid ? r : -1);
+    const double *sp = (src >= 0) ? J.src + (long long)src * J.lds : nullptr;
+    double *dp = J.dst + (long long)r * J.ldd;
+    double ss = 0.0;
+    for (int c = threadIdx.x; c < J.ldd; c += blockDim.x) {
+        double v = 0.0;
+        if (sp && c < J.ncols) {
+            int sc = J.colmap ? J.colmap[c] : c;
+            v = sp[sc];
+            if (J.mean) v -= J.mean[c];
+        }
+        dp[c] = v;
+        ss += v * v;
+    }
+    __shared__ double red[8];
+    ss = warp_sum(ss);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = ss;
+    __syncthreads();
+    if (threadIdx.x == 0 && J.norm) {
+        double t = 0.0;
+        for (int w = 0; w < (int)(blockDim.x >> 5); w++) t += red[w];
+        J.norm[r] = t;
+    }
+}
+
+// Column sums and non-zero flags over a list of rows (support detection + centring).
+// grid (ceil(D/256), row chunks); thread = one column over ROWS_PER_BLOCK rows.
+constexpr int CS_ROWS = 64;
+__global__ void __launch_bounds__(256) colstats_kernel(const double *x, long long ldx, const int *rows, int nrows, int D,
+                                                       double *colsum, unsigned *colnz) {
+    int c = blockIdx.x * 256 + threadIdx.x;
+    if (c >= D) return;
+    int r0 = blockIdx.y * CS_ROWS, r1 = min(nrows, r0 + CS_ROWS);
+    double s = 0.0;
+    unsigned nz = 0;
+    for (int i = r0; i < r1; i++) {
+        int r = rows ? rows[i] : i;
+        double v = x[(long long)r * ldx + c];
+        s += v;
+        nz |= (v != 0.0);
+    }
+    if (colsum) atomicAdd(colsum + c, s);
+    if (nz) atomicOr(colnz + c, 1u);
+}
+
+__global__ void scale_gather_kernel(const double *colsum, const int *colmap, int n, double scale, double *mean) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) mean[i] = colsum[colmap ? colmap[i] : i] * scale;
+}
+
+// K[k][a][b] += cnt1[a][e] * (nas2[b] - cnt2[b][e]) * exp(1e9 * isig[k][z_e])  -- the reference gives
+// element-mismatched pairs d2 = 1e9 (fkernels.f90:73), which is not exactly 0 for very wide sigmas.
+__global__ void mismatch_kernel(const int *cnt1, const int *cnt2, const int *nas2, const double *term, int nel, int nm1,
+                                int nm2, int nsig, double *K) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (long long)nm1 * nm2) return;
+    int a = (int)(i / nm2), b = (int)(i % nm2);
+    for (int k = 0; k < nsig; k++) {
+        double s = 0.0;
+        for (int e = 0; e < nel; e++)
+            s += (double)cnt1[a * nel + e] * (double)(nas2[b] - cnt2[b * nel + e]) * term[k * nel + e];
+        K[((long long)k * nm1 + a) * nm2 + b] += s;
+    }
+}
+
+void launch_pack(const PackJob &J, int nrows_packed, cudaStream_t st) {
+    if (nrows_packed <= 0) return;
+    pack_rows_kernel<<<nrows_packed, 256, 0, st>>>(J);
+    AQML_LAUNCH_CHECK();
+}
+
+void launch_colstats(const double *x, long long ldx, const int *rows, int nrows, int D, double *colsum, unsigned *colnz,
+                     cudaStream_t st) {
+    if (nrows <= 0 || D <= 0) return;
+    dim3 grid((D + 255) / 256, (nrows + CS_ROWS - 1) / CS_ROWS);
+    colstats_kernel<<<grid, 256, 0, st>>>(x, ldx, rows, nrows, D, colsum, colnz);
+    AQML_LAUNCH_CHECK();
+}
+
+// =============================================================================================
+// host helpers
+// =============================================================================================
+// Split a molecule-sorted row list into <=128-row tiles that start on molecule boundaries (a
+// molecule longer than a tile is split).  rowmap/seg get -1 padding up to 128 per tile.
+void build_tiles(const std::vector<int> &rows, const std::vector<int> &mol_of_row, std::vector<int> &rowmap,
+                 std::vector<int> &seg) {
+    rowmap.clear();
+    seg.clear();
+    size_t i = 0, n = rows.size();
+    while (i < n) {
+        size_t fill = 0;
+        while (i < n && fill < (size_t)BM) {
+            size_t j = i;
+            while (j < n && mol_of_row[j] == mol_of_row[i]) j++;
+            size_t len = j - i;
+            if (fill + len <= (size_t)BM) {
+                for (size_t q = i; q < j; q++) { rowmap.push_back(rows[q]); seg.push_back(mol_of_row[q]); }
+                fill += len;
+                i = j;
+            } else if (fill == 0) {  // one molecule with more rows than a tile: split it
+                for (size_t q = i; q < i + BM; q++) { rowmap.push_back(rows[q]); seg.push_back(mol_of_row[q]); }
+                fill = BM;
+                i += BM;
+            } else {
+                break;
+            }
+        }
+        while (fill < (size_t)BM) { rowmap.push_back(-1); seg.push_back(-1); fill++; }
+    }
+}
+
+static std::vector<int> mol_index(const int *nas, int nm, int &A) {
+    std::vector<int> m;
+    A = 0;
+    for (int i = 0; i < nm; i++) {
+        AQML_REQUIRE(nas[i] >= 0, "negative atom count for molecule %d", i);
+        A += nas[i];
+    }
+    m.reserve(A);
+    for (int i = 0; i < nm; i++) m.insert(m.end(), nas[i], i);
+    return m;
+}
+
+static void run_pairs(int mode, int epi, const std::vector<PairGroup> &groups, PairParams P, Workspace &ws) {
+    int total = 0;
+    std::vector<PairGroup> gs = groups;
+    for (auto &g : gs) { g.tile_begin = total; total += g.tilesM * g.tilesN; }
+    if (total == 0) return;
+    P.groups = ws.upload(gs);
+    P.ngroups = (int)gs.size();
+    cudaStream_t st = ws.stream();
+#define AQML_DISPATCH(M, E) if (mode == M && epi == E) { launch_pair_tiles<M, E>(P, total, st); return; }
+    AQML_DISPATCH(MODE_DOT, EPI_EXP_STORE)
+    AQML_DISPATCH(MODE_DOT, EPI_DIST_STORE)
+    AQML_DISPATCH(MODE_DOT, EPI_MAX)
+    AQML_DISPATCH(MODE_DOT, EPI_LOCAL)
+    AQML_DISPATCH(MODE_L1, EPI_EXP_STORE)
+    AQML_DISPATCH(MODE_L1, EPI_DIST_STORE)
+    AQML_DISPATCH(MODE_L1, EPI_MAX)
+    AQML_DISPATCH(MODE_L1, EPI_LOCAL)
+#undef AQML_DISPATCH
+    fail(AQML_EINVAL, "bad pair-tile mode");
+}
+
+void run_pairs_public(int mode, int epi, const std::vector<PairGroup> &groups, PairParams P, Workspace &ws) {
+    run_pairs(mode, epi, groups, P, ws);
+}
+
+static PairGroup blank_group() {
+    PairGroup g;
+    memset(&g, 0, sizeof(g));
+    g.segA_n = 0x7fffffff;
+    return g;
+}
+
+// dense (n, D) rows -> packed [round_up(n,128)][round_up(D,16)] (+ norms), optional mean
+struct Packed {
+    double *x = nullptr, *norm = nullptr;
+    long long ld = 0;
+    int rows = 0, tiles = 0;
+};
+static Packed pack_dense(Workspace &ws, const double *src, long long lds, int n, int D, const double *mean, bool want_norm) {
+    Packed p;
+    p.ld = round_up(std::max(D, 1), BK);
+    p.tiles = (n + BM - 1) / BM;
+    p.rows = p.tiles * BM;
+    p.x = ws.alloc<double>((size_t)p.rows * p.ld);
+    p.norm = want_norm ? ws.alloc<double>(p.rows) : nullptr;
+    PackJob J{};
+    J.src = src; J.lds = lds; J.rowmap = nullptr; J.colmap = nullptr; J.mean = mean;
+    J.dst = p.x; J.ldd = p.ld; J.norm = p.norm; J.ncols = D; J.nvalid = n;
+    launch_pack(J, p.rows, ws.stream());
+    return p;
+}
+
+static const double *column_mean(Workspace &ws, const double *x, long long ldx, int n, int D) {
+    double *sum = ws.zeros<double>(D);
+    unsigned *nz = ws.zeros<unsigned>(D);
+    launch_colstats(x, ldx, nullptr, n, D, sum, nz, ws.stream());
+    double *mean = ws.alloc<double>(D);
+    scale_gather_kernel<<<(D + 255) / 256, 256, 0, ws.stream()>>>(sum, nullptr, D, 1.0 / std::max(n, 1), mean);
+    AQML_LAUNCH_CHECK();
+    return mean;
+}
+
+static std::vector<double> inv_sigma_table(int kind, const double *sigmas, size_t n) {
+    std::vector<double> t(n);
+    for (size_t i = 0; i < n; i++)
+        t[i] = (kind == AQML_KERNEL_GAUSSIAN) ? -0.5 / (sigmas[i] * sigmas[i]) : -1.0 / sigmas[i];
+    return t;
+}
+
+// =============================================================================================
+// global kernels / distances
+// =============================================================================================
+// epi: EPI_EXP_STORE (K (nsig,na,nb)), EPI_DIST_STORE (D (na,nb)), EPI_MAX (out[0] bits)
+static void global_pairs(int kind, int epi, const double *a, int na, long long lda, const double *b, int nb, long long ldb,
+                         int D, const double *sigmas, int nsig, int center, double *out, cudaStream_t st) {
+    AQML_REQUIRE(na >= 0 && nb >= 0 && D >= 1, "bad shape na=%d nb=%d D=%d", na, nb, D);
+    AQML_REQUIRE(lda >= D && ldb >= D, "row pitch smaller than D");
+    if (na == 0 || nb == 0) return;
+    require_device();
+    Workspace ws(st);
+    const int mode = (kind == AQML_KERNEL_GAUSSIAN) ? MODE_DOT : MODE_L1;
+    const double *mean = (mode == MODE_DOT && center) ? column_mean(ws, b, ldb, nb, D) : nullptr;
+    const bool same = (a == b && na == nb && lda == ldb);
+    Packed pb = pack_dense(ws, b, ldb, nb, D, mean, mode == MODE_DOT);
+    Packed pa = same ? pb : pack_dense(ws, a, lda, na, D, mean, mode == MODE_DOT);
+    PairGroup g = blank_group();
+    g.A = pa.x; g.B = pb.x; g.normA = pa.norm; g.normB = pb.norm; g.ld = pa.ld;
+    g.nA = na; g.nB = nb; g.tilesM = pa.tiles; g.tilesN = pb.tiles;
+    g.sym = (epi == EPI_MAX && same) ? 1 : 0;
+    PairParams P{};
+    P.out = out; P.ldo = nb; P.slab = (long long)na * nb; P.nsig = nsig; P.zstride = 1;
+    if (epi == EPI_EXP_STORE) {
+        AQML_REQUIRE(nsig >= 1 && sigmas, "need at least one sigma");
+        for (int s = 0; s < nsig; s++) AQML_REQUIRE(sigmas[s] != 0.0, "sigma[%d] is zero", s);
+        P.isig = ws.upload(inv_sigma_table(kind, sigmas, nsig));
+    }
+    run_pairs(mode, epi, {g}, P, ws);
+}
+
+// host-buffer wrapper: K column-major (na, nb) == row-major (nb, na) of the swapped problem
+static void global_host(int kind, int epi, const double *a, int na, const double *b, int nb, int D, double *k, double sigma) {
+    AQML_REQUIRE(a && b && k, "null pointer");
+    AQML_REQUIRE(na >= 0 && nb >= 0 && D >= 1, "bad shape");
+    if (na == 0 || nb == 0) return;
+    require_device();
+    cudaStream_t st = 0;
+    Workspace ws(st);
+    double *da = ws.upload(a, (size_t)na * D), *db = ws.upload(b, (size_t)nb * D);
+    double *dk = ws.alloc<double>((size_t)na * nb);
+    global_pairs(kind, epi, db, nb, D, da, na, D, D, &sigma, 1, 1, dk, st);
+    AQML_CUDA(cudaMemcpyAsync(k, dk, sizeof(double) * (size_t)na * nb, cudaMemcpyDeviceToHost, st));
+    AQML_CUDA(cudaStreamSynchronize(st));
+}
+
+// =============================================================================================
+// local kernels
+// =============================================================================================
+struct ElementRows {
+    std::vector<int> rowmap, seg;  // tile-padded
+    int n = 0;                      // valid rows
+};
+
+static void local_gaussian(const double *x1, long long ldx1, const double *x2, long long ldx2, const int *zs1,
+                           const int *zs2, const int *nas1, const int *nas2, int zmax, int iab, const double *sigmas,
+                           int nm1, int nm2, int S, int D, int center, double *K, cudaStream_t st) {
+    AQML_REQUIRE(x1 && x2 && zs1 && zs2 && nas1 && nas2 && sigmas && K, "null pointer");
+    AQML_REQUIRE(nm1 >= 0 && nm2 >= 0 && S >= 1 && D >= 1 && zmax >= 1, "bad shape");
+    AQML_REQUIRE(ldx1 >= D && ldx2 >= D, "row pitch smaller than D");
+    require_device();
+    int A1, A2;
+    std::vector<int> mol1 = mol_index(nas1, nm1, A1), mol2 = mol_index(nas2, nm2, A2);
+    for (int i = 0; i < A1; i++) AQML_REQUIRE(zs1[i] >= 1 && zs1[i] <= zmax, "zs1[%d]=%d outside 1..zmax", i, zs1[i]);
+    for (int i = 0; i < A2; i++) AQML_REQUIRE(zs2[i] >= 1 && zs2[i] <= zmax, "zs2[%d]=%d outside 1..zmax", i, zs2[i]);
+    for (int i = 0; i < S * zmax; i++) AQML_REQUIRE(sigmas[i] != 0.0, "sigma is zero");
+    AQML_CUDA(cudaMemsetAsync(K, 0, sizeof(double) * (size_t)S * nm1 * nm2, st));
+    if (nm1 == 0 || nm2 == 0 || A1 == 0 || A2 == 0) return;
+    Workspace ws(st);
+    std::vector<double> isig = inv_sigma_table(AQML_KERNEL_GAUSSIAN, sigmas, (size_t)S * zmax);
+    PairParams P{};
+    P.isig = ws.upload(isig); P.nsig = S; P.zstride = zmax;
+    P.out = K; P.ldo = nm2; P.slab = (long long)nm1 * nm2;
+    std::vector<PairGroup> groups;
+
+    if (iab) {
+        // every atom pair, width of the first argument's atom (fkernels.f90:76): one group, full D
+        std::vector<int> rows1(A1), rows2(A2), rm1, sg1, rm2, sg2;
+        std::iota(rows1.begin(), rows1.end(), 0);
+        std::iota(rows2.begin(), rows2.end(), 0);
+        build_tiles(rows1, mol1, rm1, sg1);
+        build_tiles(rows2, mol2, rm2, sg2);
+        std::vector<int> z1p(rm1.size());
+        for (size_t i = 0; i < rm1.size(); i++) z1p[i] = rm1[i] >= 0 ? zs1[rm1[i]] - 1 : 0;
+        const double *mean = center ? column_mean(ws, x2, ldx2, A2, D) : nullptr;
+        long long ld = round_up(D, BK);
+        auto pack = [&](const double *x, long long ldx, const std::vector<int> &rm, double *&px, double *&pn) {
+            px = ws.alloc<double>(rm.size() * (size_t)ld);
+            pn = ws.alloc<double>(rm.size());
+            PackJob J{};
+            J.src = x; J.lds = ldx; J.rowmap = ws.upload(rm); J.colmap = nullptr; J.mean = mean;
+            J.dst = px; J.ldd = ld; J.norm = pn; J.ncols = D; J.nvalid = 0;
+            launch_pack(J, (int)rm.size(), st);
+        };
+        double *p1, *n1, *p2, *n2;
+        pack(x1, ldx1, rm1, p1, n1);
+        pack(x2, ldx2, rm2, p2, n2);
+        PairGroup g = blank_group();
+        g.A = p1; g.B = p2; g.normA = n1; g.normB = n2; g.ld = ld;
+        g.segA = ws.upload(sg1); g.segB = ws.upload(sg2); g.zA = ws.upload(z1p);
+        g.tilesM = (int)rm1.size() / BM; g.tilesN = (int)rm2.size() / BN;
+        groups.push_back(g);
+        run_pairs(MODE_DOT, EPI_LOCAL, groups, P, ws);
+        return;
+    }
+
+    // ---- element-matched: one group per element present on both sides ---------------------------
+    std::vector<std::vector<int>> r1(zmax + 1), r2(zmax + 1);
+    for (int i = 0; i < A1; i++) r1[zs1[i]].push_back(i);
+    for (int i = 0; i < A2; i++) r2[zs2[i]].push_back(i);
+    std::vector<int> els;
+    for (int z = 1; z <= zmax; z++) if (!r1[z].empty() && !r2[z].empty()) els.push_back(z);
+    const int ne = (int)els.size();
+
+    // element-mismatched pairs: exp(1e9 * isig) (exactly 0 unless sigma is huge)
+    {
+        std::vector<int> allz;
+        for (int z = 1; z <= zmax; z++) if (!r1[z].empty()) allz.push_back(z);
+        std::vector<double> term((size_t)S * allz.size());
+        bool any = false;
+        for (int k = 0; k < S; k++)
+            for (size_t e = 0; e < allz.size(); e++) {
+                term[k * allz.size() + e] = std::exp((double)1.e9f * isig[(size_t)k * zmax + allz[e] - 1]);
+                any |= term[k * allz.size() + e] != 0.0;
+            }
+        if (any) {
+            int nel = (int)allz.size();
+            std::vector<int> c1((size_t)nm1 * nel, 0), c2((size_t)nm2 * nel, 0), zi(zmax + 1, -1);
+            for (int e = 0; e < nel; e++) zi[allz[e]] = e;
+            for (int i = 0; i < A1; i++) c1[(size_t)mol1[i] * nel + zi[zs1[i]]]++;
+            for (int i = 0; i < A2; i++) if (zi[zs2[i]] >= 0) c2[(size_t)mol2[i] * nel + zi[zs2[i]]]++;
+            long long n = (long long)nm1 * nm2;
+            mismatch_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(ws.upload(c1), ws.upload(c2), ws.upload(nas2, nm2),
+                                                                        ws.upload(term), nel, nm1, nm2, S, K);
+            AQML_LAUNCH_CHECK();
+        }
+    }
+    if (ne == 0) return;
+
+    // column support (and sums for centring) per element over both sets
+    double *colsum = ws.zeros<double>((size_t)ne * D);
+    unsigned *colnz = ws.zeros<unsigned>((size_t)ne * D);
+    std::vector<int *> d_rows1(ne), d_rows2(ne);
+    for (int e = 0; e < ne; e++) {
+        int z = els[e];
+        d_rows1[e] = ws.upload(r1[z]);
+        d_rows2[e] = ws.upload(r2[z]);
+        launch_colstats(x1, ldx1, d_rows1[e], (int)r1[z].size(), D, colsum + (size_t)e * D, colnz + (size_t)e * D, st);
+        launch_colstats(x2, ldx2, d_rows2[e], (int)r2[z].size(), D, colsum + (size_t)e * D, colnz + (size_t)e * D, st);
+    }
+    std::vector<unsigned> nz((size_t)ne * D);
+    AQML_CUDA(cudaMemcpyAsync(nz.data(), colnz, sizeof(unsigned) * nz.size(), cudaMemcpyDeviceToHost, st));
+    AQML_CUDA(cudaStreamSynchronize(st));
+
+    for (int e = 0; e < ne; e++) {
+        int z = els[e];
+        std::vector<int> colmap;
+        for (int c = 0; c < D; c++) if (nz[(size_t)e * D + c]) colmap.push_back(c);
+        if (colmap.empty()) colmap.push_back(0);  // all-zero rows: d2 = 0 for every pair
+        int Dz = (int)colmap.size();
+        long long ld = round_up(Dz, BK);
+        int *d_colmap = ws.upload(colmap);
+        double *mean = nullptr;
+        if (center) {
+            mean = ws.alloc<double>(Dz);
+            double scale = 1.0 / (double)(r1[z].size() + r2[z].size());
+            scale_gather_kernel<<<(Dz + 255) / 256, 256, 0, st>>>(colsum + (size_t)e * D, d_colmap, Dz, scale, mean);
+            AQML_LAUNCH_CHECK();
+        }
+        std::vector<int> m1(r1[z].size()), m2(r2[z].size()), rm1, sg1, rm2, sg2;
+        for (size_t i = 0; i < m1.size(); i++) m1[i] = mol1[r1[z][i]];
+        for (size_t i = 0; i < m2.size(); i++) m2[i] = mol2[r2[z][i]];
+        build_tiles(r1[z], m1, rm1, sg1);
+        build_tiles(r2[z], m2, rm2, sg2);
+        auto pack = [&](const double *x, long long ldx, const std::vector<int> &rm, double *&px, double *&pn) {
+            px = ws.alloc<double>(rm.size() * (size_t)ld);
+            pn = ws.alloc<double>(rm.size());
+            PackJob J{};
+            J.src = x; J.lds = ldx; J.rowmap = ws.upload(rm); J.colmap = d_colmap; J.mean = mean;
+            J.dst = px; J.ldd = ld; J.norm = pn; J.ncols = Dz; J.nvalid = 0;
+            launch_pack(J, (int)rm.size(), st);
+        };
+        double *p1, *n1, *p2, *n2;
+        pack(x1, ldx1, rm1, p1, n1);
+        pack(x2, ldx2, rm2, p2, n2);
+        PairGroup g = blank_group();
+        g.A = p1; g.B = p2; g.normA = n1; g.normB = n2; g.ld = ld;
+        g.segA = ws.upload(sg1); g.segB = ws.upload(sg2); g.zA = nullptr; g.zcol = z - 1;
+        g.tilesM = (int)rm1.size() / BM; g.tilesN = (int)rm2.size() / BN;
+        groups.push_back(g);
+    }
+    run_pairs(MODE_DOT, EPI_LOCAL, groups, P, ws);
+}
+
+static void local_laplacian(const double *x1, long long ldx1, const double *x2, long long ldx2, const int *nas1,
+                            const int *nas2, const double *sigmas, int nm1, int nm2, int S, int D, double *K,
+                            cudaStream_t st) {
+    AQML_REQUIRE(x1 && x2 && nas1 && nas2 && sigmas && K, "null pointer");
+    AQML_REQUIRE(nm1 >= 0 && nm2 >= 0 && S >= 1 && D >= 1, "bad shape");
+    require_device();
+    int A1, A2;
+    std::vector<int> mol1 = mol_index(nas1, nm1, A1), mol2 = mol_index(nas2, nm2, A2);
+    for (int i = 0; i < S; i++) AQML_REQUIRE(sigmas[i] != 0.0, "sigma is zero");
+    AQML_CUDA(cudaMemsetAsync(K, 0, sizeof(double) * (size_t)S * nm1 * nm2, st));
+    if (A1 == 0 || A2 == 0) return;
+    Workspace ws(st);
+    std::vector<int> rows1(A1), rows2(A2), rm1, sg1, rm2, sg2;
+    std::iota(rows1.begin(), rows1.end(), 0);
+    std::iota(rows2.begin(), rows2.end(), 0);
+    build_tiles(rows1, mol1, rm1, sg1);
+    build_tiles(rows2, mol2, rm2, sg2);
+    long long ld = round_up(D, BK);
+    auto pack = [&](const double *x, long long ldx, const std::vector<int> &rm) {
+        double *px = ws.alloc<double>(rm.size() * (size_t)ld);
+        PackJob J{};
+        J.src = x; J.lds = ldx; J.rowmap = ws.upload(rm); J.dst = px; J.ldd = ld; J.ncols = D;
+        launch_pack(J, (int)rm.size(), st);
+        return px;
+    };
+    PairGroup g = blank_group();
+    g.A = pack(x1, ldx1, rm1); g.B = pack(x2, ldx2, rm2); g.ld = ld;
+    g.segA = ws.upload(sg1); g.segB = ws.upload(sg2);
+    g.tilesM = (int)rm1.size() / BM; g.tilesN = (int)rm2.size() / BN;
+    PairParams P{};
+    P.isig = ws.upload(inv_sigma_table(AQML_KERNEL_LAPLACIAN, sigmas, S)); P.nsig = S; P.zstride = 1;
+    P.out = K; P.ldo = nm2; P.slab = (long long)nm1 * nm2;
+    run_pairs(MODE_L1, EPI_LOCAL, {g}, P, ws);
+}
+
+// per-element max distance, algo/aqml.py:204-255 (cab=False)
+static void kernel_width(int p, const double *x, long long ldx, const int *zs, int A, int D, int zmax, double *dso,
+                         cudaStream_t st) {
+    AQML_REQUIRE(x && zs && dso && A >= 1 && D >= 1 && zmax >= 1, "bad argument");
+    AQML_REQUIRE(p == 1 || p == 2, "p must be 1 or 2");
+    require_device();
+    for (int i = 0; i < A; i++) AQML_REQUIRE(zs[i] >= 1 && zs[i] <= zmax, "zs[%d]=%d outside 1..zmax", i, zs[i]);
+    Workspace ws(st);
+    std::vector<std::vector<int>> rz(zmax + 1);
+    for (int i = 0; i < A; i++) rz[zs[i]].push_back(i);
+    std::vector<int> els;
+    for (int z = 1; z <= zmax; z++) if (!rz[z].empty()) els.push_back(z);
+    const int ne = (int)els.size();
+    unsigned *colnz = ws.zeros<unsigned>((size_t)ne * D);
+    double *colsum = ws.zeros<double>((size_t)ne * D);
+    std::vector<int *> d_rows(ne);
+    for (int e = 0; e < ne; e++) {
+        d_rows[e] = ws.upload(rz[els[e]]);
+        launch_colstats(x, ldx, d_rows[e], (int)rz[els[e]].size(), D, colsum + (size_t)e * D, colnz + (size_t)e * D, st);
+    }
+    std::vector<unsigned> nz((size_t)ne * D);
+    AQML_CUDA(cudaMemcpyAsync(nz.data(), colnz, sizeof(unsigned) * nz.size(), cudaMemcpyDeviceToHost, st));
+    AQML_CUDA(cudaStreamSynchronize(st));
+    unsigned long long *outbits = ws.zeros<unsigned long long>(ne);
+    std::vector<PairGroup> groups;
+    for (int e = 0; e < ne; e++) {
+        std::vector<int> colmap;
+        for (int c = 0; c < D; c++) if (nz[(size_t)e * D + c]) colmap.push_back(c);
+        if (colmap.empty()) colmap.push_back(0);
+        int Dz = (int)colmap.size(), n = (int)rz[els[e]].size();
+        long long ld = round_up(Dz, BK);
+        int tiles = (n + BM - 1) / BM;
+        int *d_colmap = ws.upload(colmap);
+        double *mean = nullptr;
+        if (p == 2) {
+            mean = ws.alloc<double>(Dz);
+            scale_gather_kernel<<<(Dz + 255) / 256, 256, 0, st>>>(colsum + (size_t)e * D, d_colmap, Dz, 1.0 / n, mean);
+            AQML_LAUNCH_CHECK();
+        }
+        std::vector<int> rm(rz[els[e]]);
+        rm.resize((size_t)tiles * BM, -1);
+        double *px = ws.alloc<double>(rm.size() * (size_t)ld), *pn = ws.alloc<double>(rm.size());
+        PackJob J{};
+        J.src = x; J.lds = ldx; J.rowmap = ws.upload(rm); J.colmap = d_colmap; J.mean = mean;
+        J.dst = px; J.ldd = ld; J.norm = pn; J.ncols = Dz;
+        launch_pack(J, (int)rm.size(), st);
+        PairGroup g = blank_group();
+        g.A = g.B = px; g.normA = g.normB = pn; g.ld = ld; g.nA = g.nB = n; g.tilesM = g.tilesN = tiles;
+        g.out_slot = e; g.sym = 1;
+        groups.push_back(g);
+    }
+    PairParams P{};
+    P.out = reinterpret_cast<double *>(outbits);
+    run_pairs(p == 2 ? MODE_DOT : MODE_L1, EPI_MAX, groups, P, ws);
+    std::vector<double> mx(ne);
+    AQML_CUDA(cudaMemcpyAsync(mx.data(), outbits, sizeof(double) * ne, cudaMemcpyDeviceToHost, st));
+    AQML_CUDA(cudaStreamSynchronize(st));
+    for (int z = 0; z < zmax; z++) dso[z] = 1.e-9;
+    for (int e = 0; e < ne; e++) dso[els[e] - 1] = (p == 2) ? std::sqrt(mx[e]) : mx[e];
+}
+
+}  // namespace aqml
+
+// =============================================================================================
+// C ABI
+// =============================================================================================
+using namespace aqml;
+
+extern "C" {
+
+int aqml_version(void) { return 100; }
+const char *aqml_last_error(void) { return last_error_ref().c_str(); }
+int aqml_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+int64_t aqml_launch_count(void) { return (int64_t)g_launches.load(); }
+
+int aqml_fgaussian_kernel(const double *a, int na, const double *b, int nb, int D, double *k, double sigma) {
+    return guarded([&] {
+        AQML_REQUIRE(sigma != 0.0, "sigma is zero");
+        global_host(AQML_KERNEL_GAUSSIAN, EPI_EXP_STORE, a, na, b, nb, D, k, sigma);
+    });
+}
+int aqml_flaplacian_kernel(const double *a, int na, const double *b, int nb, int D, double *k, double sigma) {
+    return guarded([&] {
+        AQML_REQUIRE(sigma != 0.0, "sigma is zero");
+        global_host(AQML_KERNEL_LAPLACIAN, EPI_EXP_STORE, a, na, b, nb, D, k, sigma);
+    });
+}
+int aqml_fl2_distance(const double *A, const double *B, int n1, int n2, int nc, double *Dm) {
+    return guarded([&] { global_host(AQML_KERNEL_GAUSSIAN, EPI_DIST_STORE, A, n1, B, n2, nc, Dm, 1.0); });
+}
+int aqml_fl1_distance(const double *A, const double *B, int n1, int n2, int nc, double *Dm) {
+    return guarded([&] { global_host(AQML_KERNEL_LAPLACIAN, EPI_DIST_STORE, A, n1, B, n2, nc, Dm, 1.0); });
+}
+
+int aqml_global_kernel_dev(int kind, const double *a, int na, int64_t lda, const double *b, int nb, int64_t ldb, int D,
+                           const double *sigmas, int nsig, int center, double *K, void *stream) {
+    return guarded([&] {
+        AQML_REQUIRE(kind == AQML_KERNEL_GAUSSIAN || kind == AQML_KERNEL_LAPLACIAN, "bad kernel kind %d", kind);
+        AQML_REQUIRE(a && b && K && sigmas, "null pointer");
+        global_pairs(kind, EPI_EXP_STORE, a, na, lda, b, nb, ldb, D, sigmas, nsig, center, K, (cudaStream_t)stream);
+    });
+}
+
+int aqml_max_distance_dev(int p, const double *a, int na, int64_t lda, const double *b, int nb, int64_t ldb, int D,
+                          double *dmax, void *stream) {
+    return guarded([&] {
+        AQML_REQUIRE(p == 1 || p == 2, "p must be 1 or 2");
+        AQML_REQUIRE(a && b && dmax && na >= 1 && nb >= 1, "bad argument");
+        cudaStream_t st = (cudaStream_t)stream;
+        require_device();
+        unsigned long long *bits = nullptr;
+        AQML_CUDA(cudaMallocAsync((void **)&bits, 8, st));
+        AQML_CUDA(cudaMemsetAsync(bits, 0, 8, st));
+        try {
+            global_pairs(p == 2 ? AQML_KERNEL_GAUSSIAN : AQML_KERNEL_LAPLACIAN, EPI_MAX, a, na, lda, b, nb, ldb, D, nullptr, 0,
+                         1, reinterpret_cast<double *>(bits), st);
+            double v = 0.0;
+            AQML_CUDA(cudaMemcpyAsync(&v, bits, 8, cudaMemcpyDeviceToHost, st));
+            AQML_CUDA(cudaStreamSynchronize(st));
+            *dmax = (p == 2) ? std::sqrt(v) : v;
+        } catch (...) {
+            cudaFreeAsync(bits, st);
+            throw;
+        }
+        cudaFreeAsync(bits, st);
+    });
+}
+
+int aqml_calc_lk_gaussian_dev(const double *x1, int64_t ldx1, const double *x2, int64_t ldx2, const int *zs1,
+                              const int *zs2, const int *nas1, const int *nas2, int zmax, int iab, const double *sigmas,
+                              int nm1, int nm2, int nsigmas, int D, int center, double *kernels, void *stream) {
+    return guarded([&] {
+        local_gaussian(x1, ldx1, x2, ldx2, zs1, zs2, nas1, nas2, zmax, iab, sigmas, nm1, nm2, nsigmas, D, center, kernels,
+                       (cudaStream_t)stream);
+    });
+}
+
+int aqml_calc_lk_gaussian(const double *x1, const double *x2, const int *zs1, const int *zs2, const int *nas1,
+                          const int *nas2, int zmax, int iab, const double *sigmas, int nm1, int nm2, int nsigmas, int D,
+                          double *kernels) {
+    return guarded([&] {
+        AQML_REQUIRE(x1 && x2 && nas1 && nas2 && kernels, "null pointer");
+        AQML_REQUIRE(nm1 >= 0 && nm2 >= 0 && nsigmas >= 1 && D >= 1, "bad shape");
+        require_device();
+        int A1, A2;
+        mol_index(nas1, nm1, A1);
+        mol_index(nas2, nm2, A2);
+        cudaStream_t st = 0;
+        Workspace ws(st);
+        const bool same = (x1 == x2 && A1 == A2);
+        double *d1 = ws.upload(x1, (size_t)A1 * D);
+        double *d2 = same ? d1 : ws.upload(x2, (size_t)A2 * D);
+        size_t nk = (size_t)nsigmas * nm1 * nm2;
+        double *dk = ws.alloc<double>(nk);
+        local_gaussian(d1, D, d2, D, zs1, zs2, nas1, nas2, zmax, iab, sigmas, nm1, nm2, nsigmas, D, 1, dk, st);
+        AQML_CUDA(cudaMemcpyAsync(kernels, dk, sizeof(double) * nk, cudaMemcpyDeviceToHost, st));
+        AQML_CUDA(cudaStreamSynchronize(st));
+    });
+}
+
+int aqml_calc_lk_laplacian_dev(const double *x1, int64_t ldx1, const double *x2, int64_t ldx2, const int *nas1,
+                               const int *nas2, const double *sigmas, int nm1, int nm2, int nsigmas, int D, double *kernels,
+                               void *stream) {
+    return guarded([&] {
+        local_laplacian(x1, ldx1, x2, ldx2, nas1, nas2, sigmas, nm1, nm2, nsigmas, D, kernels, (cudaStream_t)stream);
+    });
+}
+
+int aqml_calc_lk_laplacian(const double *x1, const double *x2, const int *nas1, const int *nas2, const double *sigmas,
+                           int nm1, int nm2, int nsigmas, int D, double *kernels) {
+    return guarded([&] {
+        AQML_REQUIRE(x1 && x2 && nas1 && nas2 && kernels, "null pointer");
+        AQML_REQUIRE(nm1 >= 0 && nm2 >= 0 && nsigmas >= 1 && D >= 1, "bad shape");
+        require_device();
+        int A1, A2;
+        mol_index(nas1, nm1, A1);
+        mol_index(nas2, nm2, A2);
+        cudaStream_t st = 0;
+        Workspace ws(st);
+        const bool same = (x1 == x2 && A1 == A2);
+        double *d1 = ws.upload(x1, (size_t)A1 * D);
+        double *d2 = same ? d1 : ws.upload(x2, (size_t)A2 * D);
+        size_t nk = (size_t)nsigmas * nm1 * nm2;
+        double *dk = ws.alloc<double>(nk);
+        local_laplacian(d1, D, d2, D, nas1, nas2, sigmas, nm1, nm2, nsigmas, D, dk, st);
+        AQML_CUDA(cudaMemcpyAsync(kernels, dk, sizeof(double) * nk, cudaMemcpyDeviceToHost, st));
+        AQML_CUDA(cudaStreamSynchronize(st));
+    });
+}
+
+int aqml_kernel_width_dev(int p, const double *x, int64_t ldx, const int *zs, int A, int D, int zmax, double *dso,
+                          void *stream) {
+    return guarded([&] { kernel_width(p, x, ldx, zs, A, D, zmax, dso, (cudaStream_t)stream); });
+}
+
+}  // extern "C"

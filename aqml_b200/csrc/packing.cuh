@@ -1,0 +1,28 @@
+// Declarations shared between kernels.cu and slatm.cu.
+#pragma once
+#include "common.cuh"
+#include "pairtile.cuh"
+
+namespace aqml {
+
+struct PackJob {
+    const double *src;   // (rows, lds)
+    long long lds;
+    const int *rowmap;   // packed row -> source row, -1 = zero row; null -> identity for r < nvalid
+    const int *colmap;   // packed col -> source col; null -> identity
+    const double *mean;  // per packed col, subtracted; may be null
+    double *dst;         // (packed rows, ldd)
+    long long ldd;
+    double *norm;        // |row|^2 per packed row; may be null
+    int ncols;           // valid packed columns (< = ldd)
+    int nvalid;          // valid rows when rowmap is null
+};
+
+void launch_pack(const PackJob &J, int nrows_packed, cudaStream_t st);
+void launch_colstats(const double *x, long long ldx, const int *rows, int nrows, int D, double *colsum, unsigned *colnz,
+                     cudaStream_t st);
+void build_tiles(const std::vector<int> &rows, const std::vector<int> &mol_of_row, std::vector<int> &rowmap,
+                 std::vector<int> &seg);
+void run_pairs_public(int mode, int epi, const std::vector<PairGroup> &groups, PairParams P, Workspace &ws);
+
+}  // namespace aqml

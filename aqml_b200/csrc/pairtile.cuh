@@ -1,0 +1,313 @@
+// Pair-tile engine: every kernel-matrix / distance routine of the hot path is one instance of
+//
+//     for a 128x128 tile of (row i of A, row j of B):  v_ij = reduce_k f(A[i,k], B[j,k])
+//     then an epilogue on v_ij
+//
+//   MODE_DOT : v = max(|a|^2 + |b|^2 - 2 a.b, 0); the cross term runs on the FP64 tensor cores
+//              (DMMA.8x8x4), operands staged through a 4-deep cp.async shared-memory pipeline.
+//   MODE_L1  : v = sum_k |a_k - b_k| on the FP64 CUDA cores (not a contraction), same staging.
+//
+//   EPI_EXP_STORE  : K[s][i][j] = exp(v * isig[s])          global Gaussian/Laplacian, all sigmas in one pass
+//   EPI_DIST_STORE : D[i][j]   = sqrt(v) | v                l2 / l1 distance matrices
+//   EPI_MAX        : out[slot] = max(out[slot], v)          kernel-width heuristic (never stores D)
+//   EPI_LOCAL      : K[s][mol(i)][mol(j)] += exp(v*isig[s][z_i])   local kernels: per-warp staged,
+//                    segmented (molecule-pair) reduction, then one FP64 RED per molecule pair.
+//
+// Work is described by a small table of PairGroups (one per element for the element-matched
+// local kernels -- the block-sparse mask of the design: only same-element atom pairs are ever
+// contracted, and only over the columns in that element's support).
+#pragma once
+#include "common.cuh"
+
+namespace aqml {
+
+constexpr int BM = 128, BN = 128, BK = 16;
+constexpr int PITCH = BK + 4;  // doubles; (PITCH mod 16) == 4 -> conflict-free 8x4 fragment loads
+constexpr int STAGES = 4;
+constexpr int NT = 256;        // 8 warps: 2 (M) x 4 (N), warp tile 64 x 32
+constexpr int STAGE_DOUBLES = (BM + BN) * PITCH;
+constexpr int PIPE_BYTES = STAGES * STAGE_DOUBLES * 8;  // 163840
+constexpr int EPITCH = 40;     // per-warp staging pitch (doubles) for the segmented epilogue
+static_assert(8 * 64 * EPITCH * 8 <= PIPE_BYTES, "epilogue staging must fit in the pipeline buffers");
+
+enum { MODE_DOT = 0, MODE_L1 = 1 };
+enum { EPI_EXP_STORE = 0, EPI_DIST_STORE = 1, EPI_MAX = 2, EPI_LOCAL = 3 };
+
+struct PairGroup {
+    const double *A, *B;          // packed operands, row pitch ld (multiple of BK), rows padded to 128
+    const double *normA, *normB;  // |row|^2 (MODE_DOT)
+    const int *segA, *segB;       // output index per packed row, -1 = padding; null -> identity < nA/nB
+    const int *zA;                // sigma column per packed A row; null -> zcol
+    long long ld;
+    int nA, nB;                   // valid rows when seg* is null
+    int tilesM, tilesN;
+    int tile_begin;               // first flattened tile id of this group
+    int zcol;
+    int out_slot;                 // EPI_MAX
+    int segA_off, segA_n;         // keep rows with segA_off <= seg < segA_off+segA_n, output row = seg - segA_off
+    int sym;                      // A == B: skip tiles below the diagonal (EPI_MAX only)
+};
+
+struct PairParams {
+    const PairGroup *groups;
+    int ngroups;
+    const double *isig;  // device (nsig, zstride)
+    int nsig, zstride;
+    double *out;
+    long long ldo, slab;  // row pitch, per-sigma stride (elements)
+};
+
+template <int MODE, int EPI>
+__global__ void __launch_bounds__(NT, 1) pair_tile_kernel(const PairParams P) {
+    extern __shared__ __align__(16) double smem[];
+    __shared__ int sSegA[BM], sSegB[BN], sZA[BM];
+    __shared__ double sNA[BM], sNB[BN];
+    __shared__ double sRed[NT / 32];
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int wm = warp >> 2, wn = warp & 3;
+    const int g = lane >> 2, t4 = lane & 3;
+
+    // ---- locate group and tile -------------------------------------------------------------
+    int gi = 0;
+    while (gi + 1 < P.ngroups && (int)blockIdx.x >= P.groups[gi + 1].tile_begin) gi++;
+    const PairGroup G = P.groups[gi];
+    const int t = blockIdx.x - G.tile_begin;
+    constexpr int GM = 16;  // tile rows per raster band: 16 A panels stay L2-resident while B streams
+    const int band = t / (GM * G.tilesN), rem = t % (GM * G.tilesN);
+    const int gm = min(GM, G.tilesM - band * GM);
+    const int tm = band * GM + rem % gm, tn = rem / gm;
+    if (EPI == EPI_MAX && G.sym && tn < tm) return;
+
+    // ---- tile metadata ---------------------------------------------------------------------
+    if (tid < BM) {
+        int r = tm * BM + tid;
+        int s = G.segA ? G.segA[r] : (r < G.nA ? r : -1);
+        s = (s >= G.segA_off && s - G.segA_off < G.segA_n) ? s - G.segA_off : -1;
+        sSegA[tid] = s;
+        sNA[tid] = G.normA ? G.normA[r] : 0.0;
+        sZA[tid] = G.zA ? G.zA[r] : G.zcol;
+    } else {
+        int c = tid - BM, r = tn * BN + c;
+        sSegB[c] = G.segB ? G.segB[r] : (r < G.nB ? r : -1);
+        sNB[c] = G.normB ? G.normB[r] : 0.0;
+    }
+    {
+        int any = (tid < BM) ? (sSegA[tid] >= 0) : 0;
+        if (!__syncthreads_or(any)) return;  // no row of this tile is wanted (row-block sharding)
+    }
+
+    // ---- main loop: 4-stage cp.async pipeline ------------------------------------------------
+    const double *gA = G.A + (long long)tm * BM * G.ld;
+    const double *gB = G.B + (long long)tn * BN * G.ld;
+    const int KT = (int)(G.ld / BK);
+
+    auto load_stage = [&](int stage, int kt) {
+        double *sA = smem + stage * STAGE_DOUBLES;
+        double *sB = sA + BM * PITCH;
+#pragma unroll
+        for (int i = 0; i < (BM * 8) / NT; i++) {
+            int c = tid + i * NT, row = c >> 3, ch = c & 7;
+            cp_async16(sA + row * PITCH + ch * 2, gA + (long long)row * G.ld + kt * BK + ch * 2);
+        }
+#pragma unroll
+        for (int i = 0; i < (BN * 8) / NT; i++) {
+            int c = tid + i * NT, row = c >> 3, ch = c & 7;
+            cp_async16(sB + row * PITCH + ch * 2, gB + (long long)row * G.ld + kt * BK + ch * 2);
+        }
+    };
+
+    double acc[8][4][2];
+#pragma unroll
+    for (int mi = 0; mi < 8; mi++)
+#pragma unroll
+        for (int ni = 0; ni < 4; ni++) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
+
+#pragma unroll
+    for (int s = 0; s < STAGES - 1; s++) {
+        if (s < KT) load_stage(s, s);
+        cp_async_commit();
+    }
+    for (int kt = 0; kt < KT; kt++) {
+        cp_async_wait<STAGES - 2>();
+        __syncthreads();
+        {
+            int nk = kt + STAGES - 1;
+            if (nk < KT) load_stage(nk % STAGES, nk);
+            cp_async_commit();
+        }
+        const double *sA = smem + (kt % STAGES) * STAGE_DOUBLES;
+        const double *sB = sA + BM * PITCH;
+        if (MODE == MODE_DOT) {
+            const double *pa = sA + (wm * 64 + g) * PITCH + t4;
+            const double *pb = sB + (wn * 32 + g) * PITCH + t4;
+#pragma unroll
+            for (int kk = 0; kk < BK / 4; kk++) {
+                double a[8], b[4];
+#pragma unroll
+                for (int mi = 0; mi < 8; mi++) a[mi] = pa[mi * 8 * PITCH + kk * 4];
+#pragma unroll
+                for (int ni = 0; ni < 4; ni++) b[ni] = pb[ni * 8 * PITCH + kk * 4];
+#pragma unroll
+                for (int mi = 0; mi < 8; mi++)
+#pragma unroll
+                    for (int ni = 0; ni < 4; ni++) dmma884(acc[mi][ni][0], acc[mi][ni][1], a[mi], b[ni]);
+            }
+        } else {
+            // same accumulator ownership as the DMMA C fragment: rows 8*mi+g, cols 8*ni+2*t4+{0,1}
+            const double *pa = sA + (wm * 64 + g) * PITCH;
+            const double *pb = sB + (wn * 32 + 2 * t4) * PITCH;
+#pragma unroll 2
+            for (int kk = 0; kk < BK; kk += 2) {
+                double2 a[8], b[4][2];
+#pragma unroll
+                for (int mi = 0; mi < 8; mi++) a[mi] = *reinterpret_cast<const double2 *>(pa + mi * 8 * PITCH + kk);
+#pragma unroll
+                for (int ni = 0; ni < 4; ni++) {
+                    b[ni][0] = *reinterpret_cast<const double2 *>(pb + (ni * 8) * PITCH + kk);
+                    b[ni][1] = *reinterpret_cast<const double2 *>(pb + (ni * 8 + 1) * PITCH + kk);
+                }
+#pragma unroll
+                for (int mi = 0; mi < 8; mi++)
+#pragma unroll
+                    for (int ni = 0; ni < 4; ni++)
+#pragma unroll
+                        for (int e = 0; e < 2; e++) {
+                            double v = acc[mi][ni][e];
+                            v += fabs(a[mi].x - b[ni][e].x);  // k ascending, as the reference's sum(abs(..))
+                            v += fabs(a[mi].y - b[ni][e].y);
+                            acc[mi][ni][e] = v;
+                        }
+            }
+        }
+    }
+    cp_async_wait<0>();
+    __syncthreads();  // pipeline buffers are free from here on
+
+    // ---- v_ij -------------------------------------------------------------------------------
+    if (MODE == MODE_DOT) {
+#pragma unroll
+        for (int mi = 0; mi < 8; mi++) {
+            double na = sNA[wm * 64 + mi * 8 + g];
+#pragma unroll
+            for (int ni = 0; ni < 4; ni++)
+#pragma unroll
+                for (int e = 0; e < 2; e++) {
+                    double nb = sNB[wn * 32 + ni * 8 + 2 * t4 + e];
+                    acc[mi][ni][e] = fmax(na + nb - 2.0 * acc[mi][ni][e], 0.0);
+                }
+        }
+    }
+
+    // ---- epilogues ----------------------------------------------------------------------------
+    if (EPI == EPI_EXP_STORE) {
+        for (int s = 0; s < P.nsig; s++) {
+            double *outS = P.out + (long long)s * P.slab;
+#pragma unroll
+            for (int mi = 0; mi < 8; mi++) {
+                int row = wm * 64 + mi * 8 + g;
+                int sr = sSegA[row];
+                if (sr < 0) continue;
+                double f = P.isig[s * P.zstride + sZA[row]];
+#pragma unroll
+                for (int ni = 0; ni < 4; ni++)
+#pragma unroll
+                    for (int e = 0; e < 2; e++) {
+                        int sc = sSegB[wn * 32 + ni * 8 + 2 * t4 + e];
+                        if (sc >= 0) outS[(long long)sr * P.ldo + sc] = exp(acc[mi][ni][e] * f);
+                    }
+            }
+        }
+    } else if (EPI == EPI_DIST_STORE) {
+#pragma unroll
+        for (int mi = 0; mi < 8; mi++) {
+            int sr = sSegA[wm * 64 + mi * 8 + g];
+            if (sr < 0) continue;
+#pragma unroll
+            for (int ni = 0; ni < 4; ni++)
+#pragma unroll
+                for (int e = 0; e < 2; e++) {
+                    int sc = sSegB[wn * 32 + ni * 8 + 2 * t4 + e];
+                    if (sc >= 0) P.out[(long long)sr * P.ldo + sc] = (MODE == MODE_DOT) ? sqrt(acc[mi][ni][e]) : acc[mi][ni][e];
+                }
+        }
+    } else if (EPI == EPI_MAX) {
+        double m = 0.0;
+#pragma unroll
+        for (int mi = 0; mi < 8; mi++) {
+            if (sSegA[wm * 64 + mi * 8 + g] < 0) continue;
+#pragma unroll
+            for (int ni = 0; ni < 4; ni++)
+#pragma unroll
+                for (int e = 0; e < 2; e++)
+                    if (sSegB[wn * 32 + ni * 8 + 2 * t4 + e] >= 0) m = fmax(m, acc[mi][ni][e]);
+        }
+        m = warp_max(m);
+        if (lane == 0) sRed[warp] = m;
+        __syncthreads();
+        if (tid == 0) {
+            for (int w = 1; w < NT / 32; w++) m = fmax(m, sRed[w]);
+            // v >= 0: IEEE order == unsigned integer order of the bit patterns
+            atomicMax(reinterpret_cast<unsigned long long *>(P.out) + G.out_slot, (unsigned long long)__double_as_longlong(m));
+        }
+    } else {  // EPI_LOCAL
+        // Each warp owns a 64x32 patch of atom pairs.  Per sigma: exp -> warp-private smem patch
+        // (conflict-free 16-byte stores), then lane c walks column c down the rows, summing the rows
+        // of one molecule (row segment); at each row-segment end a segmented shuffle reduction sums
+        // the lanes of one molecule (column segment) and the segment head issues one RED.F64.
+        double *patch = smem + warp * (64 * EPITCH);
+        const int colseg = sSegB[wn * 32 + lane];
+        const int prevseg = __shfl_up_sync(0xffffffffu, colseg, 1);
+        const bool head = (lane == 0) || (prevseg != colseg);
+        const unsigned heads = __ballot_sync(0xffffffffu, head);
+        // last lane of my run
+        const unsigned above = (lane == 31) ? 0u : (heads >> (lane + 1));
+        const int run_end = above ? (lane + __ffs(above) - 1) : 31;
+        const int *rowseg = sSegA + wm * 64;
+        for (int s = 0; s < P.nsig; s++) {
+#pragma unroll
+            for (int mi = 0; mi < 8; mi++) {
+                int row = mi * 8 + g;
+                double f = P.isig[s * P.zstride + sZA[wm * 64 + row]];
+#pragma unroll
+                for (int ni = 0; ni < 4; ni++) {
+                    double2 v;
+                    v.x = exp(acc[mi][ni][0] * f);
+                    v.y = exp(acc[mi][ni][1] * f);
+                    *reinterpret_cast<double2 *>(patch + row * EPITCH + ni * 8 + 2 * t4) = v;
+                }
+            }
+            __syncwarp();
+            double *outS = P.out + (long long)s * P.slab;
+            double run = 0.0;
+            for (int r = 0; r < 64; r++) {
+                const int sr = rowseg[r];
+                if (sr >= 0) run += patch[r * EPITCH + lane];
+                const bool last = (r == 63) || (rowseg[r + 1] != sr);
+                if (last) {
+                    if (sr >= 0) {
+                        double v = run;
+#pragma unroll
+                        for (int o = 1; o < 32; o <<= 1) {
+                            double u = __shfl_down_sync(0xffffffffu, v, o);
+                            if (lane + o <= run_end) v += u;
+                        }
+                        if (head && colseg >= 0) atomicAdd(outS + (long long)sr * P.ldo + colseg, v);
+                    }
+                    run = 0.0;
+                }
+            }
+            __syncwarp();
+        }
+    }
+}
+
+template <int MODE, int EPI>
+void launch_pair_tiles(const PairParams &P, int total_tiles, cudaStream_t stream) {
+    if (total_tiles <= 0) return;
+    AQML_CUDA(cudaFuncSetAttribute(pair_tile_kernel<MODE, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, PIPE_BYTES));
+    pair_tile_kernel<MODE, EPI><<<total_tiles, NT, PIPE_BYTES, stream>>>(P);
+    AQML_LAUNCH_CHECK();
+}
+
+}  // namespace aqml

@@ -1,0 +1,748 @@
+// SLATM / aSLATM generation (replaces coreml/cml/representation/fslatm.f90 + the Python double loop of
+// representation/core.py:430-554) and the fused element-packed representation (aqml_rep).
+//
+// One thread block per atom (local) or per (molecule, element) (global).  The block
+//   1. loads the molecule, builds the centre's neighbour list sorted by element (list order kept),
+//   2. two-body:   thread <-> (partner element, grid point) accumulates London terms in registers,
+//   3. three-body: neighbour pairs are enumerated block by block (a block = one [z1,zc,z3] type),
+//      their geometry (angle, two cosines, 1/r^3) is computed once into shared memory, then
+//      thread <-> (block, grid point) accumulates the ATM terms over the block's pairs,
+//   4. the spectrum (shared memory, laid out as the centre element's support) is written with
+//      coalesced stores either into the dense (row, D) API layout or straight into the
+//      element-packed operand the local-kernel GEMM consumes (+ |row|^2).
+// Every output element has exactly one owner thread: no atomics, deterministic, and the
+// accumulation order over pairs equals the reference's loop order (i ascending, k ascending).
+#include "packing.cuh"
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <map>
+#include <memory>
+
+namespace aqml {
+
+constexpr int MAXEL = 16;
+constexpr int SL_THREADS = 128;
+constexpr int PCH = 512;  // neighbour pairs per shared-memory chunk
+
+struct SlatmDev {
+    int n_el, nmb, nx2, nx3, D;
+    double sigma2, sigma3, dgrid2, dgrid3, coeff2, coeff3, rcut, rpower;
+    int el_label[MAXEL];
+    double el_w[MAXEL];
+    int pdim[MAXEL], pld[MAXEL];  // support size of each centre element in the current layout (+16-padded)
+    const int *slot_kind, *slot_col, *slot_e0;  // per mbtype: 1|2|3, dense column, element index of a 1-body type
+    const int *bop_slot;                        // [MAXEL*MAXEL] slot or -1 (symmetric)
+    const int *bot_slot;                        // [MAXEL^3] (e1,ec,e3) -> 2*slot+flip or -1 (both orientations filled)
+    const int *lay_col;                         // [n_el*nmb] column of slot in element e's layout or -1
+    const int *owner;                           // [nmb] owning element of a slot in global mode
+    const double *xs2, *xpow2, *xs3, *cosx3;    // grids (host libm): xs, xs**rpower, angles, cos(angles)
+};
+
+struct SlatmJob {
+    const double *coords;  // (A,3)
+    const int *zs;         // (A) element labels
+    const int *mol_off;    // (nmol+1)
+    const int *atom_mol;   // (A)
+    int nmol, A, local;
+    // dense output
+    double *out;
+    long long ldo;
+    // packed output (local only): per element destination
+    const int *atom_prow;  // (A) packed row inside the element's buffer, -1 = skip
+    double *px[MAXEL];
+    double *pnorm[MAXEL];
+};
+
+// geometry with the oracle's operation order and no FMA contraction (decisions / angles are
+// discontinuous or ill-conditioned, SURVEY 7 hard part 9)
+__device__ __forceinline__ double dist2_rn(double ax, double ay, double az, double bx, double by, double bz) {
+    double dx = __dsub_rn(ax, bx), dy = __dsub_rn(ay, by), dz = __dsub_rn(az, bz);
+    return __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
+}
+// cosine of the angle at b (utils.f90:82-103)
+__device__ __forceinline__ double cos_angle_rn(const double *a, const double *b, const double *c) {
+    double v1x = __dsub_rn(a[0], b[0]), v1y = __dsub_rn(a[1], b[1]), v1z = __dsub_rn(a[2], b[2]);
+    double v2x = __dsub_rn(c[0], b[0]), v2y = __dsub_rn(c[1], b[1]), v2z = __dsub_rn(c[2], b[2]);
+    double n1 = __dsqrt_rn(__dadd_rn(__dadd_rn(__dmul_rn(v1x, v1x), __dmul_rn(v1y, v1y)), __dmul_rn(v1z, v1z)));
+    double n2 = __dsqrt_rn(__dadd_rn(__dadd_rn(__dmul_rn(v2x, v2x), __dmul_rn(v2y, v2y)), __dmul_rn(v2z, v2z)));
+    v1x = __ddiv_rn(v1x, n1); v1y = __ddiv_rn(v1y, n1); v1z = __ddiv_rn(v1z, n1);
+    v2x = __ddiv_rn(v2x, n2); v2y = __ddiv_rn(v2y, n2); v2z = __ddiv_rn(v2z, n2);
+    return __dadd_rn(__dadd_rn(__dmul_rn(v1x, v2x), __dmul_rn(v1y, v2y)), __dmul_rn(v1z, v2z));
+}
+
+struct Block3 {
+    int e1, e3, col, flip, p0;  // pair offset p0; pairs = n1*n3 or n1(n1-1)/2
+    double c0;
+};
+
+// dynamic shared memory carve-up (doubles first)
+//   spec[pldmax] | mx,my,mz[na_max] | nbx,nby,nbz,nbd,nbr2[na_max] | pair[4*PCH] | ints: mel[na_max], nbi[na_max], nbe[na_max], nbf[na_max]
+__global__ void __launch_bounds__(SL_THREADS) slatm_kernel(const SlatmDev T, const SlatmJob J, int pldmax, int na_max) {
+    extern __shared__ __align__(16) double sm[];
+    double *spec = sm;
+    double *mx = spec + pldmax, *my = mx + na_max, *mz = my + na_max;
+    double *nbx = mz + na_max, *nby = nbx + na_max, *nbz = nby + na_max, *nbd = nbz + na_max, *nbr2 = nbd + na_max;
+    double *pair = nbr2 + na_max;
+    int *mel = reinterpret_cast<int *>(pair + 4 * PCH);
+    int *nbi = mel + na_max, *nbe = nbi + na_max, *nbf = nbe + na_max;
+    __shared__ int s_cnt[MAXEL], s_start[MAXEL + 1];
+    __shared__ Block3 s_blk[MAXEL * (MAXEL + 1) / 2];
+    __shared__ int s_nblk, s_ptot;
+    __shared__ double s_red[SL_THREADS / 32];
+
+    const int tid = threadIdx.x;
+    const double eps = 2.220446049250313e-16;
+    const double rcut = T.rcut, rcut2 = __dmul_rn(rcut, rcut);
+
+    int m, ec, c_first, c_last;  // centre range inside the molecule
+    if (J.local) {
+        int a = blockIdx.x;
+        m = J.atom_mol[a];
+        c_first = a - J.mol_off[m];
+        c_last = c_first + 1;
+        ec = -2;  // from the atom
+    } else {
+        m = blockIdx.x / T.n_el;
+        ec = blockIdx.x % T.n_el;
+        c_first = 0;
+        c_last = J.mol_off[m + 1] - J.mol_off[m];
+    }
+    const int o = J.mol_off[m], na = J.mol_off[m + 1] - o;
+
+    for (int i = tid; i < na; i += SL_THREADS) {
+        mx[i] = J.coords[3 * (long long)(o + i)];
+        my[i] = J.coords[3 * (long long)(o + i) + 1];
+        mz[i] = J.coords[3 * (long long)(o + i) + 2];
+        int z = J.zs[o + i], e = -1;
+        for (int q = 0; q < T.n_el; q++)
+            if (T.el_label[q] == z) e = q;
+        mel[i] = e;
+    }
+    __syncthreads();
+    if (J.local) ec = mel[c_first];
+    const int pld = (ec >= 0) ? T.pld[ec] : 0;
+    for (int i = tid; i < pld; i += SL_THREADS) spec[i] = 0.0;
+
+    if (ec >= 0) {
+        const int *lay = T.lay_col + ec * T.nmb;
+        for (int c = c_first; c < c_last; c++) {
+            if (mel[c] != ec) continue;  // block-uniform
+            __syncthreads();
+            // ---- neighbour list, sorted by element, list order preserved ---------------------
+            if (tid < T.n_el) {
+                int e = tid, n = 0;
+                for (int q = 0; q < na; q++) {
+                    if (q == c || mel[q] != e) continue;
+                    double r2 = dist2_rn(mx[c], my[c], mz[c], mx[q], my[q], mz[q]);
+                    double d = __dsqrt_rn(r2);
+                    int f2 = (r2 < rcut2), f3 = (d > eps) && (d <= rcut);
+                    n += (f2 | f3);
+                }
+                s_cnt[e] = n;
+            }
+            __syncthreads();
+            if (tid == 0) {
+                int acc = 0;
+                for (int e = 0; e < T.n_el; e++) { s_start[e] = acc; acc += s_cnt[e]; }
+                s_start[T.n_el] = acc;
+            }
+            __syncthreads();
+            if (tid < T.n_el) {
+                int e = tid, w = s_start[e];
+                for (int q = 0; q < na; q++) {
+                    if (q == c || mel[q] != e) continue;
+                    double r2 = dist2_rn(mx[c], my[c], mz[c], mx[q], my[q], mz[q]);
+                    double d = __dsqrt_rn(r2);
+                    int f2 = (r2 < rcut2), f3 = (d > eps) && (d <= rcut);
+                    if (f2 | f3) {
+                        nbx[w] = mx[q]; nby[w] = my[q]; nbz[w] = mz[q]; nbd[w] = d; nbr2[w] = r2;
+                        nbi[w] = q; nbe[w] = e; nbf[w] = f2 | (f3 << 1);
+                        w++;
+                    }
+                }
+            }
+            // ---- three-body block table -----------------------------------------------------------
+            if (tid == 0) {
+                int nb = 0, p = 0;
+                for (int e1 = 0; e1 < T.n_el; e1++)
+                    for (int e3 = e1; e3 < T.n_el; e3++) {
+                        int sl = T.bot_slot[(e1 * MAXEL + ec) * MAXEL + e3];
+                        if (sl < 0) continue;
+                        int n1 = s_cnt[e1], n3 = s_cnt[e3];
+                        int np = (e1 == e3) ? n1 * (n1 - 1) / 2 : n1 * n3;
+                        if (np <= 0) continue;
+                        Block3 b;
+                        b.e1 = e1; b.e3 = e3; b.col = lay[sl >> 1]; b.flip = sl & 1; b.p0 = p;
+                        // c0 = prefactor * (Z1*Z2*Z3) * coeff * dgrid   (fslatm.f90:324-332), mbtype order
+                        double w1 = T.el_w[b.flip ? e3 : e1], w3 = T.el_w[b.flip ? e1 : e3];
+                        b.c0 = (1.0 / 3.0) * (w1 * T.el_w[ec] * w3) * T.coeff3 * T.dgrid3;
+                        s_blk[nb++] = b;
+                        p += np;
+                    }
+                s_nblk = nb;
+                s_ptot = p;
+            }
+            __syncthreads();
+
+            // ---- two-body: thread <-> (partner element, grid point) ---------------------------------
+            {
+                const double inv2 = -0.5 / (T.sigma2 * T.sigma2);
+                const double pref = J.local ? 0.5 : 1.0;
+                for (int oidx = tid; oidx < T.n_el * T.nx2; oidx += SL_THREADS) {
+                    int e2 = oidx / T.nx2, x = oidx - e2 * T.nx2;
+                    int sl = T.bop_slot[ec * MAXEL + e2];
+                    if (sl < 0) continue;
+                    if (!J.local && e2 < ec) continue;  // owned by the other element's block
+                    int col = lay[sl];
+                    if (col < 0) continue;
+                    double c0 = pref * (T.el_w[ec] * T.el_w[e2]) * T.coeff2;
+                    double w = c0 / T.xpow2[x] * T.dgrid2;
+                    double xg = T.xs2[x];
+                    double acc = 0.0;
+                    for (int n = s_start[e2]; n < s_start[e2 + 1]; n++) {
+                        if (!(nbf[n] & 1)) continue;
+                        if (!J.local && e2 == ec && nbi[n] < c) continue;  // unordered pair counted once
+                        double t = xg - sqrt(nbr2[n]);
+                        acc += w * exp(inv2 * (t * t));
+                    }
+                    spec[col + x] += acc;
+                }
+            }
+
+            // ---- three-body, chunked over the pair list ------------------------------------------
+            const int ptot = s_ptot, nblk = s_nblk;
+            const double inv3 = -1.0 / (2 * T.sigma3 * T.sigma3);
+            const double cc[3] = {mx[c], my[c], mz[c]};
+            for (int P0 = 0; P0 < ptot; P0 += PCH) {
+                const int P1 = min(ptot, P0 + PCH);
+                __syncthreads();
+                for (int p = P0 + tid; p < P1; p += SL_THREADS) {
+                    int b = 0;
+                    while (b + 1 < nblk && p >= s_blk[b + 1].p0) b++;
+                    const Block3 B = s_blk[b];
+                    int q = p - B.p0, i, k;
+                    int n1 = s_cnt[B.e1], n3 = s_cnt[B.e3];
+                    if (B.e1 == B.e3) {
+                        i = 0;
+                        while (q >= n1 - 1 - i) { q -= n1 - 1 - i; i++; }
+                        k = i + 1 + q;
+                    } else {
+                        i = q / n3;
+                        k = q - i * n3;
+                    }
+                    i += s_start[B.e1];
+                    k += s_start[B.e3];
+                    double ang = 0.0, cak = 0.0, cai = 0.0, rinv3 = 0.0;
+                    if ((nbf[i] & 2) && (nbf[k] & 2)) {
+                        // reference roles: "i" is the atom of the type's first element (flip swaps)
+                        int I = B.flip ? k : i, K = B.flip ? i : k;
+                        double pi[3] = {nbx[I], nby[I], nbz[I]}, pk[3] = {nbx[K], nby[K], nbz[K]};
+                        double dik = __dsqrt_rn(dist2_rn(pi[0], pi[1], pi[2], pk[0], pk[1], pk[2]));
+                        if (dik <= rcut) {
+                            double ca = cos_angle_rn(pi, cc, pk);
+                            ca = fmin(1.0, fmax(-1.0, ca));
+                            ang = acos(ca);
+                            cak = cos_angle_rn(pi, pk, cc);
+                            cai = cos_angle_rn(pk, pi, cc);
+                            double r = __dmul_rn(__dmul_rn(nbd[I], dik), nbd[K]);
+                            rinv3 = 1.0 / (r * r * r);
+                        }
+                    }
+                    double *pp = pair + 4 * (p - P0);
+                    pp[0] = ang; pp[1] = cak; pp[2] = cai; pp[3] = rinv3;
+                }
+                __syncthreads();
+                for (int oidx = tid; oidx < nblk * T.nx3; oidx += SL_THREADS) {
+                    int b = oidx / T.nx3, x = oidx - b * T.nx3;
+                    const int q0 = max(s_blk[b].p0, P0);
+                    const int q1 = min((b + 1 < nblk) ? s_blk[b + 1].p0 : ptot, P1);
+                    if (q0 >= q1) continue;
+                    const double c0 = s_blk[b].c0;
+                    const double cosc = T.cosx3[x] * c0;  // cos_xs(i) = cos(xs(i)) * c0, fslatm.f90:338-340
+                    const double xg = T.xs3[x];
+                    double acc = 0.0;
+                    for (int p = q0; p < q1; p++) {
+                        const double *pp = pair + 4 * (p - P0);
+                        double rinv3 = pp[3];
+                        if (rinv3 == 0.0) continue;
+                        double t = xg - pp[0];
+                        acc += (c0 + cosc * pp[1] * pp[2]) * rinv3 * exp((t * t) * inv3);
+                    }
+                    spec[s_blk[b].col + x] += acc;
+                }
+            }
+        }
+    }
+    __syncthreads();
+
+    // ---- output ---------------------------------------------------------------------------------
+    if (J.local) {
+        const int a = blockIdx.x;
+        if (J.out) {
+            double *row = J.out + (long long)a * J.ldo;
+            const int z = J.zs[a];
+            for (int s = 0; s < T.nmb; s++) {
+                int kind = T.slot_kind[s], col = T.slot_col[s];
+                if (kind == 1) {
+                    if (tid == 0) row[col] = (ec >= 0 && T.slot_e0[s] == ec) ? (double)z : 0.0;
+                } else {
+                    int len = (kind == 2) ? T.nx2 : T.nx3;
+                    int lc = (ec >= 0) ? T.lay_col[ec * T.nmb + s] : -1;
+                    for (int x = tid; x < len; x += SL_THREADS) row[col + x] = (lc >= 0) ? spec[lc + x] : 0.0;
+                }
+            }
+        }
+        if (J.atom_prow && ec >= 0) {
+            int pr = J.atom_prow[a];
+            if (pr >= 0) {
+                double *row = J.px[ec] + (long long)pr * pld;
+                double ss = 0.0;
+                for (int i = tid; i < pld; i += SL_THREADS) {
+                    double v = spec[i];
+                    row[i] = v;
+                    ss += v * v;
+                }
+                ss = warp_sum(ss);
+                if ((tid & 31) == 0) s_red[tid >> 5] = ss;
+                __syncthreads();
+                if (tid == 0) {
+                    double t = 0.0;
+                    for (int w = 0; w < SL_THREADS / 32; w++) t += s_red[w];
+                    J.pnorm[ec][pr] = t;
+                }
+            }
+        }
+    } else {
+        double *row = J.out + (long long)m * J.ldo;
+        for (int s = 0; s < T.nmb; s++) {
+            if (T.owner[s] != ec) continue;
+            int kind = T.slot_kind[s], col = T.slot_col[s];
+            if (kind == 1) {
+                if (tid == 0) {
+                    int cnt = 0;
+                    for (int q = 0; q < na; q++) cnt += (mel[q] == ec);
+                    row[col] = (double)(T.el_label[ec] * cnt);
+                }
+            } else {
+                int len = (kind == 2) ? T.nx2 : T.nx3;
+                int lc = T.lay_col[ec * T.nmb + s];
+                for (int x = tid; x < len; x += SL_THREADS) row[col + x] = (lc >= 0) ? spec[lc + x] : 0.0;
+            }
+        }
+    }
+}
+
+__global__ void zero_rows_kernel(double *x, long long ld, const int *rows, int nrows, double *norm) {
+    int r = rows[blockIdx.x];
+    for (long long i = threadIdx.x; i < ld; i += blockDim.x) x[(long long)r * ld + i] = 0.0;
+    if (threadIdx.x == 0 && norm) norm[r] = 0.0;
+}
+
+// =============================================================================================
+// host: tables
+// =============================================================================================
+static double zstar_host(int z) {
+    static const int zs[20] = {1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15, 16, 17, 18, 35, 53};
+    static const float ze[20] = {1.0f, 1.688f, 1.279f, 1.912f, 2.421f, 3.136f, 3.834f, 4.453f, 5.100f, 5.758f,
+                                 2.507f, 3.308f, 4.066f, 4.285f, 4.886f, 5.482f, 6.116f, 6.764f, 9.028f, 11.612f};
+    for (int j = 0; j < 20; j++) if (zs[j] == z) return (double)ze[j];  // atomdb.f90:97-106 (single-precision literals)
+    fail(AQML_EINVAL, "izeff: no effective nuclear charge tabulated for Z=%d (atomdb.f90:94-96)", z);
+}
+
+struct SlatmTables {
+    SlatmDev dev;
+    std::vector<int> labels;  // element labels, ascending
+    int pldmax = 0;
+    int nmb = 0;
+    std::vector<int> owner_h;
+};
+
+static void check_params(const aqml_slatm_params *p) {
+    AQML_REQUIRE(p && p->mbtypes && p->nmb >= 1, "missing many-body types");
+    AQML_REQUIRE(p->nx2 >= 2 && p->nx3 >= 2, "grids need at least 2 points");
+    AQML_REQUIRE(p->sigma2 > 0 && p->sigma3 > 0 && p->rcut > 0, "sigma/rcut must be positive");
+}
+
+// mode_local: layout of element e = every 2-body block containing e + every 3-body block centred on e
+// global: 2-body block owned by the smaller element index, 3-body by its centre
+static SlatmTables build_tables(const aqml_slatm_params *p, bool mode_local, Workspace &ws) {
+    check_params(p);
+    SlatmTables t;
+    t.nmb = p->nmb;
+    std::vector<int> &labels = t.labels;
+    for (int s = 0; s < p->nmb; s++)
+        for (int q = 0; q < 3; q++) {
+            int z = p->mbtypes[3 * s + q];
+            if (z >= 0) labels.push_back(z);
+            else AQML_REQUIRE(q > 0, "mbtype %d is empty", s);
+        }
+    std::sort(labels.begin(), labels.end());
+    labels.erase(std::unique(labels.begin(), labels.end()), labels.end());
+    const int ne = (int)labels.size();
+    if (ne > MAXEL) fail(AQML_ELIMIT, "%d distinct elements in mbtypes, limit is %d", ne, MAXEL);
+    auto eidx = [&](int z) { return (int)(std::lower_bound(labels.begin(), labels.end(), z) - labels.begin()); };
+
+    SlatmDev &d = t.dev;
+    memset(&d, 0, sizeof(d));
+    d.n_el = ne; d.nmb = p->nmb; d.nx2 = p->nx2; d.nx3 = p->nx3;
+    d.sigma2 = p->sigma2; d.sigma3 = p->sigma3; d.dgrid2 = p->dgrid2; d.dgrid3 = p->dgrid3;
+    d.coeff2 = p->coeff2; d.coeff3 = p->coeff3; d.rcut = p->rcut; d.rpower = p->rpower;
+    for (int e = 0; e < ne; e++) {
+        d.el_label[e] = labels[e];
+        d.el_w[e] = p->izeff ? zstar_host(labels[e]) : (double)(labels[e] % 1000);
+    }
+    std::vector<int> kind(p->nmb), col(p->nmb), e0(p->nmb, -1), owner(p->nmb, -1);
+    std::vector<int> bop(MAXEL * MAXEL, -1), bot(MAXEL * MAXEL * MAXEL, -1);
+    std::vector<int> boa_seen(MAXEL, 0);
+    int D = 0;
+    for (int s = 0; s < p->nmb; s++) {
+        const int *mb = p->mbtypes + 3 * s;
+        col[s] = D;
+        if (mb[1] < 0) {
+            kind[s] = 1; D += 1; e0[s] = eidx(mb[0]); owner[s] = e0[s];
+            if (boa_seen[e0[s]]++) fail(AQML_ELIMIT, "duplicate one-body type [%d]", mb[0]);
+        } else if (mb[2] < 0) {
+            kind[s] = 2; D += p->nx2;
+            int a = eidx(mb[0]), b = eidx(mb[1]);
+            if (bop[a * MAXEL + b] >= 0) fail(AQML_ELIMIT, "two-body type [%d,%d] listed twice (either order)", mb[0], mb[1]);
+            bop[a * MAXEL + b] = bop[b * MAXEL + a] = s;
+            owner[s] = std::min(a, b);
+        } else {
+            kind[s] = 3; D += p->nx3;
+            int a = eidx(mb[0]), c = eidx(mb[1]), b = eidx(mb[2]);
+            if (bot[(a * MAXEL + c) * MAXEL + b] >= 0)
+                fail(AQML_ELIMIT, "three-body type [%d,%d,%d] listed twice (either orientation)", mb[0], mb[1], mb[2]);
+            // kernel enumerates neighbour pairs with e1 <= e3; flip=1 when the listed type has z1 > z3
+            bot[(a * MAXEL + c) * MAXEL + b] = 2 * s + (a > b ? 1 : 0);
+            bot[(b * MAXEL + c) * MAXEL + a] = 2 * s + (a > b ? 1 : 0);
+            owner[s] = c;
+        }
+    }
+    d.D = D;
+    std::vector<int> lay((size_t)ne * p->nmb, -1);
+    for (int e = 0; e < ne; e++) {
+        int w = 0;
+        for (int pass = 2; pass <= 3; pass++)
+            for (int s = 0; s < p->nmb; s++) {
+                if (kind[s] != pass) continue;
+                const int *mb = p->mbtypes + 3 * s;
+                bool in;
+                if (pass == 2) in = mode_local ? (eidx(mb[0]) == e || eidx(mb[1]) == e) : (owner[s] == e);
+                else in = (eidx(mb[1]) == e);
+                if (in) { lay[(size_t)e * p->nmb + s] = w; w += (pass == 2 ? p->nx2 : p->nx3); }
+            }
+        d.pdim[e] = w;
+        d.pld[e] = (int)round_up(std::max(w, 1), BK);
+        t.pldmax = std::max(t.pldmax, d.pld[e]);
+    }
+    // grids on the host (same libm as the CPU reference): utils.f90:29-50, slatm.py:60-62,118-122
+    std::vector<double> xs2(p->nx2), xp2(p->nx2), xs3(p->nx3), cx3(p->nx3);
+    {
+        double step = (p->rcut - 0.1) / (p->nx2 - 1);
+        for (int i = 0; i < p->nx2; i++) { xs2[i] = 0.1 + i * step; xp2[i] = std::pow(xs2[i], p->rpower); }
+        const double pi = 4.0 * std::atan(1.0), d2r = pi / 180.0, a0 = -20.0 * d2r, a1 = pi + 20.0 * d2r;
+        double st3 = (a1 - a0) / (p->nx3 - 1);
+        for (int i = 0; i < p->nx3; i++) { xs3[i] = a0 + i * st3; cx3[i] = std::cos(xs3[i]); }
+    }
+    d.slot_kind = ws.upload(kind); d.slot_col = ws.upload(col); d.slot_e0 = ws.upload(e0);
+    d.bop_slot = ws.upload(bop); d.bot_slot = ws.upload(bot); d.lay_col = ws.upload(lay); d.owner = ws.upload(owner);
+    d.xs2 = ws.upload(xs2); d.xpow2 = ws.upload(xp2); d.xs3 = ws.upload(xs3); d.cosx3 = ws.upload(cx3);
+    t.owner_h = owner;
+    return t;
+}
+
+static size_t slatm_smem_bytes(int pldmax, int na_max) {
+    return sizeof(double) * ((size_t)pldmax + 8 * (size_t)na_max + 4 * PCH) + sizeof(int) * 4 * (size_t)na_max;
+}
+
+static void launch_slatm(const SlatmTables &t, const SlatmJob &J, int na_max, cudaStream_t st) {
+    int nblocks = J.local ? J.A : J.nmol * t.dev.n_el;
+    if (nblocks <= 0) return;
+    na_max = (int)round_up(std::max(na_max, 1), 2);
+    size_t smem = slatm_smem_bytes(t.pldmax, na_max);
+    if (smem > 200 * 1024)
+        fail(AQML_ELIMIT, "molecule with %d atoms / support %d needs %zu B of shared memory (limit 200 KiB)", na_max, t.pldmax, smem);
+    AQML_CUDA(cudaFuncSetAttribute(slatm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    slatm_kernel<<<nblocks, SL_THREADS, smem, st>>>(t.dev, J, t.pldmax, na_max);
+    AQML_LAUNCH_CHECK();
+}
+
+struct MolIndex {
+    std::vector<int> off, atom_mol;
+    int A = 0, na_max = 0;
+};
+static MolIndex index_molecules(const int *nas, int nmol) {
+    MolIndex mi;
+    mi.off.resize(nmol + 1, 0);
+    for (int i = 0; i < nmol; i++) {
+        AQML_REQUIRE(nas[i] >= 0, "negative atom count");
+        mi.off[i + 1] = mi.off[i] + nas[i];
+        mi.na_max = std::max(mi.na_max, nas[i]);
+    }
+    mi.A = mi.off[nmol];
+    mi.atom_mol.reserve(mi.A);
+    for (int i = 0; i < nmol; i++) mi.atom_mol.insert(mi.atom_mol.end(), nas[i], i);
+    return mi;
+}
+
+static void slatm_batch_dev(const double *coords, const int *zs_dev, const int *nas, int nmol, const aqml_slatm_params *p,
+                            int local, double *out, long long ldo, cudaStream_t st) {
+    AQML_REQUIRE(coords && zs_dev && nas && out && nmol >= 0, "bad argument");
+    require_device();
+    if (nmol == 0) return;
+    Workspace ws(st);
+    SlatmTables t = build_tables(p, local != 0, ws);
+    AQML_REQUIRE(ldo >= t.dev.D, "output pitch %lld smaller than D=%d", ldo, t.dev.D);
+    MolIndex mi = index_molecules(nas, nmol);
+    if (mi.A == 0 && local) return;
+    SlatmJob J;
+    memset(&J, 0, sizeof(J));
+    J.coords = coords; J.zs = zs_dev; J.mol_off = ws.upload(mi.off); J.atom_mol = ws.upload(mi.atom_mol);
+    J.nmol = nmol; J.A = mi.A; J.local = local ? 1 : 0; J.out = out; J.ldo = ldo;
+    launch_slatm(t, J, mi.na_max, st);
+}
+
+}  // namespace aqml
+
+// =============================================================================================
+// aqml_rep: element-packed aSLATM
+// =============================================================================================
+struct aqml_rep {
+    int nmol = 0, ne = 0;
+    cudaStream_t stream = 0;
+    std::vector<void *> owned;
+    int64_t bytes = 0;
+    struct El {
+        int label, n, tiles, ld;
+        double *x, *norm;
+        int *seg;
+    };
+    std::vector<El> els;
+    std::vector<int> nas;
+    std::vector<std::vector<int>> cnt;  // [el][mol]
+};
+
+namespace aqml {
+
+static void rep_create(const double *coords, int on_dev, const int *zs, const int *nas, int nmol,
+                       const aqml_slatm_params *p, cudaStream_t st, aqml_rep **out) {
+    AQML_REQUIRE(coords && zs && nas && out && nmol >= 1, "bad argument");
+    require_device();
+    Workspace ws(st);     // temporaries
+    Workspace keep(st);   // becomes the rep's storage
+    SlatmTables t = build_tables(p, true, ws);
+    MolIndex mi = index_molecules(nas, nmol);
+    AQML_REQUIRE(mi.A >= 1, "no atoms");
+    const int ne = t.dev.n_el;
+    auto eidx = [&](int z) {
+        auto it = std::lower_bound(t.labels.begin(), t.labels.end(), z);
+        return (it != t.labels.end() && *it == z) ? (int)(it - t.labels.begin()) : -1;
+    };
+    std::unique_ptr<aqml_rep> rep(new aqml_rep());
+    rep->nmol = nmol; rep->stream = st; rep->nas.assign(nas, nas + nmol);
+    std::vector<std::vector<int>> rows(ne), mols(ne);
+    rep->cnt.assign(ne, std::vector<int>(nmol, 0));
+    for (int a = 0; a < mi.A; a++) {
+        int e = eidx(zs[a]);
+        if (e < 0) continue;  // element without any many-body type: contributes nothing
+        rows[e].push_back(a);
+        mols[e].push_back(mi.atom_mol[a]);
+        rep->cnt[e][mi.atom_mol[a]]++;
+    }
+    std::vector<int> atom_prow(mi.A, -1);
+    SlatmJob J;
+    memset(&J, 0, sizeof(J));
+    for (int e = 0; e < ne; e++) {
+        std::vector<int> rm, sg;
+        build_tiles(rows[e], mols[e], rm, sg);
+        aqml_rep::El el;
+        el.label = t.labels[e]; el.n = (int)rows[e].size(); el.tiles = (int)rm.size() / BM; el.ld = t.dev.pld[e];
+        size_t nr = rm.size();
+        el.x = keep.alloc<double>(nr * (size_t)el.ld);
+        el.norm = keep.alloc<double>(nr);
+        el.seg = keep.upload(sg);
+        rep->bytes += (int64_t)(nr * (size_t)el.ld * 8 + nr * 12);
+        std::vector<int> pad;
+        for (size_t r = 0; r < nr; r++) {
+            if (rm[r] >= 0) atom_prow[rm[r]] = (int)r;
+            else pad.push_back((int)r);
+        }
+        if (!pad.empty()) {
+            zero_rows_kernel<<<(unsigned)pad.size(), 128, 0, st>>>(el.x, el.ld, ws.upload(pad), (int)pad.size(), el.norm);
+            AQML_LAUNCH_CHECK();
+        }
+        J.px[e] = el.x; J.pnorm[e] = el.norm;
+        rep->els.push_back(el);
+    }
+    rep->ne = ne;
+    const double *dcoords = on_dev ? coords : ws.upload(coords, (size_t)mi.A * 3);
+    J.coords = dcoords; J.zs = ws.upload(zs, mi.A); J.mol_off = ws.upload(mi.off); J.atom_mol = ws.upload(mi.atom_mol);
+    J.nmol = nmol; J.A = mi.A; J.local = 1; J.out = nullptr; J.ldo = 0; J.atom_prow = ws.upload(atom_prow);
+    launch_slatm(t, J, mi.na_max, st);
+    rep->owned = keep.pointers();
+    keep.release_all();
+    *out = rep.release();
+}
+
+static void rep_groups(const aqml_rep *r1, const aqml_rep *r2, int zmax, std::vector<PairGroup> &groups,
+                       std::vector<int> &labels) {
+    for (const auto &a : r1->els)
+        for (const auto &b : r2->els) {
+            if (a.label != b.label || a.n == 0 || b.n == 0) continue;
+            AQML_REQUIRE(a.ld == b.ld, "representations were built with different many-body types");
+            int z = a.label % 1000;
+            AQML_REQUIRE(z >= 1 && z <= zmax, "element %d outside 1..zmax=%d", z, zmax);
+            PairGroup g;
+            memset(&g, 0, sizeof(g));
+            g.A = a.x; g.B = b.x; g.normA = a.norm; g.normB = b.norm; g.segA = a.seg; g.segB = b.seg;
+            g.ld = a.ld; g.tilesM = a.tiles; g.tilesN = b.tiles; g.zcol = z - 1; g.segA_off = 0; g.segA_n = 0x7fffffff;
+            groups.push_back(g);
+            labels.push_back(a.label);
+        }
+}
+
+}  // namespace aqml
+
+using namespace aqml;
+
+extern "C" {
+
+int aqml_slatm_dim(const aqml_slatm_params *p) {
+    if (!p || !p->mbtypes) return AQML_EINVAL;
+    int D = 0;
+    for (int s = 0; s < p->nmb; s++) {
+        const int *mb = p->mbtypes + 3 * s;
+        D += (mb[1] < 0) ? 1 : (mb[2] < 0 ? p->nx2 : p->nx3);
+    }
+    return D;
+}
+
+int aqml_generate_slatm_batch_dev(const double *coords, const int *zs_dev, const int *nas, int nmol,
+                                  const aqml_slatm_params *p, int local, double *out, int64_t ldo, void *stream) {
+    return guarded([&] { slatm_batch_dev(coords, zs_dev, nas, nmol, p, local, out, ldo, (cudaStream_t)stream); });
+}
+
+int aqml_generate_slatm_batch(const double *coords, const int *zs, const int *nas, int nmol, const aqml_slatm_params *p,
+                              int local, double *out) {
+    return guarded([&] {
+        AQML_REQUIRE(coords && zs && nas && out && nmol >= 0, "bad argument");
+        require_device();
+        if (nmol == 0) return;
+        check_params(p);
+        int D = aqml_slatm_dim(p);
+        MolIndex mi = index_molecules(nas, nmol);
+        size_t rows = local ? (size_t)mi.A : (size_t)nmol;
+        if (rows == 0) return;
+        cudaStream_t st = 0;
+        Workspace ws(st);
+        double *dc = ws.upload(coords, (size_t)mi.A * 3);
+        int *dz = ws.upload(zs, (size_t)mi.A);
+        double *dout = ws.alloc<double>(rows * (size_t)D);
+        slatm_batch_dev(dc, dz, nas, nmol, p, local, dout, D, st);
+        AQML_CUDA(cudaMemcpyAsync(out, dout, sizeof(double) * rows * (size_t)D, cudaMemcpyDeviceToHost, st));
+        AQML_CUDA(cudaStreamSynchronize(st));
+    });
+}
+
+static int single_type(const double *coords, const int *zs, int na, int ia, int izeff, const int *mb, double rcut, int nx,
+                       double dgrid, double sigma, double coeff, double rpower, double *ys) {
+    return guarded([&] {
+        AQML_REQUIRE(coords && zs && ys && na >= 1 && nx >= 2, "bad argument");
+        AQML_REQUIRE(ia >= -1 && ia < na, "centre atom %d outside the molecule", ia);
+        aqml_slatm_params p;
+        memset(&p, 0, sizeof(p));
+        p.nmb = 1; p.mbtypes = mb; p.izeff = izeff; p.nx2 = nx; p.nx3 = nx;
+        p.sigma2 = p.sigma3 = sigma; p.dgrid2 = p.dgrid3 = dgrid; p.coeff2 = p.coeff3 = coeff;
+        p.rcut = rcut; p.rpower = rpower;
+        size_t rows = (ia >= 0) ? (size_t)na : 1;
+        std::vector<double> tmp(rows * (size_t)nx);
+        int rc = aqml_generate_slatm_batch(coords, zs, &na, 1, &p, ia >= 0, tmp.data());
+        if (rc != AQML_OK) fail(rc, "%s", aqml_last_error());
+        memcpy(ys, tmp.data() + (ia >= 0 ? (size_t)ia * nx : 0), sizeof(double) * nx);
+    });
+}
+
+int aqml_calc_sbop(const double *coords, const int *zs, int na, int ia, int izeff, int z1, int z2, double rcut, int nx,
+                   double dgrid, double sigma, double coeff, double rpower, double *ys) {
+    int mb[3] = {z1, z2, -1};
+    return single_type(coords, zs, na, ia, izeff, mb, rcut, nx, dgrid, sigma, coeff, rpower, ys);
+}
+
+int aqml_calc_sbot(const double *coords, const int *zs, int na, int ia, int izeff, int z1, int z2, int z3, double rcut,
+                   int nx, double dgrid, double sigma, double coeff, double *ys) {
+    int mb[3] = {z1, z2, z3};
+    return single_type(coords, zs, na, ia, izeff, mb, rcut, nx, dgrid, sigma, coeff, 6.0, ys);
+}
+
+int aqml_rep_create(const double *coords, int coords_on_device, const int *zs, const int *nas, int nmol,
+                    const aqml_slatm_params *p, void *stream, aqml_rep **out) {
+    return guarded([&] { rep_create(coords, coords_on_device, zs, nas, nmol, p, (cudaStream_t)stream, out); });
+}
+
+void aqml_rep_destroy(aqml_rep *r) {
+    if (!r) return;
+    for (void *p : r->owned) cudaFreeAsync(p, r->stream);
+    delete r;
+}
+
+int64_t aqml_rep_bytes(const aqml_rep *r) { return r ? r->bytes : 0; }
+
+int aqml_rep_local_gaussian(const aqml_rep *r1, const aqml_rep *r2, const double *sigmas, int nsigmas, int zmax, int row0,
+                            int nrows, double *K, void *stream) {
+    return guarded([&] {
+        AQML_REQUIRE(r1 && r2 && sigmas && K && nsigmas >= 1 && zmax >= 1, "bad argument");
+        AQML_REQUIRE(row0 >= 0 && nrows >= 0 && row0 + nrows <= r1->nmol, "row block outside r1");
+        require_device();
+        cudaStream_t st = (cudaStream_t)stream;
+        for (int i = 0; i < nsigmas * zmax; i++) AQML_REQUIRE(sigmas[i] != 0.0, "sigma is zero");
+        AQML_CUDA(cudaMemsetAsync(K, 0, sizeof(double) * (size_t)nsigmas * nrows * r2->nmol, st));
+        if (nrows == 0) return;
+        Workspace ws(st);
+        std::vector<PairGroup> groups;
+        std::vector<int> labels;
+        rep_groups(r1, r2, zmax, groups, labels);
+        for (auto &g : groups) { g.segA_off = row0; g.segA_n = nrows; }
+        std::vector<double> isig((size_t)nsigmas * zmax);
+        for (size_t i = 0; i < isig.size(); i++) isig[i] = -0.5 / (sigmas[i] * sigmas[i]);
+        // element-mismatched pairs carry d2 = 1e9 in the reference (fkernels.f90:73): exactly 0 after exp
+        // unless sigma is enormous; refuse instead of silently dropping them
+        for (const auto &a : r1->els)
+            for (int k = 0; k < nsigmas; k++) {
+                int z = a.label % 1000;
+                if (a.n && z >= 1 && z <= zmax)
+                    AQML_REQUIRE(std::exp((double)1.e9f * isig[(size_t)k * zmax + z - 1]) == 0.0,
+                                 "sigma %g for Z=%d is so wide that element-mismatched pairs do not vanish; use aqml_calc_lk_gaussian",
+                                 sigmas[(size_t)k * zmax + z - 1], z);
+            }
+        PairParams P{};
+        P.isig = ws.upload(isig); P.nsig = nsigmas; P.zstride = zmax;
+        P.out = K; P.ldo = r2->nmol; P.slab = (long long)nrows * r2->nmol;
+        run_pairs_public(MODE_DOT, EPI_LOCAL, groups, P, ws);
+    });
+}
+
+int aqml_rep_kernel_width(const aqml_rep *r1, const aqml_rep *r2, int zmax, double *dso, void *stream) {
+    return guarded([&] {
+        AQML_REQUIRE(r1 && r2 && dso && zmax >= 1, "bad argument");
+        require_device();
+        cudaStream_t st = (cudaStream_t)stream;
+        Workspace ws(st);
+        std::vector<PairGroup> groups;
+        std::vector<int> labels;
+        rep_groups(r1, r2, zmax, groups, labels);
+        unsigned long long *bits = ws.zeros<unsigned long long>(groups.size() + 1);
+        for (size_t i = 0; i < groups.size(); i++) { groups[i].out_slot = (int)i; groups[i].sym = (r1 == r2); }
+        PairParams P{};
+        P.out = reinterpret_cast<double *>(bits);
+        run_pairs_public(MODE_DOT, EPI_MAX, groups, P, ws);
+        std::vector<double> mx(groups.size() + 1);
+        AQML_CUDA(cudaMemcpyAsync(mx.data(), bits, sizeof(double) * groups.size(), cudaMemcpyDeviceToHost, st));
+        AQML_CUDA(cudaStreamSynchronize(st));
+        for (int z = 0; z < zmax; z++) dso[z] = 1.e-9;
+        for (size_t i = 0; i < groups.size(); i++) dso[labels[i] % 1000 - 1] = std::sqrt(mx[i]);
+    });
+}
+
+}  // extern "C"

@@ -1,0 +1,73 @@
+"""Device-resident fused path: molecules -> element-packed aSLATM -> local Gaussian kernel.
+
+The reference materialises dense (atoms, D) arrays on the host between ``generate_slatm`` and
+``get_local_kernels_gaussian`` (algo/aqml.py:711-789).  Here the aSLATM kernel writes each atom
+directly into the operand layout the FP64 tensor-core contraction reads (rows grouped by element,
+columns restricted to that element's support), so neither the dense matrix nor a host round trip
+ever exists.  Results are identical to the two-step route (tests/test_gpu_fused.py).
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib as L
+
+
+class PackedRep:
+    """aSLATM of a set of molecules, packed by element on the current CUDA device."""
+
+    def __init__(self, coordinates, nuclear_charges, nas, mbtypes, izeff=False, sigmas=(0.05, 0.05),
+                 dgrids=(0.03, 0.03), rcut=4.8, rpower=6):
+        import torch
+        self._h = C.c_void_p()
+        self.nas = L.i32(nas)
+        self.zs = L.i32(nuclear_charges)
+        self.nmol = len(self.nas)
+        p = L.slatm_params(mbtypes, izeff, sigmas, dgrids, rcut, rpower)
+        on_dev = L.is_tensor(coordinates)
+        coords = L.dev_f64(coordinates).contiguous() if on_dev else L.f64(coordinates)
+        self.device = coords.device if on_dev else torch.device("cuda", torch.cuda.current_device())
+        with torch.cuda.device(self.device):
+            L.call("aqml_rep_create", L.ptr(coords), int(on_dev), L.ptr(self.zs), L.ptr(self.nas), self.nmol, p,
+                   L.current_stream(), C.byref(self._h))
+
+    @property
+    def nbytes(self):
+        return int(L.load().aqml_rep_bytes(self._h))
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            L.load().aqml_rep_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def local_gaussian(rep1, rep2, sigmas, zmax, row0=0, nrows=None, out=None):
+    """K[k, a, b] for a in rep1[row0:row0+nrows], b in rep2; sigmas (nsigmas, zmax).  CUDA tensor."""
+    import torch
+    sig = L.f64(sigmas)
+    sig = sig.reshape(len(sig), -1)
+    if sig.shape[1] != zmax:
+        raise ValueError(f"sigmas must have shape (nsigmas, zmax={zmax})")
+    nrows = rep1.nmol - row0 if nrows is None else nrows
+    K = out if out is not None else torch.empty((sig.shape[0], nrows, rep2.nmol), dtype=torch.float64, device=rep1.device)
+    with torch.cuda.device(rep1.device):
+        L.call("aqml_rep_local_gaussian", rep1._h, rep2._h, L.ptr(sig), sig.shape[0], int(zmax), int(row0), int(nrows),
+               L.ptr(K), L.current_stream())
+    return K
+
+
+def kernel_width(rep1, rep2, zmax):
+    """Per-element max L2 distance between rep1 and rep2 atoms (get_kernel_width, aqml.py:204-255)."""
+    import torch
+    dso = np.zeros(zmax)
+    with torch.cuda.device(rep1.device):
+        L.call("aqml_rep_kernel_width", rep1._h, rep2._h, int(zmax), L.ptr(dso), L.current_stream())
+    return dso

@@ -1,0 +1,2 @@
+"""f2py module name of coreml/cml/fkernels.f90."""
+from aqml_b200.kernels import fgaussian_kernel, flaplacian_kernel, calc_lk_gaussian, calc_lk_laplacian  # noqa: F401

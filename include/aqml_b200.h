@@ -1,0 +1,182 @@
+/*
+ * aqml_b200 -- C ABI of the B200-native AQML hot path (SLATM/aSLATM generation and
+ * global / local Gaussian + Laplacian kernel-matrix assembly).
+ *
+ * This header is the drop-in boundary.  Every entry point names the reference interface it
+ * replaces (binghuang2018/aqml, paths relative to the reference tree).  The reference binds
+ * its Fortran through f2py (coreml/setup.py:48-64); the f2py-level routines are mirrored
+ * one-to-one below with plain pointers and sizes (no torch / numpy types).
+ *
+ * Conventions
+ *   - all reals are IEEE double, all integers int32 (f2py: INTEGER*4), row-major ("C order")
+ *     unless a parameter says column-major.  A row-major (n, D) matrix is bit-for-bit the
+ *     Fortran x(D, n) the reference passes (kernels.py:35,64,234: "Transposed for Fortran").
+ *   - functions WITHOUT a `_dev` suffix take HOST pointers, copy to the current CUDA device,
+ *     run, copy back and return when the result is complete (like an f2py call).
+ *   - functions WITH a `_dev` suffix take DEVICE pointers for the bulk arrays (stated per
+ *     parameter), enqueue on `stream` (a cudaStream_t passed as void*; NULL = default stream)
+ *     and return without waiting for the kernels unless stated.  Small metadata arrays
+ *     (element numbers, atom counts, sigmas, many-body types) are always HOST pointers.
+ *   - return value: 0 on success, negative AQML_E* on failure; aqml_last_error() gives the
+ *     message (thread-local).  Nothing aborts the process (the Fortran `stop`s,
+ *     fslatm.f90:52-57).
+ *   - there is no CPU fallback: without a CUDA device every compute entry point fails with
+ *     AQML_ECUDA.
+ */
+#ifndef AQML_B200_H
+#define AQML_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define AQML_OK        0
+#define AQML_EINVAL   -1   /* bad argument */
+#define AQML_ECUDA    -2   /* CUDA runtime error (no device, launch failure, out of memory) */
+#define AQML_ELIMIT   -3   /* outside an implementation limit */
+
+#define AQML_KERNEL_GAUSSIAN  0
+#define AQML_KERNEL_LAPLACIAN 1
+
+int aqml_version(void);
+const char *aqml_last_error(void);
+/* number of visible CUDA devices (0 when none / no driver); never fails */
+int aqml_device_count(void);
+
+/* ------------------------------------------------------------------------------------------
+ * Global kernels and distances
+ * ---------------------------------------------------------------------------------------- */
+
+/* fgaussian_kernel(a, na, b, nb, k, sigma)   coreml/cml/fkernels.f90:327-359
+ *   (Python: kernels.gaussian_kernel, coreml/cml/kernels.py:40-67)
+ * a (na, D), b (nb, D) row-major; k column-major (na, nb) caller-allocated, overwritten:
+ * k[j + na*i] = exp(-0.5 * |a_j - b_i|^2 / sigma^2). */
+int aqml_fgaussian_kernel(const double *a, int na, const double *b, int nb, int D, double *k, double sigma);
+
+/* flaplacian_kernel(a, na, b, nb, k, sigma)  coreml/cml/fkernels.f90:361-387
+ *   (Python: kernels.laplacian_kernel, kernels.py:11-38)   k = exp(-|a_j - b_i|_1 / sigma) */
+int aqml_flaplacian_kernel(const double *a, int na, const double *b, int nb, int D, double *k, double sigma);
+
+/* fl2_distance(A, B) -> D(n1, n2)            coreml/cml/fdistance.f90:25-44
+ *   (Python: distance.l2_distance, distance.py:39-68)   Dm column-major (n1, n2). */
+int aqml_fl2_distance(const double *A, const double *B, int n1, int n2, int nc, double *Dm);
+/* fl1_distance                                coreml/cml/fdistance.f90:3-22 */
+int aqml_fl1_distance(const double *A, const double *B, int n1, int n2, int nc, double *Dm);
+
+/* All sigmas in one pass (the reference re-runs the whole distance loop per sigma:
+ * representation/xa.py:223, slatm_x.py:565).  kind = AQML_KERNEL_*.
+ * a (na, lda>=D), b (nb, ldb>=D) row-major DEVICE; sigmas HOST (nsig); K DEVICE row-major
+ * (nsig, na, nb): K[s][i][j] = k(a_i, b_j; sigma_s).  Row-block sharding over GPUs = calling
+ * this with a pointer into a's row block.  center != 0 subtracts the column mean of b from
+ * both operands before the Gaussian contraction (distance-preserving, conditions the
+ * |x|^2+|y|^2-2xy expansion). */
+int aqml_global_kernel_dev(int kind, const double *a, int na, int64_t lda, const double *b, int nb, int64_t ldb,
+                           int D, const double *sigmas, int nsig, int center, double *K, void *stream);
+
+/* max_{i,j} |a_i - b_j|_p (p = 2 or 1) without materialising the distance matrix: the
+ * reduction get_kernel_width needs (algo/aqml.py:204-255: np.max(l2_distance(x_z, x_z))).
+ * a, b DEVICE; result written to HOST *dmax (synchronises the stream). */
+int aqml_max_distance_dev(int p, const double *a, int na, int64_t lda, const double *b, int nb, int64_t ldb, int D,
+                          double *dmax, void *stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Local (atomic) kernels
+ * ---------------------------------------------------------------------------------------- */
+
+/* calc_lk_gaussian(x1,x2,zs1,zs2,nas1,nas2,zmax,iab,sigmas,nm1,nm2,nsigmas) -> kernels
+ *   coreml/cml/fkernels.f90:23-93   (Python: kernels.get_local_kernels_gaussian, kernels.py:193-235)
+ * x1 (sum nas1, D), x2 (sum nas2, D) row-major; zs* element number per atom (1..zmax);
+ * sigmas row-major (nsigmas, zmax), column Z-1; kernels row-major (nsigmas, nm1, nm2):
+ * K[k][a][b] = sum_{i in a} sum_{j in b} exp(-0.5 d2_ij / sigmas[k][Z1_i - 1]^2) over pairs with
+ * Z1_i == Z2_j (all pairs when iab != 0).  Only same-element pairs are contracted, and only on
+ * the columns where that element's atoms are non-zero (detected from the data, exact). */
+int aqml_calc_lk_gaussian(const double *x1, const double *x2, const int *zs1, const int *zs2, const int *nas1,
+                          const int *nas2, int zmax, int iab, const double *sigmas, int nm1, int nm2, int nsigmas,
+                          int D, double *kernels);
+/* same; x1, x2, kernels DEVICE (ldx* = row pitch in doubles), everything else HOST */
+int aqml_calc_lk_gaussian_dev(const double *x1, int64_t ldx1, const double *x2, int64_t ldx2, const int *zs1,
+                              const int *zs2, const int *nas1, const int *nas2, int zmax, int iab,
+                              const double *sigmas, int nm1, int nm2, int nsigmas, int D, int center,
+                              double *kernels, void *stream);
+
+/* calc_lk_laplacian(x1,x2,nas1,nas2,sigmas,nm1,nm2,nsigmas) -> kernels
+ *   coreml/cml/fkernels.f90:97-183  (Python: kernels.get_local_kernels_laplacian, kernels.py:237-276)
+ * no element matching, sigmas (nsigmas). */
+int aqml_calc_lk_laplacian(const double *x1, const double *x2, const int *nas1, const int *nas2,
+                           const double *sigmas, int nm1, int nm2, int nsigmas, int D, double *kernels);
+int aqml_calc_lk_laplacian_dev(const double *x1, int64_t ldx1, const double *x2, int64_t ldx2, const int *nas1,
+                               const int *nas2, const double *sigmas, int nm1, int nm2, int nsigmas, int D,
+                               double *kernels, void *stream);
+
+/* Per-element max distance, the kernel-width heuristic's reduction
+ *   algo/aqml.py:204-255 get_kernel_width (cab=False): dso[z-1] = max_{i,j in z} |x_i - x_j|_p,
+ *   1e-9 for absent elements.  x DEVICE (A, ldx), zs HOST (A), dso HOST (zmax). p = 2 | 1. */
+int aqml_kernel_width_dev(int p, const double *x, int64_t ldx, const int *zs, int A, int D, int zmax, double *dso,
+                          void *stream);
+
+/* ------------------------------------------------------------------------------------------
+ * SLATM / aSLATM
+ * ---------------------------------------------------------------------------------------- */
+
+/* Parameters of generate_slatm (representation/core.py:382-384) after the Python wrappers
+ * get_sbop / get_sbot (representation/slatm.py:22-130) resolved the grids:
+ *   nx2 = int((rcut-0.1)/dgrid2)+1, nx3 = int((pi+40deg)/dgrid3)+1, coeff = 1/sqrt(2 sigma^2 pi). */
+typedef struct {
+    int nmb;             /* number of many-body types */
+    const int *mbtypes;  /* HOST (nmb, 3), -1 padded: [z], [z1,z2], [z1,z2,z3]; column order of X */
+    int izeff;           /* use the Z* table, atomdb.f90:90-116 */
+    int nx2, nx3;
+    double sigma2, sigma3, dgrid2, dgrid3, coeff2, coeff3;
+    double rcut, rpower;
+} aqml_slatm_params;
+
+/* feature length D = sum over types of 1 | nx2 | nx3 */
+int aqml_slatm_dim(const aqml_slatm_params *p);
+
+/* calc_sbop / calc_sbop_local   coreml/cml/representation/fslatm.f90:413-527 / :531-655
+ * calc_sbot / calc_sbot_local   coreml/cml/representation/fslatm.f90:4-202   / :206-409
+ * coords row-major (na,3) [the f2py wrapper copies to Fortran order itself], zs (na),
+ * ia = 0-based centre atom (ia_python) or -1 for the global routine; ys (nx) out.
+ * cg is not a parameter: the reference always passes all-ones (slatm.py:53,107). */
+int aqml_calc_sbop(const double *coords, const int *zs, int na, int ia, int izeff, int z1, int z2, double rcut,
+                   int nx, double dgrid, double sigma, double coeff, double rpower, double *ys);
+int aqml_calc_sbot(const double *coords, const int *zs, int na, int ia, int izeff, int z1, int z2, int z3,
+                   double rcut, int nx, double dgrid, double sigma, double coeff, double *ys);
+
+/* generate_slatm for a batch of molecules (representation/core.py:382-556, one call instead of
+ * natoms x nmbtypes f2py crossings per molecule).  coords (A,3), zs (A), nas (nmol).
+ * local != 0: out (A, D) one aSLATM row per atom; else out (nmol, D) one SLATM row per molecule. */
+int aqml_generate_slatm_batch(const double *coords, const int *zs, const int *nas, int nmol,
+                              const aqml_slatm_params *p, int local, double *out);
+/* coords DEVICE (A,3), zs_dev DEVICE (A) int32, out DEVICE with row pitch ldo >= D; nas HOST. */
+int aqml_generate_slatm_batch_dev(const double *coords, const int *zs_dev, const int *nas, int nmol,
+                                  const aqml_slatm_params *p, int local, double *out, int64_t ldo, void *stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Fused path: molecules -> element-packed aSLATM -> local Gaussian kernel, all device resident.
+ * No reference equivalent (the reference materialises dense x1/x2 on the host between
+ * generate_slatm and get_local_kernels_gaussian, algo/aqml.py:711-789).
+ * ---------------------------------------------------------------------------------------- */
+typedef struct aqml_rep aqml_rep; /* aSLATM rows grouped by element, columns restricted to the element's support */
+
+/* coords: DEVICE if coords_on_device else HOST; zs, nas HOST.  Asynchronous on `stream`. */
+int aqml_rep_create(const double *coords, int coords_on_device, const int *zs, const int *nas, int nmol,
+                    const aqml_slatm_params *p, void *stream, aqml_rep **out);
+void aqml_rep_destroy(aqml_rep *r);
+int64_t aqml_rep_bytes(const aqml_rep *r);
+/* K DEVICE row-major (nsigmas, r1.nmol, r2.nmol), element matched; sigmas HOST (nsigmas, zmax).
+ * row0/nrows select a block of r1's molecules (row-block sharding); K has nrows rows. */
+int aqml_rep_local_gaussian(const aqml_rep *r1, const aqml_rep *r2, const double *sigmas, int nsigmas, int zmax,
+                            int row0, int nrows, double *K, void *stream);
+/* per-element max L2 distance over r1 x r2 atoms (get_kernel_width on packed rows); dso HOST (zmax) */
+int aqml_rep_kernel_width(const aqml_rep *r1, const aqml_rep *r2, int zmax, double *dso, void *stream);
+
+/* counters for bench.py: number of device kernels this library launched since load */
+int64_t aqml_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AQML_B200_H */

@@ -1,0 +1,85 @@
+"""CPU-only checks of the host side: the C-ABI library loads and exports every symbol the header
+declares, fails loudly without a device, and the host logic (mbtypes, grids) matches the oracle."""
+import os
+import re
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, mbtypes_from_array
+from aqml_b200 import _lib as L
+from aqml_b200 import synth
+from aqml_b200.representation import core as rcore
+from oracle import np_oracle as o
+
+
+def header_symbols():
+    src = open(os.path.join(ROOT, "include", "aqml_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(aqml_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_header_symbol():
+    lib = L.load()
+    syms = header_symbols()
+    assert len(syms) >= 20
+    for s in syms:
+        assert hasattr(lib, s), f"{s} declared in include/aqml_b200.h but not exported"
+        assert s in L.SIGNATURES, f"{s} has no ctypes signature"
+    assert set(L.SIGNATURES) == set(syms)
+    assert lib.aqml_version() >= 100
+
+
+def test_no_cpu_fallback():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from aqml_b200 import kernels
+    with pytest.raises(L.AqmlError, match="no CUDA device"):
+        kernels.gaussian_kernel(np.ones((3, 4)), np.ones((2, 4)), 1.0)
+    with pytest.raises(L.AqmlError, match="no CUDA device"):
+        rcore.generate_slatm(np.zeros((2, 3)), [1, 1], [[1], [1, 1]])
+
+
+def test_product_does_not_import_oracle():
+    import subprocess
+    import sys
+    code = ("import sys; import aqml_b200, aqml_b200.kernels, aqml_b200.distance, aqml_b200.representation, "
+            "aqml_b200.fused, aqml_b200.algo.aqml, aqml_b200.parallel, cml.kernels; "
+            "assert not any(m == 'oracle' or m.startswith('oracle.') for m in sys.modules), 'oracle imported'")
+    subprocess.check_call([sys.executable, "-c", code], cwd=ROOT)
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "aqml_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                txt = open(os.path.join(dirpath, f)).read()
+                assert "import oracle" not in txt and "from oracle" not in txt, f
+
+
+def test_mbtypes_match_oracle_and_golden(demo):
+    nas, zs = demo["nas"], demo["zs"]
+    zs_list = synth.split_zs(nas, zs)
+    assert rcore.get_slatm_mbtypes(zs_list) == mbtypes_from_array(demo["mbtypes"])
+    nas2, zs2, _ = synth.qm9_like(40, 3)
+    zl = synth.split_zs(nas2, zs2)
+    assert rcore.get_slatm_mbtypes(zl) == o.get_slatm_mbtypes(zl)
+    assert rcore.get_slatm_mbtypes(zl, pbc=True) == o.get_slatm_mbtypes(zl, pbc=True)
+
+
+def test_slatm_params_grids():
+    mb = [[1], [6], [1, 1], [1, 6], [6, 6], [1, 6, 1]]
+    p = L.slatm_params(mb, sigmas=(.05, .05), dgrids=(.04, .04), rcut=4.8)
+    assert (p.nx2, p.nx3) == (118, 96) == (o.grid2(4.8, .04), o.grid3(.04))
+    p = L.slatm_params(mb)
+    assert (p.nx2, p.nx3) == (157, 128)
+    assert L.load().aqml_slatm_dim(p) == 2 + 3 * 157 + 128
+    with pytest.raises(L.AqmlError):
+        L.slatm_params([[1, 2, 3, 4]])
+
+
+def test_synth_is_deterministic():
+    a = synth.qm9_like_fast(700, 5, pool=64)
+    b = synth.qm9_like_fast(700, 5, pool=64)
+    assert all(np.array_equal(x, y) for x, y in zip(a, b))
+    nas, zs, co = a
+    assert nas.sum() == len(zs) == len(co) and nas.max() <= 29
+    assert set(np.unique(zs)) <= {1, 6, 7, 8, 9}

@@ -1,0 +1,56 @@
+"""world_size-2 gloo tests of the multi-GPU host logic (row-block sharding, prediction all-reduce)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from aqml_b200 import parallel
+
+
+def test_shard_range_covers_everything():
+    for n in (0, 1, 7, 8, 100001):
+        for world in (1, 2, 3, 8):
+            r = [parallel.shard_range(n, k, world) for k in range(world)]
+            assert r[0][0] == 0 and r[-1][1] == n
+            assert all(a[1] == b[0] for a, b in zip(r, r[1:]))
+            assert max(h - l for l, h in r) - min(h - l for l, h in r) <= 1
+
+
+def test_shard_by_cost_balances():
+    rng = np.random.default_rng(0)
+    costs = rng.integers(1, 400, size=5000)
+    parts = parallel.shard_by_cost(costs, 8)
+    assert parts[0][0] == 0 and parts[-1][1] == 5000
+    tot = [costs[l:h].sum() for l, h in parts]
+    assert max(tot) < 1.05 * costs.sum() / 8 + 400
+
+
+def _worker(rank, world, port, tmp):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        g = torch.Generator().manual_seed(1234)
+        K = torch.rand((3, 11, 37), dtype=torch.float64, generator=g)       # (S, n_test, n_train) full
+        alpha = torch.rand((37,), dtype=torch.float64, generator=g)
+        alpha_s = torch.rand((3, 37), dtype=torch.float64, generator=g)
+        lo, hi = parallel.shard_range(37, rank, world)
+        y = parallel.predict_allreduce(K[:, :, lo:hi].contiguous(), alpha[lo:hi])
+        assert torch.allclose(y, K @ alpha, rtol=1e-13, atol=0)
+        y2 = parallel.predict_allreduce(K[:, :, lo:hi].contiguous(), alpha_s[:, lo:hi].contiguous())
+        assert torch.allclose(y2, torch.einsum("stn,sn->st", K, alpha_s), rtol=1e-13, atol=0)
+        rlo, rhi = parallel.shard_range(11, rank, world)
+        full = parallel.gather_rows(K[:, rlo:rhi].contiguous())
+        assert torch.equal(full, K)
+        open(os.path.join(tmp, f"ok{rank}"), "w").write("ok")
+    finally:
+        dist.destroy_process_group()
+
+
+def test_gloo_world2(tmp_path):
+    port = 29500 + (os.getpid() % 2000)
+    mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    assert all((tmp_path / f"ok{r}").exists() for r in range(2))

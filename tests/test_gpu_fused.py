@@ -1,0 +1,77 @@
+"""GPU: fused device-resident path and the KRR known-answer test through the CUDA code."""
+import numpy as np
+import pytest
+
+from conftest import mbtypes_from_array, rel_err
+from aqml_b200 import fused, kernels, synth
+from aqml_b200.algo import aqml as algo
+from aqml_b200.representation import core as rcore
+from oracle import c_oracle as co
+from oracle import np_oracle as o
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-10
+
+
+def test_fused_equals_two_step_and_oracle():
+    import torch
+    nas, zs, coords = synth.qm9_like(70, 31)
+    n1 = 50
+    off = np.concatenate(([0], np.cumsum(nas)))
+    A1 = off[n1]
+    mb = o.get_slatm_mbtypes(synth.split_zs(nas, zs))
+    kw = dict(sigmas=(.05, .05), dgrids=(.04, .04), rcut=4.8)
+    xl = co.generate_slatm_batch(coords, zs, nas, mb, True, **kw)
+    zmax = 9
+    dso = co.get_kernel_width(nas, zs, xl)
+    dso = np.concatenate((dso, np.full(zmax - len(dso), 1e-9)))
+    sig = np.array([c * dso / np.sqrt(2 * np.log(2)) for c in (0.5, 1.0, 2.0, 4.0)])
+    ref = co.calc_lk_gaussian(xl[A1:], xl[:A1], zs[A1:], zs[:A1], nas[n1:], nas[:n1], zmax, False, sig)
+    train = fused.PackedRep(coords[:A1], zs[:A1], nas[:n1], mb, **kw)
+    test = fused.PackedRep(torch.as_tensor(coords[A1:], device="cuda"), zs[A1:], nas[n1:], mb, **kw)
+    K = fused.local_gaussian(test, train, sig, zmax).cpu().numpy()
+    assert rel_err(K, ref) < TOL
+    # row-block sharding: rows 5..12 of the test set
+    Kb = fused.local_gaussian(test, train, sig, zmax, row0=5, nrows=7).cpu().numpy()
+    assert rel_err(Kb, ref[:, 5:12]) < TOL
+    # width heuristic on packed rows == dense get_kernel_width on train+test
+    both = fused.PackedRep(coords, zs, nas, mb, **kw)
+    assert np.allclose(fused.kernel_width(both, both, zmax), dso, rtol=1e-10)
+    # device two-step route
+    xd = rcore.generate_slatm_batch(torch.as_tensor(coords, device="cuda"), zs, nas, mb, local=True,
+                                    sigmas=[.05, .05], dgrids=[.04, .04], rcut=4.8)
+    K2 = kernels.get_local_kernels_gaussian(xd[A1:], xd[:A1], zs[A1:], zs[:A1], nas[n1:], nas[:n1], False, zmax, sig)
+    assert rel_err(K2.cpu().numpy(), ref) < TOL
+
+
+def test_demo_learning_curve_through_gpu(demo):
+    """The reference's only KAT (demo/example/README.md:57-63), every stage on the GPU path:
+    aSLATM -> per-element dmax -> sigma -> local Gaussian kernels; KRR solve on the host as upstream."""
+    n1 = int(demo["n1"])
+    nas, zs, coords = demo["nas"], demo["zs"], demo["coords"]
+    mb = mbtypes_from_array(demo["mbtypes"])
+    off = np.concatenate(([0], np.cumsum(nas)))
+    zs_list = synth.split_zs(nas, zs)
+    x = np.concatenate([np.array(rcore.generate_slatm(coords[off[i]:off[i + 1]], zs_list[i], mb, local=True,
+                                                       sigmas=[.05, .05], dgrids=[.04, .04], rcut=4.8))
+                        for i in range(len(nas))])
+    A1 = off[n1]
+    dsmax = algo.get_kernel_width(nas, zs, x)
+    fun = algo.fobj('g')
+    sigmas = np.array([fun._factor * dsmax * 1.0])
+    zmax = int(zs.max())
+    ks1 = fun.k(x[:A1], x[:A1], zs[:A1], zs[:A1], nas[:n1], nas[:n1], False, zmax, sigmas)
+    ks2 = fun.k(x[A1:], x[:A1], zs[A1:], zs[:A1], nas[n1:], nas[:n1], False, zmax, sigmas)
+    zsu = np.unique(zs)
+    ngs = np.array([[(z == zz).sum() for zz in zsu] for z in zs_list])
+    nheav = np.array([(z > 1).sum() for z in zs_list[:n1]])
+    ys = demo["energies"] * o.H2KC
+    rows = o.learning_curve(ks1[0], ks2[0], ngs, ys, nheav, zsu)
+    readme = demo["readme_curve"]
+    for r, ref in zip(rows, readme):
+        assert (r[0], r[1]) == (ref[0], ref[1])
+        assert abs(r[2] - ref[2]) < 5.1e-5 and abs(r[3] - ref[3]) < 5.1e-5
+    # predictions within 1e-8 Ha of the oracle's own pipeline
+    rows_ref = o.learning_curve(demo["k1"][1], demo["k2"][1], ngs, ys, nheav, zsu)
+    for r, rr in zip(rows, rows_ref):
+        assert np.max(np.abs(r[5] - rr[5])) < 1e-8 * o.H2KC

@@ -1,0 +1,175 @@
+"""GPU parity: kernel matrices / distances through the C ABI vs the CPU oracle (bit-level goal:
+<= 1e-10 relative per element, BASELINE.json north_star)."""
+import numpy as np
+import pytest
+
+from conftest import rel_err
+from aqml_b200 import distance, kernels, synth
+from aqml_b200.algo import aqml as algo
+from oracle import c_oracle as co
+from oracle import np_oracle as o
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-10
+
+
+@pytest.fixture(scope="module")
+def slatm_set():
+    """60 QM9-shaped molecules, aSLATM + SLATM from the CPU oracle."""
+    nas, zs, coords = synth.qm9_like(60, 20251019)
+    mb = o.get_slatm_mbtypes(synth.split_zs(nas, zs))
+    kw = dict(sigmas=(.05, .05), dgrids=(.04, .04), rcut=4.8)
+    xl = co.generate_slatm_batch(coords, zs, nas, mb, True, **kw)
+    xg = co.generate_slatm_batch(coords, zs, nas, mb, False, **kw)
+    return dict(nas=nas, zs=zs, coords=coords, mb=mb, xl=xl, xg=xg)
+
+
+@pytest.mark.parametrize("shape", [(1, 1, 1), (5, 3, 7), (37, 53, 129), (200, 131, 1000), (129, 257, 16)])
+def test_global_gaussian_random(shape):
+    n1, n2, D = shape
+    rng = np.random.default_rng(n1 * 1000 + n2)
+    A, B = rng.random((n1, D)), rng.random((n2, D))
+    for sigma in (0.3 * np.sqrt(D), 2.0 * np.sqrt(D)):
+        K = kernels.gaussian_kernel(A, B, sigma)
+        assert K.shape == (n1, n2) and K.flags.f_contiguous
+        assert rel_err(K, co.gaussian_kernel(A, B, sigma)) < TOL
+        Kl = kernels.laplacian_kernel(A, B, sigma * 3)
+        assert rel_err(Kl, co.laplacian_kernel(A, B, sigma * 3)) < TOL
+
+
+def test_global_kernels_on_slatm(slatm_set):
+    X = slatm_set["xg"]
+    A, B = X[:45], X[45:]
+    dmax = co.l2_distance(A, A).max()
+    for c in (0.25, 1.0, 4.0):  # both ends of a sigma list
+        sigma = c * dmax / np.sqrt(2 * np.log(2))
+        assert rel_err(kernels.gaussian_kernel(B, A, sigma), co.gaussian_kernel(B, A, sigma)) < TOL
+        K = kernels.gaussian_kernel(A, A, sigma)  # symmetric, exact-duplicate rows on the diagonal
+        assert rel_err(K, co.gaussian_kernel(A, A, sigma)) < TOL
+        assert np.allclose(np.diag(K), 1.0, rtol=0, atol=1e-12)
+    l1max = co.l1_distance(A, A).max()
+    assert rel_err(kernels.laplacian_kernel(B, A, l1max / np.log(2)), co.laplacian_kernel(B, A, l1max / np.log(2))) < TOL
+    # near-duplicate rows
+    A2 = A.copy()
+    A2[1] = A2[0] * (1 + 1e-9)
+    assert rel_err(kernels.gaussian_kernel(A2, A2, dmax), co.gaussian_kernel(A2, A2, dmax)) < TOL
+
+
+def test_distances(slatm_set):
+    X = slatm_set["xg"]
+    A, B = X[:33], X[20:]
+    D2 = distance.l2_distance(A, B)
+    ref = co.l2_distance(A, B)
+    assert D2.shape == ref.shape and D2.flags.f_contiguous
+    # absolute tolerance scaled by the largest distance: sqrt amplifies rounding near d = 0
+    assert np.max(np.abs(D2 - ref)) < 1e-7 * ref.max()
+    mask = ref > 1e-3 * ref.max()
+    assert rel_err(D2[mask], ref[mask]) < TOL
+    D1 = distance.l1_distance(A, B)
+    assert rel_err(D1, co.l1_distance(A, B)) < 1e-13
+    with pytest.raises(ValueError):
+        distance.l2_distance(A, B[:, :-1])
+    with pytest.raises(ValueError):
+        distance.l2_distance(A[0], B)
+
+
+def test_multi_sigma_device_path(slatm_set):
+    import torch
+    X = slatm_set["xg"]
+    A, B = X[:45], X[45:]
+    sig = np.array([50., 100., 200., 400.])
+    At, Bt = torch.as_tensor(A, device="cuda"), torch.as_tensor(B, device="cuda")
+    for kern, ref in (("gaussian", co.gaussian_kernel), ("laplacian", co.laplacian_kernel)):
+        s = sig if kern == "gaussian" else sig * 40
+        K = kernels.global_kernels(At, Bt, s, kern).cpu().numpy()
+        assert K.shape == (4, 45, 15)
+        for i in range(4):
+            assert rel_err(K[i], ref(A, B, s[i])) < TOL
+    # row-block sharding == slicing rows of A
+    Kb = kernels.global_kernels(At[10:30], Bt, sig, "gaussian").cpu().numpy()
+    Kf = kernels.global_kernels(At, Bt, sig, "gaussian").cpu().numpy()
+    assert np.array_equal(Kb, Kf[:, 10:30])
+
+
+@pytest.mark.parametrize("iab", [False, True])
+def test_local_gaussian_synthetic(slatm_set, iab):
+    s = slatm_set
+    n1 = 40
+    off = np.concatenate(([0], np.cumsum(s["nas"])))
+    A1 = off[n1]
+    x1, x2 = s["xl"][:A1], s["xl"][A1:]
+    zs1, zs2 = s["zs"][:A1], s["zs"][A1:]
+    nas1, nas2 = s["nas"][:n1], s["nas"][n1:]
+    zmax = 9
+    dso = co.get_kernel_width(s["nas"], s["zs"], s["xl"])
+    dso = np.concatenate((dso, np.full(zmax - len(dso), 1e-9)))
+    sig = np.array([c * dso / np.sqrt(2 * np.log(2)) for c in (0.5, 1.0, 2.0, 4.0)])
+    if iab:
+        sig = np.maximum(sig, 5.0)
+    for (a, za, na, b, zb, nb) in ((x2, zs2, nas2, x1, zs1, nas1), (x1, zs1, nas1, x1, zs1, nas1)):
+        K = kernels.get_local_kernels_gaussian(a, b, za, zb, na, nb, iab, zmax, sig)
+        ref = co.calc_lk_gaussian(a, b, za, zb, na, nb, zmax, iab, sig)
+        assert K.shape == ref.shape == (4, len(na), len(nb))
+        assert rel_err(K, ref) < TOL
+        Knc = kernels.get_local_kernels_gaussian(a, b, za, zb, na, nb, iab, zmax, sig, center=False)
+        assert rel_err(Knc, ref) < TOL
+
+
+def test_local_gaussian_wide_sigma_mismatch_term(slatm_set):
+    """Element-mismatched pairs carry d2 = 1e9 (fkernels.f90:73): visible for sigma >~ 1e3."""
+    s = slatm_set
+    n = 6
+    A = int(s["nas"][:n].sum())
+    x, zs, nas = s["xl"][:A], s["zs"][:A], s["nas"][:n]
+    sig = np.full((2, 9), 3000.0)
+    sig[1] = 9000.0
+    K = kernels.get_local_kernels_gaussian(x, x, zs, zs, nas, nas, False, 9, sig)
+    assert rel_err(K, co.calc_lk_gaussian(x, x, zs, zs, nas, nas, 9, False, sig)) < TOL
+
+
+def test_local_gaussian_golden_demo(demo):
+    n1 = int(demo["n1"])
+    nas, zs, x = demo["nas"], demo["zs"], demo["x_local"]
+    A1 = int(nas[:n1].sum())
+    k1 = kernels.get_local_kernels_gaussian(x[:A1], x[:A1], zs[:A1], zs[:A1], nas[:n1], nas[:n1], False, 8, demo["sigmas"])
+    k2 = kernels.get_local_kernels_gaussian(x[A1:], x[:A1], zs[A1:], zs[:A1], nas[n1:], nas[:n1], False, 8, demo["sigmas"])
+    assert rel_err(k1, demo["k1"]) < TOL
+    assert rel_err(k2, demo["k2"]) < TOL
+
+
+def test_local_laplacian(slatm_set):
+    s = slatm_set
+    n1 = 12
+    off = np.concatenate(([0], np.cumsum(s["nas"])))
+    x1, x2 = s["xl"][:off[n1]], s["xl"][off[n1]:off[n1 + 9]]
+    nas1, nas2 = s["nas"][:n1], s["nas"][n1:n1 + 9]
+    sig = [200., 800., 3200.]
+    K = kernels.get_local_kernels_laplacian(x2, x1, nas2, nas1, sig)
+    assert rel_err(K, co.calc_lk_laplacian(x2, x1, nas2, nas1, sig)) < TOL
+
+
+def test_kernel_width(demo, slatm_set):
+    dso = algo.get_kernel_width(demo["nas"], demo["zs"], demo["x_local"])
+    assert np.allclose(dso, demo["dso"], rtol=1e-9, atol=0)
+    s = slatm_set
+    ref = co.get_kernel_width(s["nas"], s["zs"], s["xl"])
+    assert np.allclose(algo.get_kernel_width(s["nas"], s["zs"], s["xl"]), ref, rtol=1e-10, atol=0)
+    ref1 = co.get_kernel_width(s["nas"], s["zs"], s["xl"], kernel='l')
+    assert np.allclose(algo.get_kernel_width(s["nas"], s["zs"], s["xl"], kernel='l'), ref1, rtol=1e-12, atol=0)
+
+
+def test_ragged_and_empty(slatm_set):
+    s = slatm_set
+    x = s["xl"][:int(s["nas"][:3].sum())]
+    zs, nas = s["zs"][:len(x)], s["nas"][:3]
+    sig = np.full((1, 9), 10.0)
+    # molecule with zero atoms in the middle
+    nas0 = np.array([nas[0], 0, nas[1] + nas[2]], dtype=np.int32)
+    K = kernels.get_local_kernels_gaussian(x, x, zs, zs, nas0, nas, False, 9, sig)
+    ref = co.calc_lk_gaussian(x, x, zs, zs, nas0, nas, 9, False, sig)
+    assert rel_err(K, ref) < TOL and np.all(K[0, 1] == 0)
+    with pytest.raises(AssertionError):
+        kernels.get_local_kernels_gaussian(x, x, zs, zs, nas, nas[:2], False, 9, sig)
+    from aqml_b200._lib import AqmlError
+    with pytest.raises(AqmlError):
+        kernels.get_local_kernels_gaussian(x, x, zs + 20, zs, nas, nas, False, 9, sig)
