@@ -1,0 +1,379 @@
+#!/usr/bin/env python
+"""Benchmark of the AQML hot path on B200 (contract: see the task prompt / DESIGN.md section 6).
+
+Workload (BASELINE.json configs[1]): 20k train x 2k test QM9-shaped molecules, local aSLATM
+element-matched Gaussian kernel, FP64, 4 sigmas.  One *step* = the whole hot path for one batch:
+
+    coordinates -> aSLATM (train + test, written element-packed) -> K[4, n_test, n_train]
+
+`value`  : kernel elements/s with coordinates already resident in HBM (device timed, CUDA events).
+`e2e`    : same metric through the C ABI with HOST buffers (coords H2D, K D2H inside the timing).
+N > 1    : weak scaling -- every rank owns its own 2k test molecules (a row block of K) against
+           the same 20k training molecules; no data-path collective.
+`--impl reference`: the restated reference loops (C/OpenMP, oracle/c_oracle.c -- the Fortran cannot
+           be compiled in this image) on the host cores, bounded sample of the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+SEED = 20251019 + 2
+COEFFS = (0.5, 1.0, 2.0, 4.0)
+SLATM_KW = dict(sigmas=(.05, .05), dgrids=(.04, .04), rcut=4.8)
+ZMAX = 9
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--n-train", type=int, default=20000)
+    ap.add_argument("--n-test", type=int, default=2000)
+    ap.add_argument("--cpu-train", type=int, default=256, help="CPU-baseline sample: training molecules")
+    ap.add_argument("--cpu-test", type=int, default=48, help="CPU-baseline sample: test molecules")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+def make_sets(n_train, n_test, rank):
+    from aqml_b200 import synth
+    train = synth.qm9_like_fast(n_train, SEED, pool=512)
+    test = synth.qm9_like_fast(n_test, SEED + 1000 * (rank + 1), pool=256)
+    return train, test
+
+
+def mbtypes_for(train, test):
+    from aqml_b200 import synth
+    from aqml_b200.representation import core as rcore
+    zl = synth.split_zs(train[0][:2000], train[1][:int(train[0][:2000].sum())]) + \
+        synth.split_zs(test[0][:500], test[1][:int(test[0][:500].sum())])
+    # all five QM9 elements with full multiplicity (n1/n2/n3 = 5/15/75, D = 8975 at dgrid 0.04)
+    zl.append(np.array([1, 1, 1, 6, 6, 6, 7, 7, 7, 8, 8, 8, 9, 9, 9]))
+    return rcore.get_slatm_mbtypes(zl)
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap,power.draw")
+
+    def __init__(self, index):
+        self.samples = []
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.samples.append((time.time(), line.strip()))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons, power = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for t, line in self.samples:
+            if not (t0 <= t <= t1 + 0.3):
+                continue
+            f = [x.strip() for x in line.split(",")]
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+                power.append(float(f[6]))
+            except Exception:
+                continue
+            for n, v in zip(names, f[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "power_w_max": max(power) if power else None, "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU arm (restated reference loops)
+# ------------------------------------------------------------------------------------------------
+def cpu_sample(args, steps=1, warmup=0):
+    """Time molecules -> aSLATM -> local Gaussian kernel on the host cores for a bounded sample."""
+    from aqml_b200 import synth
+    from oracle import c_oracle as co
+    train, test = make_sets(args.cpu_train, args.cpu_test, 0)
+    mb = mbtypes_for(*make_sets(2000, 500, 0))
+    sig = np.array([c * np.full(ZMAX, 16.0) / np.sqrt(2 * np.log(2)) for c in COEFFS])
+    co.load(fast=True)
+    cores = co.num_threads(fast=True)
+
+    def one():
+        t0 = time.perf_counter()
+        x1 = co.generate_slatm_batch(train[2], train[1], train[0], mb, True, fast=True, **SLATM_KW)
+        x2 = co.generate_slatm_batch(test[2], test[1], test[0], mb, True, fast=True, **SLATM_KW)
+        t1 = time.perf_counter()
+        K = co.calc_lk_gaussian(x2, x1, test[1], train[1], test[0], train[0], ZMAX, False, sig, fast=True)
+        t2 = time.perf_counter()
+        return t1 - t0, t2 - t1, K
+
+    for _ in range(warmup):
+        one()
+    ts, tk = [], []
+    for _ in range(max(steps, 1)):
+        a, b, K = one()
+        ts.append(a)
+        tk.append(b)
+    t_slatm, t_kernel = float(np.median(ts)), float(np.median(tk))
+    elems = len(COEFFS) * args.cpu_test * args.cpu_train
+    atoms = int(train[0].sum() + test[0].sum())
+    return dict(value=elems / (t_slatm + t_kernel), unit="kernel elements/s", cores=cores, kind="port",
+                sample=f"{args.cpu_test} test x {args.cpu_train} train QM9-shaped molecules ({atoms} atoms, D=8975, "
+                       f"4 sigmas), molecules->aSLATM->K; restated reference loops (C/OpenMP -O3 -march=native), "
+                       f"not gfortran",
+                aslatm_atoms_per_sec=atoms / t_slatm, seconds=t_slatm + t_kernel,
+                seconds_slatm=t_slatm, seconds_kernel=t_kernel)
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    t0 = time.perf_counter()
+    r = cpu_sample(args, steps=args.steps, warmup=min(args.warmup, 1))
+    ms = r["seconds"] * 1e3
+    line = {"impl": "reference", "metric": "local_gaussian_kernel_elements_per_sec", "value": r["value"],
+            "unit": "kernel elements/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic",
+            "config": {"workload": "config2: 20k train x 2k test QM9-shaped, local aSLATM element-matched Gaussian "
+                                   "kernel, 4 sigmas (CPU arm: bounded sample of it)", "sample": r["sample"]},
+            "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "aslatm_atoms_per_sec": r["aslatm_atoms_per_sec"],
+            "e2e": {"value": r["value"], "unit": "kernel elements/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "wall_s": time.perf_counter() - t0}
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------------
+def fp64_peak_tflops(torch):
+    """cuBLAS DGEMM 8192^3, best of 10 (MEASURED_PEAKS.json has no FP64 entry)."""
+    n = 8192
+    a = torch.randn((n, n), dtype=torch.float64, device="cuda")
+    b = torch.randn((n, n), dtype=torch.float64, device="cuda")
+    c = torch.empty_like(a)
+    best = 1e9
+    for i in range(12):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        torch.matmul(a, b, out=c)
+        e1.record()
+        torch.cuda.synchronize()
+        if i >= 2:
+            best = min(best, e0.elapsed_time(e1))
+    del a, b, c
+    return 2.0 * n ** 3 / (best * 1e-3) / 1e12
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from aqml_b200 import _lib as L
+    from aqml_b200 import fused
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    lib = L.load()
+
+    train, test = make_sets(args.n_train, args.n_test, rank)
+    mb = mbtypes_for(train, test)
+    S = len(COEFFS)
+    dev = torch.device("cuda", local_rank)
+    c1 = torch.as_tensor(train[2], device=dev)
+    c2 = torch.as_tensor(test[2], device=dev)
+    K = torch.empty((S, args.n_test, args.n_train), dtype=torch.float64, device=dev)
+
+    # sigmas from the per-element dmax of a training subsample (width heuristic, aqml.py:204-255,775)
+    nsub = min(args.n_train, 400)
+    asub = int(train[0][:nsub].sum())
+    sub = fused.PackedRep(train[2][:asub], train[1][:asub], train[0][:nsub], mb, **SLATM_KW)
+    dso = fused.kernel_width(sub, sub, ZMAX)
+    sub.close()
+    sig = np.array([c * dso / np.sqrt(2 * np.log(2)) for c in COEFFS])
+
+    def ev():
+        return torch.cuda.Event(enable_timing=True)
+
+    def step(timing=None):
+        e = [ev() for _ in range(3)] if timing is not None else None
+        if e:
+            e[0].record()
+        r1 = fused.PackedRep(c1, train[1], train[0], mb, **SLATM_KW)
+        r2 = fused.PackedRep(c2, test[1], test[0], mb, **SLATM_KW)
+        if e:
+            e[1].record()
+        fused.local_gaussian(r2, r1, sig, ZMAX, out=K)
+        if e:
+            e[2].record()
+            timing.append(e)
+        nbytes = r1.nbytes + r2.nbytes
+        r1.close()
+        r2.close()
+        return nbytes
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        rep_bytes = step()
+    barrier()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    launches0 = lib.aqml_launch_count()
+    timing = []
+    w0 = time.time()
+    e_start, e_end = ev(), ev()
+    e_start.record()
+    for _ in range(args.steps):
+        step(timing)
+    e_end.record()
+    barrier()
+    w1 = time.time()
+    launches = int(lib.aqml_launch_count() - launches0)
+    t_total_ms = e_start.elapsed_time(e_end)
+    t_slatm_ms = float(np.mean([e[0].elapsed_time(e[1]) for e in timing]))
+    t_kernel_ms = float(np.mean([e[1].elapsed_time(e[2]) for e in timing]))
+    clocks = sampler.stop(w0, w1) if sampler else None
+
+    # ---- end-to-end through the C ABI with host buffers -----------------------------------------
+    e2e_ms = None
+    if not args.no_e2e:
+        kh = torch.empty((S, args.n_test, args.n_train), dtype=torch.float64, pin_memory=True)
+        pc1 = torch.as_tensor(train[2]).pin_memory().numpy()
+        pc2 = torch.as_tensor(test[2]).pin_memory().numpy()
+
+        def e2e_step():
+            r1 = fused.PackedRep(pc1, train[1], train[0], mb, **SLATM_KW)   # coords H2D inside
+            r2 = fused.PackedRep(pc2, test[1], test[0], mb, **SLATM_KW)
+            fused.local_gaussian(r2, r1, sig, ZMAX, out=K)
+            kh.copy_(K, non_blocking=True)                                    # K D2H
+            r1.close()
+            r2.close()
+        for _ in range(2):
+            e2e_step()
+        barrier()
+        a, b = ev(), ev()
+        a.record()
+        n_e2e = max(2, min(args.steps, 3))
+        for _ in range(n_e2e):
+            e2e_step()
+        b.record()
+        barrier()
+        e2e_ms = a.elapsed_time(b) / n_e2e
+        h2d = int(train[2].nbytes + test[2].nbytes + 4 * (len(train[1]) + len(test[1])) + sig.nbytes)
+        d2h = int(K.numel() * 8)
+
+    # ---- reduce over ranks ---------------------------------------------------------------------
+    vals = torch.tensor([t_total_ms, t_slatm_ms, t_kernel_ms, e2e_ms or 0.0], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(vals, op=dist.ReduceOp.MAX)
+    t_total_ms, t_slatm_ms, t_kernel_ms, e2e_max = [float(v) for v in vals.cpu()]
+    ms_per_step = t_total_ms / args.steps
+    elems_rank = S * args.n_test * args.n_train
+    atoms_rank = int(train[0].sum() + test[0].sum())
+
+    if rank == 0:
+        # algorithmic work of the dominant kernel (pair_tile_kernel<DOT,LOCAL>): 2 * sum_z D_z n1_z n2_z
+        p = L.slatm_params(mb, **{k: SLATM_KW[k] for k in SLATM_KW})
+        nel = 5
+        d_z = {z: nel * p.nx2 + (nel * (nel + 1) // 2) * p.nx3 for z in (1, 6, 7, 8, 9)}
+        flops = 0.0
+        for z in d_z:
+            flops += 2.0 * d_z[z] * float((test[1] == z).sum()) * float((train[1] == z).sum())
+        peak_tf = fp64_peak_tflops(torch)
+        ach_tf = flops / (t_kernel_ms * 1e-3) / 1e12
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        hbm_peak = peaks.get("hbm_gbs", 6650.0)
+        slatm_bytes = float(rep_bytes)
+        line = {
+            "metric": "local_gaussian_kernel_elements_per_sec",
+            "value": world * elems_rank / (ms_per_step * 1e-3), "unit": "kernel elements/s",
+            "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "config2: 20k train x 2k test QM9-shaped molecules, local aSLATM element-matched "
+                                   "Gaussian kernel, FP64, 4 sigmas; step = coords -> aSLATM(train+test) -> K",
+                       "n_train": args.n_train, "n_test_per_gpu": args.n_test, "atoms_per_gpu": atoms_rank,
+                       "D": int(lib.aqml_slatm_dim(p)), "D_z": d_z[6], "nsigmas": S,
+                       "sharding": "row blocks of K (test molecules) per GPU, no collective",
+                       "l2": "inputs larger than L2 (packed operands %.1f GB per step)" % (rep_bytes / 1e9)},
+            "aslatm_atoms_per_sec": world * atoms_rank / (t_slatm_ms * 1e-3),
+            "phases_ms": {"aslatm": t_slatm_ms, "kernel": t_kernel_ms},
+            "gpu_launches": launches,
+            "clocks": clocks,
+            "roofline": {"bound": "tensor", "kernel": "pair_tile_kernel<MODE_DOT,EPI_LOCAL> (FP64 DMMA.8x8x4)",
+                         "achieved": ach_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach_tf / peak_tf,
+                         "traffic": None, "algorithmic_flops_per_launch": flops,
+                         "peak_source": "cuBLAS DGEMM 8192^3 best of 10 measured in this run "
+                                        "(MEASURED_PEAKS.json has no FP64 entry)"},
+            "roofline_aslatm": {"bound": "hbm", "kernel": "slatm_kernel (packed output)",
+                                "achieved": slatm_bytes / (t_slatm_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                                "frac": slatm_bytes / (t_slatm_ms * 1e-3) / 1e9 / hbm_peak,
+                                "algorithmic_bytes_per_step": slatm_bytes,
+                                "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650"},
+        }
+        if e2e_ms is not None:
+            line["e2e"] = {"value": world * elems_rank / (e2e_max * 1e-3), "unit": "kernel elements/s",
+                           "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": e2e_max}
+        if world == 1 and not args.no_cpu_baseline:
+            r = cpu_sample(args, steps=1, warmup=0)
+            line["cpu_baseline"] = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}
+            line["cpu_baseline"]["aslatm_atoms_per_sec"] = r["aslatm_atoms_per_sec"]
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()
