@@ -24,6 +24,18 @@ void require_device() {
         fail(AQML_ECUDA, "no CUDA device available (aqml_b200 has no CPU fallback): %s",
              e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
     }
+    // Keep freed workspace blocks in the stream-ordered pool instead of returning them to the driver at
+    // every synchronisation (default release threshold 0): a step re-uses the same ~9 GB of operands.
+    static std::atomic<unsigned> configured{0};
+    int dev = 0;
+    AQML_CUDA(cudaGetDevice(&dev));
+    if (dev < 32 && !(configured.load() & (1u << dev))) {
+        cudaMemPool_t pool;
+        AQML_CUDA(cudaDeviceGetDefaultMemPool(&pool, dev));
+        unsigned long long keep = ~0ull;
+        AQML_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+        configured.fetch_or(1u << dev);
+    }
 }
 
 // =============================================================================================
@@ -243,7 +255,7 @@ static void global_pairs(int kind, int epi, const double *a, int na, long long l
     Packed pa = same ? pb : pack_dense(ws, a, lda, na, D, mean, mode == MODE_DOT);
     PairGroup g = blank_group();
     g.A = pa.x; g.B = pb.x; g.normA = pa.norm; g.normB = pb.norm; g.ld = pa.ld;
-    g.nA = na; g.nB = nb; g.tilesM = pa.tiles; g.tilesN = pb.tiles;
+    g.nA = na; g.nB = nb; g.tilesM = pa.rows / BM; g.tilesN = pb.rows / BN;
     g.sym = (epi == EPI_MAX && same) ? 1 : 0;
     PairParams P{};
     P.out = out; P.ldo = nb; P.slab = (long long)na * nb; P.nsig = nsig; P.zstride = 1;
@@ -500,7 +512,7 @@ static void kernel_width(int p, const double *x, long long ldx, const int *zs, i
         J.dst = px; J.ldd = ld; J.norm = pn; J.ncols = Dz;
         launch_pack(J, (int)rm.size(), st);
         PairGroup g = blank_group();
-        g.A = g.B = px; g.normA = g.normB = pn; g.ld = ld; g.nA = g.nB = n; g.tilesM = g.tilesN = tiles;
+        g.A = g.B = px; g.normA = g.normB = pn; g.ld = ld; g.nA = g.nB = n; g.tilesM = tiles; g.tilesN = tiles * (BM / BN);
         g.out_slot = e; g.sym = 1;
         groups.push_back(g);
     }

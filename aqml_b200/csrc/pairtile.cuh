@@ -1,6 +1,6 @@
 // Pair-tile engine: every kernel-matrix / distance routine of the hot path is one instance of
 //
-//     for a 128x128 tile of (row i of A, row j of B):  v_ij = reduce_k f(A[i,k], B[j,k])
+//     for a 128x64 tile of (row i of A, row j of B):  v_ij = reduce_k f(A[i,k], B[j,k])
 //     then an epilogue on v_ij
 //
 //   MODE_DOT : v = max(|a|^2 + |b|^2 - 2 a.b, 0); the cross term runs on the FP64 tensor cores
@@ -21,14 +21,18 @@
 
 namespace aqml {
 
-constexpr int BM = 128, BN = 128, BK = 16;
+// CTA tile 128 x 64, 4 warps (2 x 2, warp tile 64 x 32), 3-stage pipeline -> 92 KB of shared memory and
+// <= 240 registers x 128 threads, so TWO CTAs are resident per SM: one CTA's epilogue / barrier bubbles
+// are covered by the other CTA's DMMA stream (measured: tensor pipe 76% busy with one 128x128 CTA).
+constexpr int BM = 128, BN = 64, BK = 16;
 constexpr int PITCH = BK + 4;  // doubles; (PITCH mod 16) == 4 -> conflict-free 8x4 fragment loads
-constexpr int STAGES = 4;
-constexpr int NT = 256;        // 8 warps: 2 (M) x 4 (N), warp tile 64 x 32
+constexpr int STAGES = 3;
+constexpr int WARPS_N = BN / 32;
+constexpr int NT = 64 * WARPS_N;  // 2 (M) x WARPS_N (N) warps
 constexpr int STAGE_DOUBLES = (BM + BN) * PITCH;
-constexpr int PIPE_BYTES = STAGES * STAGE_DOUBLES * 8;  // 163840
+constexpr int PIPE_BYTES = STAGES * STAGE_DOUBLES * 8;  // 92160
 constexpr int EPITCH = 40;     // per-warp staging pitch (doubles) for the segmented epilogue
-static_assert(8 * 64 * EPITCH * 8 <= PIPE_BYTES, "epilogue staging must fit in the pipeline buffers");
+static_assert((NT / 32) * 64 * EPITCH * 8 <= PIPE_BYTES, "epilogue staging must fit in the pipeline buffers");
 
 enum { MODE_DOT = 0, MODE_L1 = 1 };
 enum { EPI_EXP_STORE = 0, EPI_DIST_STORE = 1, EPI_MAX = 2, EPI_LOCAL = 3 };
@@ -58,14 +62,14 @@ struct PairParams {
 };
 
 template <int MODE, int EPI>
-__global__ void __launch_bounds__(NT, 1) pair_tile_kernel(const PairParams P) {
+__global__ void __launch_bounds__(NT, 2) pair_tile_kernel(const PairParams P) {
     extern __shared__ __align__(16) double smem[];
     __shared__ int sSegA[BM], sSegB[BN], sZA[BM];
     __shared__ double sNA[BM], sNB[BN];
     __shared__ double sRed[NT / 32];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int wm = warp >> 2, wn = warp & 3;
+    const int wm = warp / WARPS_N, wn = warp % WARPS_N;
     const int g = lane >> 2, t4 = lane & 3;
 
     // ---- locate group and tile -------------------------------------------------------------
@@ -77,25 +81,26 @@ __global__ void __launch_bounds__(NT, 1) pair_tile_kernel(const PairParams P) {
     const int band = t / (GM * G.tilesN), rem = t % (GM * G.tilesN);
     const int gm = min(GM, G.tilesM - band * GM);
     const int tm = band * GM + rem % gm, tn = rem / gm;
-    if (EPI == EPI_MAX && G.sym && tn < tm) return;
+    if (EPI == EPI_MAX && G.sym && (tn + 1) * BN <= tm * BM) return;  // tile entirely below the diagonal
 
     // ---- tile metadata ---------------------------------------------------------------------
-    if (tid < BM) {
-        int r = tm * BM + tid;
-        int s = G.segA ? G.segA[r] : (r < G.nA ? r : -1);
-        s = (s >= G.segA_off && s - G.segA_off < G.segA_n) ? s - G.segA_off : -1;
-        sSegA[tid] = s;
-        sNA[tid] = G.normA ? G.normA[r] : 0.0;
-        sZA[tid] = G.zA ? G.zA[r] : G.zcol;
-    } else {
-        int c = tid - BM, r = tn * BN + c;
-        sSegB[c] = G.segB ? G.segB[r] : (r < G.nB ? r : -1);
-        sNB[c] = G.normB ? G.normB[r] : 0.0;
+    int any = 0;
+    for (int i = tid; i < BM + BN; i += NT) {
+        if (i < BM) {
+            int r = tm * BM + i;
+            int s = G.segA ? G.segA[r] : (r < G.nA ? r : -1);
+            s = (s >= G.segA_off && s - G.segA_off < G.segA_n) ? s - G.segA_off : -1;
+            sSegA[i] = s;
+            any |= (s >= 0);
+            sNA[i] = G.normA ? G.normA[r] : 0.0;
+            sZA[i] = G.zA ? G.zA[r] : G.zcol;
+        } else {
+            int c = i - BM, r = tn * BN + c;
+            sSegB[c] = G.segB ? G.segB[r] : (r < G.nB ? r : -1);
+            sNB[c] = G.normB ? G.normB[r] : 0.0;
+        }
     }
-    {
-        int any = (tid < BM) ? (sSegA[tid] >= 0) : 0;
-        if (!__syncthreads_or(any)) return;  // no row of this tile is wanted (row-block sharding)
-    }
+    if (!__syncthreads_or(any)) return;  // no row of this tile is wanted (row-block sharding)
 
     // ---- main loop: 4-stage cp.async pipeline ------------------------------------------------
     const double *gA = G.A + (long long)tm * BM * G.ld;
@@ -264,6 +269,17 @@ __global__ void __launch_bounds__(NT, 1) pair_tile_kernel(const PairParams P) {
         const unsigned above = (lane == 31) ? 0u : (heads >> (lane + 1));
         const int run_end = above ? (lane + __ffs(above) - 1) : 31;
         const int *rowseg = sSegA + wm * 64;
+        // row-segment structure of this warp's 64 rows as bit masks (identical for all lanes)
+        unsigned last_lo, last_hi, valid_lo, valid_hi;
+        {
+            int r0 = lane, r1 = lane + 32;
+            int s0 = rowseg[r0], s1 = rowseg[r1];
+            int n0 = rowseg[r0 + 1], n1 = (r1 == 63) ? -2 : rowseg[r1 + 1];
+            last_lo = __ballot_sync(0xffffffffu, n0 != s0);
+            last_hi = __ballot_sync(0xffffffffu, n1 != s1);
+            valid_lo = __ballot_sync(0xffffffffu, s0 >= 0);
+            valid_hi = __ballot_sync(0xffffffffu, s1 >= 0);
+        }
         for (int s = 0; s < P.nsig; s++) {
 #pragma unroll
             for (int mi = 0; mi < 8; mi++) {
@@ -280,21 +296,29 @@ __global__ void __launch_bounds__(NT, 1) pair_tile_kernel(const PairParams P) {
             __syncwarp();
             double *outS = P.out + (long long)s * P.slab;
             double run = 0.0;
-            for (int r = 0; r < 64; r++) {
-                const int sr = rowseg[r];
-                if (sr >= 0) run += patch[r * EPITCH + lane];
-                const bool last = (r == 63) || (rowseg[r + 1] != sr);
-                if (last) {
-                    if (sr >= 0) {
-                        double v = run;
+#pragma unroll 1
+            for (int rb = 0; rb < 64; rb += 8) {
+                double v8[8];
 #pragma unroll
-                        for (int o = 1; o < 32; o <<= 1) {
-                            double u = __shfl_down_sync(0xffffffffu, v, o);
-                            if (lane + o <= run_end) v += u;
+                for (int j = 0; j < 8; j++) v8[j] = patch[(rb + j) * EPITCH + lane];  // 8 independent loads
+                const unsigned lastb = ((rb < 32 ? last_lo : last_hi) >> (rb & 31)) & 0xffu;
+                const unsigned validb = ((rb < 32 ? valid_lo : valid_hi) >> (rb & 31)) & 0xffu;
+#pragma unroll
+                for (int j = 0; j < 8; j++) {
+                    if ((validb >> j) & 1u) run += v8[j];
+                    if ((lastb >> j) & 1u) {  // warp-uniform
+                        if ((validb >> j) & 1u) {
+                            const int sr = rowseg[rb + j];
+                            double v = run;
+#pragma unroll
+                            for (int o = 1; o < 32; o <<= 1) {
+                                double u = __shfl_down_sync(0xffffffffu, v, o);
+                                if (lane + o <= run_end) v += u;
+                            }
+                            if (head && colseg >= 0) atomicAdd(outS + (long long)sr * P.ldo + colseg, v);
                         }
-                        if (head && colseg >= 0) atomicAdd(outS + (long long)sr * P.ldo + colseg, v);
+                        run = 0.0;
                     }
-                    run = 0.0;
                 }
             }
             __syncwarp();

@@ -26,6 +26,12 @@ constexpr int MAXEL = 16;
 constexpr int SL_THREADS = 128;
 constexpr int PCH = 512;  // neighbour pairs per shared-memory chunk
 
+constexpr int MAXBLK = MAXEL * (MAXEL + 1) / 2;
+struct Block3 {
+    int e1, e3, col, flip, p0;  // pair offset p0; pairs = n1*n3 or n1(n1-1)/2
+    double c0;
+};
+
 struct SlatmDev {
     int n_el, nmb, nx2, nx3, D;
     double sigma2, sigma3, dgrid2, dgrid3, coeff2, coeff3, rcut, rpower;
@@ -38,6 +44,8 @@ struct SlatmDev {
     const int *lay_col;                         // [n_el*nmb] column of slot in element e's layout or -1
     const int *owner;                           // [nmb] owning element of a slot in global mode
     const double *xs2, *xpow2, *xs3, *cosx3;    // grids (host libm): xs, xs**rpower, angles, cos(angles)
+    const Block3 *blk;                          // [n_el*MAXBLK] three-body blocks (e1<=e3) per centre element
+    int nblk[MAXEL];
 };
 
 struct SlatmJob {
@@ -72,27 +80,23 @@ __device__ __forceinline__ double cos_angle_rn(const double *a, const double *b,
     return __dadd_rn(__dadd_rn(__dmul_rn(v1x, v2x), __dmul_rn(v1y, v2y)), __dmul_rn(v1z, v2z));
 }
 
-struct Block3 {
-    int e1, e3, col, flip, p0;  // pair offset p0; pairs = n1*n3 or n1(n1-1)/2
-    double c0;
-};
-
 // dynamic shared memory carve-up (doubles first)
-//   spec[pldmax] | mx,my,mz[na_max] | nbx,nby,nbz,nbd,nbr2[na_max] | pair[4*PCH] | ints: mel[na_max], nbi[na_max], nbe[na_max], nbf[na_max]
+//   spec[pldmax] | mx,my,mz | nbx,nby,nbz,nbd,nbr2 | md,mr2 (each [na_max]) | pair[4*PCH] | ints: mel,nbi,nbe,nbf,mfl [na_max]
 __global__ void __launch_bounds__(SL_THREADS) slatm_kernel(const SlatmDev T, const SlatmJob J, int pldmax, int na_max) {
     extern __shared__ __align__(16) double sm[];
     double *spec = sm;
     double *mx = spec + pldmax, *my = mx + na_max, *mz = my + na_max;
     double *nbx = mz + na_max, *nby = nbx + na_max, *nbz = nby + na_max, *nbd = nbz + na_max, *nbr2 = nbd + na_max;
-    double *pair = nbr2 + na_max;
+    double *md = nbr2 + na_max, *mr2 = md + na_max;
+    double *pair = mr2 + na_max;
     int *mel = reinterpret_cast<int *>(pair + 4 * PCH);
-    int *nbi = mel + na_max, *nbe = nbi + na_max, *nbf = nbe + na_max;
+    int *nbi = mel + na_max, *nbe = nbi + na_max, *nbf = nbe + na_max, *mfl = nbf + na_max;
     __shared__ int s_cnt[MAXEL], s_start[MAXEL + 1];
-    __shared__ Block3 s_blk[MAXEL * (MAXEL + 1) / 2];
+    __shared__ Block3 s_blk[MAXBLK];
     __shared__ int s_nblk, s_ptot;
     __shared__ double s_red[SL_THREADS / 32];
 
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const double eps = 2.220446049250313e-16;
     const double rcut = T.rcut, rcut2 = __dmul_rn(rcut, rcut);
 
@@ -131,16 +135,27 @@ __global__ void __launch_bounds__(SL_THREADS) slatm_kernel(const SlatmDev T, con
             if (mel[c] != ec) continue;  // block-uniform
             __syncthreads();
             // ---- neighbour list, sorted by element, list order preserved ---------------------
-            if (tid < T.n_el) {
-                int e = tid, n = 0;
-                for (int q = 0; q < na; q++) {
-                    if (q == c || mel[q] != e) continue;
-                    double r2 = dist2_rn(mx[c], my[c], mz[c], mx[q], my[q], mz[q]);
-                    double d = __dsqrt_rn(r2);
-                    int f2 = (r2 < rcut2), f3 = (d > eps) && (d <= rcut);
-                    n += (f2 | f3);
+            // pass A (all threads): distance / cut-off flags of every atom w.r.t. the centre
+            for (int q = tid; q < na; q += SL_THREADS) {
+                int fl = 0;
+                double r2 = 0.0, d = 0.0;
+                if (q != c && mel[q] >= 0) {
+                    r2 = dist2_rn(mx[c], my[c], mz[c], mx[q], my[q], mz[q]);
+                    d = __dsqrt_rn(r2);
+                    fl = (int)(r2 < rcut2) | ((int)((d > eps) && (d <= rcut)) << 1);  // bit0: 2-body, bit1: 3-body
                 }
-                s_cnt[e] = n;
+                md[q] = d; mr2[q] = r2; mfl[q] = fl;
+            }
+            __syncthreads();
+            // pass B (one warp per element): counts by ballot
+            for (int e = warp; e < T.n_el; e += SL_THREADS / 32) {
+                int n = 0;
+                for (int q0 = 0; q0 < na; q0 += 32) {
+                    int q = q0 + lane;
+                    bool keep = (q < na) && mfl[q] && mel[q] == e;
+                    n += __popc(__ballot_sync(0xffffffffu, keep));
+                }
+                if (lane == 0) s_cnt[e] = n;
             }
             __syncthreads();
             if (tid == 0) {
@@ -149,40 +164,46 @@ __global__ void __launch_bounds__(SL_THREADS) slatm_kernel(const SlatmDev T, con
                 s_start[T.n_el] = acc;
             }
             __syncthreads();
-            if (tid < T.n_el) {
-                int e = tid, w = s_start[e];
-                for (int q = 0; q < na; q++) {
-                    if (q == c || mel[q] != e) continue;
-                    double r2 = dist2_rn(mx[c], my[c], mz[c], mx[q], my[q], mz[q]);
-                    double d = __dsqrt_rn(r2);
-                    int f2 = (r2 < rcut2), f3 = (d > eps) && (d <= rcut);
-                    if (f2 | f3) {
-                        nbx[w] = mx[q]; nby[w] = my[q]; nbz[w] = mz[q]; nbd[w] = d; nbr2[w] = r2;
-                        nbi[w] = q; nbe[w] = e; nbf[w] = f2 | (f3 << 1);
-                        w++;
+            // pass C: ordered compaction
+            for (int e = warp; e < T.n_el; e += SL_THREADS / 32) {
+                int w = s_start[e];
+                for (int q0 = 0; q0 < na; q0 += 32) {
+                    int q = q0 + lane;
+                    bool keep = (q < na) && mfl[q] && mel[q] == e;
+                    unsigned mk = __ballot_sync(0xffffffffu, keep);
+                    if (keep) {
+                        int pos = w + __popc(mk & ((1u << lane) - 1u));
+                        nbx[pos] = mx[q]; nby[pos] = my[q]; nbz[pos] = mz[q]; nbd[pos] = md[q]; nbr2[pos] = mr2[q];
+                        nbi[pos] = q; nbe[pos] = e; nbf[pos] = mfl[q];
                     }
+                    w += __popc(mk);
                 }
             }
-            // ---- three-body block table -----------------------------------------------------------
-            if (tid == 0) {
-                int nb = 0, p = 0;
-                for (int e1 = 0; e1 < T.n_el; e1++)
-                    for (int e3 = e1; e3 < T.n_el; e3++) {
-                        int sl = T.bot_slot[(e1 * MAXEL + ec) * MAXEL + e3];
-                        if (sl < 0) continue;
-                        int n1 = s_cnt[e1], n3 = s_cnt[e3];
-                        int np = (e1 == e3) ? n1 * (n1 - 1) / 2 : n1 * n3;
-                        if (np <= 0) continue;
-                        Block3 b;
-                        b.e1 = e1; b.e3 = e3; b.col = lay[sl >> 1]; b.flip = sl & 1; b.p0 = p;
-                        // c0 = prefactor * (Z1*Z2*Z3) * coeff * dgrid   (fslatm.f90:324-332), mbtype order
-                        double w1 = T.el_w[b.flip ? e3 : e1], w3 = T.el_w[b.flip ? e1 : e3];
-                        b.c0 = (1.0 / 3.0) * (w1 * T.el_w[ec] * w3) * T.coeff3 * T.dgrid3;
-                        s_blk[nb++] = b;
-                        p += np;
+            // ---- three-body block table: static per centre element (host built), pair offsets by scan ----
+            {
+                const int nb = T.nblk[ec];
+                const Block3 *tab = T.blk + ec * MAXBLK;
+                if (warp == 0) {
+                    int carry = 0;
+                    for (int b0 = 0; b0 < nb; b0 += 32) {
+                        int b = b0 + lane, np = 0;
+                        Block3 B;
+                        if (b < nb) {
+                            B = tab[b];
+                            int n1 = s_cnt[B.e1], n3 = s_cnt[B.e3];
+                            np = (B.e1 == B.e3) ? n1 * (n1 - 1) / 2 : n1 * n3;
+                        }
+                        int incl = np;
+#pragma unroll
+                        for (int o = 1; o < 32; o <<= 1) {
+                            int u = __shfl_up_sync(0xffffffffu, incl, o);
+                            if (lane >= o) incl += u;
+                        }
+                        if (b < nb) { B.p0 = carry + incl - np; s_blk[b] = B; }
+                        carry += __shfl_sync(0xffffffffu, incl, 31);
                     }
-                s_nblk = nb;
-                s_ptot = p;
+                    if (lane == 0) { s_nblk = nb; s_ptot = carry; }
+                }
             }
             __syncthreads();
 
@@ -437,6 +458,24 @@ static SlatmTables build_tables(const aqml_slatm_params *p, bool mode_local, Wor
         d.pld[e] = (int)round_up(std::max(w, 1), BK);
         t.pldmax = std::max(t.pldmax, d.pld[e]);
     }
+    // static three-body block table per centre element: (e1 <= e3) with a listed type
+    std::vector<Block3> blk((size_t)ne * MAXBLK);
+    for (int ec = 0; ec < ne; ec++) {
+        int nb = 0;
+        for (int e1 = 0; e1 < ne; e1++)
+            for (int e3 = e1; e3 < ne; e3++) {
+                int sl = bot[(e1 * MAXEL + ec) * MAXEL + e3];
+                if (sl < 0) continue;
+                Block3 b;
+                b.e1 = e1; b.e3 = e3; b.col = lay[(size_t)ec * p->nmb + (sl >> 1)]; b.flip = sl & 1; b.p0 = 0;
+                // c0 = prefactor * (Z1*Z2*Z3) * coeff * dgrid (fslatm.f90:324-332), factors in the listed order
+                double w1 = d.el_w[b.flip ? e3 : e1], w3 = d.el_w[b.flip ? e1 : e3];
+                b.c0 = (1.0 / 3.0) * (w1 * d.el_w[ec] * w3) * p->coeff3 * p->dgrid3;
+                blk[(size_t)ec * MAXBLK + nb++] = b;
+            }
+        d.nblk[ec] = nb;
+    }
+    d.blk = ws.upload(blk);
     // grids on the host (same libm as the CPU reference): utils.f90:29-50, slatm.py:60-62,118-122
     std::vector<double> xs2(p->nx2), xp2(p->nx2), xs3(p->nx3), cx3(p->nx3);
     {
@@ -454,7 +493,7 @@ static SlatmTables build_tables(const aqml_slatm_params *p, bool mode_local, Wor
 }
 
 static size_t slatm_smem_bytes(int pldmax, int na_max) {
-    return sizeof(double) * ((size_t)pldmax + 8 * (size_t)na_max + 4 * PCH) + sizeof(int) * 4 * (size_t)na_max;
+    return sizeof(double) * ((size_t)pldmax + 10 * (size_t)na_max + 4 * PCH) + sizeof(int) * 5 * (size_t)na_max;
 }
 
 static void launch_slatm(const SlatmTables &t, const SlatmJob &J, int na_max, cudaStream_t st) {
@@ -597,7 +636,7 @@ static void rep_groups(const aqml_rep *r1, const aqml_rep *r2, int zmax, std::ve
             PairGroup g;
             memset(&g, 0, sizeof(g));
             g.A = a.x; g.B = b.x; g.normA = a.norm; g.normB = b.norm; g.segA = a.seg; g.segB = b.seg;
-            g.ld = a.ld; g.tilesM = a.tiles; g.tilesN = b.tiles; g.zcol = z - 1; g.segA_off = 0; g.segA_n = 0x7fffffff;
+            g.ld = a.ld; g.tilesM = a.tiles; g.tilesN = b.tiles * (BM / BN); g.zcol = z - 1; g.segA_off = 0; g.segA_n = 0x7fffffff;
             groups.push_back(g);
             labels.push_back(a.label);
         }
