@@ -127,33 +127,16 @@ void launch_colstats(const double *x, long long ldx, const int *rows, int nrows,
 // =============================================================================================
 // host helpers
 // =============================================================================================
-// Split a molecule-sorted row list into <=128-row tiles that start on molecule boundaries (a
-// molecule longer than a tile is split).  rowmap/seg get -1 padding up to 128 per tile.
+// Pack a molecule-sorted row list into 128-row tiles (-1 padding only at the very end).  Molecules may
+// straddle tile / warp-patch boundaries: their partial sums meet in K through the FP64 REDs.  (Aligning
+// tiles to molecule boundaries wasted ~5% of the rows per side, ~9% of the DMMA work, for hydrogen.)
 void build_tiles(const std::vector<int> &rows, const std::vector<int> &mol_of_row, std::vector<int> &rowmap,
                  std::vector<int> &seg) {
-    rowmap.clear();
-    seg.clear();
-    size_t i = 0, n = rows.size();
-    while (i < n) {
-        size_t fill = 0;
-        while (i < n && fill < (size_t)BM) {
-            size_t j = i;
-            while (j < n && mol_of_row[j] == mol_of_row[i]) j++;
-            size_t len = j - i;
-            if (fill + len <= (size_t)BM) {
-                for (size_t q = i; q < j; q++) { rowmap.push_back(rows[q]); seg.push_back(mol_of_row[q]); }
-                fill += len;
-                i = j;
-            } else if (fill == 0) {  // one molecule with more rows than a tile: split it
-                for (size_t q = i; q < i + BM; q++) { rowmap.push_back(rows[q]); seg.push_back(mol_of_row[q]); }
-                fill = BM;
-                i += BM;
-            } else {
-                break;
-            }
-        }
-        while (fill < (size_t)BM) { rowmap.push_back(-1); seg.push_back(-1); fill++; }
-    }
+    rowmap = rows;
+    seg = mol_of_row;
+    size_t padded = (size_t)round_up((int64_t)rows.size(), BM);
+    rowmap.resize(padded, -1);
+    seg.resize(padded, -1);
 }
 
 static std::vector<int> mol_index(const int *nas, int nm, int &A) {
@@ -176,6 +159,7 @@ static void run_pairs(int mode, int epi, const std::vector<PairGroup> &groups, P
     P.groups = ws.upload(gs);
     P.ngroups = (int)gs.size();
     cudaStream_t st = ws.stream();
+    P.sm_arrive = (total >= 1024) ? ws.zeros<int>(1024) : nullptr;
 #define AQML_DISPATCH(M, E) if (mode == M && epi == E) { launch_pair_tiles<M, E>(P, total, st); return; }
     AQML_DISPATCH(MODE_DOT, EPI_EXP_STORE)
     AQML_DISPATCH(MODE_DOT, EPI_DIST_STORE)

@@ -59,6 +59,7 @@ struct PairParams {
     int nsig, zstride;
     double *out;
     long long ldo, slab;  // row pitch, per-sigma stride (elements)
+    int *sm_arrive;       // [>= #SMs] zeroed per launch, or null: stagger the two resident CTAs of an SM
 };
 
 template <int MODE, int EPI>
@@ -82,6 +83,23 @@ __global__ void __launch_bounds__(NT, 2) pair_tile_kernel(const PairParams P) {
     const int gm = min(GM, G.tilesM - band * GM);
     const int tm = band * GM + rem % gm, tn = rem / gm;
     if (EPI == EPI_MAX && G.sym && (tn + 1) * BN <= tm * BM) return;  // tile entirely below the diagonal
+
+    // ---- de-phase the two CTAs that share an SM --------------------------------------------------
+    // All tiles of a group cost the same, so the two resident CTAs would run in lockstep and reach
+    // their (tensor-idle) epilogues together.  The second CTA to arrive on each SM waits half a tile
+    // once; from then on one CTA's epilogue / barrier bubbles overlap the other's DMMA stream.
+    if (P.sm_arrive) {
+        if (tid == 0) {
+            unsigned smid;
+            asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+            if (atomicAdd(P.sm_arrive + smid, 1) == 1) {
+                const long long wait = (long long)(G.ld / BK) * 2048;  // ~half a tile of DMMA time
+                const long long t0 = clock64();
+                while (clock64() - t0 < wait) __nanosleep(1000);
+            }
+        }
+        __syncthreads();
+    }
 
     // ---- tile metadata ---------------------------------------------------------------------
     int any = 0;
