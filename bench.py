@@ -127,6 +127,7 @@ def cpu_sample(args, steps=1, warmup=0):
     mb = mbtypes_for(*make_sets(2000, 500, 0))
     sig = np.array([c * np.full(ZMAX, 16.0) / np.sqrt(2 * np.log(2)) for c in COEFFS])
     co.load(fast=True)
+    co.set_num_threads(len(os.sched_getaffinity(0)), fast=True)  # torchrun exports OMP_NUM_THREADS=1
     cores = co.num_threads(fast=True)
 
     def one():

@@ -58,6 +58,11 @@ def num_threads(fast=False):
     return int(load(fast).oracle_num_threads())
 
 
+def set_num_threads(n, fast=False):
+    """torchrun exports OMP_NUM_THREADS=1; the CPU arm must still use every host core."""
+    load(fast).oracle_set_num_threads(C.c_int(int(n)))
+
+
 def mbtypes_array(mbtypes):
     mb = np.full((len(mbtypes), 3), -1, dtype=np.int32)
     for i, t in enumerate(mbtypes):
