@@ -35,6 +35,7 @@ SIGNATURES = {
     "aqml_last_error": (C.c_char_p, []),
     "aqml_device_count": (_I, []),
     "aqml_launch_count": (_L, []),
+    "aqml_pair_stats": (_I, [_P, _P, _I]),
     "aqml_fgaussian_kernel": (_I, [_P, _I, _P, _I, _I, _P, _D]),
     "aqml_flaplacian_kernel": (_I, [_P, _I, _P, _I, _I, _P, _D]),
     "aqml_fl2_distance": (_I, [_P, _P, _I, _I, _I, _P]),

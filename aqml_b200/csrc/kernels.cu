@@ -49,6 +49,10 @@ __global__ void __launch_bounds__(256) pack_rows_kernel(PackJob J) {
     const double *sp = (src >= 0) ? J.src + (long long)src * J.lds : nullptr;
     double *dp = J.dst + (long long)r * J.ldd;
     double ss = 0.0;
+    __shared__ unsigned smask[32];
+    const bool want_mask = J.mask && J.maskw <= 32;
+    if (want_mask && threadIdx.x < 32) smask[threadIdx.x] = 0u;
+    if (want_mask) __syncthreads();
     for (int c = threadIdx.x; c < J.ldd; c += blockDim.x) {
         double v = 0.0;
         if (sp && c < J.ncols) {
@@ -58,6 +62,12 @@ __global__ void __launch_bounds__(256) pack_rows_kernel(PackJob J) {
         }
         dp[c] = v;
         ss += v * v;
+        if (want_mask && v != 0.0) atomicOr(&smask[c >> 9], 1u << ((c >> 4) & 31));
+    }
+    if (want_mask) {
+        __syncthreads();
+        if ((int)threadIdx.x < J.maskw && smask[threadIdx.x])
+            atomicOr(J.mask + (long long)(r >> 6) * J.maskw + threadIdx.x, smask[threadIdx.x]);
     }
     __shared__ double red[8];
     ss = warp_sum(ss);
@@ -139,6 +149,44 @@ void build_tiles(const std::vector<int> &rows, const std::vector<int> &mol_of_ro
     seg.resize(padded, -1);
 }
 
+// Order molecules by composition class (which elements they contain, once / more than once) so that a
+// 64/128-row block of packed rows holds molecules with the same set of non-zero many-body blocks: whole
+// k-tiles of such a block are exactly zero and the pair kernel skips them.  Heavier elements are the
+// more significant digits, so the rare ones (F, then O, N ...) separate first.
+std::vector<int> class_sorted_molecules(const int *zs, const int *nas, int nm) {
+    std::vector<unsigned long long> key(nm, 0ull);
+    std::vector<int> zlist;
+    size_t a0 = 0;
+    {
+        std::vector<char> seen(4096, 0);
+        size_t A = 0;
+        for (int m = 0; m < nm; m++) A += nas[m];
+        for (size_t a = 0; a < A; a++) {
+            int z = zs[a] % 1000;
+            if (z >= 0 && z < 4096) seen[z] = 1;
+        }
+        for (int z = 0; z < 4096; z++) if (seen[z]) zlist.push_back(z);
+    }
+    std::vector<int> rank(4096, -1);
+    for (size_t i = 0; i < zlist.size(); i++) rank[zlist[i]] = (int)i;
+    std::vector<int> cnt(zlist.size());
+    for (int m = 0; m < nm; m++) {
+        std::fill(cnt.begin(), cnt.end(), 0);
+        for (int i = 0; i < nas[m]; i++) {
+            int z = zs[a0 + i] % 1000;
+            if (z >= 0 && z < 4096) cnt[rank[z]]++;
+        }
+        a0 += nas[m];
+        unsigned long long k = 0;
+        for (size_t e = zlist.size(); e-- > 0;) k = k * 3ull + (unsigned long long)std::min(cnt[e], 2);
+        key[m] = k;
+    }
+    std::vector<int> order(nm);
+    std::iota(order.begin(), order.end(), 0);
+    std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return key[x] < key[y]; });
+    return order;
+}
+
 static std::vector<int> mol_index(const int *nas, int nm, int &A) {
     std::vector<int> m;
     A = 0;
@@ -151,6 +199,8 @@ static std::vector<int> mol_index(const int *nas, int nm, int &A) {
     return m;
 }
 
+unsigned long long *pair_stats_buffer();
+
 static void run_pairs(int mode, int epi, const std::vector<PairGroup> &groups, PairParams P, Workspace &ws) {
     int total = 0;
     std::vector<PairGroup> gs = groups;
@@ -160,6 +210,7 @@ static void run_pairs(int mode, int epi, const std::vector<PairGroup> &groups, P
     P.ngroups = (int)gs.size();
     cudaStream_t st = ws.stream();
     P.sm_arrive = (total >= 1024) ? ws.zeros<int>(1024) : nullptr;
+    P.stats = pair_stats_buffer();
 #define AQML_DISPATCH(M, E) if (mode == M && epi == E) { launch_pair_tiles<M, E>(P, total, st); return; }
     AQML_DISPATCH(MODE_DOT, EPI_EXP_STORE)
     AQML_DISPATCH(MODE_DOT, EPI_DIST_STORE)
@@ -175,6 +226,19 @@ static void run_pairs(int mode, int epi, const std::vector<PairGroup> &groups, P
 
 void run_pairs_public(int mode, int epi, const std::vector<PairGroup> &groups, PairParams P, Workspace &ws) {
     run_pairs(mode, epi, groups, P, ws);
+}
+
+// device-side counters of executed vs dense k-tiles (bench.py reports the executed DMMA work)
+unsigned long long *pair_stats_buffer() {
+    static unsigned long long *buf[32] = {nullptr};
+    int dev = 0;
+    AQML_CUDA(cudaGetDevice(&dev));
+    if (dev >= 32) return nullptr;
+    if (!buf[dev]) {
+        AQML_CUDA(cudaMalloc((void **)&buf[dev], 16));
+        AQML_CUDA(cudaMemset(buf[dev], 0, 16));
+    }
+    return buf[dev];
 }
 
 static PairGroup blank_group() {
@@ -327,9 +391,17 @@ static void local_gaussian(const double *x1, long long ldx1, const double *x2, l
     }
 
     // ---- element-matched: one group per element present on both sides ---------------------------
+    // rows of an element: molecules in composition-class order (block sparsity), atoms in list order
     std::vector<std::vector<int>> r1(zmax + 1), r2(zmax + 1);
-    for (int i = 0; i < A1; i++) r1[zs1[i]].push_back(i);
-    for (int i = 0; i < A2; i++) r2[zs2[i]].push_back(i);
+    {
+        std::vector<int> off1(nm1 + 1, 0), off2(nm2 + 1, 0);
+        for (int m = 0; m < nm1; m++) off1[m + 1] = off1[m] + nas1[m];
+        for (int m = 0; m < nm2; m++) off2[m + 1] = off2[m] + nas2[m];
+        for (int m : class_sorted_molecules(zs1, nas1, nm1))
+            for (int i = off1[m]; i < off1[m + 1]; i++) r1[zs1[i]].push_back(i);
+        for (int m : class_sorted_molecules(zs2, nas2, nm2))
+            for (int i = off2[m]; i < off2[m + 1]; i++) r2[zs2[i]].push_back(i);
+    }
     std::vector<int> els;
     for (int z = 1; z <= zmax; z++) if (!r1[z].empty() && !r2[z].empty()) els.push_back(z);
     const int ne = (int)els.size();
@@ -394,19 +466,25 @@ static void local_gaussian(const double *x1, long long ldx1, const double *x2, l
         for (size_t i = 0; i < m2.size(); i++) m2[i] = mol2[r2[z][i]];
         build_tiles(r1[z], m1, rm1, sg1);
         build_tiles(r2[z], m2, rm2, sg2);
-        auto pack = [&](const double *x, long long ldx, const std::vector<int> &rm, double *&px, double *&pn) {
+        const int mw = mask_words(ld);
+        const bool sparse = !center && mw <= 32;  // centring turns structural zeros into -mean
+        auto pack = [&](const double *x, long long ldx, const std::vector<int> &rm, double *&px, double *&pn,
+                        unsigned *&pm) {
             px = ws.alloc<double>(rm.size() * (size_t)ld);
             pn = ws.alloc<double>(rm.size());
+            pm = sparse ? ws.zeros<unsigned>(rm.size() / 64 * (size_t)mw) : nullptr;
             PackJob J{};
             J.src = x; J.lds = ldx; J.rowmap = ws.upload(rm); J.colmap = d_colmap; J.mean = mean;
-            J.dst = px; J.ldd = ld; J.norm = pn; J.ncols = Dz; J.nvalid = 0;
+            J.dst = px; J.ldd = ld; J.norm = pn; J.ncols = Dz; J.nvalid = 0; J.mask = pm; J.maskw = mw;
             launch_pack(J, (int)rm.size(), st);
         };
         double *p1, *n1, *p2, *n2;
-        pack(x1, ldx1, rm1, p1, n1);
-        pack(x2, ldx2, rm2, p2, n2);
+        unsigned *k1, *k2;
+        pack(x1, ldx1, rm1, p1, n1, k1);
+        pack(x2, ldx2, rm2, p2, n2, k2);
         PairGroup g = blank_group();
         g.A = p1; g.B = p2; g.normA = n1; g.normB = n2; g.ld = ld;
+        g.maskA = k1; g.maskB = k2; g.maskw = mw;
         g.segA = ws.upload(sg1); g.segB = ws.upload(sg2); g.zA = nullptr; g.zcol = z - 1;
         g.tilesM = (int)rm1.size() / BM; g.tilesN = (int)rm2.size() / BN;
         groups.push_back(g);
@@ -527,6 +605,21 @@ int aqml_device_count(void) {
     return n;
 }
 int64_t aqml_launch_count(void) { return (int64_t)g_launches.load(); }
+
+int aqml_pair_stats(int64_t *executed_ktiles, int64_t *dense_ktiles, int reset) {
+    return guarded([&] {
+        require_device();
+        unsigned long long *buf = pair_stats_buffer();
+        unsigned long long h[2] = {0, 0};
+        if (buf) {
+            AQML_CUDA(cudaDeviceSynchronize());
+            AQML_CUDA(cudaMemcpy(h, buf, 16, cudaMemcpyDeviceToHost));
+            if (reset) AQML_CUDA(cudaMemset(buf, 0, 16));
+        }
+        if (executed_ktiles) *executed_ktiles = (int64_t)h[0];
+        if (dense_ktiles) *dense_ktiles = (int64_t)h[1];
+    });
+}
 
 int aqml_fgaussian_kernel(const double *a, int na, const double *b, int nb, int D, double *k, double sigma) {
     return guarded([&] {

@@ -16,13 +16,19 @@ struct PackJob {
     double *norm;        // |row|^2 per packed row; may be null
     int ncols;           // valid packed columns (< = ldd)
     int nvalid;          // valid rows when rowmap is null
+    unsigned *mask;      // [packed rows / 64][maskw] non-zero k-tile bits (pre-zeroed), or null
+    int maskw;
 };
+
+// words of k-tile mask per 64-row block for a row pitch of ld columns
+inline int mask_words(long long ld) { return (int)((ld / BK + 31) / 32); }
 
 void launch_pack(const PackJob &J, int nrows_packed, cudaStream_t st);
 void launch_colstats(const double *x, long long ldx, const int *rows, int nrows, int D, double *colsum, unsigned *colnz,
                      cudaStream_t st);
 void build_tiles(const std::vector<int> &rows, const std::vector<int> &mol_of_row, std::vector<int> &rowmap,
                  std::vector<int> &seg);
+std::vector<int> class_sorted_molecules(const int *zs, const int *nas, int nm);
 void run_pairs_public(int mode, int epi, const std::vector<PairGroup> &groups, PairParams P, Workspace &ws);
 
 }  // namespace aqml

@@ -50,6 +50,11 @@ struct PairGroup {
     int out_slot;                 // EPI_MAX
     int segA_off, segA_n;         // keep rows with segA_off <= seg < segA_off+segA_n, output row = seg - segA_off
     int sym;                      // A == B: skip tiles below the diagonal (EPI_MAX only)
+    // Feature-space block sparsity: one bit per 16-column k-tile and per 64-row block, set when the block
+    // holds any non-zero.  A k-tile whose A-block or B-block is all zero contributes exactly 0 to a.b (and to
+    // sum|a-b| when both are zero), so it is skipped -- bit-identical results, fewer DMMAs.  null = dense.
+    const unsigned *maskA, *maskB;
+    int maskw;                    // 32-bit words per 64-row block
 };
 
 struct PairParams {
@@ -60,7 +65,10 @@ struct PairParams {
     double *out;
     long long ldo, slab;  // row pitch, per-sigma stride (elements)
     int *sm_arrive;       // [>= #SMs] zeroed per launch, or null: stagger the two resident CTAs of an SM
+    unsigned long long *stats;  // [2] executed / dense k-tile counts (summed over tiles), or null
 };
+
+constexpr int KT_LIST_MAX = 1024;  // active-k-tile list capacity (ld <= 16384 columns)
 
 template <int MODE, int EPI>
 __global__ void __launch_bounds__(NT, 2) pair_tile_kernel(const PairParams P) {
@@ -68,6 +76,8 @@ __global__ void __launch_bounds__(NT, 2) pair_tile_kernel(const PairParams P) {
     __shared__ int sSegA[BM], sSegB[BN], sZA[BM];
     __shared__ double sNA[BM], sNB[BN];
     __shared__ double sRed[NT / 32];
+    __shared__ unsigned short sKt[KT_LIST_MAX];
+    __shared__ int sNact;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int wm = warp / WARPS_N, wn = warp % WARPS_N;
@@ -93,7 +103,7 @@ __global__ void __launch_bounds__(NT, 2) pair_tile_kernel(const PairParams P) {
             unsigned smid;
             asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
             if (atomicAdd(P.sm_arrive + smid, 1) == 1) {
-                const long long wait = (long long)(G.ld / BK) * 2048;  // ~half a tile of DMMA time
+                const long long wait = (long long)(G.ld / BK) * (G.maskA ? 1024 : 2048);  // ~half a tile of DMMA time
                 const long long t0 = clock64();
                 while (clock64() - t0 < wait) __nanosleep(1000);
             }
@@ -125,7 +135,44 @@ __global__ void __launch_bounds__(NT, 2) pair_tile_kernel(const PairParams P) {
     const double *gB = G.B + (long long)tn * BN * G.ld;
     const int KT = (int)(G.ld / BK);
 
-    auto load_stage = [&](int stage, int kt) {
+    // ---- active k-tile list ------------------------------------------------------------------------
+    const bool use_list = (G.maskA != nullptr) && (G.maskB != nullptr) && KT <= KT_LIST_MAX && G.maskw <= 32;
+    int nact = KT;
+    if (use_list) {
+        if (warp == 0) {
+            unsigned bits = 0;
+            if (lane < G.maskw) {
+                const unsigned a0 = G.maskA[(long long)(2 * tm) * G.maskw + lane];
+                const unsigned a1 = G.maskA[(long long)(2 * tm + 1) * G.maskw + lane];
+                const unsigned b = G.maskB[(long long)tn * G.maskw + lane];
+                bits = (MODE == MODE_DOT) ? ((a0 | a1) & b) : (a0 | a1 | b);
+                const int hi = KT - lane * 32;  // clip bits beyond KT
+                if (hi < 32) bits &= (hi <= 0) ? 0u : ((1u << hi) - 1u);
+            }
+            int cnt = __popc(bits), incl = cnt;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                int u = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += u;
+            }
+            int off = incl - cnt;
+            while (bits) {
+                int bpos = __ffs(bits) - 1;
+                bits &= bits - 1;
+                sKt[off++] = (unsigned short)(lane * 32 + bpos);
+            }
+            if (lane == 31) sNact = incl;
+        }
+        __syncthreads();
+        nact = sNact;
+    }
+    if (P.stats && tid == 0) {
+        atomicAdd(P.stats, (unsigned long long)nact);
+        atomicAdd(P.stats + 1, (unsigned long long)KT);
+    }
+
+    auto load_stage = [&](int stage, int it) {
+        const int kt = use_list ? (int)sKt[it] : it;
         double *sA = smem + stage * STAGE_DOUBLES;
         double *sB = sA + BM * PITCH;
 #pragma unroll
@@ -148,15 +195,15 @@ __global__ void __launch_bounds__(NT, 2) pair_tile_kernel(const PairParams P) {
 
 #pragma unroll
     for (int s = 0; s < STAGES - 1; s++) {
-        if (s < KT) load_stage(s, s);
+        if (s < nact) load_stage(s, s);
         cp_async_commit();
     }
-    for (int kt = 0; kt < KT; kt++) {
+    for (int kt = 0; kt < nact; kt++) {
         cp_async_wait<STAGES - 2>();
         __syncthreads();
         {
             int nk = kt + STAGES - 1;
-            if (nk < KT) load_stage(nk % STAGES, nk);
+            if (nk < nact) load_stage(nk % STAGES, nk);
             cp_async_commit();
         }
         const double *sA = smem + (kt % STAGES) * STAGE_DOUBLES;

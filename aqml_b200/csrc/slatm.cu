@@ -61,6 +61,8 @@ struct SlatmJob {
     const int *atom_prow;  // (A) packed row inside the element's buffer, -1 = skip
     double *px[MAXEL];
     double *pnorm[MAXEL];
+    unsigned *pmask[MAXEL];  // [rows/64][maskw] non-zero k-tile bits of the packed rows (pre-zeroed) or null
+    int maskw[MAXEL];
 };
 
 // geometry with the oracle's operation order and no FMA contraction (decisions / angles are
@@ -95,6 +97,7 @@ __global__ void __launch_bounds__(SL_THREADS) slatm_kernel(const SlatmDev T, con
     __shared__ Block3 s_blk[MAXBLK];
     __shared__ int s_nblk, s_ptot;
     __shared__ double s_red[SL_THREADS / 32];
+    __shared__ unsigned s_mask[32];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const double eps = 2.220446049250313e-16;
@@ -320,10 +323,21 @@ __global__ void __launch_bounds__(SL_THREADS) slatm_kernel(const SlatmDev T, con
             if (pr >= 0) {
                 double *row = J.px[ec] + (long long)pr * pld;
                 double ss = 0.0;
+                const bool want_mask = J.pmask[ec] != nullptr;
+                if (want_mask) {
+                    if (tid < 32) s_mask[tid] = 0u;
+                    __syncthreads();
+                }
                 for (int i = tid; i < pld; i += SL_THREADS) {
                     double v = spec[i];
                     row[i] = v;
                     ss += v * v;
+                    if (want_mask && v != 0.0) atomicOr(&s_mask[i >> 9], 1u << ((i >> 4) & 31));
+                }
+                if (want_mask) {
+                    __syncthreads();
+                    if (tid < J.maskw[ec] && s_mask[tid])
+                        atomicOr(J.pmask[ec] + (long long)(pr >> 6) * J.maskw[ec] + tid, s_mask[tid]);
                 }
                 ss = warp_sum(ss);
                 if ((tid & 31) == 0) s_red[tid >> 5] = ss;
@@ -557,6 +571,8 @@ struct aqml_rep {
         int label, n, tiles, ld;
         double *x, *norm;
         int *seg;
+        unsigned *mask;
+        int maskw;
     };
     std::vector<El> els;
     std::vector<int> nas;
@@ -583,13 +599,15 @@ static void rep_create(const double *coords, int on_dev, const int *zs, const in
     rep->nmol = nmol; rep->stream = st; rep->nas.assign(nas, nas + nmol);
     std::vector<std::vector<int>> rows(ne), mols(ne);
     rep->cnt.assign(ne, std::vector<int>(nmol, 0));
-    for (int a = 0; a < mi.A; a++) {
-        int e = eidx(zs[a]);
-        if (e < 0) continue;  // element without any many-body type: contributes nothing
-        rows[e].push_back(a);
-        mols[e].push_back(mi.atom_mol[a]);
-        rep->cnt[e][mi.atom_mol[a]]++;
-    }
+    // molecules in composition-class order: blocks of packed rows share their zero many-body blocks
+    for (int m : class_sorted_molecules(zs, nas, nmol))
+        for (int a = mi.off[m]; a < mi.off[m + 1]; a++) {
+            int e = eidx(zs[a]);
+            if (e < 0) continue;  // element without any many-body type: contributes nothing
+            rows[e].push_back(a);
+            mols[e].push_back(m);
+            rep->cnt[e][m]++;
+        }
     std::vector<int> atom_prow(mi.A, -1);
     SlatmJob J;
     memset(&J, 0, sizeof(J));
@@ -602,6 +620,8 @@ static void rep_create(const double *coords, int on_dev, const int *zs, const in
         el.x = keep.alloc<double>(nr * (size_t)el.ld);
         el.norm = keep.alloc<double>(nr);
         el.seg = keep.upload(sg);
+        el.maskw = mask_words(el.ld);
+        el.mask = (el.maskw <= 32 && nr) ? keep.zeros<unsigned>(nr / 64 * (size_t)el.maskw) : nullptr;
         rep->bytes += (int64_t)(nr * (size_t)el.ld * 8 + nr * 12);
         std::vector<int> pad;
         for (size_t r = 0; r < nr; r++) {
@@ -612,7 +632,7 @@ static void rep_create(const double *coords, int on_dev, const int *zs, const in
             zero_rows_kernel<<<(unsigned)pad.size(), 128, 0, st>>>(el.x, el.ld, ws.upload(pad), (int)pad.size(), el.norm);
             AQML_LAUNCH_CHECK();
         }
-        J.px[e] = el.x; J.pnorm[e] = el.norm;
+        J.px[e] = el.x; J.pnorm[e] = el.norm; J.pmask[e] = el.mask; J.maskw[e] = el.maskw;
         rep->els.push_back(el);
     }
     rep->ne = ne;
@@ -637,6 +657,7 @@ static void rep_groups(const aqml_rep *r1, const aqml_rep *r2, int zmax, std::ve
             memset(&g, 0, sizeof(g));
             g.A = a.x; g.B = b.x; g.normA = a.norm; g.normB = b.norm; g.segA = a.seg; g.segB = b.seg;
             g.ld = a.ld; g.tilesM = a.tiles; g.tilesN = b.tiles * (BM / BN); g.zcol = z - 1; g.segA_off = 0; g.segA_n = 0x7fffffff;
+            g.maskA = a.mask; g.maskB = b.mask; g.maskw = a.maskw;
             groups.push_back(g);
             labels.push_back(a.label);
         }

@@ -175,6 +175,10 @@ int aqml_rep_kernel_width(const aqml_rep *r1, const aqml_rep *r2, int zmax, doub
 
 /* counters for bench.py: number of device kernels this library launched since load */
 int64_t aqml_launch_count(void);
+/* k-tiles (16 columns x one 128x64 tile) the pair kernels executed vs. a dense sweep would have, summed
+ * over all tiles since the last reset (all-zero k-tiles are skipped exactly);
+ * synchronises the device. */
+int aqml_pair_stats(int64_t *executed_ktiles, int64_t *dense_ktiles, int reset);
 
 #ifdef __cplusplus
 }
