@@ -201,6 +201,33 @@ static std::vector<int> mol_index(const int *nas, int nm, int &A) {
 
 unsigned long long *pair_stats_buffer();
 
+// Evaluation plan for the sigma ladder: all rows of the host table (nsig x zstride) must be exact
+// power-of-two multiples of the widest sigma's row; otherwise every sigma gets its own exp.
+void plan_sigma_chain(PairParams &P, const std::vector<double> &isig) {
+    P.chain = 0;
+    const int S = P.nsig, Z = P.zstride;
+    if (S < 2 || S > 16 || Z < 1 || (int)isig.size() != S * Z) return;
+    std::vector<int> ord(S);
+    std::iota(ord.begin(), ord.end(), 0);
+    std::stable_sort(ord.begin(), ord.end(), [&](int a, int b) { return std::fabs(isig[(size_t)a * Z]) < std::fabs(isig[(size_t)b * Z]); });
+    int nsq[16] = {0};
+    for (int i = 1; i < S; i++) {
+        int k = -1;
+        for (int z = 0; z < Z; z++) {
+            double a = isig[(size_t)ord[i] * Z + z], b = isig[(size_t)ord[i - 1] * Z + z];
+            if (!(std::isfinite(a) && std::isfinite(b)) || b == 0.0) return;
+            int e = 0;
+            double m = std::frexp(a / b, &e);           // a/b = m * 2^e, m in [0.5,1)
+            if (m != 0.5 || e - 1 < 0 || e - 1 > 16) return;  // ratio must be 2^k, k >= 0
+            if (a != std::ldexp(b, e - 1)) return;       // exact
+            if (k < 0) k = e - 1; else if (k != e - 1) return;
+        }
+        nsq[i] = k;  // ratio 2^k: k squarings ( x -> x^(2^k) )
+    }
+    P.chain = 1;
+    for (int i = 0; i < S; i++) { P.order[i] = ord[i]; P.nsq[i] = nsq[i]; }
+}
+
 static void run_pairs(int mode, int epi, const std::vector<PairGroup> &groups, PairParams P, Workspace &ws) {
     int total = 0;
     std::vector<PairGroup> gs = groups;
@@ -310,7 +337,9 @@ static void global_pairs(int kind, int epi, const double *a, int na, long long l
     if (epi == EPI_EXP_STORE) {
         AQML_REQUIRE(nsig >= 1 && sigmas, "need at least one sigma");
         for (int s = 0; s < nsig; s++) AQML_REQUIRE(sigmas[s] != 0.0, "sigma[%d] is zero", s);
-        P.isig = ws.upload(inv_sigma_table(kind, sigmas, nsig));
+        std::vector<double> tab = inv_sigma_table(kind, sigmas, nsig);
+        P.isig = ws.upload(tab);
+        plan_sigma_chain(P, tab);
     }
     run_pairs(mode, epi, {g}, P, ws);
 }
@@ -356,6 +385,7 @@ static void local_gaussian(const double *x1, long long ldx1, const double *x2, l
     std::vector<double> isig = inv_sigma_table(AQML_KERNEL_GAUSSIAN, sigmas, (size_t)S * zmax);
     PairParams P{};
     P.isig = ws.upload(isig); P.nsig = S; P.zstride = zmax;
+    plan_sigma_chain(P, isig);
     P.out = K; P.ldo = nm2; P.slab = (long long)nm1 * nm2;
     std::vector<PairGroup> groups;
 
@@ -522,7 +552,9 @@ static void local_laplacian(const double *x1, long long ldx1, const double *x2, 
     g.segA = ws.upload(sg1); g.segB = ws.upload(sg2);
     g.tilesM = (int)rm1.size() / BM; g.tilesN = (int)rm2.size() / BN;
     PairParams P{};
-    P.isig = ws.upload(inv_sigma_table(AQML_KERNEL_LAPLACIAN, sigmas, S)); P.nsig = S; P.zstride = 1;
+    std::vector<double> tab = inv_sigma_table(AQML_KERNEL_LAPLACIAN, sigmas, S);
+    P.isig = ws.upload(tab); P.nsig = S; P.zstride = 1;
+    plan_sigma_chain(P, tab);
     P.out = K; P.ldo = nm2; P.slab = (long long)nm1 * nm2;
     run_pairs(MODE_L1, EPI_LOCAL, {g}, P, ws);
 }

@@ -29,6 +29,7 @@ void launch_colstats(const double *x, long long ldx, const int *rows, int nrows,
 void build_tiles(const std::vector<int> &rows, const std::vector<int> &mol_of_row, std::vector<int> &rowmap,
                  std::vector<int> &seg);
 std::vector<int> class_sorted_molecules(const int *zs, const int *nas, int nm);
+void plan_sigma_chain(PairParams &P, const std::vector<double> &isig);
 void run_pairs_public(int mode, int epi, const std::vector<PairGroup> &groups, PairParams P, Workspace &ws);
 
 }  // namespace aqml

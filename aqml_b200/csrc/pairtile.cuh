@@ -66,6 +66,12 @@ struct PairParams {
     long long ldo, slab;  // row pitch, per-sigma stride (elements)
     int *sm_arrive;       // [>= #SMs] zeroed per launch, or null: stagger the two resident CTAs of an SM
     unsigned long long *stats;  // [2] executed / dense k-tile counts (summed over tiles), or null
+    // Sigma chain: when every sigma is an exact power-of-two multiple of the widest one (the usual
+    // coefficient ladder 0.5, 1, 2, 4 ...), exp(v*isig[s]) = exp(v*isig[base])^(4^k) exactly in real
+    // arithmetic: one exp for the widest sigma, then 2k squarings each (<= 64 ulp, 1e-14 relative).
+    int chain;            // 1: use order/nsq below
+    int order[16];        // evaluation order: widest sigma first
+    int nsq[16];          // squarings that take order[i-1]'s values to order[i]'s
 };
 
 constexpr int KT_LIST_MAX = 1024;  // active-k-tile list capacity (ld <= 16384 columns)
@@ -271,20 +277,35 @@ __global__ void __launch_bounds__(NT, 2) pair_tile_kernel(const PairParams P) {
 
     // ---- epilogues ----------------------------------------------------------------------------
     if (EPI == EPI_EXP_STORE) {
-        for (int s = 0; s < P.nsig; s++) {
+        for (int si = 0; si < P.nsig; si++) {
+            const int s = P.chain ? P.order[si] : si;
+            const bool do_exp = !P.chain || si == 0;  // warp-uniform
+            if (!do_exp)
+                for (int q = 0; q < P.nsq[si]; q++)
+#pragma unroll
+                    for (int mi = 0; mi < 8; mi++)
+#pragma unroll
+                        for (int ni = 0; ni < 4; ni++) {
+                            acc[mi][ni][0] *= acc[mi][ni][0];
+                            acc[mi][ni][1] *= acc[mi][ni][1];
+                        }
             double *outS = P.out + (long long)s * P.slab;
 #pragma unroll
             for (int mi = 0; mi < 8; mi++) {
                 int row = wm * 64 + mi * 8 + g;
                 int sr = sSegA[row];
-                if (sr < 0) continue;
                 double f = P.isig[s * P.zstride + sZA[row]];
 #pragma unroll
                 for (int ni = 0; ni < 4; ni++)
 #pragma unroll
                     for (int e = 0; e < 2; e++) {
+                        double v = acc[mi][ni][e];
+                        if (do_exp) {
+                            v = exp(v * f);
+                            if (P.chain) acc[mi][ni][e] = v;
+                        }
                         int sc = sSegB[wn * 32 + ni * 8 + 2 * t4 + e];
-                        if (sc >= 0) outS[(long long)sr * P.ldo + sc] = exp(acc[mi][ni][e] * f);
+                        if (sr >= 0 && sc >= 0) outS[(long long)sr * P.ldo + sc] = v;
                     }
             }
         }
@@ -334,18 +355,30 @@ __global__ void __launch_bounds__(NT, 2) pair_tile_kernel(const PairParams P) {
         const unsigned above = (lane == 31) ? 0u : (heads >> (lane + 1));
         const int run_end = above ? (lane + __ffs(above) - 1) : 31;
         const int *rowseg = sSegA + wm * 64;
-        // row-segment structure of this warp's 64 rows as bit masks (identical for all lanes)
+        // row-segment structure of this warp's 64 rows as bit masks (identical for all lanes).  The rows
+        // are walked as two independent 32-row chains (ILP), so row 31 always closes a segment.
         unsigned last_lo, last_hi, valid_lo, valid_hi;
         {
             int r0 = lane, r1 = lane + 32;
             int s0 = rowseg[r0], s1 = rowseg[r1];
-            int n0 = rowseg[r0 + 1], n1 = (r1 == 63) ? -2 : rowseg[r1 + 1];
+            int n0 = (r0 == 31) ? -2 : rowseg[r0 + 1], n1 = (r1 == 63) ? -2 : rowseg[r1 + 1];
             last_lo = __ballot_sync(0xffffffffu, n0 != s0);
             last_hi = __ballot_sync(0xffffffffu, n1 != s1);
             valid_lo = __ballot_sync(0xffffffffu, s0 >= 0);
             valid_hi = __ballot_sync(0xffffffffu, s1 >= 0);
         }
-        for (int s = 0; s < P.nsig; s++) {
+        for (int si = 0; si < P.nsig; si++) {
+            const int s = P.chain ? P.order[si] : si;
+            const bool do_exp = !P.chain || si == 0;  // warp-uniform
+            if (!do_exp)
+                for (int q = 0; q < P.nsq[si]; q++)
+#pragma unroll
+                    for (int mi = 0; mi < 8; mi++)
+#pragma unroll
+                        for (int ni = 0; ni < 4; ni++) {
+                            acc[mi][ni][0] *= acc[mi][ni][0];
+                            acc[mi][ni][1] *= acc[mi][ni][1];
+                        }
 #pragma unroll
             for (int mi = 0; mi < 8; mi++) {
                 int row = mi * 8 + g;
@@ -353,36 +386,48 @@ __global__ void __launch_bounds__(NT, 2) pair_tile_kernel(const PairParams P) {
 #pragma unroll
                 for (int ni = 0; ni < 4; ni++) {
                     double2 v;
-                    v.x = exp(acc[mi][ni][0] * f);
-                    v.y = exp(acc[mi][ni][1] * f);
+                    v.x = acc[mi][ni][0];
+                    v.y = acc[mi][ni][1];
+                    if (do_exp) {
+                        v.x = exp(v.x * f);
+                        v.y = exp(v.y * f);
+                        if (P.chain) { acc[mi][ni][0] = v.x; acc[mi][ni][1] = v.y; }
+                    }
                     *reinterpret_cast<double2 *>(patch + row * EPITCH + ni * 8 + 2 * t4) = v;
                 }
             }
             __syncwarp();
             double *outS = P.out + (long long)s * P.slab;
-            double run = 0.0;
-#pragma unroll 1
-            for (int rb = 0; rb < 64; rb += 8) {
-                double v8[8];
+            auto flush = [&](double v, int sr) {  // called warp-uniformly
 #pragma unroll
-                for (int j = 0; j < 8; j++) v8[j] = patch[(rb + j) * EPITCH + lane];  // 8 independent loads
-                const unsigned lastb = ((rb < 32 ? last_lo : last_hi) >> (rb & 31)) & 0xffu;
-                const unsigned validb = ((rb < 32 ? valid_lo : valid_hi) >> (rb & 31)) & 0xffu;
+                for (int o = 1; o < 32; o <<= 1) {
+                    double u = __shfl_down_sync(0xffffffffu, v, o);
+                    if (lane + o <= run_end) v += u;
+                }
+                if (head && colseg >= 0) atomicAdd(outS + (long long)sr * P.ldo + colseg, v);
+            };
+            double run0 = 0.0, run1 = 0.0;
+#pragma unroll 1
+            for (int rb = 0; rb < 32; rb += 8) {
+                double u8[8], w8[8];
 #pragma unroll
                 for (int j = 0; j < 8; j++) {
-                    if ((validb >> j) & 1u) run += v8[j];
-                    if ((lastb >> j) & 1u) {  // warp-uniform
-                        if ((validb >> j) & 1u) {
-                            const int sr = rowseg[rb + j];
-                            double v = run;
+                    u8[j] = patch[(rb + j) * EPITCH + lane];
+                    w8[j] = patch[(32 + rb + j) * EPITCH + lane];
+                }
+                const unsigned lb0 = (last_lo >> rb) & 0xffu, vb0 = (valid_lo >> rb) & 0xffu;
+                const unsigned lb1 = (last_hi >> rb) & 0xffu, vb1 = (valid_hi >> rb) & 0xffu;
 #pragma unroll
-                            for (int o = 1; o < 32; o <<= 1) {
-                                double u = __shfl_down_sync(0xffffffffu, v, o);
-                                if (lane + o <= run_end) v += u;
-                            }
-                            if (head && colseg >= 0) atomicAdd(outS + (long long)sr * P.ldo + colseg, v);
-                        }
-                        run = 0.0;
+                for (int j = 0; j < 8; j++) {
+                    if ((vb0 >> j) & 1u) run0 += u8[j];
+                    if ((vb1 >> j) & 1u) run1 += w8[j];
+                    if ((lb0 >> j) & 1u) {
+                        if ((vb0 >> j) & 1u) flush(run0, rowseg[rb + j]);
+                        run0 = 0.0;
+                    }
+                    if ((lb1 >> j) & 1u) {
+                        if ((vb1 >> j) & 1u) flush(run1, rowseg[32 + rb + j]);
+                        run1 = 0.0;
                     }
                 }
             }

@@ -778,6 +778,7 @@ int aqml_rep_local_gaussian(const aqml_rep *r1, const aqml_rep *r2, const double
             }
         PairParams P{};
         P.isig = ws.upload(isig); P.nsig = nsigmas; P.zstride = zmax;
+        plan_sigma_chain(P, isig);
         P.out = K; P.ldo = r2->nmol; P.slab = (long long)nrows * r2->nmol;
         run_pairs_public(MODE_DOT, EPI_LOCAL, groups, P, ws);
     });

@@ -115,6 +115,29 @@ def test_local_gaussian_synthetic(slatm_set, iab):
         assert rel_err(Knc, ref) < TOL
 
 
+def test_local_gaussian_arbitrary_sigmas(slatm_set):
+    """Sigmas that are NOT power-of-two multiples of each other (no squaring chain), per-element ratios differ."""
+    s = slatm_set
+    n1 = 25
+    off = np.concatenate(([0], np.cumsum(s["nas"])))
+    A1 = off[n1]
+    x1, x2 = s["xl"][:A1], s["xl"][A1:off[n1 + 20]]
+    zs1, zs2 = s["zs"][:A1], s["zs"][A1:off[n1 + 20]]
+    nas1, nas2 = s["nas"][:n1], s["nas"][n1:n1 + 20]
+    rng = np.random.default_rng(3)
+    sig = 6.0 + 20.0 * rng.random((5, 9))
+    for center in (True, False):
+        K = kernels.get_local_kernels_gaussian(x2, x1, zs2, zs1, nas2, nas1, False, 9, sig, center=center)
+        assert rel_err(K, co.calc_lk_gaussian(x2, x1, zs2, zs1, nas2, nas1, 9, False, sig)) < TOL
+    # a ladder with a factor-sqrt(2) step (isig ratio 2: one squaring) and a repeated sigma
+    base = 5.0 + rng.random(9)
+    sig = np.array([base * 4, base * 2 * np.sqrt(2.0), base * 2, base * 2, base])
+    K = kernels.get_local_kernels_gaussian(x2, x1, zs2, zs1, nas2, nas1, False, 9, sig, center=False)
+    assert rel_err(K, co.calc_lk_gaussian(x2, x1, zs2, zs1, nas2, nas1, 9, False, sig)) < TOL
+    Kl = kernels.get_local_kernels_laplacian(x2, x1, nas2, nas1, [300., 777., 1500.])
+    assert rel_err(Kl, co.calc_lk_laplacian(x2, x1, nas2, nas1, [300., 777., 1500.])) < TOL
+
+
 def test_local_gaussian_wide_sigma_mismatch_term(slatm_set):
     """Element-mismatched pairs carry d2 = 1e9 (fkernels.f90:73): visible for sigma >~ 1e3."""
     s = slatm_set
