@@ -36,6 +36,7 @@ SIGNATURES = {
     "aqml_device_count": (_I, []),
     "aqml_launch_count": (_L, []),
     "aqml_pair_stats": (_I, [_P, _P, _I]),
+    "aqml_tile_shape": (None, [_P, _P, _P]),
     "aqml_fgaussian_kernel": (_I, [_P, _I, _P, _I, _I, _P, _D]),
     "aqml_flaplacian_kernel": (_I, [_P, _I, _P, _I, _I, _P, _D]),
     "aqml_fl2_distance": (_I, [_P, _P, _I, _I, _I, _P]),

@@ -638,6 +638,12 @@ int aqml_device_count(void) {
 }
 int64_t aqml_launch_count(void) { return (int64_t)g_launches.load(); }
 
+void aqml_tile_shape(int *bm, int *bn, int *bk) {
+    if (bm) *bm = BM;
+    if (bn) *bn = BN;
+    if (bk) *bk = BK;
+}
+
 int aqml_pair_stats(int64_t *executed_ktiles, int64_t *dense_ktiles, int reset) {
     return guarded([&] {
         require_device();

@@ -21,10 +21,17 @@
 
 namespace aqml {
 
-// CTA tile 128 x 64, 4 warps (2 x 2, warp tile 64 x 32), 3-stage pipeline -> 92 KB of shared memory and
-// <= 240 registers x 128 threads, so TWO CTAs are resident per SM: one CTA's epilogue / barrier bubbles
-// are covered by the other CTA's DMMA stream (measured: tensor pipe 76% busy with one 128x128 CTA).
-constexpr int BM = 128, BN = 64, BK = 16;
+// CTA tile (16*MI) x 64, 4 warps (2 x 2, warp tile (8*MI) x 32), 3-stage pipeline.  MI=8: 128x64 tile,
+// 92 KB smem, <=240 regs -> 2 CTAs/SM.  MI=4: 64x64 tile, 61 KB smem, <=168 regs -> 3 CTAs/SM.  Several
+// resident CTAs matter because the epilogue (exp + segmented reduction) and the per-k-tile barrier leave
+// the tensor pipe idle: another CTA's DMMA stream fills those gaps (measured: 76% busy with one 128x128 CTA).
+#ifndef AQML_MI
+#define AQML_MI 4
+#endif
+constexpr int MI = AQML_MI;        // 8x8 MMA row blocks per warp: warp tile (8*MI) x 32
+constexpr int WROWS = 8 * MI;
+constexpr int BM = 2 * WROWS, BN = 64, BK = 16;
+constexpr int CTAS_PER_SM = (MI == 8) ? 2 : 3;
 constexpr int PITCH = BK + 4;  // doubles; (PITCH mod 16) == 4 -> conflict-free 8x4 fragment loads
 constexpr int STAGES = 3;
 constexpr int WARPS_N = BN / 32;
@@ -32,7 +39,7 @@ constexpr int NT = 64 * WARPS_N;  // 2 (M) x WARPS_N (N) warps
 constexpr int STAGE_DOUBLES = (BM + BN) * PITCH;
 constexpr int PIPE_BYTES = STAGES * STAGE_DOUBLES * 8;  // 92160
 constexpr int EPITCH = 40;     // per-warp staging pitch (doubles) for the segmented epilogue
-static_assert((NT / 32) * 64 * EPITCH * 8 <= PIPE_BYTES, "epilogue staging must fit in the pipeline buffers");
+static_assert((NT / 32) * WROWS * EPITCH * 8 <= PIPE_BYTES, "epilogue staging must fit in the pipeline buffers");
 
 enum { MODE_DOT = 0, MODE_L1 = 1 };
 enum { EPI_EXP_STORE = 0, EPI_DIST_STORE = 1, EPI_MAX = 2, EPI_LOCAL = 3 };
@@ -77,7 +84,7 @@ struct PairParams {
 constexpr int KT_LIST_MAX = 1024;  // active-k-tile list capacity (ld <= 16384 columns)
 
 template <int MODE, int EPI>
-__global__ void __launch_bounds__(NT, 2) pair_tile_kernel(const PairParams P) {
+__global__ void __launch_bounds__(NT, CTAS_PER_SM) pair_tile_kernel(const PairParams P) {
     extern __shared__ __align__(16) double smem[];
     __shared__ int sSegA[BM], sSegB[BN], sZA[BM];
     __shared__ double sNA[BM], sNB[BN];
@@ -108,8 +115,11 @@ __global__ void __launch_bounds__(NT, 2) pair_tile_kernel(const PairParams P) {
         if (tid == 0) {
             unsigned smid;
             asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
-            if (atomicAdd(P.sm_arrive + smid, 1) == 1) {
-                const long long wait = (long long)(G.ld / BK) * (G.maskA ? 1024 : 2048);  // ~half a tile of DMMA time
+            const int k = atomicAdd(P.sm_arrive + smid, 1);
+            if (k >= 1 && k < CTAS_PER_SM) {
+                // one full tile of one CTA takes ~ (active k-tiles) * MI*16*16 * CTAS_PER_SM cycles of DMMA issue
+                const long long tile = (long long)(G.ld / BK) * (MI * 256) * CTAS_PER_SM / (G.maskA ? 2 : 1);
+                const long long wait = tile * k / CTAS_PER_SM;
                 const long long t0 = clock64();
                 while (clock64() - t0 < wait) __nanosleep(1000);
             }
@@ -148,10 +158,11 @@ __global__ void __launch_bounds__(NT, 2) pair_tile_kernel(const PairParams P) {
         if (warp == 0) {
             unsigned bits = 0;
             if (lane < G.maskw) {
-                const unsigned a0 = G.maskA[(long long)(2 * tm) * G.maskw + lane];
-                const unsigned a1 = G.maskA[(long long)(2 * tm + 1) * G.maskw + lane];
-                const unsigned b = G.maskB[(long long)tn * G.maskw + lane];
-                bits = (MODE == MODE_DOT) ? ((a0 | a1) & b) : (a0 | a1 | b);
+                unsigned a0 = 0;
+#pragma unroll
+                for (int h = 0; h < BM / 64; h++) a0 |= G.maskA[(long long)(tm * (BM / 64) + h) * G.maskw + lane];
+                const unsigned b = G.maskB[(long long)tn * (BN / 64) * G.maskw + lane];
+                bits = (MODE == MODE_DOT) ? (a0 & b) : (a0 | b);
                 const int hi = KT - lane * 32;  // clip bits beyond KT
                 if (hi < 32) bits &= (hi <= 0) ? 0u : ((1u << hi) - 1u);
             }
@@ -193,9 +204,9 @@ __global__ void __launch_bounds__(NT, 2) pair_tile_kernel(const PairParams P) {
         }
     };
 
-    double acc[8][4][2];
+    double acc[MI][4][2];
 #pragma unroll
-    for (int mi = 0; mi < 8; mi++)
+    for (int mi = 0; mi < MI; mi++)
 #pragma unroll
         for (int ni = 0; ni < 4; ni++) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
 
@@ -215,36 +226,36 @@ __global__ void __launch_bounds__(NT, 2) pair_tile_kernel(const PairParams P) {
         const double *sA = smem + (kt % STAGES) * STAGE_DOUBLES;
         const double *sB = sA + BM * PITCH;
         if (MODE == MODE_DOT) {
-            const double *pa = sA + (wm * 64 + g) * PITCH + t4;
+            const double *pa = sA + (wm * WROWS + g) * PITCH + t4;
             const double *pb = sB + (wn * 32 + g) * PITCH + t4;
 #pragma unroll
             for (int kk = 0; kk < BK / 4; kk++) {
-                double a[8], b[4];
+                double a[MI], b[4];
 #pragma unroll
-                for (int mi = 0; mi < 8; mi++) a[mi] = pa[mi * 8 * PITCH + kk * 4];
+                for (int mi = 0; mi < MI; mi++) a[mi] = pa[mi * 8 * PITCH + kk * 4];
 #pragma unroll
                 for (int ni = 0; ni < 4; ni++) b[ni] = pb[ni * 8 * PITCH + kk * 4];
 #pragma unroll
-                for (int mi = 0; mi < 8; mi++)
+                for (int mi = 0; mi < MI; mi++)
 #pragma unroll
                     for (int ni = 0; ni < 4; ni++) dmma884(acc[mi][ni][0], acc[mi][ni][1], a[mi], b[ni]);
             }
         } else {
             // same accumulator ownership as the DMMA C fragment: rows 8*mi+g, cols 8*ni+2*t4+{0,1}
-            const double *pa = sA + (wm * 64 + g) * PITCH;
+            const double *pa = sA + (wm * WROWS + g) * PITCH;
             const double *pb = sB + (wn * 32 + 2 * t4) * PITCH;
 #pragma unroll 2
             for (int kk = 0; kk < BK; kk += 2) {
-                double2 a[8], b[4][2];
+                double2 a[MI], b[4][2];
 #pragma unroll
-                for (int mi = 0; mi < 8; mi++) a[mi] = *reinterpret_cast<const double2 *>(pa + mi * 8 * PITCH + kk);
+                for (int mi = 0; mi < MI; mi++) a[mi] = *reinterpret_cast<const double2 *>(pa + mi * 8 * PITCH + kk);
 #pragma unroll
                 for (int ni = 0; ni < 4; ni++) {
                     b[ni][0] = *reinterpret_cast<const double2 *>(pb + (ni * 8) * PITCH + kk);
                     b[ni][1] = *reinterpret_cast<const double2 *>(pb + (ni * 8 + 1) * PITCH + kk);
                 }
 #pragma unroll
-                for (int mi = 0; mi < 8; mi++)
+                for (int mi = 0; mi < MI; mi++)
 #pragma unroll
                     for (int ni = 0; ni < 4; ni++)
 #pragma unroll
@@ -263,8 +274,8 @@ __global__ void __launch_bounds__(NT, 2) pair_tile_kernel(const PairParams P) {
     // ---- v_ij -------------------------------------------------------------------------------
     if (MODE == MODE_DOT) {
 #pragma unroll
-        for (int mi = 0; mi < 8; mi++) {
-            double na = sNA[wm * 64 + mi * 8 + g];
+        for (int mi = 0; mi < MI; mi++) {
+            double na = sNA[wm * WROWS + mi * 8 + g];
 #pragma unroll
             for (int ni = 0; ni < 4; ni++)
 #pragma unroll
@@ -283,7 +294,7 @@ __global__ void __launch_bounds__(NT, 2) pair_tile_kernel(const PairParams P) {
             if (!do_exp)
                 for (int q = 0; q < P.nsq[si]; q++)
 #pragma unroll
-                    for (int mi = 0; mi < 8; mi++)
+                    for (int mi = 0; mi < MI; mi++)
 #pragma unroll
                         for (int ni = 0; ni < 4; ni++) {
                             acc[mi][ni][0] *= acc[mi][ni][0];
@@ -291,8 +302,8 @@ __global__ void __launch_bounds__(NT, 2) pair_tile_kernel(const PairParams P) {
                         }
             double *outS = P.out + (long long)s * P.slab;
 #pragma unroll
-            for (int mi = 0; mi < 8; mi++) {
-                int row = wm * 64 + mi * 8 + g;
+            for (int mi = 0; mi < MI; mi++) {
+                int row = wm * WROWS + mi * 8 + g;
                 int sr = sSegA[row];
                 double f = P.isig[s * P.zstride + sZA[row]];
 #pragma unroll
@@ -311,8 +322,8 @@ __global__ void __launch_bounds__(NT, 2) pair_tile_kernel(const PairParams P) {
         }
     } else if (EPI == EPI_DIST_STORE) {
 #pragma unroll
-        for (int mi = 0; mi < 8; mi++) {
-            int sr = sSegA[wm * 64 + mi * 8 + g];
+        for (int mi = 0; mi < MI; mi++) {
+            int sr = sSegA[wm * WROWS + mi * 8 + g];
             if (sr < 0) continue;
 #pragma unroll
             for (int ni = 0; ni < 4; ni++)
@@ -325,8 +336,8 @@ __global__ void __launch_bounds__(NT, 2) pair_tile_kernel(const PairParams P) {
     } else if (EPI == EPI_MAX) {
         double m = 0.0;
 #pragma unroll
-        for (int mi = 0; mi < 8; mi++) {
-            if (sSegA[wm * 64 + mi * 8 + g] < 0) continue;
+        for (int mi = 0; mi < MI; mi++) {
+            if (sSegA[wm * WROWS + mi * 8 + g] < 0) continue;
 #pragma unroll
             for (int ni = 0; ni < 4; ni++)
 #pragma unroll
@@ -346,7 +357,7 @@ __global__ void __launch_bounds__(NT, 2) pair_tile_kernel(const PairParams P) {
         // (conflict-free 16-byte stores), then lane c walks column c down the rows, summing the rows
         // of one molecule (row segment); at each row-segment end a segmented shuffle reduction sums
         // the lanes of one molecule (column segment) and the segment head issues one RED.F64.
-        double *patch = smem + warp * (64 * EPITCH);
+        double *patch = smem + warp * (WROWS * EPITCH);
         const int colseg = sSegB[wn * 32 + lane];
         const int prevseg = __shfl_up_sync(0xffffffffu, colseg, 1);
         const bool head = (lane == 0) || (prevseg != colseg);
@@ -354,18 +365,20 @@ __global__ void __launch_bounds__(NT, 2) pair_tile_kernel(const PairParams P) {
         // last lane of my run
         const unsigned above = (lane == 31) ? 0u : (heads >> (lane + 1));
         const int run_end = above ? (lane + __ffs(above) - 1) : 31;
-        const int *rowseg = sSegA + wm * 64;
+        const int *rowseg = sSegA + wm * WROWS;
         // row-segment structure of this warp's 64 rows as bit masks (identical for all lanes).  The rows
         // are walked as two independent 32-row chains (ILP), so row 31 always closes a segment.
+        constexpr int HALF = WROWS / 2;
         unsigned last_lo, last_hi, valid_lo, valid_hi;
         {
-            int r0 = lane, r1 = lane + 32;
+            const bool in = lane < HALF;
+            int r0 = in ? lane : 0, r1 = r0 + HALF;
             int s0 = rowseg[r0], s1 = rowseg[r1];
-            int n0 = (r0 == 31) ? -2 : rowseg[r0 + 1], n1 = (r1 == 63) ? -2 : rowseg[r1 + 1];
-            last_lo = __ballot_sync(0xffffffffu, n0 != s0);
-            last_hi = __ballot_sync(0xffffffffu, n1 != s1);
-            valid_lo = __ballot_sync(0xffffffffu, s0 >= 0);
-            valid_hi = __ballot_sync(0xffffffffu, s1 >= 0);
+            int n0 = (r0 == HALF - 1) ? -2 : rowseg[r0 + 1], n1 = (r1 == WROWS - 1) ? -2 : rowseg[r1 + 1];
+            last_lo = __ballot_sync(0xffffffffu, in && n0 != s0);
+            last_hi = __ballot_sync(0xffffffffu, in && n1 != s1);
+            valid_lo = __ballot_sync(0xffffffffu, in && s0 >= 0);
+            valid_hi = __ballot_sync(0xffffffffu, in && s1 >= 0);
         }
         for (int si = 0; si < P.nsig; si++) {
             const int s = P.chain ? P.order[si] : si;
@@ -373,16 +386,16 @@ __global__ void __launch_bounds__(NT, 2) pair_tile_kernel(const PairParams P) {
             if (!do_exp)
                 for (int q = 0; q < P.nsq[si]; q++)
 #pragma unroll
-                    for (int mi = 0; mi < 8; mi++)
+                    for (int mi = 0; mi < MI; mi++)
 #pragma unroll
                         for (int ni = 0; ni < 4; ni++) {
                             acc[mi][ni][0] *= acc[mi][ni][0];
                             acc[mi][ni][1] *= acc[mi][ni][1];
                         }
 #pragma unroll
-            for (int mi = 0; mi < 8; mi++) {
+            for (int mi = 0; mi < MI; mi++) {
                 int row = mi * 8 + g;
-                double f = P.isig[s * P.zstride + sZA[wm * 64 + row]];
+                double f = P.isig[s * P.zstride + sZA[wm * WROWS + row]];
 #pragma unroll
                 for (int ni = 0; ni < 4; ni++) {
                     double2 v;
@@ -408,12 +421,12 @@ __global__ void __launch_bounds__(NT, 2) pair_tile_kernel(const PairParams P) {
             };
             double run0 = 0.0, run1 = 0.0;
 #pragma unroll 1
-            for (int rb = 0; rb < 32; rb += 8) {
+            for (int rb = 0; rb < HALF; rb += 8) {
                 double u8[8], w8[8];
 #pragma unroll
                 for (int j = 0; j < 8; j++) {
                     u8[j] = patch[(rb + j) * EPITCH + lane];
-                    w8[j] = patch[(32 + rb + j) * EPITCH + lane];
+                    w8[j] = patch[(HALF + rb + j) * EPITCH + lane];
                 }
                 const unsigned lb0 = (last_lo >> rb) & 0xffu, vb0 = (valid_lo >> rb) & 0xffu;
                 const unsigned lb1 = (last_hi >> rb) & 0xffu, vb1 = (valid_hi >> rb) & 0xffu;
@@ -426,7 +439,7 @@ __global__ void __launch_bounds__(NT, 2) pair_tile_kernel(const PairParams P) {
                         run0 = 0.0;
                     }
                     if ((lb1 >> j) & 1u) {
-                        if ((vb1 >> j) & 1u) flush(run1, rowseg[32 + rb + j]);
+                        if ((vb1 >> j) & 1u) flush(run1, rowseg[HALF + rb + j]);
                         run1 = 0.0;
                     }
                 }

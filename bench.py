@@ -275,6 +275,9 @@ def run_ours(args):
     kt_exec, kt_dense = C.c_int64(0), C.c_int64(0)
     L.call("aqml_pair_stats", C.c_void_p(C.addressof(kt_exec)), C.c_void_p(C.addressof(kt_dense)), 1)
     kt_exec, kt_dense = kt_exec.value / args.steps, kt_dense.value / args.steps  # per launch
+    bm, bn, bk = C.c_int(0), C.c_int(0), C.c_int(0)
+    lib.aqml_tile_shape(C.c_void_p(C.addressof(bm)), C.c_void_p(C.addressof(bn)), C.c_void_p(C.addressof(bk)))
+    ktile_flops = 2.0 * bm.value * bn.value * bk.value
     t_total_ms = e_start.elapsed_time(e_end)
     t_slatm_ms = float(np.mean([e[0].elapsed_time(e[1]) for e in timing]))
     t_kernel_ms = float(np.mean([e[1].elapsed_time(e[2]) for e in timing]))
@@ -354,9 +357,9 @@ def run_ours(args):
                          "traffic": None, "algorithmic_flops_per_launch": flops,
                          # all-zero 16-column k-tiles are skipped exactly: the DMMA work
                          # actually issued, incl. row/column padding, and its share of the dense sweep
-                         "executed_flops_per_launch": kt_exec * 2.0 * 128 * 64 * 16,
-                         "executed_tflops": kt_exec * 2.0 * 128 * 64 * 16 / (t_kernel_ms * 1e-3) / 1e12,
-                         "executed_frac_of_peak": kt_exec * 2.0 * 128 * 64 * 16 / (t_kernel_ms * 1e-3) / 1e12 / peak_tf,
+                         "executed_flops_per_launch": kt_exec * ktile_flops,
+                         "executed_tflops": kt_exec * ktile_flops / (t_kernel_ms * 1e-3) / 1e12,
+                         "executed_frac_of_peak": kt_exec * ktile_flops / (t_kernel_ms * 1e-3) / 1e12 / peak_tf,
                          "ktiles_executed_over_dense": kt_exec / max(kt_dense, 1.0),
                          "peak_source": "cuBLAS DGEMM 8192^3 best of 10 measured in this run "
                                         "(MEASURED_PEAKS.json has no FP64 entry)"},

@@ -179,6 +179,8 @@ int64_t aqml_launch_count(void);
  * over all tiles since the last reset (all-zero k-tiles are skipped exactly);
  * synchronises the device. */
 int aqml_pair_stats(int64_t *executed_ktiles, int64_t *dense_ktiles, int reset);
+/* CTA tile of the pair kernels: bm x bn atom pairs, bk columns per k-tile (2*bm*bn*bk flops each) */
+void aqml_tile_shape(int *bm, int *bn, int *bk);
 
 #ifdef __cplusplus
 }
