@@ -53,3 +53,48 @@ def get_kernel_width(nas, zs, x, cab=F, kernel='g', itarget=F, debug=F):
         L.call("aqml_kernel_width_dev", p, L.ptr(xt), xt.stride(0), L.ptr(L.i32(zs)), xt.shape[0], xt.shape[1], zmax,
                L.ptr(dso), L.current_stream())
     return dso
+
+
+def calc_ka(x2, x1, zs2, zs1, nas2, nas1, cab, zmax, sigmas, zaq=None, kernel='g'):
+    """aqml.py:258-309: atomic kernel matrix.  Per element z the (atoms2_z x atoms1_z) Gaussian-on-distance
+    block ``exp(-0.5 (d/sigma_z)^2)`` (d = L2 for 'g', L1 for 'l'), all sigmas from one device pass; with
+    ``zaq=None`` the training-atom axis is summed per training molecule -> (nsigmas, natoms2, nmol1)."""
+    import torch
+    if cab:
+        raise Exception('??')  # aqml.py:277-278
+    sig = np.asarray(sigmas, dtype=np.float64)
+    nsg = len(sig)
+    zs1 = np.asarray(zs1)
+    zs2 = np.asarray(zs2)
+    dev = x1.device if L.is_tensor(x1) else torch.device("cuda")
+    x1t = x1 if L.is_tensor(x1) else torch.as_tensor(L.f64(x1), device=dev)
+    x2t = x2 if L.is_tensor(x2) else torch.as_tensor(L.f64(x2), device=dev)
+    na1, na2, n1 = len(zs1), len(zs2), len(nas1)
+    zsu = np.unique(zs2) if zaq is None else [zaq]
+    blocks = {}
+    for zi in zsu:
+        i1 = np.nonzero(zs1 == zi)[0]
+        i2 = np.nonzero(zs2 == zi)[0]
+        if len(i1) == 0 or len(i2) == 0:
+            blocks[zi] = (i1, i2, torch.zeros((nsg, len(i2), len(i1)), dtype=torch.float64, device=dev))
+            continue
+        a = x2t[torch.as_tensor(i2, device=dev)]
+        b = x1t[torch.as_tensor(i1, device=dev)]
+        s_z = sig[:, zi - 1]
+        if kernel[0] == 'g':
+            k = cmlk.global_kernels(a, b, s_z, "gaussian")
+        else:  # exp(-0.5 (d1/sigma)^2) on the Manhattan distance: exp(-d1/s)-kernel with log -> square
+            d1 = -torch.log(cmlk.global_kernels(a, b, [1.0], "laplacian")[0])
+            k = torch.stack([torch.exp(-0.5 * (d1 / s) ** 2) for s in s_z])
+        blocks[zi] = (i1, i2, k)
+    if zaq is not None:
+        out = blocks[zaq][2]
+        return out if L.is_tensor(x1) else out.cpu().numpy()
+    ksa = torch.zeros((nsg, na2, na1), dtype=torch.float64, device=dev)
+    for zi, (i1, i2, k) in blocks.items():
+        if len(i1) and len(i2):
+            ksa[:, torch.as_tensor(i2, device=dev)[:, None], torch.as_tensor(i1, device=dev)[None, :]] = k
+    mol1 = torch.as_tensor(np.repeat(np.arange(n1), np.asarray(nas1)), device=dev)
+    ks = torch.zeros((nsg, na2, n1), dtype=torch.float64, device=dev)
+    ks.index_add_(2, mol1, ksa)
+    return ks if L.is_tensor(x1) else ks.cpu().numpy()

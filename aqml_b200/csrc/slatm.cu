@@ -19,6 +19,7 @@
 #include <cstring>
 #include <map>
 #include <memory>
+#include <cstdlib>
 
 namespace aqml {
 
@@ -523,6 +524,10 @@ __global__ void __launch_bounds__(SL_THREADS) slatm_kernel(const SlatmDev T, con
     }
 }
 
+}  // namespace aqml
+#include "slatm_units.cuh"
+namespace aqml {
+
 __global__ void zero_rows_kernel(double *x, long long ld, const int *rows, int nrows, double *norm) {
     int r = rows[blockIdx.x];
     for (long long i = threadIdx.x; i < ld; i += blockDim.x) x[(long long)r * ld + i] = 0.0;
@@ -672,40 +677,6 @@ static SlatmTables build_tables(const aqml_slatm_params *p, bool mode_local, Wor
     return t;
 }
 
-static size_t slatm_smem_bytes(int pldmax, int na_max, int m2, int m3) {
-    size_t doubles = (size_t)pldmax + 10 * (size_t)na_max + 4 * PCH;
-    size_t ints = 5 * (size_t)na_max + (na_max & 1);
-    size_t extra = (m2 > 0) ? (size_t)NG * 8 * std::max(m2, m3) + 16 * (size_t)m2 + 16 * (size_t)m3 : 0;
-    return sizeof(double) * (doubles + extra) + sizeof(int) * ints;
-}
-
-template <int M2, int M3>
-static void launch_slatm_t(const SlatmTables &t, const SlatmJob &J, int nblocks, int na_max, cudaStream_t st) {
-    size_t smem = slatm_smem_bytes(t.pldmax, na_max, M2, M3);
-    if (smem > 200 * 1024)
-        fail(AQML_ELIMIT, "molecule with %d atoms / support %d needs %zu B of shared memory (limit 200 KiB)", na_max, t.pldmax, smem);
-    AQML_CUDA(cudaFuncSetAttribute(slatm_kernel<M2, M3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    slatm_kernel<M2, M3><<<nblocks, SL_THREADS, smem, st>>>(t.dev, J, t.pldmax, na_max);
-    AQML_LAUNCH_CHECK();
-}
-
-static void launch_slatm(const SlatmTables &t, const SlatmJob &J, int na_max, cudaStream_t st) {
-    int nblocks = J.local ? J.A : J.nmol * t.dev.n_el;
-    if (nblocks <= 0) return;
-    na_max = (int)round_up(std::max(na_max, 1), 2);
-    const SlatmDev &d = t.dev;
-    const int m2 = (d.nx2 + 7) / 8, m3 = (d.nx3 + 7) / 8;
-    // the recurrence walks at most M grid steps from an exactly evaluated anchor; keep the anchor's exponent
-    // (M h)^2 / (2 sigma^2) far from the double range, otherwise use one exp per grid point
-    auto safe = [&](int M2, int M3) {
-        return m2 <= M2 && m3 <= M3 && (M2 * d.h2) * (M2 * d.h2) * d.cst2 < 300.0 && (M3 * d.h3) * (M3 * d.h3) * d.cst3 < 300.0;
-    };
-    if (safe(15, 12)) launch_slatm_t<15, 12>(t, J, nblocks, na_max, st);
-    else if (safe(20, 16)) launch_slatm_t<20, 16>(t, J, nblocks, na_max, st);
-    else if (safe(32, 32)) launch_slatm_t<32, 32>(t, J, nblocks, na_max, st);
-    else launch_slatm_t<0, 0>(t, J, nblocks, na_max, st);
-}
-
 struct MolIndex {
     std::vector<int> off, atom_mol;
     int A = 0, na_max = 0;
@@ -724,6 +695,81 @@ static MolIndex index_molecules(const int *nas, int nmol) {
     return mi;
 }
 
+static size_t slatm_smem_bytes(int pldmax, int na_max, int m2, int m3) {
+    size_t doubles = (size_t)pldmax + 10 * (size_t)na_max + 4 * PCH;
+    size_t ints = 5 * (size_t)na_max + (na_max & 1);
+    size_t extra = (m2 > 0) ? (size_t)NG * 8 * std::max(m2, m3) + 16 * (size_t)m2 + 16 * (size_t)m3 : 0;
+    return sizeof(double) * (doubles + extra) + sizeof(int) * ints;
+}
+
+template <int M2, int M3>
+static void launch_slatm_t(const SlatmTables &t, const SlatmJob &J, int nblocks, int na_max, cudaStream_t st) {
+    size_t smem = slatm_smem_bytes(t.pldmax, na_max, M2, M3);
+    if (smem > 200 * 1024)
+        fail(AQML_ELIMIT, "molecule with %d atoms / support %d needs %zu B of shared memory (limit 200 KiB)", na_max, t.pldmax, smem);
+    AQML_CUDA(cudaFuncSetAttribute(slatm_kernel<M2, M3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    slatm_kernel<M2, M3><<<nblocks, SL_THREADS, smem, st>>>(t.dev, J, t.pldmax, na_max);
+    AQML_LAUNCH_CHECK();
+}
+
+template <int M2, int M3>
+static bool launch_units_t(const SlatmTables &t, const SlatmJob &J, const MolIndex &mi, Workspace &ws) {
+    // batches: contiguous centre atoms of one molecule; the neighbour tables of a batch take 11 B per
+    // (centre, atom) pair of shared memory -- 35 B with the unit vectors
+    std::vector<Batch> batches;
+    int nbn_max = 1, ba_max = 1;
+    for (int m = 0; m < J.nmol; m++) {
+        int na = mi.off[m + 1] - mi.off[m];
+        if (na == 0) continue;
+        int ba = std::max(1, std::min(std::min(32, na), 45000 / (35 * na)));
+        for (int a0 = 0; a0 < na; a0 += ba) {
+            Batch b{m, a0, std::min(ba, na - a0), 0};
+            batches.push_back(b);
+            nbn_max = std::max(nbn_max, b.cnt * na);
+            ba_max = std::max(ba_max, b.cnt);
+        }
+    }
+    if (batches.empty()) return true;
+    int nblk_max = 0;
+    for (int e = 0; e < t.dev.n_el; e++) nblk_max = std::max(nblk_max, t.dev.nblk[e]);
+    const int uc = t.dev.n_el + nblk_max;
+    const int na_max = (int)round_up(std::max(mi.na_max, 1), 2);
+    nbn_max = (int)round_up(nbn_max, 4);
+    size_t smem = sizeof(double) * (3 * (size_t)na_max + 4 * (size_t)nbn_max + (size_t)ba_max * uc + 16 * M2 + 16 * M3) +
+                  sizeof(int) * na_max + sizeof(short) * ((size_t)nbn_max + (size_t)ba_max * (MAXEL + 1) + 4) + nbn_max + 16;
+    if (smem > 160 * 1024 || mi.na_max > 30000) return false;
+    AQML_CUDA(cudaFuncSetAttribute(slatm_units_kernel<M2, M3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    slatm_units_kernel<M2, M3><<<(unsigned)batches.size(), SL_THREADS, smem, ws.stream()>>>(
+        t.dev, J, ws.upload(batches), na_max, nbn_max, ba_max, uc);
+    AQML_LAUNCH_CHECK();
+    return true;
+}
+
+static void launch_slatm(const SlatmTables &t, const SlatmJob &J, const MolIndex &mi, Workspace &ws) {
+    cudaStream_t st = ws.stream();
+    int nblocks = J.local ? J.A : J.nmol * t.dev.n_el;
+    if (nblocks <= 0) return;
+    int na_max = (int)round_up(std::max(mi.na_max, 1), 2);
+    const SlatmDev &d = t.dev;
+    const int m2 = (d.nx2 + 7) / 8, m3 = (d.nx3 + 7) / 8;
+    // the recurrence walks at most M grid steps from an exactly evaluated anchor; keep the anchor's exponent
+    // (M h)^2 / (2 sigma^2) far from the double range, otherwise use one exp per grid point
+    auto safe = [&](int M2, int M3) {
+        return m2 <= M2 && m3 <= M3 && (M2 * d.h2) * (M2 * d.h2) * d.cst2 < 300.0 && (M3 * d.h3) * (M3 * d.h3) * d.cst3 < 300.0;
+    };
+    static const bool force_legacy = getenv("AQML_SLATM_LEGACY") != nullptr;
+    if (J.local && !force_legacy) {  // work-unit kernel (aSLATM)
+        if (safe(15, 12)) { if (launch_units_t<15, 12>(t, J, mi, ws)) return; }
+        else if (safe(20, 16)) { if (launch_units_t<20, 16>(t, J, mi, ws)) return; }
+        else if (safe(32, 32)) { if (launch_units_t<32, 32>(t, J, mi, ws)) return; }
+    }
+    // block-per-centre kernel: global SLATM, and aSLATM outside the recurrence's safe range
+    if (safe(15, 12)) launch_slatm_t<15, 12>(t, J, nblocks, na_max, st);
+    else if (safe(20, 16)) launch_slatm_t<20, 16>(t, J, nblocks, na_max, st);
+    else if (safe(32, 32)) launch_slatm_t<32, 32>(t, J, nblocks, na_max, st);
+    else launch_slatm_t<0, 0>(t, J, nblocks, na_max, st);
+}
+
 static void slatm_batch_dev(const double *coords, const int *zs_dev, const int *nas, int nmol, const aqml_slatm_params *p,
                             int local, double *out, long long ldo, cudaStream_t st) {
     AQML_REQUIRE(coords && zs_dev && nas && out && nmol >= 0, "bad argument");
@@ -738,7 +784,7 @@ static void slatm_batch_dev(const double *coords, const int *zs_dev, const int *
     memset(&J, 0, sizeof(J));
     J.coords = coords; J.zs = zs_dev; J.mol_off = ws.upload(mi.off); J.atom_mol = ws.upload(mi.atom_mol);
     J.nmol = nmol; J.A = mi.A; J.local = local ? 1 : 0; J.out = out; J.ldo = ldo;
-    launch_slatm(t, J, mi.na_max, st);
+    launch_slatm(t, J, mi, ws);
 }
 
 }  // namespace aqml
@@ -823,7 +869,7 @@ static void rep_create(const double *coords, int on_dev, const int *zs, const in
     const double *dcoords = on_dev ? coords : ws.upload(coords, (size_t)mi.A * 3);
     J.coords = dcoords; J.zs = ws.upload(zs, mi.A); J.mol_off = ws.upload(mi.off); J.atom_mol = ws.upload(mi.atom_mol);
     J.nmol = nmol; J.A = mi.A; J.local = 1; J.out = nullptr; J.ldo = 0; J.atom_prow = ws.upload(atom_prow);
-    launch_slatm(t, J, mi.na_max, st);
+    launch_slatm(t, J, mi, ws);
     rep->owned = keep.pointers();
     keep.release_all();
     *out = rep.release();

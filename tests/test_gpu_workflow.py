@@ -1,0 +1,85 @@
+"""GPU: the reference workflow's consumers on top of the CUDA kernels."""
+import numpy as np
+import pytest
+
+from conftest import rel_err
+from aqml_b200 import kernels, synth
+from aqml_b200.algo import aqml as algo
+from aqml_b200.algo import krr
+from oracle import c_oracle as co
+from oracle import np_oracle as o
+
+pytestmark = pytest.mark.gpu
+
+
+def _ref_calc_ka(x2, x1, zs2, zs1, nas1, sigmas, kernel):
+    """aqml.py:258-309 restated with the oracle distances."""
+    dist = co.l2_distance if kernel == 'g' else co.l1_distance
+    ksa = np.zeros((len(sigmas), len(zs2), len(zs1)))
+    for z in np.unique(zs2):
+        i1, i2 = np.nonzero(zs1 == z)[0], np.nonzero(zs2 == z)[0]
+        if len(i1) == 0:
+            continue
+        ds = dist(x2[i2], x1[i1])
+        for k, s in enumerate(sigmas):
+            ksa[k][np.ix_(i2, i1)] = np.exp(-0.5 * (ds / s[z - 1]) ** 2)
+    off = np.concatenate(([0], np.cumsum(nas1)))
+    return np.stack([ksa[:, :, off[i]:off[i + 1]].sum(axis=2) for i in range(len(nas1))], axis=2), ksa
+
+
+def test_calc_ka_matches_restated_reference():
+    nas, zs, coords = synth.qm9_like(14, 42)
+    mb = o.get_slatm_mbtypes(synth.split_zs(nas, zs))
+    x = co.generate_slatm_batch(coords, zs, nas, mb, True, sigmas=(.05, .05), dgrids=(.08, .08), rcut=4.8)
+    n1 = 10
+    A1 = int(nas[:n1].sum())
+    zmax = 9
+    dso = co.get_kernel_width(nas, zs, x)
+    dso = np.concatenate((dso, np.full(zmax - len(dso), 1e-9)))
+    sig = np.array([c * dso / np.sqrt(2 * np.log(2)) for c in (1.0, 2.0)])
+    for kern in ('g', 'l'):
+        s = sig if kern == 'g' else sig * 30
+        ref_ks, ref_ksa = _ref_calc_ka(x[A1:], x[:A1], zs[A1:], zs[:A1], nas[:n1], s, kern)
+        ks = algo.calc_ka(x[A1:], x[:A1], zs[A1:], zs[:A1], nas[n1:], nas[:n1], False, zmax, s, kernel=kern)
+        assert ks.shape == ref_ks.shape
+        assert rel_err(ks, ref_ks) < 1e-9
+        kz = algo.calc_ka(x[A1:], x[:A1], zs[A1:], zs[:A1], nas[n1:], nas[:n1], False, zmax, s, zaq=6, kernel=kern)
+        assert rel_err(kz, ref_ksa[:, zs[A1:] == 6][:, :, zs[:A1] == 6]) < 1e-9
+    # the sum of the atomic contributions over test-molecule atoms is the local kernel (aqml.py:913)
+    ks = algo.calc_ka(x[A1:], x[:A1], zs[A1:], zs[:A1], nas[n1:], nas[:n1], False, zmax, sig)
+    kl = kernels.get_local_kernels_gaussian(x[A1:], x[:A1], zs[A1:], zs[:A1], nas[n1:], nas[:n1], False, zmax, sig)
+    off2 = np.concatenate(([0], np.cumsum(nas[n1:])))
+    summed = np.stack([ks[:, off2[i]:off2[i + 1]].sum(axis=1) for i in range(len(nas) - n1)], axis=1)
+    assert rel_err(summed, kl) < 1e-10
+
+
+def test_learning_curve_and_multifidelity(demo):
+    n1 = int(demo["n1"])
+    nas, zs = demo["nas"], demo["zs"]
+    zs_list = synth.split_zs(nas, zs)
+    zsu = np.unique(zs)
+    ngs = np.array([[(z == zz).sum() for zz in zsu] for z in zs_list])
+    nheav = np.array([(z > 1).sum() for z in zs_list[:n1]])
+    ys = demo["energies"] * krr.H2KC
+    free = [krr.H2KC * o.ORCA_B3LYPVDZ[int(z)] for z in zsu]
+    for device in (False, True):
+        rows = krr.learning_curve(demo["k1"][1], demo["k2"][1], ngs, ys, nheav, free, 1e-4, device=device)
+        readme = demo["readme_curve"]
+        for r, ref in zip(rows, readme):
+            assert (r[0], r[1]) == (ref[0], ref[1]) and abs(r[2] - ref[2]) < 5.1e-5
+    # multi-fidelity: a two-level problem whose high level differs from the low level by a smooth term
+    rng = np.random.default_rng(0)
+    k1, k2 = demo["k1"][1], demo["k2"][1]
+    y0 = ys[:n1]
+    y1 = y0 + 3.0 + 0.01 * ngs[:n1] @ rng.random(len(zsu))
+    yl = np.stack([y0, y1], axis=1)
+    got = krr.multi_fidelity_predict(k1, k2, yl, [n1, 10], ngs[:n1].astype(float), ngs[n1:].astype(float), 1e-6)
+    # restated rkrr.py:203-228
+    pred = np.zeros(1)
+    for l, n in enumerate([n1, 10]):
+        tgt = yl[:n, l] if l == 0 else yl[:n, l] - yl[:n, l - 1]
+        esb = np.linalg.lstsq(ngs[:n].astype(float), tgt, rcond=None)[0]
+        kk = k1[:n, :n].copy()
+        kk[np.diag_indices_from(kk)] += 1e-6
+        pred += k2[:, :n] @ np.linalg.solve(kk, tgt - ngs[:n] @ esb) + ngs[n1:] @ esb
+    assert np.allclose(got, pred, rtol=1e-12, atol=1e-9)
