@@ -46,6 +46,12 @@ def parse():
     ap.add_argument("--cpu-test", type=int, default=48, help="CPU-baseline sample: test molecules")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--workload", default="config2", choices=["config2", "config3"],
+                    help="config2 (default, the headline line) | config3: global SLATM Gaussian kernel, "
+                         "row block of --rows-per-gpu molecules x --n-cols molecules per GPU, 4 sigmas")
+    ap.add_argument("--n-cols", type=int, default=100000)
+    ap.add_argument("--rows-per-gpu", type=int, default=12500)
+    ap.add_argument("--kernel", default="gaussian", choices=["gaussian", "laplacian"])
     return ap.parse_args()
 
 
@@ -382,10 +388,93 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+def run_config3(args):
+    """BASELINE.json configs[2]: 100k x 100k global SLATM kernel with 4 sigmas, row-block sharded: every rank
+    builds K[:, rows_r, :] for its own --rows-per-gpu molecules against all --n-cols molecules (no collective).
+    Step = coordinates -> global SLATM (rows + columns) -> K block resident in HBM."""
+    import torch
+    import torch.distributed as dist
+    from aqml_b200 import _lib as L
+    from aqml_b200 import kernels, synth
+    from aqml_b200.representation import core as rcore
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    dev = torch.device("cuda", local_rank)
+    cols = synth.qm9_like_fast(args.n_cols, SEED + 7, pool=512)
+    rows = synth.qm9_like_fast(args.rows_per_gpu, SEED + 7 + 1000 * (rank + 1), pool=256)
+    mb = mbtypes_for(cols, rows)
+    kw = dict(sigmas=[.05, .05], dgrids=[.04, .04], rcut=4.8)
+    cc, cr = torch.as_tensor(cols[2], device=dev), torch.as_tensor(rows[2], device=dev)
+    xs = rcore.generate_slatm_batch(cc[:int(cols[0][:2000].sum())], cols[1][:int(cols[0][:2000].sum())], cols[0][:2000],
+                                    mb, local=False, **kw)
+    from aqml_b200 import distance
+    dmax = distance.max_distance(xs, xs, 2 if args.kernel == "gaussian" else 1)
+    del xs
+    fac = 1.0 / np.sqrt(2 * np.log(2)) if args.kernel == "gaussian" else 1.0 / np.log(2)
+    sig = np.array([c * dmax * fac for c in COEFFS])
+    D = int(L.load().aqml_slatm_dim(L.slatm_params(mb, **SLATM_KW)))
+    ev = lambda: torch.cuda.Event(enable_timing=True)  # noqa: E731
+
+    def step(tm=None):
+        e = [ev() for _ in range(3)]
+        e[0].record()
+        xc = rcore.generate_slatm_batch(cc, cols[1], cols[0], mb, local=False, **kw)
+        xr = rcore.generate_slatm_batch(cr, rows[1], rows[0], mb, local=False, **kw)
+        e[1].record()
+        K = kernels.global_kernels(xr, xc, sig, args.kernel)
+        e[2].record()
+        if tm is not None:
+            tm.append(e)
+        return K
+
+    for _ in range(max(args.warmup, 3)):
+        K = step()
+        del K
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    tm = []
+    a, b = ev(), ev()
+    a.record()
+    for _ in range(args.steps):
+        K = step(tm)
+        del K
+    b.record()
+    torch.cuda.synchronize()
+    t = torch.tensor([a.elapsed_time(b), float(np.mean([e[0].elapsed_time(e[1]) for e in tm])),
+                      float(np.mean([e[1].elapsed_time(e[2]) for e in tm]))], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    tot, t_sl, t_k = [float(v) for v in t.cpu()]
+    if rank == 0:
+        ms = tot / args.steps
+        S = len(COEFFS)
+        ops = 2.0 * D * args.rows_per_gpu * args.n_cols
+        print(json.dumps({
+            "metric": "global_%s_kernel_elements_per_sec" % args.kernel,
+            "value": world * S * args.rows_per_gpu * args.n_cols / (ms * 1e-3), "unit": "kernel elements/s",
+            "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "config3: global SLATM %s kernel, 4 sigmas, %d rows per GPU x %d columns, D=%d; "
+                                   "row-block sharded, no collective" % (args.kernel, args.rows_per_gpu, args.n_cols, D)},
+            "phases_ms": {"slatm": t_sl, "kernel_incl_pack": t_k},
+            "slatm_molecules_per_sec": world * (args.n_cols + args.rows_per_gpu) / (t_sl * 1e-3),
+            "kernel_tera_ops": ops / (t_k * 1e-3) / 1e12}))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
 def main():
     args = parse()
     if args.impl == "reference":
         run_reference(args)
+    elif args.workload == "config3":
+        run_config3(args)
     else:
         run_ours(args)
 
