@@ -34,6 +34,23 @@ SLATM_KW = dict(sigmas=(.05, .05), dgrids=(.04, .04), rcut=4.8)
 ZMAX = 9
 
 
+def init_nccl(local_rank):
+    """NCCL prints its version banner on stdout; keep stdout for the single JSON line."""
+    import torch
+    import torch.distributed as dist
+    sys.stdout.flush()
+    saved = os.dup(1)
+    os.dup2(2, 1)
+    try:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        dist.barrier()
+        torch.cuda.synchronize()
+    finally:
+        sys.stdout.flush()
+        os.dup2(saved, 1)
+        os.close(saved)
+
+
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -216,7 +233,7 @@ def run_ours(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     torch.cuda.set_device(local_rank)
     if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        init_nccl(local_rank)
     lib = L.load()
 
     train, test = make_sets(args.n_train, args.n_test, rank)
@@ -402,7 +419,7 @@ def run_config3(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     torch.cuda.set_device(local_rank)
     if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        init_nccl(local_rank)
     dev = torch.device("cuda", local_rank)
     cols = synth.qm9_like_fast(args.n_cols, SEED + 7, pool=512)
     rows = synth.qm9_like_fast(args.rows_per_gpu, SEED + 7 + 1000 * (rank + 1), pool=256)
