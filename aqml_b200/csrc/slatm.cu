@@ -722,6 +722,10 @@ static bool launch_units_t(const SlatmTables &t, const SlatmJob &J, const MolInd
         int na = mi.off[m + 1] - mi.off[m];
         if (na == 0) continue;
         int ba = std::max(1, std::min(std::min(32, na), 45000 / (35 * na)));
+        if (!J.local) {  // global SLATM: all centres of the molecule in one batch
+            if (na > 36) return false;
+            ba = na;
+        }
         for (int a0 = 0; a0 < na; a0 += ba) {
             Batch b{m, a0, std::min(ba, na - a0), 0};
             batches.push_back(b);
@@ -735,6 +739,7 @@ static bool launch_units_t(const SlatmTables &t, const SlatmJob &J, const MolInd
     const int uc = t.dev.n_el + nblk_max;
     const int na_max = (int)round_up(std::max(mi.na_max, 1), 2);
     nbn_max = (int)round_up(nbn_max, 4);
+    ba_max = std::max(ba_max, t.dev.n_el);
     size_t smem = sizeof(double) * (3 * (size_t)na_max + 4 * (size_t)nbn_max + (size_t)ba_max * uc + 16 * M2 + 16 * M3) +
                   sizeof(int) * na_max + sizeof(short) * ((size_t)nbn_max + (size_t)ba_max * (MAXEL + 1) + 4) + nbn_max + 16;
     if (smem > 160 * 1024 || mi.na_max > 30000) return false;
@@ -758,7 +763,7 @@ static void launch_slatm(const SlatmTables &t, const SlatmJob &J, const MolIndex
         return m2 <= M2 && m3 <= M3 && (M2 * d.h2) * (M2 * d.h2) * d.cst2 < 300.0 && (M3 * d.h3) * (M3 * d.h3) * d.cst3 < 300.0;
     };
     static const bool force_legacy = getenv("AQML_SLATM_LEGACY") != nullptr;
-    if (J.local && !force_legacy) {  // work-unit kernel (aSLATM)
+    if (!force_legacy) {  // work-unit kernel (aSLATM; SLATM of molecules with <= 36 atoms)
         if (safe(15, 12)) { if (launch_units_t<15, 12>(t, J, mi, ws)) return; }
         else if (safe(20, 16)) { if (launch_units_t<20, 16>(t, J, mi, ws)) return; }
         else if (safe(32, 32)) { if (launch_units_t<32, 32>(t, J, mi, ws)) return; }

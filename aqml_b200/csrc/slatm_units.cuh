@@ -70,8 +70,9 @@ slatm_units_kernel(const SlatmDev T, const SlatmJob J, const Batch *batches, int
     if (tid == 0) s_next = 0;
     // dense output: clear the rows, the units overwrite their blocks after the barrier
     if (J.out) {
-        for (int ai = 0; ai < bt.cnt; ai++) {
-            double *row = J.out + (long long)(o + bt.a0 + ai) * J.ldo;
+        const int nrows = J.local ? bt.cnt : 1;
+        for (int ai = 0; ai < nrows; ai++) {
+            double *row = J.out + (long long)(J.local ? (o + bt.a0 + ai) : bt.mol) * J.ldo;
             for (int x = tid; x < T.D; x += SL_THREADS) row[x] = 0.0;
         }
     }
@@ -122,22 +123,21 @@ slatm_units_kernel(const SlatmDev T, const SlatmJob J, const Batch *batches, int
     // R(x_j0) = Rg * exp(-2 j0 h^2 c): Rg (first grid point) is computed once per entry and shared
     const double qm2 = exp(-2.0 * (ch * M2) * T.h2 * T.h2 * T.cst2);
     const double qm3 = exp(-2.0 * (ch * M3) * T.h3 * T.h3 * T.cst3);
-    const int nunits = bt.cnt * uc;
+    const bool loc = J.local != 0;
+    const int nunits = (loc ? bt.cnt : T.n_el) * uc;  // global SLATM: unit = (element, block), summed over its centres
     for (;;) {
         int u = 0;
         if (ch == 0) u = atomicAdd(&s_next, 1);
         u = __shfl_sync(gmask, u, gbase);
         if (u >= nunits) break;
-        const int ai = u / uc, ci = u - ai * uc;
-        const int c = bt.a0 + ai, ec = mel[c];
+        const int ui = u / uc, ci = u - ui * uc;
+        const int ec = loc ? mel[bt.a0 + ui] : ui;
+        const int c_lo = loc ? ui : 0, c_hi = loc ? ui + 1 : bt.cnt;   // centres (batch-relative) of this unit
+        const long long orow = loc ? (long long)(o + bt.a0 + ui) : (long long)bt.mol;
         double ssq = 0.0;  // this thread's share of the block's sum of squares
         if (ec >= 0) {
             const int *lay = T.lay_col + ec * T.nmb;
-            const short *st = sstart + ai * (MAXEL + 1);
-            const short *nb = nbidx + ai * na;
-            const double *dr = dd + ai * na;
-            const unsigned char *fr = fls + ai * na;
-            const int pr = J.atom_prow ? J.atom_prow[o + c] : -1;
+            const int pr = (loc && J.atom_prow) ? J.atom_prow[o + bt.a0 + ui] : -1;
             int col = -1, dcol = -1, nx = 0;
             if (ci < T.n_el) {
                 const int sl = T.bop_slot[ec * MAXEL + ci];
@@ -148,12 +148,20 @@ slatm_units_kernel(const SlatmDev T, const SlatmJob J, const Batch *batches, int
 #pragma unroll
                     for (int j = 0; j < M2; j++) a2[j] = 0.0;
                     const double xa = sx2[j0];
+                    for (int ai = c_lo; ai < c_hi; ai++) {
+                    const int c = bt.a0 + ai;
+                    if (mel[c] != ec) continue;
+                    const short *st = sstart + ai * (MAXEL + 1);
+                    const short *nb = nbidx + ai * na;
+                    const double *dr = dd + ai * na;
+                    const unsigned char *fr = fls + ai * na;
                     for (int n0 = st[e2]; n0 < st[e2 + 1]; n0 += 8) {
                         // my neighbour of this octet: distance and the grid-start ratio, shared by shuffles
                         double g_r = -1.0, g_R = 0.0;
                         if (n0 + ch < st[e2 + 1]) {
                             const int q = nb[n0 + ch];
-                            if (fr[q] & 1) {
+                            // global SLATM counts an unordered same-element pair once (fslatm.f90:501-502)
+                            if ((fr[q] & 1) && (loc || e2 != ec || q > c)) {
                                 g_r = dr[q];
                                 g_R = exp(-(2.0 * (sx2[0] - g_r) * T.h2 + T.h2 * T.h2) * T.cst2);
                             }
@@ -168,14 +176,15 @@ slatm_units_kernel(const SlatmDev T, const SlatmJob J, const Batch *batches, int
                             for (int j = 0; j < M2; j++) { a2[j] += E; E *= R; R *= T.q2; }
                         }
                     }
-                    const double c0 = 0.5 * (T.el_w[ec] * T.el_w[e2]) * T.coeff2;  // fslatm.f90:610-617
+                    }
+                    const double c0 = (loc ? 0.5 : 1.0) * (T.el_w[ec] * T.el_w[e2]) * T.coeff2;  // fslatm.f90:610-617 / :487-491
                     unsigned bits0 = 0, bits1 = 0;
                     const int kt0 = (col + j0) >> 4;
 #pragma unroll
                     for (int j = 0; j < M2; j++) {
                         const double v = a2[j] * (c0 * sinv2[j0 + j]);
                         if (j0 + j < nx) {
-                            if (J.out) J.out[(long long)(o + c) * J.ldo + dcol + j0 + j] = v;
+                            if (J.out) J.out[orow * J.ldo + dcol + j0 + j] = v;
                             if (pr >= 0) J.px[ec][(long long)pr * T.pld[ec] + col + j0 + j] = v;
                             ssq += v * v;
                             if (v != 0.0) {
@@ -197,13 +206,19 @@ slatm_units_kernel(const SlatmDev T, const SlatmJob J, const Batch *batches, int
                 // dense column of this block's type: find it through the slot table
                 dcol = T.slot_col[T.bot_slot[(B.e1 * MAXEL + ec) * MAXEL + B.e3] >> 1];
                 if (col >= 0) {
-                    const int n1 = st[B.e1 + 1] - st[B.e1], n3 = st[B.e3 + 1] - st[B.e3];
-                    const int np = (B.e1 == B.e3) ? n1 * (n1 - 1) / 2 : n1 * n3;
                     const int j0 = ch * M3;
                     const double xa = sx3[j0];
                     double a3[M3];
 #pragma unroll
                     for (int j = 0; j < M3; j++) a3[j] = 0.0;
+                    for (int ai = c_lo; ai < c_hi; ai++) {
+                    if (mel[bt.a0 + ai] != ec) continue;
+                    const short *st = sstart + ai * (MAXEL + 1);
+                    const short *nb = nbidx + ai * na;
+                    const double *dr = dd + ai * na;
+                    const unsigned char *fr = fls + ai * na;
+                    const int n1 = st[B.e1 + 1] - st[B.e1], n3 = st[B.e3 + 1] - st[B.e3];
+                    const int np = (B.e1 == B.e3) ? n1 * (n1 - 1) / 2 : n1 * n3;
                     for (int p0 = 0; p0 < np; p0 += 8) {
                         // my pair of this octet: geometry once, shared with the group by shuffles
                         double g_ang = 0.0, g_A = 0.0, g_B = 0.0, g_R = 0.0;
@@ -255,13 +270,14 @@ slatm_units_kernel(const SlatmDev T, const SlatmJob J, const Batch *batches, int
                             for (int j = 0; j < M3; j++) { a3[j] += fma(scos3[j0 + j], B0, A0) * E; E *= R; R *= T.q3; }
                         }
                     }
+                    }
                     unsigned bits0 = 0, bits1 = 0;
                     const int kt0 = (col + j0) >> 4;
 #pragma unroll
                     for (int j = 0; j < M3; j++) {
                         const double v = a3[j];
                         if (j0 + j < nx) {
-                            if (J.out) J.out[(long long)(o + c) * J.ldo + dcol + j0 + j] = v;
+                            if (J.out) J.out[orow * J.ldo + dcol + j0 + j] = v;
                             if (pr >= 0) J.px[ec][(long long)pr * T.pld[ec] + col + j0 + j] = v;
                             ssq += v * v;
                             if (v != 0.0) {
@@ -283,11 +299,21 @@ slatm_units_kernel(const SlatmDev T, const SlatmJob J, const Batch *batches, int
         ssq += __shfl_xor_sync(gmask, ssq, 1);
         ssq += __shfl_xor_sync(gmask, ssq, 2);
         ssq += __shfl_xor_sync(gmask, ssq, 4);
-        if (ch == 0) s_norm[ai * uc + ci] = ssq;
+        if (ch == 0) s_norm[ui * uc + ci] = ssq;
     }
     __syncthreads();
 
     // ---- phase 3: one-body slots (dense), padding columns and |row|^2 (packed) --------------------------
+    if (!loc) {  // global SLATM one-body slots: Z * count (slatm.py:17-18)
+        if (J.out)
+            for (int s = tid; s < T.nmb; s += SL_THREADS)
+                if (T.slot_kind[s] == 1) {
+                    int cnt = 0;
+                    for (int q = 0; q < na; q++) cnt += (mel[q] == T.slot_e0[s]);
+                    J.out[(long long)bt.mol * J.ldo + T.slot_col[s]] = (double)(T.el_label[T.slot_e0[s]] * cnt);
+                }
+        return;
+    }
     for (int ai = tid; ai < bt.cnt; ai += SL_THREADS) {
         const int c = bt.a0 + ai, ec = mel[c];
         if (J.out && ec >= 0) {
