@@ -188,20 +188,23 @@ __global__ void __launch_bounds__(NT, CTAS_PER_SM) pair_tile_kernel(const PairPa
         atomicAdd(P.stats + 1, (unsigned long long)KT);
     }
 
-    auto load_stage = [&](int stage, int it) {
+    // one quarter of a stage per call: the copies are spread over the four k-steps of the k-tile being
+    // computed instead of being issued back to back behind the barrier (LDGSTS issue throttling)
+    constexpr int CHUNKS = (BM + BN) * 8 / NT;  // 16-byte chunks per thread per stage
+    static_assert(CHUNKS % 4 == 0, "stage copy must split into four parts");
+    auto load_part = [&](int stage, int it, int part) {
         const int kt = use_list ? (int)sKt[it] : it;
         double *sA = smem + stage * STAGE_DOUBLES;
-        double *sB = sA + BM * PITCH;
 #pragma unroll
-        for (int i = 0; i < (BM * 8) / NT; i++) {
-            int c = tid + i * NT, row = c >> 3, ch = c & 7;
-            cp_async16(sA + row * PITCH + ch * 2, gA + (long long)row * G.ld + kt * BK + ch * 2);
+        for (int i = part * (CHUNKS / 4); i < (part + 1) * (CHUNKS / 4); i++) {
+            const int c = tid + i * NT, row = c >> 3, ch = c & 7;  // rows 0..BM-1 -> A, BM.. -> B (contiguous in smem)
+            const double *src = (row < BM) ? gA + (long long)row * G.ld : gB + (long long)(row - BM) * G.ld;
+            cp_async16(sA + row * PITCH + ch * 2, src + kt * BK + ch * 2);
         }
+    };
+    auto load_stage = [&](int stage, int it) {
 #pragma unroll
-        for (int i = 0; i < (BN * 8) / NT; i++) {
-            int c = tid + i * NT, row = c >> 3, ch = c & 7;
-            cp_async16(sB + row * PITCH + ch * 2, gB + (long long)row * G.ld + kt * BK + ch * 2);
-        }
+        for (int part = 0; part < 4; part++) load_part(stage, it, part);
     };
 
     double acc[MI][4][2];
@@ -218,11 +221,8 @@ __global__ void __launch_bounds__(NT, CTAS_PER_SM) pair_tile_kernel(const PairPa
     for (int kt = 0; kt < nact; kt++) {
         cp_async_wait<STAGES - 2>();
         __syncthreads();
-        {
-            int nk = kt + STAGES - 1;
-            if (nk < nact) load_stage(nk % STAGES, nk);
-            cp_async_commit();
-        }
+        const int nk = kt + STAGES - 1;
+        const bool pf = nk < nact;
         const double *sA = smem + (kt % STAGES) * STAGE_DOUBLES;
         const double *sB = sA + BM * PITCH;
         if (MODE == MODE_DOT) {
@@ -230,6 +230,7 @@ __global__ void __launch_bounds__(NT, CTAS_PER_SM) pair_tile_kernel(const PairPa
             const double *pb = sB + (wn * 32 + g) * PITCH + t4;
 #pragma unroll
             for (int kk = 0; kk < BK / 4; kk++) {
+                if (pf) load_part(nk % STAGES, nk, kk);
                 double a[MI], b[4];
 #pragma unroll
                 for (int mi = 0; mi < MI; mi++) a[mi] = pa[mi * 8 * PITCH + kk * 4];
@@ -244,8 +245,9 @@ __global__ void __launch_bounds__(NT, CTAS_PER_SM) pair_tile_kernel(const PairPa
             // same accumulator ownership as the DMMA C fragment: rows 8*mi+g, cols 8*ni+2*t4+{0,1}
             const double *pa = sA + (wm * WROWS + g) * PITCH;
             const double *pb = sB + (wn * 32 + 2 * t4) * PITCH;
-#pragma unroll 2
+#pragma unroll
             for (int kk = 0; kk < BK; kk += 2) {
+                if (pf && (kk & 3) == 0) load_part(nk % STAGES, nk, kk >> 2);
                 double2 a[MI], b[4][2];
 #pragma unroll
                 for (int mi = 0; mi < MI; mi++) a[mi] = *reinterpret_cast<const double2 *>(pa + mi * 8 * PITCH + kk);
@@ -267,6 +269,7 @@ __global__ void __launch_bounds__(NT, CTAS_PER_SM) pair_tile_kernel(const PairPa
                         }
             }
         }
+        cp_async_commit();  // the prefetch issued piecewise above (possibly empty: keeps the group count uniform)
     }
     cp_async_wait<0>();
     __syncthreads();  // pipeline buffers are free from here on
