@@ -81,13 +81,13 @@ __global__ void __launch_bounds__(256) pack_rows_kernel(PackJob J) {
 }
 
 // Column sums and non-zero flags over a list of rows (support detection + centring).
-// grid (ceil(D/256), row chunks); thread = one column over ROWS_PER_BLOCK rows.
+// grid (row chunks, ceil(D/256)); thread = one column over CS_ROWS rows.
 constexpr int CS_ROWS = 64;
 __global__ void __launch_bounds__(256) colstats_kernel(const double *x, long long ldx, const int *rows, int nrows, int D,
                                                        double *colsum, unsigned *colnz) {
-    int c = blockIdx.x * 256 + threadIdx.x;
+    int c = blockIdx.y * 256 + threadIdx.x;
     if (c >= D) return;
-    int r0 = blockIdx.y * CS_ROWS, r1 = min(nrows, r0 + CS_ROWS);
+    int r0 = blockIdx.x * CS_ROWS, r1 = min(nrows, r0 + CS_ROWS);
     double s = 0.0;
     unsigned nz = 0;
     for (int i = r0; i < r1; i++) {
@@ -129,7 +129,7 @@ void launch_pack(const PackJob &J, int nrows_packed, cudaStream_t st) {
 void launch_colstats(const double *x, long long ldx, const int *rows, int nrows, int D, double *colsum, unsigned *colnz,
                      cudaStream_t st) {
     if (nrows <= 0 || D <= 0) return;
-    dim3 grid((D + 255) / 256, (nrows + CS_ROWS - 1) / CS_ROWS);
+    dim3 grid((nrows + CS_ROWS - 1) / CS_ROWS, (D + 255) / 256);  // row chunks on x (no 65535 limit)
     colstats_kernel<<<grid, 256, 0, st>>>(x, ldx, rows, nrows, D, colsum, colnz);
     AQML_LAUNCH_CHECK();
 }

@@ -56,7 +56,8 @@ struct PairGroup {
     int zcol;
     int out_slot;                 // EPI_MAX
     int segA_off, segA_n;         // keep rows with segA_off <= seg < segA_off+segA_n, output row = seg - segA_off
-    int sym;                      // A == B: skip tiles below the diagonal (EPI_MAX only)
+    int sym;                      // A == B: skip tiles below the diagonal (EPI_MAX); EPI_LOCAL additionally keeps only
+                                  // pairs with packed column > packed row (the caller mirrors K and adds the i == j terms)
     // Feature-space block sparsity: one bit per 16-column k-tile and per 64-row block, set when the block
     // holds any non-zero.  A k-tile whose A-block or B-block is all zero contributes exactly 0 to a.b (and to
     // sum|a-b| when both are zero), so it is skipped -- bit-identical results, fewer DMMAs.  null = dense.
@@ -105,7 +106,7 @@ __global__ void __launch_bounds__(NT, CTAS_PER_SM) pair_tile_kernel(const PairPa
     const int band = t / (GM * G.tilesN), rem = t % (GM * G.tilesN);
     const int gm = min(GM, G.tilesM - band * GM);
     const int tm = band * GM + rem % gm, tn = rem / gm;
-    if (EPI == EPI_MAX && G.sym && (tn + 1) * BN <= tm * BM) return;  // tile entirely below the diagonal
+    if ((EPI == EPI_MAX || EPI == EPI_LOCAL) && G.sym && (tn + 1) * BN <= tm * BM) return;  // tile entirely below the diagonal
 
     // ---- de-phase the two CTAs that share an SM --------------------------------------------------
     // All tiles of a group cost the same, so the two resident CTAs would run in lockstep and reach
@@ -286,6 +287,20 @@ __global__ void __launch_bounds__(NT, CTAS_PER_SM) pair_tile_kernel(const PairPa
                     double nb = sNB[wn * 32 + ni * 8 + 2 * t4 + e];
                     acc[mi][ni][e] = fmax(na + nb - 2.0 * acc[mi][ni][e], 0.0);
                 }
+        }
+    }
+
+    if (EPI == EPI_LOCAL && G.sym && tn * BN < (tm + 1) * BM) {
+        // diagonal-crossing tile of a symmetric kernel: drop pairs on or below the diagonal
+        // (v = +inf -> exp(v * isig) = 0 for every sigma, also through the squaring chain)
+#pragma unroll
+        for (int mi = 0; mi < MI; mi++) {
+            const int r = tm * BM + wm * WROWS + mi * 8 + g;
+#pragma unroll
+            for (int ni = 0; ni < 4; ni++)
+#pragma unroll
+                for (int e = 0; e < 2; e++)
+                    if (tn * BN + wn * 32 + ni * 8 + 2 * t4 + e <= r) acc[mi][ni][e] = __longlong_as_double(0x7ff0000000000000LL);
         }
     }
 

@@ -528,6 +528,35 @@ __global__ void __launch_bounds__(SL_THREADS) slatm_kernel(const SlatmDev T, con
 #include "slatm_units.cuh"
 namespace aqml {
 
+// K <- Kc + Kc^T (+ diag), in place, one 32x32 tile pair per block: Kc holds, for every unordered atom pair,
+// the term once (at (mol_i, mol_j) in packed order), and nothing for i == j.
+__global__ void __launch_bounds__(256) symmetrize_kernel(double *K, int n, int nsig, const double *diag) {
+    __shared__ double ta[32][33], tb[32][33];
+    const int ti = blockIdx.y, tj = blockIdx.x;
+    if (tj < ti) return;
+    double *Ks = K + (long long)blockIdx.z * n * n;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    for (int r = ty; r < 32; r += 8) {
+        int a = ti * 32 + r, b = tj * 32 + tx;
+        ta[r][tx] = (a < n && b < n) ? Ks[(long long)a * n + b] : 0.0;
+        int a2 = tj * 32 + r, b2 = ti * 32 + tx;
+        tb[r][tx] = (a2 < n && b2 < n) ? Ks[(long long)a2 * n + b2] : 0.0;
+    }
+    __syncthreads();
+    for (int r = ty; r < 32; r += 8) {
+        int a = ti * 32 + r, b = tj * 32 + tx;
+        if (a < n && b < n) {
+            double v = ta[r][tx] + tb[tx][r];
+            if (a == b) v = 2.0 * ta[r][tx] + diag[a];
+            Ks[(long long)a * n + b] = v;
+        }
+        if (ti != tj) {
+            int a2 = tj * 32 + r, b2 = ti * 32 + tx;
+            if (a2 < n && b2 < n) Ks[(long long)a2 * n + b2] = tb[r][tx] + ta[tx][r];
+        }
+    }
+}
+
 __global__ void zero_rows_kernel(double *x, long long ld, const int *rows, int nrows, double *norm) {
     int r = rows[blockIdx.x];
     for (long long i = threadIdx.x; i < ld; i += blockDim.x) x[(long long)r * ld + i] = 0.0;
@@ -1016,6 +1045,44 @@ int aqml_rep_local_gaussian(const aqml_rep *r1, const aqml_rep *r2, const double
         plan_sigma_chain(P, isig);
         P.out = K; P.ldo = r2->nmol; P.slab = (long long)nrows * r2->nmol;
         run_pairs_public(MODE_DOT, EPI_LOCAL, groups, P, ws);
+    });
+}
+
+int aqml_rep_local_gaussian_sym(const aqml_rep *r, const double *sigmas, int nsigmas, int zmax, double *K, void *stream) {
+    return guarded([&] {
+        AQML_REQUIRE(r && sigmas && K && nsigmas >= 1 && zmax >= 1, "bad argument");
+        require_device();
+        cudaStream_t st = (cudaStream_t)stream;
+        const int n = r->nmol;
+        for (int i = 0; i < nsigmas * zmax; i++) AQML_REQUIRE(sigmas[i] != 0.0, "sigma is zero");
+        AQML_CUDA(cudaMemsetAsync(K, 0, sizeof(double) * (size_t)nsigmas * n * n, st));
+        Workspace ws(st);
+        std::vector<PairGroup> groups;
+        std::vector<int> labels;
+        rep_groups(r, r, zmax, groups, labels);
+        for (auto &g : groups) g.sym = 1;
+        std::vector<double> isig((size_t)nsigmas * zmax);
+        for (size_t i = 0; i < isig.size(); i++) isig[i] = -0.5 / (sigmas[i] * sigmas[i]);
+        // i == j terms: exp(0) = 1 for every atom whose element has a group (exactly what the reference adds)
+        std::vector<double> diag(n, 0.0);
+        for (size_t e = 0; e < r->els.size(); e++) {
+            const auto &el = r->els[e];
+            int z = el.label % 1000;
+            if (!el.n) continue;
+            for (int k = 0; k < nsigmas; k++)
+                AQML_REQUIRE(std::exp((double)1.e9f * isig[(size_t)k * zmax + z - 1]) == 0.0,
+                             "sigma %g for Z=%d is so wide that element-mismatched pairs do not vanish; use aqml_calc_lk_gaussian",
+                             sigmas[(size_t)k * zmax + z - 1], z);
+            for (int m = 0; m < n; m++) diag[m] += r->cnt[e][m];
+        }
+        PairParams P{};
+        P.isig = ws.upload(isig); P.nsig = nsigmas; P.zstride = zmax;
+        plan_sigma_chain(P, isig);
+        P.out = K; P.ldo = n; P.slab = (long long)n * n;
+        run_pairs_public(MODE_DOT, EPI_LOCAL, groups, P, ws);
+        dim3 grid((n + 31) / 32, (n + 31) / 32, nsigmas);
+        symmetrize_kernel<<<grid, 256, 0, st>>>(K, n, nsigmas, ws.upload(diag));
+        AQML_LAUNCH_CHECK();
     });
 }
 

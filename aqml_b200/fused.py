@@ -49,13 +49,23 @@ class PackedRep:
             pass
 
 
-def local_gaussian(rep1, rep2, sigmas, zmax, row0=0, nrows=None, out=None):
-    """K[k, a, b] for a in rep1[row0:row0+nrows], b in rep2; sigmas (nsigmas, zmax).  CUDA tensor."""
+def local_gaussian(rep1, rep2, sigmas, zmax, row0=0, nrows=None, out=None, symmetric=False):
+    """K[k, a, b] for a in rep1[row0:row0+nrows], b in rep2; sigmas (nsigmas, zmax).  CUDA tensor.
+    ``symmetric=True`` (rep1 is rep2, all rows): contract only the upper triangle and mirror."""
     import torch
     sig = L.f64(sigmas)
     sig = sig.reshape(len(sig), -1)
     if sig.shape[1] != zmax:
         raise ValueError(f"sigmas must have shape (nsigmas, zmax={zmax})")
+    if symmetric:
+        if rep1 is not rep2 or row0 != 0 or nrows not in (None, rep1.nmol):
+            raise ValueError("symmetric=True needs rep1 is rep2 and the full row range")
+        K = out if out is not None else torch.empty((sig.shape[0], rep1.nmol, rep1.nmol), dtype=torch.float64,
+                                                    device=rep1.device)
+        with torch.cuda.device(rep1.device):
+            L.call("aqml_rep_local_gaussian_sym", rep1._h, L.ptr(sig), sig.shape[0], int(zmax), L.ptr(K),
+                   L.current_stream())
+        return K
     nrows = rep1.nmol - row0 if nrows is None else nrows
     K = out if out is not None else torch.empty((sig.shape[0], nrows, rep2.nmol), dtype=torch.float64, device=rep1.device)
     with torch.cuda.device(rep1.device):

@@ -170,6 +170,10 @@ int64_t aqml_rep_bytes(const aqml_rep *r);
  * row0/nrows select a block of r1's molecules (row-block sharding); K has nrows rows. */
 int aqml_rep_local_gaussian(const aqml_rep *r1, const aqml_rep *r2, const double *sigmas, int nsigmas, int zmax,
                             int row0, int nrows, double *K, void *stream);
+/* K(r, r): symmetric, DEVICE row-major (nsigmas, r.nmol, r.nmol).  Only atom pairs above the diagonal of the
+ * packed order are contracted (half the work of aqml_rep_local_gaussian(r, r, ...)), then K is mirrored and
+ * the i == j terms (exactly 1 each, as in the reference) are added. */
+int aqml_rep_local_gaussian_sym(const aqml_rep *r, const double *sigmas, int nsigmas, int zmax, double *K, void *stream);
 /* per-element max L2 distance over r1 x r2 atoms (get_kernel_width on packed rows); dso HOST (zmax) */
 int aqml_rep_kernel_width(const aqml_rep *r1, const aqml_rep *r2, int zmax, double *dso, void *stream);
 

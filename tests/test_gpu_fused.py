@@ -34,6 +34,12 @@ def test_fused_equals_two_step_and_oracle():
     # row-block sharding: rows 5..12 of the test set
     Kb = fused.local_gaussian(test, train, sig, zmax, row0=5, nrows=7).cpu().numpy()
     assert rel_err(Kb, ref[:, 5:12]) < TOL
+    # symmetric K(train, train): half the contraction + mirror == the rectangular route == the oracle
+    ref11 = co.calc_lk_gaussian(xl[:A1], xl[:A1], zs[:A1], zs[:A1], nas[:n1], nas[:n1], zmax, False, sig)
+    K11 = fused.local_gaussian(train, train, sig, zmax).cpu().numpy()
+    K11s = fused.local_gaussian(train, train, sig, zmax, symmetric=True).cpu().numpy()
+    assert rel_err(K11, ref11) < TOL and rel_err(K11s, ref11) < TOL
+    assert np.array_equal(K11s, np.transpose(K11s, (0, 2, 1)))
     # width heuristic on packed rows == dense get_kernel_width on train+test
     both = fused.PackedRep(coords, zs, nas, mb, **kw)
     assert np.allclose(fused.kernel_width(both, both, zmax), dso, rtol=1e-10)
