@@ -54,11 +54,22 @@ def generate_slatm(coordinates, nuclear_charges, mbtypes, cg=None, izeff=False,
                    cell=None, local=False, sigmas=[0.05, 0.05], dgrids=[0.03, 0.03],
                    rcut=4.8, alchemy=False, pbc=False, rpower=6, ias=None):
     """core.py:382-556.  local -> list of per-atom 1-D arrays, else one 1-D array."""
-    if pbc and pbc != '000':
-        raise NotImplementedError("periodic systems are out of scope (SURVEY 8 a6)")
     if alchemy:
         raise NotImplementedError("alchemy=True (core.py:445-453) is not used by any workflow; out of scope")
     zs = np.asarray(nuclear_charges)
+    if pbc:
+        # slatm.py:40-45,96-101: one finite cluster of periodic images per query atom, query atom first
+        assert local, '#ERROR: for periodic system, plz use atomic rpst'
+        from .slatm import MolPBC
+        mol = MolPBC(zs, np.asarray(coordinates, dtype=np.float64).reshape(-1, 3), cell, rcut=rcut)
+        idx = range(len(zs)) if ias is None else ias
+        clusters = [mol.get_cluster(int(i)) for i in idx]
+        nas = [len(c[0]) for c in clusters]
+        x = generate_slatm_batch(np.concatenate([c[1] for c in clusters]), np.concatenate([c[0] for c in clusters]),
+                                 nas, mbtypes, izeff=izeff, local=True, sigmas=sigmas, dgrids=dgrids, rcut=rcut,
+                                 rpower=rpower)
+        first = np.concatenate(([0], np.cumsum(nas)[:-1]))
+        return [x[int(i)] for i in first]
     x = generate_slatm_batch(np.asarray(coordinates, dtype=np.float64).reshape(-1, 3), zs, [len(zs)], mbtypes,
                              izeff=izeff, local=local, sigmas=sigmas, dgrids=dgrids, rcut=rcut, rpower=rpower)
     if local:

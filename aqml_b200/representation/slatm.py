@@ -26,12 +26,58 @@ def _grid3(dgrid):
     return int((a1 - a0) / dgrid) + 1
 
 
+class MolPBC(object):
+    """slatm.py:134-210: finite cluster of periodic images around one atom (host side, NumPy only).
+
+    ``cell`` rows are the lattice vectors (images are ``coords + idx @ cell``); the number of images tried
+    along an axis uses the column norms of ``cell`` and the fractional coordinate, exactly as upstream."""
+
+    def __init__(self, zs, coords, cell, rcut=9.0):
+        self.zs = np.asarray(zs)
+        self.coords = np.asarray(coords, dtype=np.float64)
+        self.cell = np.array(cell, dtype=np.float64)
+        self.na = len(self.zs)
+        self.coords_f = np.linalg.solve(self.cell.T, self.coords.T).T
+        self.ls = np.linalg.norm(self.cell, axis=0)
+        self.rcut = rcut
+
+    def get_nmax(self, ia, axis, sign):
+        n = sign
+        while True:
+            far = self.ls[axis] * np.abs(n - self.coords_f[ia][axis]) > self.rcut
+            n += sign
+            if far:
+                return n
+
+    def get_cluster(self, ia):
+        lo_hi = [(self.get_nmax(ia, ax, -1), self.get_nmax(ia, ax, +1)) for ax in range(3)]
+        zs = [self.zs[ia]]
+        coords = [self.coords[ia]]
+        for i in range(lo_hi[0][0], lo_hi[0][1] + 1):
+            for j in range(lo_hi[1][0], lo_hi[1][1] + 1):
+                for k in range(lo_hi[2][0], lo_hi[2][1] + 1):
+                    shifted = self.coords + np.dot((i, j, k), self.cell)
+                    d = np.sqrt(((shifted - self.coords[ia]) ** 2).sum(axis=1))
+                    for ja in np.nonzero(d <= self.rcut)[0]:
+                        if ja == ia and (i, j, k) == (0, 0, 0):
+                            continue
+                        zs.append(self.zs[ja])
+                        coords.append(shifted[ja])
+        coords = np.array(coords)
+        if len(coords) > 1:
+            dd = np.sqrt(((coords[:, None] - coords[None]) ** 2).sum(axis=2))
+            assert np.all(dd[np.triu_indices(len(coords), 1)] > 0)  # slatm.py:209
+        return [np.array(zs), coords]
+
+
 def _single(fn, mbtype, obj, izeff, iloc, ia, normalize, sigma, rcut, dgrid, nx, rpower, pbc):
-    zs, coords, _ = obj
-    if pbc:
-        raise NotImplementedError("periodic systems (MolPBC.get_cluster, slatm.py:134-210) are out of scope")
+    zs, coords, cell = obj
     if iloc:
         assert ia is not None, '#ERROR: plz specify `za and `ia '
+    if pbc:
+        assert iloc, '#ERROR: for periodic system, plz use atomic rpst'  # slatm.py:43,99
+        zs, coords = MolPBC(zs, coords, cell, rcut=rcut).get_cluster(ia)
+        ia = 0  # slatm.py:68,125: the query atom is the first atom of the cluster
     coords = L.f64(coords)
     zs = L.i32(zs)
     if coords.shape != (len(zs), 3):

@@ -359,6 +359,13 @@ def run_ours(args):
         except Exception:
             pass
         hbm_peak = peaks.get("hbm_gbs", 6650.0)
+        traffic = None
+        try:  # dram__bytes_read+write of one launch, from the committed ncu --set full capture of this command
+            tr = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))["pair_tile_kernel<MODE_DOT,EPI_LOCAL>"]
+            if args.n_train == 20000 and args.n_test == 2000:
+                traffic = float(tr["dram_bytes_read"] + tr["dram_bytes_write"])
+        except Exception:
+            pass
         slatm_bytes = float(rep_bytes)
         line = {
             "metric": "local_gaussian_kernel_elements_per_sec",
@@ -377,7 +384,8 @@ def run_ours(args):
             "clocks": clocks,
             "roofline": {"bound": "tensor", "kernel": "pair_tile_kernel<MODE_DOT,EPI_LOCAL> (FP64 DMMA.8x8x4)",
                          "achieved": ach_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach_tf / peak_tf,
-                         "traffic": None, "algorithmic_flops_per_launch": flops,
+                         "traffic": traffic, "traffic_unit": "bytes of DRAM per launch (profiles/r01_traffic.json)",
+                         "algorithmic_flops_per_launch": flops,
                          # all-zero 16-column k-tiles are skipped exactly: the DMMA work
                          # actually issued, incl. row/column padding, and its share of the dense sweep
                          "executed_flops_per_launch": kt_exec * ktile_flops,

@@ -475,3 +475,44 @@ def read_xyz(path, prop='b3lypvdz'):
         zs.append(sym2z[s[0]])
         coords.append([float(s[1]), float(s[2]), float(s[3])])
     return np.array(zs, dtype=np.int64), np.array(coords, dtype=np.float64), props.get(prop)
+
+
+# --------------------------------------------------------------------------------------
+# periodic systems: representation/slatm.py:134-210 (MolPBC.get_cluster)
+# --------------------------------------------------------------------------------------
+def pbc_cluster(zs, coords, cell, ia, rcut):
+    """Finite cluster around atom ia: the atom itself first, then every periodic image within rcut
+    (images indexed by integer triples whose range per axis follows get_nmax, slatm.py:166-181)."""
+    zs = np.asarray(zs)
+    coords = np.asarray(coords, dtype=np.float64)
+    cell = np.array(cell, dtype=np.float64)
+    frac = np.linalg.solve(cell.T, coords.T).T
+    ls = np.linalg.norm(cell, axis=0)
+
+    def nmax(axis, sign):
+        n = sign
+        while True:
+            if ls[axis] * abs(n - frac[ia][axis]) > rcut:
+                return n + sign
+            n += sign
+
+    rng = [range(nmax(ax, -1), nmax(ax, 1) + 1) for ax in range(3)]
+    out_z, out_x = [zs[ia]], [coords[ia]]
+    for idx in itertools.product(*rng):
+        img = coords + np.dot(idx, cell)
+        ds = np.sqrt(((img - coords[ia]) ** 2).sum(axis=1))
+        for ja in range(len(zs)):
+            if ds[ja] <= rcut and not (ja == ia and idx == (0, 0, 0)):
+                out_z.append(zs[ja])
+                out_x.append(img[ja])
+    return np.array(out_z), np.array(out_x)
+
+
+def generate_slatm_pbc(coordinates, nuclear_charges, cell, mbtypes, **kw):
+    """generate_slatm(..., local=True, pbc=True): row of the query atom in its own cluster."""
+    rows = []
+    rcut = kw.get('rcut', 4.8)
+    for ia in range(len(nuclear_charges)):
+        z, x = pbc_cluster(nuclear_charges, coordinates, cell, ia, rcut)
+        rows.append(generate_slatm(x, z, mbtypes, local=True, ias=[0], **kw)[0])
+    return rows

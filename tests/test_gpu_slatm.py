@@ -134,3 +134,31 @@ def test_f2py_level_single_type_calls():
     assert rel_err(ys, ref) < TOL
     with pytest.raises(ValueError):
         rslatm.get_sbop([1, 6], [zs[:-1], coords, None])
+
+
+def test_random_tiny_molecules_all_branches():
+    """Randomised small cases: 1-7 atoms, 1-3 elements, atoms in and out of the cut-off, every type
+    orientation (z1==z2, z1!=z2, z1==z3, z1!=z3, centre not of type), local and global, both kernels paths."""
+    rng = np.random.default_rng(2024)
+    for trial in range(12):
+        nmol = int(rng.integers(1, 6))
+        nas = rng.integers(1, 8, size=nmol).astype(np.int32)
+        pool = rng.choice([1, 6, 7, 8, 16], size=int(rng.integers(1, 4)), replace=False)
+        zs = rng.choice(pool, size=int(nas.sum())).astype(np.int32)
+        coords = rng.uniform(-2.2, 2.2, size=(int(nas.sum()), 3))
+        # keep atoms apart (coincident atoms are covered by test_edge_cases)
+        off = np.concatenate(([0], np.cumsum(nas)))
+        for m in range(nmol):
+            x = coords[off[m]:off[m + 1]]
+            for i in range(1, len(x)):
+                while np.min(np.linalg.norm(x[:i] - x[i], axis=1)) < 0.5:
+                    x[i] = rng.uniform(-2.2, 2.2, size=3)
+        mb = o.get_slatm_mbtypes(synth.split_zs(nas, zs))
+        rng.shuffle(mb)  # arbitrary order of the type list = arbitrary column order
+        cfg = dict(sigmas=(.05, .05), dgrids=(.04, .04), rcut=float(rng.choice([1.5, 3.0, 4.8])))
+        if trial % 3 == 2:
+            cfg = dict(sigmas=(.1, .08), dgrids=(.25, .2), rcut=3.0, rpower=4, izeff=bool(set(pool) <= {1, 6, 7, 8, 16}))
+        for local in (True, False):
+            ref = co.generate_slatm_batch(coords, zs, nas, mb, local, **cfg)
+            got = rcore.generate_slatm_batch(coords, zs, nas, mb, local=local, **cfg)
+            assert rel_err(got, ref) < TOL, (trial, local, cfg)
