@@ -102,7 +102,7 @@ __global__ void __launch_bounds__(NT, CTAS_PER_SM) pair_tile_kernel(const PairPa
     while (gi + 1 < P.ngroups && (int)blockIdx.x >= P.groups[gi + 1].tile_begin) gi++;
     const PairGroup G = P.groups[gi];
     const int t = blockIdx.x - G.tile_begin;
-    constexpr int GM = 16;  // tile rows per raster band: 16 A panels stay L2-resident while B streams
+    constexpr int GM = 32;  // tile rows per raster band: the A panels (32 x 64 rows) stay L2-resident while B streams
     const int band = t / (GM * G.tilesN), rem = t % (GM * G.tilesN);
     const int gm = min(GM, G.tilesM - band * GM);
     const int tm = band * GM + rem % gm, tn = rem / gm;

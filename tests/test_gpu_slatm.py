@@ -162,3 +162,25 @@ def test_random_tiny_molecules_all_branches():
             ref = co.generate_slatm_batch(coords, zs, nas, mb, local, **cfg)
             got = rcore.generate_slatm_batch(coords, zs, nas, mb, local=local, **cfg)
             assert rel_err(got, ref) < TOL, (trial, local, cfg)
+
+
+def test_periodic_clusters():
+    """pbc: one finite cluster of periodic images per query atom (slatm.py:134-210), query atom first."""
+    zs = np.array([11, 17, 11, 17], dtype=np.int32)
+    a = 4.2
+    cell = np.array([[a, 0.0, 0.0], [0.3, a, 0.0], [0.0, 0.4, a]])
+    frac = np.array([[0.0, 0.0, 0.0], [0.5, 0.5, 0.5], [0.5, 0.5, 0.02], [0.02, 0.0, 0.5]])
+    coords = frac @ cell
+    mb = rcore.get_slatm_mbtypes([zs], pbc=True)
+    assert mb == o.get_slatm_mbtypes([zs], pbc=True) and [11, 11, 11] in mb
+    kw = dict(sigmas=[.05, .05], dgrids=[.1, .1], rcut=3.5)
+    got = rcore.generate_slatm(coords, zs, mb, local=True, pbc='111', cell=cell, **kw)
+    ref = o.generate_slatm_pbc(coords, zs, cell, mb, **kw)
+    assert len(got) == 4
+    assert rel_err(np.array(got), np.array(ref)) < TOL
+    cz, cx = rslatm.MolPBC(zs, coords, cell, rcut=3.5).get_cluster(1)
+    oz, ox = o.pbc_cluster(zs, coords, cell, 1, 3.5)
+    assert np.array_equal(cz, oz) and np.array_equal(cx, ox) and len(cz) > 5
+    y = rslatm.get_sbop([11, 17], [zs, coords, cell], iloc=True, ia=1, pbc='111', rcut=3.5, dgrid=0.1)
+    yr = o.get_sbop([11, 17], [oz, ox, None], iloc=True, ia=0, rcut=3.5, dgrid=0.1)
+    assert rel_err(y, yr) < TOL
