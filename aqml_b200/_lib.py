@@ -41,6 +41,8 @@ SIGNATURES = {
     "aqml_flaplacian_kernel": (_I, [_P, _I, _P, _I, _I, _P, _D]),
     "aqml_fl2_distance": (_I, [_P, _P, _I, _I, _I, _P]),
     "aqml_fl1_distance": (_I, [_P, _P, _I, _I, _I, _P]),
+    "aqml_flinear_kernel": (_I, [_P, _I, _P, _I, _I, _P]),
+    "aqml_distance_dev": (_I, [_I, _P, _I, _L, _P, _I, _L, _I, _P, _P]),
     "aqml_global_kernel_dev": (_I, [_I, _P, _I, _L, _P, _I, _L, _I, _P, _I, _I, _P, _P]),
     "aqml_max_distance_dev": (_I, [_I, _P, _I, _L, _P, _I, _L, _I, _P, _P]),
     "aqml_calc_lk_gaussian": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _P, _I, _I, _I, _I, _P]),

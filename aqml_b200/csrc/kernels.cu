@@ -243,6 +243,7 @@ static void run_pairs(int mode, int epi, const std::vector<PairGroup> &groups, P
     AQML_DISPATCH(MODE_DOT, EPI_DIST_STORE)
     AQML_DISPATCH(MODE_DOT, EPI_MAX)
     AQML_DISPATCH(MODE_DOT, EPI_LOCAL)
+    AQML_DISPATCH(MODE_DOT, EPI_DOT_STORE)
     AQML_DISPATCH(MODE_L1, EPI_EXP_STORE)
     AQML_DISPATCH(MODE_L1, EPI_DIST_STORE)
     AQML_DISPATCH(MODE_L1, EPI_MAX)
@@ -324,7 +325,7 @@ static void global_pairs(int kind, int epi, const double *a, int na, long long l
     require_device();
     Workspace ws(st);
     const int mode = (kind == AQML_KERNEL_GAUSSIAN) ? MODE_DOT : MODE_L1;
-    const double *mean = (mode == MODE_DOT && center) ? column_mean(ws, b, ldb, nb, D) : nullptr;
+    const double *mean = (mode == MODE_DOT && center && epi != EPI_DOT_STORE) ? column_mean(ws, b, ldb, nb, D) : nullptr;
     const bool same = (a == b && na == nb && lda == ldb);
     Packed pb = pack_dense(ws, b, ldb, nb, D, mean, mode == MODE_DOT);
     Packed pa = same ? pb : pack_dense(ws, a, lda, na, D, mean, mode == MODE_DOT);
@@ -676,6 +677,18 @@ int aqml_fl2_distance(const double *A, const double *B, int n1, int n2, int nc, 
 }
 int aqml_fl1_distance(const double *A, const double *B, int n1, int n2, int nc, double *Dm) {
     return guarded([&] { global_host(AQML_KERNEL_LAPLACIAN, EPI_DIST_STORE, A, n1, B, n2, nc, Dm, 1.0); });
+}
+int aqml_flinear_kernel(const double *a, int na, const double *b, int nb, int D, double *k) {
+    return guarded([&] { global_host(AQML_KERNEL_GAUSSIAN, EPI_DOT_STORE, a, na, b, nb, D, k, 1.0); });
+}
+int aqml_distance_dev(int p, const double *a, int na, int64_t lda, const double *b, int nb, int64_t ldb, int D, double *out,
+                      void *stream) {
+    return guarded([&] {
+        AQML_REQUIRE(p == 0 || p == 1 || p == 2, "p must be 0 (dot product), 1 (L1) or 2 (L2)");
+        AQML_REQUIRE(a && b && out, "null pointer");
+        global_pairs(p == 1 ? AQML_KERNEL_LAPLACIAN : AQML_KERNEL_GAUSSIAN, p == 0 ? EPI_DOT_STORE : EPI_DIST_STORE, a, na, lda,
+                     b, nb, ldb, D, nullptr, 0, 1, out, (cudaStream_t)stream);
+    });
 }
 
 int aqml_global_kernel_dev(int kind, const double *a, int na, int64_t lda, const double *b, int nb, int64_t ldb, int D,

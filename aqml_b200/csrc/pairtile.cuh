@@ -9,6 +9,7 @@
 //
 //   EPI_EXP_STORE  : K[s][i][j] = exp(v * isig[s])          global Gaussian/Laplacian, all sigmas in one pass
 //   EPI_DIST_STORE : D[i][j]   = sqrt(v) | v                l2 / l1 distance matrices
+//   EPI_DOT_STORE  : G[i][j]   = a.b                        linear kernel (no norm transform)
 //   EPI_MAX        : out[slot] = max(out[slot], v)          kernel-width heuristic (never stores D)
 //   EPI_LOCAL      : K[s][mol(i)][mol(j)] += exp(v*isig[s][z_i])   local kernels: per-warp staged,
 //                    segmented (molecule-pair) reduction, then one FP64 RED per molecule pair.
@@ -42,7 +43,7 @@ constexpr int EPITCH = 40;     // per-warp staging pitch (doubles) for the segme
 static_assert((NT / 32) * WROWS * EPITCH * 8 <= PIPE_BYTES, "epilogue staging must fit in the pipeline buffers");
 
 enum { MODE_DOT = 0, MODE_L1 = 1 };
-enum { EPI_EXP_STORE = 0, EPI_DIST_STORE = 1, EPI_MAX = 2, EPI_LOCAL = 3 };
+enum { EPI_EXP_STORE = 0, EPI_DIST_STORE = 1, EPI_MAX = 2, EPI_LOCAL = 3, EPI_DOT_STORE = 4 };
 
 struct PairGroup {
     const double *A, *B;          // packed operands, row pitch ld (multiple of BK), rows padded to 128
@@ -276,7 +277,7 @@ __global__ void __launch_bounds__(NT, CTAS_PER_SM) pair_tile_kernel(const PairPa
     __syncthreads();  // pipeline buffers are free from here on
 
     // ---- v_ij -------------------------------------------------------------------------------
-    if (MODE == MODE_DOT) {
+    if (MODE == MODE_DOT && EPI != EPI_DOT_STORE) {
 #pragma unroll
         for (int mi = 0; mi < MI; mi++) {
             double na = sNA[wm * WROWS + mi * 8 + g];
@@ -338,7 +339,7 @@ __global__ void __launch_bounds__(NT, CTAS_PER_SM) pair_tile_kernel(const PairPa
                     }
             }
         }
-    } else if (EPI == EPI_DIST_STORE) {
+    } else if (EPI == EPI_DIST_STORE || EPI == EPI_DOT_STORE) {
 #pragma unroll
         for (int mi = 0; mi < MI; mi++) {
             int sr = sSegA[wm * WROWS + mi * 8 + g];
@@ -348,7 +349,25 @@ __global__ void __launch_bounds__(NT, CTAS_PER_SM) pair_tile_kernel(const PairPa
 #pragma unroll
                 for (int e = 0; e < 2; e++) {
                     int sc = sSegB[wn * 32 + ni * 8 + 2 * t4 + e];
-                    if (sc >= 0) P.out[(long long)sr * P.ldo + sc] = (MODE == MODE_DOT) ? sqrt(acc[mi][ni][e]) : acc[mi][ni][e];
+                    if (sc >= 0) {
+                        double v = acc[mi][ni][e];
+                        if (MODE == MODE_DOT && EPI == EPI_DIST_STORE) {
+                            // sqrt amplifies the expansion's cancellation error near d = 0 (duplicate / nearly equal
+                            // rows): recompute those few elements by direct differences, as the reference does
+                            const int row = wm * WROWS + mi * 8 + g, col = wn * 32 + ni * 8 + 2 * t4 + e;
+                            if (v < 1e-6 * (sNA[row] + sNB[col])) {
+                                const double *pa = gA + (long long)row * G.ld, *pb = gB + (long long)col * G.ld;
+                                double s2 = 0.0;
+                                for (int k = 0; k < (int)G.ld; k++) {
+                                    const double t = pa[k] - pb[k];
+                                    s2 += t * t;
+                                }
+                                v = s2;
+                            }
+                            v = sqrt(v);
+                        }
+                        P.out[(long long)sr * P.ldo + sc] = v;
+                    }
                 }
         }
     } else if (EPI == EPI_MAX) {

@@ -51,6 +51,79 @@ def laplacian_kernel(A, B, sigma):
     return _global_np("aqml_flaplacian_kernel", A, B, sigma)
 
 
+def _device_distance(A, B, p):
+    """(N, M) CUDA tensor of |A_i - B_j|_p (p = 1, 2) or A_i . B_j (p = 0); NumPy inputs are uploaded."""
+    import torch
+    if not L.is_tensor(A):
+        A = torch.as_tensor(L.f64(A), device="cuda")
+        B = torch.as_tensor(L.f64(B), device="cuda")
+    A, B = L.dev_f64(A), L.dev_f64(B)
+    if A.dim() != 2 or B.dim() != 2 or A.shape[1] != B.shape[1]:
+        raise ValueError("expected 2-D arrays with the same representation size")
+    out = torch.empty((A.shape[0], B.shape[0]), dtype=torch.float64, device=A.device)
+    with torch.cuda.device(A.device):
+        L.call("aqml_distance_dev", int(p), L.ptr(A), A.shape[0], A.stride(0), L.ptr(B), B.shape[0], B.stride(0),
+               A.shape[1], L.ptr(out), L.current_stream())
+    return out
+
+
+def _like_input(K, A):
+    return K if L.is_tensor(A) else np.asfortranarray(K.cpu().numpy())
+
+
+def linear_kernel(A, B):
+    """kernels.py:69-95 -> fkernels.f90:390 flinear_kernel: K_ij = A_i . B_j (FP64 tensor-core Gram matrix)."""
+    if L.is_tensor(A):
+        return _device_distance(A, B, 0)
+    A, B = L.f64(A), L.f64(B)
+    K = np.empty((A.shape[0], B.shape[0]), order="F")
+    L.call("aqml_flinear_kernel", L.ptr(A), A.shape[0], L.ptr(B), B.shape[0], A.shape[1], L.ptr(K))
+    return K
+
+
+def sargan_kernel(A, B, sigma, gammas):
+    """kernels.py:97-131 -> fkernels.f90:478 fsargan_kernel:
+    K = exp(-d/sigma) (1 + sum_k gamma_k (d/sigma)^k), d = |A_i - B_j|_1 (device), scalar part in torch."""
+    import torch
+    if len(gammas) == 0:
+        return laplacian_kernel(A, B, sigma)
+    d = _device_distance(A, B, 1)
+    x = d / sigma
+    poly = torch.ones_like(x)
+    for m, g in enumerate(gammas, start=1):
+        poly = poly + float(g) * x ** m
+    return _like_input(torch.exp(-x) * poly, A)
+
+
+def matern_kernel(A, B, sigma, order=0, metric="l1"):
+    """kernels.py:133-191 -> fsargan_kernel (l1) / fkernels.f90:414 fmatern_kernel_l2 (l2)."""
+    import torch
+    if metric == "l1":
+        if order == 0:
+            gammas = []
+        elif order == 1:
+            gammas, sigma = [1], sigma / np.sqrt(3)
+        elif order == 2:
+            gammas, sigma = [1, 1 / 3.0], sigma / np.sqrt(5)
+        else:
+            print("Order:%d not implemented in Matern Kernel" % order)
+            raise SystemExit
+        return sargan_kernel(A, B, sigma, gammas)
+    elif metric != "l2":
+        print("Error: Unknown distance metric %s in Matern kernel" % str(metric))
+        raise SystemExit
+    d = _device_distance(A, B, 2)
+    if order == 0:
+        K = torch.exp(-d / sigma)
+    elif order == 1:
+        s = np.sqrt(3.0) / sigma
+        K = torch.exp(-s * d) * (1.0 + s * d)
+    else:
+        s = np.sqrt(5.0) / sigma
+        K = torch.exp(-s * d) * (1.0 + s * d + 5.0 / (3.0 * sigma * sigma) * d * d)
+    return _like_input(K, A)
+
+
 # algo/aqml.py:194,198 names the global multi-sigma routines like this (absent upstream)
 def gaussian_kernels(A, B, sigmas):
     return global_kernels(A, B, sigmas, "gaussian")
@@ -123,6 +196,18 @@ def fgaussian_kernel(a_t, na, b_t, nb, k, sigma):
 
 def flaplacian_kernel(a_t, na, b_t, nb, k, sigma):
     k[...] = _global_np("aqml_flaplacian_kernel", np.asarray(a_t).T, np.asarray(b_t).T, sigma)
+
+
+def flinear_kernel(a_t, na, b_t, nb, k):
+    k[...] = linear_kernel(np.asarray(a_t).T, np.asarray(b_t).T)
+
+
+def fsargan_kernel(a_t, na, b_t, nb, k, sigma, gammas, ng=None):
+    k[...] = sargan_kernel(np.asarray(a_t).T, np.asarray(b_t).T, sigma, gammas)
+
+
+def fmatern_kernel_l2(a_t, na, b_t, nb, k, sigma, order):
+    k[...] = matern_kernel(np.asarray(a_t).T, np.asarray(b_t).T, sigma, order, "l2")
 
 
 def calc_lk_gaussian(x1_t, x2_t, zs1, zs2, nas1, nas2, zmax, iab, sigmas, nm1=None, nm2=None, nsigmas=None):

@@ -65,6 +65,14 @@ int aqml_fl2_distance(const double *A, const double *B, int n1, int n2, int nc, 
 /* fl1_distance                                coreml/cml/fdistance.f90:3-22 */
 int aqml_fl1_distance(const double *A, const double *B, int n1, int n2, int nc, double *Dm);
 
+/* flinear_kernel(a, na, b, nb, k)              coreml/cml/fkernels.f90:390-412  k[j + na*i] = a_j . b_i */
+int aqml_flinear_kernel(const double *a, int na, const double *b, int nb, int D, double *k);
+/* distance / Gram matrix on the device: p = 2 -> |a_i - b_j|_2, p = 1 -> |a_i - b_j|_1, p = 0 -> a_i . b_j.
+ * a, b, out DEVICE; out row-major (na, nb).  Building block of the Matern / Sargan kernels
+ * (fkernels.f90:414-518), whose scalar post-processing of d is not on the hot path. */
+int aqml_distance_dev(int p, const double *a, int na, int64_t lda, const double *b, int nb, int64_t ldb, int D, double *out,
+                      void *stream);
+
 /* All sigmas in one pass (the reference re-runs the whole distance loop per sigma:
  * representation/xa.py:223, slatm_x.py:565).  kind = AQML_KERNEL_*.
  * a (na, lda>=D), b (nb, ldb>=D) row-major DEVICE; sigmas HOST (nsig); K DEVICE row-major
