@@ -32,9 +32,15 @@ namespace aqml {
 constexpr int MI = AQML_MI;        // 8x8 MMA row blocks per warp: warp tile (8*MI) x 32
 constexpr int WROWS = 8 * MI;
 constexpr int BM = 2 * WROWS, BN = 64, BK = 16;
-constexpr int CTAS_PER_SM = (MI == 8) ? 2 : 3;
+#ifndef AQML_CTAS
+#define AQML_CTAS ((AQML_MI == 8) ? 2 : 3)
+#endif
+constexpr int CTAS_PER_SM = AQML_CTAS;
 constexpr int PITCH = BK + 4;  // doubles; (PITCH mod 16) == 4 -> conflict-free 8x4 fragment loads
-constexpr int STAGES = 3;
+#ifndef AQML_STAGES
+#define AQML_STAGES 3
+#endif
+constexpr int STAGES = AQML_STAGES;
 constexpr int WARPS_N = BN / 32;
 constexpr int NT = 64 * WARPS_N;  // 2 (M) x WARPS_N (N) warps
 constexpr int STAGE_DOUBLES = (BM + BN) * PITCH;

@@ -88,15 +88,9 @@ __device__ __forceinline__ double cos_angle_rn(const double *a, const double *b,
 
 // dynamic shared memory carve-up (doubles first)
 //   spec[pldmax] | mx,my,mz | nbx,nby,nbz,nbd,nbr2 | md,mr2 (each [na_max]) | pair[4*PCH] | ints: mel,nbi,nbe,nbf,mfl [na_max]
-constexpr int NG = SL_THREADS / 8;  // 8-thread groups; each thread owns a chunk of M consecutive grid points
-struct Item {
-    short cand, begin, end, pad;
-};
-constexpr int MAXITEM = MAXEL + MAXBLK + NG;
-
-// M2/M3 > 0: recurrence path with M2 (M3) grid points per thread for the 2-body (3-body) grids
-// (8*M >= nx); M2 == 0: one exp per (entry, grid point), any grid size.
-template <int M2, int M3>
+// General-purpose SLATM kernel: one exp per (entry, grid point), spectrum in shared memory, any grid size and
+// molecule size.  Used for global SLATM of molecules with more than 36 atoms and for grids outside the
+// recurrence's safe range; everything else runs slatm_units_kernel (slatm_units.cuh).
 __global__ void __launch_bounds__(SL_THREADS) slatm_kernel(const SlatmDev T, const SlatmJob J, int pldmax, int na_max) {
     extern __shared__ __align__(16) double sm[];
     double *spec = sm;
@@ -106,12 +100,7 @@ __global__ void __launch_bounds__(SL_THREADS) slatm_kernel(const SlatmDev T, con
     double *pair = mr2 + na_max;
     int *mel = reinterpret_cast<int *>(pair + 4 * PCH);
     int *nbi = mel + na_max, *nbe = nbi + na_max, *nbf = nbe + na_max, *mfl = nbf + na_max;
-    // recurrence path: grid tables and per-group partial spectra behind the int arrays (8-byte aligned: na_max even)
-    constexpr int NXS = 8 * (M2 > M3 ? M2 : M3);
-    double *slab = reinterpret_cast<double *>(mfl + na_max + (na_max & 1));
-    double *sx2 = slab + NG * NXS, *sinv2 = sx2 + 8 * M2, *sx3 = sinv2 + 8 * M2, *scos3 = sx3 + 8 * M3;
-    __shared__ Item s_items[MAXITEM];
-    __shared__ int s_nitems;
+
     __shared__ int s_cnt[MAXEL], s_start[MAXEL + 1];
     __shared__ Block3 s_blk[MAXBLK];
     __shared__ int s_nblk, s_ptot;
@@ -137,18 +126,6 @@ __global__ void __launch_bounds__(SL_THREADS) slatm_kernel(const SlatmDev T, con
     }
     const int o = J.mol_off[m], na = J.mol_off[m + 1] - o;
 
-    if (M2 > 0) {
-        for (int i = tid; i < 8 * M2; i += SL_THREADS) {
-            int q = min(i, T.nx2 - 1);
-            sx2[i] = T.xs2[q];
-            sinv2[i] = T.inv2[q];
-        }
-        for (int i = tid; i < 8 * M3; i += SL_THREADS) {
-            int q = min(i, T.nx3 - 1);
-            sx3[i] = T.xs3[q];
-            scos3[i] = T.cosx3[q];
-        }
-    }
     for (int i = tid; i < na; i += SL_THREADS) {
         mx[i] = J.coords[3 * (long long)(o + i)];
         my[i] = J.coords[3 * (long long)(o + i) + 1];
@@ -242,7 +219,7 @@ __global__ void __launch_bounds__(SL_THREADS) slatm_kernel(const SlatmDev T, con
             __syncthreads();
 
             // ---- two-body: thread <-> (partner element, grid point) ---------------------------------
-            if (M2 == 0) {
+            {
                 const double inv2 = -0.5 / (T.sigma2 * T.sigma2);
                 const double pref = J.local ? 0.5 : 1.0;
                 for (int oidx = tid; oidx < T.n_el * T.nx2; oidx += SL_THREADS) {
@@ -309,7 +286,7 @@ __global__ void __launch_bounds__(SL_THREADS) slatm_kernel(const SlatmDev T, con
                     pp[0] = ang; pp[1] = cak; pp[2] = cai; pp[3] = rinv3;
                 }
                 __syncthreads();
-                if (M2 == 0) {
+                {
                 for (int oidx = tid; oidx < nblk * T.nx3; oidx += SL_THREADS) {
                     int b = oidx / T.nx3, x = oidx - b * T.nx3;
                     const int q0 = max(s_blk[b].p0, P0);
@@ -328,128 +305,6 @@ __global__ void __launch_bounds__(SL_THREADS) slatm_kernel(const SlatmDev T, con
                     }
                     spec[s_blk[b].col + x] += acc;
                 }
-                } else {
-                    // ---- recurrence path: balanced work items over (2-body neighbours | 3-body pairs) -------------
-                    // candidate ci < n_el: 2-body range of partner element ci (first pair chunk only);
-                    // candidate n_el + b: the part of 3-body block b inside this pair chunk.
-                    auto cand_len = [&](int ci) -> int {
-                        if (ci < T.n_el) {
-                            if (P0 != 0) return 0;
-                            int sl = T.bop_slot[ec * MAXEL + ci];
-                            if (sl < 0 || lay[sl] < 0) return 0;
-                            if (!J.local && ci < ec) return 0;  // owned by the other element's block
-                            return s_cnt[ci];
-                        }
-                        int b = ci - T.n_el;
-                        int q0 = max(s_blk[b].p0, P0), q1 = min((b + 1 < nblk) ? s_blk[b + 1].p0 : ptot, P1);
-                        return max(q1 - q0, 0);
-                    };
-                    const int ncand = T.n_el + nblk;
-                    if (warp == 0) {
-                        int W = 0;
-                        for (int c0i = 0; c0i < ncand; c0i += 32) {
-                            int len = (c0i + lane < ncand) ? cand_len(c0i + lane) : 0;
-#pragma unroll
-                            for (int o2 = 16; o2 > 0; o2 >>= 1) len += __shfl_xor_sync(0xffffffffu, len, o2);
-                            W += len;
-                        }
-                        const int cap = max(4, (W + NG - 1) / NG);
-                        int carry = 0;
-                        for (int c0i = 0; c0i < ncand; c0i += 32) {
-                            int ci = c0i + lane;
-                            int len = (ci < ncand) ? cand_len(ci) : 0;
-                            int ni = (len + cap - 1) / cap, incl = ni;
-#pragma unroll
-                            for (int o2 = 1; o2 < 32; o2 <<= 1) {
-                                int u = __shfl_up_sync(0xffffffffu, incl, o2);
-                                if (lane >= o2) incl += u;
-                            }
-                            int off = carry + incl - ni;
-                            for (int k = 0; k < ni; k++) {
-                                Item it;
-                                it.cand = (short)ci; it.begin = (short)(k * cap); it.end = (short)min(len, (k + 1) * cap); it.pad = 0;
-                                s_items[off + k] = it;
-                            }
-                            carry += __shfl_sync(0xffffffffu, incl, 31);
-                        }
-                        if (lane == 0) s_nitems = carry;
-                    }
-                    __syncthreads();
-                    const int nitems = s_nitems;
-                    const int gid = tid >> 3, ch = tid & 7;
-                    for (int r0 = 0; r0 < nitems; r0 += NG) {
-                        if (r0 + gid < nitems) {
-                            const Item it = s_items[r0 + gid];
-                            if (it.cand < T.n_el) {
-                                // two-body: sum_n exp(-(x - r_n)^2 c) over this thread's M2 points, weight at the end
-                                const int e2 = it.cand;
-                                const int nb0 = s_start[e2];
-                                const int j0 = ch * M2;
-                                const double xa = sx2[j0], xb = xa + (M2 - 1) * T.h2;
-                                double a2[M2 > 0 ? M2 : 1];
-#pragma unroll
-                                for (int j = 0; j < M2; j++) a2[j] = 0.0;
-                                for (int n = nb0 + it.begin; n < nb0 + it.end; n++) {
-                                    if (!(nbf[n] & 1)) continue;
-                                    if (!J.local && e2 == ec && nbi[n] < c) continue;  // unordered pair counted once
-                                    const double r = sqrt(nbr2[n]);
-                                    if (r < xb) {  // peak left of / inside the chunk: walk forward from its first point
-                                        const double d = xa - r;
-                                        double E = exp(-(d * d) * T.cst2), R = exp(-(2.0 * d * T.h2 + T.h2 * T.h2) * T.cst2);
-#pragma unroll
-                                        for (int j = 0; j < M2; j++) { a2[j] += E; E *= R; R *= T.q2; }
-                                    } else {       // peak right of the chunk: walk backward from its last point
-                                        const double d = xb - r;
-                                        double E = exp(-(d * d) * T.cst2), R = exp((2.0 * d * T.h2 - T.h2 * T.h2) * T.cst2);
-#pragma unroll
-                                        for (int j = M2 - 1; j >= 0; j--) { a2[j] += E; E *= R; R *= T.q2; }
-                                    }
-                                }
-                                const double c0 = (J.local ? 0.5 : 1.0) * (T.el_w[ec] * T.el_w[e2]) * T.coeff2;
-#pragma unroll
-                                for (int j = 0; j < M2; j++) slab[gid * NXS + j0 + j] = a2[j] * (c0 * sinv2[j0 + j]);
-                            } else {
-                                const int b = it.cand - T.n_el;
-                                const int base = max(s_blk[b].p0, P0) - P0;
-                                const double c0 = s_blk[b].c0;
-                                const int j0 = ch * M3;
-                                const double xa = sx3[j0], xb = xa + (M3 - 1) * T.h3;
-                                double a3[M3 > 0 ? M3 : 1];
-#pragma unroll
-                                for (int j = 0; j < M3; j++) a3[j] = 0.0;
-                                for (int p = base + it.begin; p < base + it.end; p++) {
-                                    const double *pp = pair + 4 * p;
-                                    const double rinv3 = pp[3];
-                                    if (rinv3 == 0.0) continue;
-                                    const double ang = pp[0];
-                                    const double A0 = c0 * rinv3, B0 = (c0 * pp[1] * pp[2]) * rinv3;  // (c0 + cos(x) c0 cak cai)/r^3
-                                    if (ang < xb) {
-                                        const double d = xa - ang;
-                                        double E = exp(-(d * d) * T.cst3), R = exp(-(2.0 * d * T.h3 + T.h3 * T.h3) * T.cst3);
-#pragma unroll
-                                        for (int j = 0; j < M3; j++) { a3[j] += fma(scos3[j0 + j], B0, A0) * E; E *= R; R *= T.q3; }
-                                    } else {
-                                        const double d = xb - ang;
-                                        double E = exp(-(d * d) * T.cst3), R = exp((2.0 * d * T.h3 - T.h3 * T.h3) * T.cst3);
-#pragma unroll
-                                        for (int j = M3 - 1; j >= 0; j--) { a3[j] += fma(scos3[j0 + j], B0, A0) * E; E *= R; R *= T.q3; }
-                                    }
-                                }
-#pragma unroll
-                                for (int j = 0; j < M3; j++) slab[gid * NXS + j0 + j] = a3[j];
-                            }
-                        }
-                        __syncthreads();
-                        // fixed-order accumulation of the groups' partial spectra: deterministic, no atomics
-                        for (int g2 = 0; g2 < NG && r0 + g2 < nitems; g2++) {
-                            const Item it = s_items[r0 + g2];
-                            int col, nx;
-                            if (it.cand < T.n_el) { col = lay[T.bop_slot[ec * MAXEL + it.cand]]; nx = T.nx2; }
-                            else { col = s_blk[it.cand - T.n_el].col; nx = T.nx3; }
-                            for (int x = tid; x < nx; x += SL_THREADS) spec[col + x] += slab[g2 * NXS + x];
-                        }
-                        __syncthreads();
-                    }
                 }
             }
         }
@@ -724,20 +579,16 @@ static MolIndex index_molecules(const int *nas, int nmol) {
     return mi;
 }
 
-static size_t slatm_smem_bytes(int pldmax, int na_max, int m2, int m3) {
-    size_t doubles = (size_t)pldmax + 10 * (size_t)na_max + 4 * PCH;
-    size_t ints = 5 * (size_t)na_max + (na_max & 1);
-    size_t extra = (m2 > 0) ? (size_t)NG * 8 * std::max(m2, m3) + 16 * (size_t)m2 + 16 * (size_t)m3 : 0;
-    return sizeof(double) * (doubles + extra) + sizeof(int) * ints;
+static size_t slatm_smem_bytes(int pldmax, int na_max) {
+    return sizeof(double) * ((size_t)pldmax + 10 * (size_t)na_max + 4 * PCH) + sizeof(int) * (5 * (size_t)na_max + 2);
 }
 
-template <int M2, int M3>
-static void launch_slatm_t(const SlatmTables &t, const SlatmJob &J, int nblocks, int na_max, cudaStream_t st) {
-    size_t smem = slatm_smem_bytes(t.pldmax, na_max, M2, M3);
+static void launch_slatm_general(const SlatmTables &t, const SlatmJob &J, int nblocks, int na_max, cudaStream_t st) {
+    size_t smem = slatm_smem_bytes(t.pldmax, na_max);
     if (smem > 200 * 1024)
         fail(AQML_ELIMIT, "molecule with %d atoms / support %d needs %zu B of shared memory (limit 200 KiB)", na_max, t.pldmax, smem);
-    AQML_CUDA(cudaFuncSetAttribute(slatm_kernel<M2, M3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    slatm_kernel<M2, M3><<<nblocks, SL_THREADS, smem, st>>>(t.dev, J, t.pldmax, na_max);
+    AQML_CUDA(cudaFuncSetAttribute(slatm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    slatm_kernel<<<nblocks, SL_THREADS, smem, st>>>(t.dev, J, t.pldmax, na_max);
     AQML_LAUNCH_CHECK();
 }
 
@@ -797,11 +648,8 @@ static void launch_slatm(const SlatmTables &t, const SlatmJob &J, const MolIndex
         else if (safe(20, 16)) { if (launch_units_t<20, 16>(t, J, mi, ws)) return; }
         else if (safe(32, 32)) { if (launch_units_t<32, 32>(t, J, mi, ws)) return; }
     }
-    // block-per-centre kernel: global SLATM, and aSLATM outside the recurrence's safe range
-    if (safe(15, 12)) launch_slatm_t<15, 12>(t, J, nblocks, na_max, st);
-    else if (safe(20, 16)) launch_slatm_t<20, 16>(t, J, nblocks, na_max, st);
-    else if (safe(32, 32)) launch_slatm_t<32, 32>(t, J, nblocks, na_max, st);
-    else launch_slatm_t<0, 0>(t, J, nblocks, na_max, st);
+    // general kernel: global SLATM of large molecules, grids outside the recurrence's safe range
+    launch_slatm_general(t, J, nblocks, na_max, st);
 }
 
 static void slatm_batch_dev(const double *coords, const int *zs_dev, const int *nas, int nmol, const aqml_slatm_params *p,
