@@ -1,1 +1,1 @@
-from aqml_b200.algo.aqml import fobj, get_kernel_width  # noqa: F401
+from aqml_b200.algo.aqml import fobj, get_kernel_width, calc_ka  # noqa: F401
