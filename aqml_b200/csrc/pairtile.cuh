@@ -1,10 +1,11 @@
 // Pair-tile engine: every kernel-matrix / distance routine of the hot path is one instance of
 //
-//     for a 128x64 tile of (row i of A, row j of B):  v_ij = reduce_k f(A[i,k], B[j,k])
+//     for a 64x64 tile of (row i of A, row j of B):  v_ij = reduce_k f(A[i,k], B[j,k])
 //     then an epilogue on v_ij
 //
-//   MODE_DOT : v = max(|a|^2 + |b|^2 - 2 a.b, 0); the cross term runs on the FP64 tensor cores
-//              (DMMA.8x8x4), operands staged through a 4-deep cp.async shared-memory pipeline.
+//   MODE_DOT : v = max(|a|^2 + |b|^2 - 2 a.b, 0); the cross term runs on the FP64 tensor path
+//              (DMMA.8x8x4), operands staged through a 3-deep cp.async shared-memory pipeline; only
+//              the k-tiles that are non-zero in both operand blocks are visited (exact block sparsity).
 //   MODE_L1  : v = sum_k |a_k - b_k| on the FP64 CUDA cores (not a contraction), same staging.
 //
 //   EPI_EXP_STORE  : K[s][i][j] = exp(v * isig[s])          global Gaussian/Laplacian, all sigmas in one pass
@@ -25,7 +26,8 @@ namespace aqml {
 // CTA tile (16*MI) x 64, 4 warps (2 x 2, warp tile (8*MI) x 32), 3-stage pipeline.  MI=8: 128x64 tile,
 // 92 KB smem, <=240 regs -> 2 CTAs/SM.  MI=4: 64x64 tile, 61 KB smem, <=168 regs -> 3 CTAs/SM.  Several
 // resident CTAs matter because the epilogue (exp + segmented reduction) and the per-k-tile barrier leave
-// the tensor pipe idle: another CTA's DMMA stream fills those gaps (measured: 76% busy with one 128x128 CTA).
+// the FP64 units idle: another CTA's DMMA stream fills those gaps (measured: 76% busy with one 128x128 CTA,
+// 84% with 2 x (128x64), 84% on half the work with 3 x (64x64); profiles/history).
 #ifndef AQML_MI
 #define AQML_MI 4
 #endif
@@ -44,7 +46,7 @@ constexpr int STAGES = AQML_STAGES;
 constexpr int WARPS_N = BN / 32;
 constexpr int NT = 64 * WARPS_N;  // 2 (M) x WARPS_N (N) warps
 constexpr int STAGE_DOUBLES = (BM + BN) * PITCH;
-constexpr int PIPE_BYTES = STAGES * STAGE_DOUBLES * 8;  // 92160
+constexpr int PIPE_BYTES = STAGES * STAGE_DOUBLES * 8;  // 61440 for the default 64x64 tile, 3 stages
 constexpr int EPITCH = 40;     // per-warp staging pitch (doubles) for the segmented epilogue
 static_assert((NT / 32) * WROWS * EPITCH * 8 <= PIPE_BYTES, "epilogue staging must fit in the pipeline buffers");
 
