@@ -392,6 +392,11 @@ def run_ours(args):
                          "executed_tflops": kt_exec * ktile_flops / (t_kernel_ms * 1e-3) / 1e12,
                          "executed_frac_of_peak": kt_exec * ktile_flops / (t_kernel_ms * 1e-3) / 1e12 / peak_tf,
                          "ktiles_executed_over_dense": kt_exec / max(kt_dense, 1.0),
+                         "note": "achieved/frac use the SURVEY 8(d) algorithmic flop count 2*sum_z D_z*n1_z*n2_z; frac > 1 "
+                                 "because 16-column k-tiles that are all-zero in either 64-row operand block are skipped "
+                                 "(exact, bit-identical; counted on the device). Hardware utilisation = "
+                                 "executed_frac_of_peak; the FP64 DMMA/DFMA ceiling of the chip is 37.0 TF "
+                                 "(profiles/r01_micro_dmma_dfma.txt)",
                          "peak_source": "cuBLAS DGEMM 8192^3 best of 10 measured in this run "
                                         "(MEASURED_PEAKS.json has no FP64 entry)"},
             "roofline_aslatm": {"bound": "hbm", "kernel": "slatm_kernel (packed output)",
