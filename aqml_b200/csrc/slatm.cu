@@ -592,7 +592,7 @@ static void launch_slatm_general(const SlatmTables &t, const SlatmJob &J, int nb
     AQML_LAUNCH_CHECK();
 }
 
-template <int M2, int M3>
+template <int M2, int M3, int GS>
 static bool launch_units_t(const SlatmTables &t, const SlatmJob &J, const MolIndex &mi, Workspace &ws) {
     // batches: contiguous centre atoms of one molecule; the neighbour tables of a batch take 11 B per
     // (centre, atom) pair of shared memory -- 35 B with the unit vectors
@@ -620,11 +620,11 @@ static bool launch_units_t(const SlatmTables &t, const SlatmJob &J, const MolInd
     const int na_max = (int)round_up(std::max(mi.na_max, 1), 2);
     nbn_max = (int)round_up(nbn_max, 4);
     ba_max = std::max(ba_max, t.dev.n_el);
-    size_t smem = sizeof(double) * (3 * (size_t)na_max + 4 * (size_t)nbn_max + (size_t)ba_max * uc + 16 * M2 + 16 * M3) +
+    size_t smem = sizeof(double) * (3 * (size_t)na_max + 4 * (size_t)nbn_max + (size_t)ba_max * uc + 2 * GS * M2 + 2 * GS * M3) +
                   sizeof(int) * na_max + sizeof(short) * ((size_t)nbn_max + (size_t)ba_max * (MAXEL + 1) + 4) + nbn_max + 16;
     if (smem > 160 * 1024 || mi.na_max > 30000) return false;
-    AQML_CUDA(cudaFuncSetAttribute(slatm_units_kernel<M2, M3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    slatm_units_kernel<M2, M3><<<(unsigned)batches.size(), SL_THREADS, smem, ws.stream()>>>(
+    AQML_CUDA(cudaFuncSetAttribute(slatm_units_kernel<M2, M3, GS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    slatm_units_kernel<M2, M3, GS><<<(unsigned)batches.size(), SL_THREADS, smem, ws.stream()>>>(
         t.dev, J, ws.upload(batches), na_max, nbn_max, ba_max, uc);
     AQML_LAUNCH_CHECK();
     return true;
@@ -644,9 +644,10 @@ static void launch_slatm(const SlatmTables &t, const SlatmJob &J, const MolIndex
     };
     static const bool force_legacy = getenv("AQML_SLATM_LEGACY") != nullptr;
     if (!force_legacy) {  // work-unit kernel (aSLATM; SLATM of molecules with <= 36 atoms)
-        if (safe(15, 12)) { if (launch_units_t<15, 12>(t, J, mi, ws)) return; }
-        else if (safe(20, 16)) { if (launch_units_t<20, 16>(t, J, mi, ws)) return; }
-        else if (safe(32, 32)) { if (launch_units_t<32, 32>(t, J, mi, ws)) return; }
+        // 8 threads per unit measured best (4: 10.8e6 atoms/s, 8: 16.8e6, 16: 16.0e6 on the bench workload)
+        if (safe(15, 12)) { if (launch_units_t<15, 12, 8>(t, J, mi, ws)) return; }
+        else if (safe(20, 16)) { if (launch_units_t<20, 16, 8>(t, J, mi, ws)) return; }
+        else if (safe(32, 32)) { if (launch_units_t<32, 32, 8>(t, J, mi, ws)) return; }
     }
     // general kernel: global SLATM of large molecules, grids outside the recurrence's safe range
     launch_slatm_general(t, J, nblocks, na_max, st);

@@ -27,16 +27,17 @@ __device__ __forceinline__ double gshfl(double v, int src, unsigned gmask, int g
     return __shfl_sync(gmask, v, gbase + src);
 }
 
-template <int M2, int M3>
-__global__ void __launch_bounds__(SL_THREADS, 4)
+// GS = threads per work unit (4 or 8); M2/M3 = grid points per thread (GS*M >= nx)
+template <int M2, int M3, int GS>
+__global__ void __launch_bounds__(SL_THREADS, (GS == 16) ? 5 : (GS == 8) ? 4 : 3)
 slatm_units_kernel(const SlatmDev T, const SlatmJob J, const Batch *batches, int na_max, int nbn_max, int ba_max, int uc) {
     extern __shared__ __align__(16) double sm[];
     double *mx = sm, *my = mx + na_max, *mz = my + na_max;
     double *dd = mz + na_max;                          // [ba][na] distance centre -> atom q
     double *ux = dd + nbn_max, *uy = ux + nbn_max, *uz = uy + nbn_max;  // [ba][na] unit vector centre -> q
     double *s_norm = uz + nbn_max;                     // [ba][uc] sum of squares of each written block
-    double *sx2 = s_norm + ba_max * uc, *sinv2 = sx2 + 8 * M2, *sx3 = sinv2 + 8 * M2, *scos3 = sx3 + 8 * M3;
-    int *mel = reinterpret_cast<int *>(scos3 + 8 * M3);
+    double *sx2 = s_norm + ba_max * uc, *sinv2 = sx2 + GS * M2, *sx3 = sinv2 + GS * M2, *scos3 = sx3 + GS * M3;
+    int *mel = reinterpret_cast<int *>(scos3 + GS * M3);
     short *nbidx = reinterpret_cast<short *>(mel + na_max);   // [ba][na] neighbours sorted by element
     short *sstart = nbidx + nbn_max;                           // [ba][MAXEL+1]
     unsigned char *fls = reinterpret_cast<unsigned char *>(sstart + ba_max * (MAXEL + 1));  // [ba][na]
@@ -48,12 +49,12 @@ slatm_units_kernel(const SlatmDev T, const SlatmJob J, const Batch *batches, int
     const Batch bt = batches[blockIdx.x];
     const int o = J.mol_off[bt.mol], na = J.mol_off[bt.mol + 1] - o;
 
-    for (int i = tid; i < 8 * M2; i += SL_THREADS) {
+    for (int i = tid; i < GS * M2; i += SL_THREADS) {
         int q = min(i, T.nx2 - 1);
         sx2[i] = T.xs2[q];
         sinv2[i] = T.inv2[q];
     }
-    for (int i = tid; i < 8 * M3; i += SL_THREADS) {
+    for (int i = tid; i < GS * M3; i += SL_THREADS) {
         int q = min(i, T.nx3 - 1);
         sx3[i] = T.xs3[q];
         scos3[i] = T.cosx3[q];
@@ -118,8 +119,8 @@ slatm_units_kernel(const SlatmDev T, const SlatmJob J, const Batch *batches, int
     __syncthreads();
 
     // ---- phase 2: work units -----------------------------------------------------------------------
-    const int ch = tid & 7, gbase = lane & ~7;
-    const unsigned gmask = 0xffu << gbase;
+    const int ch = tid & (GS - 1), gbase = lane & ~(GS - 1);
+    const unsigned gmask = ((1u << GS) - 1u) << gbase;
     // R(x_j0) = Rg * exp(-2 j0 h^2 c): Rg (first grid point) is computed once per entry and shared
     const double qm2 = exp(-2.0 * (ch * M2) * T.h2 * T.h2 * T.cst2);
     const double qm3 = exp(-2.0 * (ch * M3) * T.h3 * T.h3 * T.cst3);
@@ -155,8 +156,8 @@ slatm_units_kernel(const SlatmDev T, const SlatmJob J, const Batch *batches, int
                     const short *nb = nbidx + ai * na;
                     const double *dr = dd + ai * na;
                     const unsigned char *fr = fls + ai * na;
-                    for (int n0 = st[e2]; n0 < st[e2 + 1]; n0 += 8) {
-                        // my neighbour of this octet: distance and the grid-start ratio, shared by shuffles
+                    for (int n0 = st[e2]; n0 < st[e2 + 1]; n0 += GS) {
+                        // my neighbour of this group-sized batch: distance and the grid-start ratio, shared by shuffles
                         double g_r = -1.0, g_R = 0.0;
                         if (n0 + ch < st[e2 + 1]) {
                             const int q = nb[n0 + ch];
@@ -166,7 +167,7 @@ slatm_units_kernel(const SlatmDev T, const SlatmJob J, const Batch *batches, int
                                 g_R = exp(-(2.0 * (sx2[0] - g_r) * T.h2 + T.h2 * T.h2) * T.cst2);
                             }
                         }
-                        const int nt = min(8, st[e2 + 1] - n0);
+                        const int nt = min(GS, st[e2 + 1] - n0);
                         for (int t = 0; t < nt; t++) {
                             const double r = gshfl(g_r, t, gmask, gbase);
                             if (r < 0.0) continue;  // outside the 2-body cut-off (group-uniform)
@@ -219,8 +220,8 @@ slatm_units_kernel(const SlatmDev T, const SlatmJob J, const Batch *batches, int
                     const unsigned char *fr = fls + ai * na;
                     const int n1 = st[B.e1 + 1] - st[B.e1], n3 = st[B.e3 + 1] - st[B.e3];
                     const int np = (B.e1 == B.e3) ? n1 * (n1 - 1) / 2 : n1 * n3;
-                    for (int p0 = 0; p0 < np; p0 += 8) {
-                        // my pair of this octet: geometry once, shared with the group by shuffles
+                    for (int p0 = 0; p0 < np; p0 += GS) {
+                        // my pair of this group-sized batch: geometry once, shared with the group by shuffles
                         double g_ang = 0.0, g_A = 0.0, g_B = 0.0, g_R = 0.0;
                         int p = p0 + ch;
                         if (p < np) {
@@ -259,7 +260,7 @@ slatm_units_kernel(const SlatmDev T, const SlatmJob J, const Batch *batches, int
                                 }
                             }
                         }
-                        const int nt = min(8, np - p0);
+                        const int nt = min(GS, np - p0);
                         for (int t = 0; t < nt; t++) {
                             const double A0 = gshfl(g_A, t, gmask, gbase);
                             if (A0 == 0.0) continue;  // pair failed a cut-off test (group-uniform)
@@ -298,7 +299,8 @@ slatm_units_kernel(const SlatmDev T, const SlatmJob J, const Batch *batches, int
         // block's sum of squares: fixed-order tree over the 8 threads of the group
         ssq += __shfl_xor_sync(gmask, ssq, 1);
         ssq += __shfl_xor_sync(gmask, ssq, 2);
-        ssq += __shfl_xor_sync(gmask, ssq, 4);
+        if (GS >= 8) ssq += __shfl_xor_sync(gmask, ssq, 4);
+        if (GS >= 16) ssq += __shfl_xor_sync(gmask, ssq, 8);
         if (ch == 0) s_norm[ui * uc + ci] = ssq;
     }
     __syncthreads();
