@@ -83,3 +83,44 @@ def test_synth_is_deterministic():
     nas, zs, co = a
     assert nas.sum() == len(zs) == len(co) and nas.max() <= 29
     assert set(np.unique(zs)) <= {1, 6, 7, 8, 9}
+
+
+def test_tile_shape_and_counters_without_device():
+    import ctypes as C
+    lib = L.load()
+    bm, bn, bk = C.c_int(0), C.c_int(0), C.c_int(0)
+    lib.aqml_tile_shape(C.c_void_p(C.addressof(bm)), C.c_void_p(C.addressof(bn)), C.c_void_p(C.addressof(bk)))
+    assert (bm.value, bn.value, bk.value) == (64, 64, 16)
+    assert lib.aqml_launch_count() >= 0 and lib.aqml_device_count() >= 0
+
+
+def test_krr_helpers_on_golden(demo):
+    """Host-side consumers (aqml.py:129-181,806-897; rkrr.py:203-228) against the golden kernels: the README curve."""
+    from aqml_b200.algo import krr
+    n1 = int(demo["n1"])
+    nas, zs = demo["nas"], demo["zs"]
+    zs_list = synth.split_zs(nas, zs)
+    zsu = np.unique(zs)
+    ngs = np.array([[(z == zz).sum() for zz in zsu] for z in zs_list])
+    nheav = np.array([(z > 1).sum() for z in zs_list[:n1]])
+    ys = demo["energies"] * krr.H2KC
+    free = [krr.H2KC * o.ORCA_B3LYPVDZ[int(z)] for z in zsu]
+    rows = krr.learning_curve(demo["k1"][1], demo["k2"][1], ngs, ys, nheav, free, 1e-4)
+    for r, ref in zip(rows, demo["readme_curve"]):
+        assert (r[0], r[1]) == (ref[0], ref[1]) and abs(r[2] - ref[2]) < 5.1e-5
+
+
+def test_reference_file_formats(tmp_path, monkeypatch):
+    """Same file names / npz keys as `aqml -savex -savek` (aqml.py:626-665,719,736,795)."""
+    from aqml_b200 import io as aio
+    monkeypatch.chdir(tmp_path)
+    assert aio.stem("g7/") == "data/g7" and aio.stem("a/b", rcut=3.0, z=6) == "data/a-b-rc3.0-z6"
+    x1 = np.arange(12.0).reshape(3, 4)
+    aio.save_x1("g7/", x1)
+    assert os.path.exists("data/g7-x1.npz") and np.array_equal(np.load("data/g7-x1.npz")["x1"], x1)
+    assert np.array_equal(aio.load_x1("g7"), x1)
+    ks1, ks2 = np.ones((2, 3, 3)), np.zeros((2, 1, 3))
+    aio.save_kernels("g7/", ks1, ks2, kernel="l")
+    assert os.path.exists("data/g7-kernels-l.npz")
+    a, b = aio.load_kernels("g7", kernel="l")
+    assert np.array_equal(a, ks1) and np.array_equal(b, ks2)
