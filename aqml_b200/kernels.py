@@ -216,3 +216,25 @@ def calc_lk_gaussian(x1_t, x2_t, zs1, zs2, nas1, nas2, zmax, iab, sigmas, nm1=No
 
 def calc_lk_laplacian(x1_t, x2_t, nas1, nas2, sigmas, nm1=None, nm2=None, nsigmas=None):
     return get_local_kernels_laplacian(np.asarray(x1_t).T, np.asarray(x2_t).T, nas1, nas2, sigmas)
+
+
+def _unpad(x_t, nas):
+    """Fortran x(D, maxatoms, nm) (f2py view of a C-ordered (nm, maxatoms, D) array) -> (sum nas, D) rows."""
+    x = np.asarray(x_t)
+    if x.ndim != 3:
+        raise ValueError("expected a 3-D padded array")
+    x = x.transpose(2, 1, 0) if x.flags.f_contiguous or x.shape[0] != len(nas) else x
+    return np.concatenate([x[i, :int(n)] for i, n in enumerate(nas)])
+
+
+def calc_vector_kernels_gaussian(x1_t, x2_t, nas1, nas2, sigmas, nm1=None, nm2=None, nsigmas=None):
+    """fkernels.f90:255-324: local Gaussian kernel on zero-padded per-molecule arrays, every atom pair, one
+    sigma set.  (No Python wrapper upstream; provided as the f2py-level name.)"""
+    a, b = _unpad(x1_t, nas1), _unpad(x2_t, nas2)
+    sig = L.f64(sigmas).reshape(-1, 1)
+    return get_local_kernels_gaussian(a, b, np.ones(len(a), np.int32), np.ones(len(b), np.int32), nas1, nas2, True, 1, sig)
+
+
+def calc_vector_kernels_laplacian(x1_t, x2_t, nas1, nas2, sigmas, nm1=None, nm2=None, nsigmas=None):
+    """fkernels.f90:185-253."""
+    return get_local_kernels_laplacian(_unpad(x1_t, nas1), _unpad(x2_t, nas2), nas1, nas2, sigmas)

@@ -218,3 +218,27 @@ def test_linear_matern_sargan(slatm_set):
     assert rel_err(kernels.sargan_kernel(A, B, s1, g), np.exp(-x) * (1 + g[0] * x + g[1] * x ** 2 + g[2] * x ** 3)) < 1e-12
     with pytest.raises(SystemExit):
         kernels.matern_kernel(A, B, 1.0, 0, "l3")
+
+
+def test_vector_kernels_on_padded_arrays(slatm_set):
+    """fkernels.f90:185-324 (f2py-level names): zero-padded (nm, maxatoms, D) inputs, all atom pairs."""
+    s = slatm_set
+    off = np.concatenate(([0], np.cumsum(s["nas"])))
+    nas1, nas2 = s["nas"][:7], s["nas"][7:12]
+    x1, x2 = s["xl"][:off[7]], s["xl"][off[7]:off[12]]
+
+    def pad(x, nas):
+        out = np.zeros((len(nas), int(nas.max()), x.shape[1]))
+        o2 = np.concatenate(([0], np.cumsum(nas)))
+        for i, n in enumerate(nas):
+            out[i, :n] = x[o2[i]:o2[i + 1]]
+        return out
+
+    p1, p2 = pad(x1, nas1), pad(x2, nas2)
+    sig = [20.0, 40.0]
+    Kg = kernels.calc_vector_kernels_gaussian(p1.T, p2.T, nas1, nas2, sig)  # .T = what f2py receives
+    z1, z2 = np.ones(len(x1), np.int32), np.ones(len(x2), np.int32)
+    ref = co.calc_lk_gaussian(x1, x2, z1, z2, nas1, nas2, 1, True, np.array(sig).reshape(-1, 1))
+    assert rel_err(Kg, ref) < TOL
+    Kl = kernels.calc_vector_kernels_laplacian(p1, p2, nas1, nas2, [500., 900.])
+    assert rel_err(Kl, co.calc_lk_laplacian(x1, x2, nas1, nas2, [500., 900.])) < TOL
