@@ -83,3 +83,41 @@ def test_learning_curve_and_multifidelity(demo):
         kk[np.diag_indices_from(kk)] += 1e-6
         pred += k2[:, :n] @ np.linalg.solve(kk, tgt - ngs[:n] @ esb) + ngs[n1:] @ esb
     assert np.allclose(got, pred, rtol=1e-12, atol=1e-9)
+
+
+def test_amons_workflow_per_query_sigmas():
+    """every query is trained on its own amon subset (maps, -1 padded) with its own
+    per-element dmax -> sigmas; compared with the restated reference iteration for each query."""
+    from aqml_b200.algo import amons as wf
+    rng = np.random.default_rng(9)
+    gen = np.random.Generator(np.random.PCG64(101))
+    heavy = ([6, 7, 8], [0.6, 0.2, 0.2])  # every element occurs many times: dmax > 0 for all of them
+
+    def make(n, lo, hi):
+        ms = [synth.make_molecule(gen, int(gen.integers(lo, hi + 1)), heavy=heavy) for _ in range(n)]
+        return (np.array([len(z) for z, _ in ms], dtype=np.int32), np.concatenate([z for z, _ in ms]),
+                np.concatenate([x for _, x in ms]))
+
+    pool, queries = make(40, 2, 5), make(4, 7, 9)
+    maps = np.full((4, 14), -1, dtype=np.int64)
+    for q in range(4):
+        k = int(rng.integers(6, 14))
+        maps[q, :k] = rng.choice(40, k, replace=False)
+    zl = synth.split_zs(pool[0], pool[1]) + synth.split_zs(queries[0], queries[1])
+    mb = o.get_slatm_mbtypes(zl)
+    kw = dict(sigmas=(.05, .05), dgrids=(.04, .04), rcut=4.8)
+    res = wf.query_kernels(pool, queries, maps, coeffs=(0.5, 1.0), mbtypes=mb)
+    zmax = int(max(pool[1].max(), queries[1].max()))
+    for q, (idx, sig, ks1, ks2) in enumerate(res):
+        assert idx == sorted(int(i) for i in maps[q][maps[q] > -1])
+        a = wf._subset(*pool, idx)
+        t = wf._subset(*queries, [q])
+        x1 = co.generate_slatm_batch(a[2], a[1], a[0], mb, True, **kw)
+        x2 = co.generate_slatm_batch(t[2], t[1], t[0], mb, True, **kw)
+        dso = co.get_kernel_width(np.concatenate((a[0], t[0])), np.concatenate((a[1], t[1])), np.concatenate((x1, x2)))
+        dso = np.concatenate((dso, np.full(zmax - len(dso), 1e-9)))
+        ref_sig = np.array([o.width_factor() * dso * c for c in (0.5, 1.0)])
+        assert np.allclose(sig, ref_sig, rtol=1e-10, atol=0)
+        r1 = co.calc_lk_gaussian(x1, x1, a[1], a[1], a[0], a[0], zmax, False, ref_sig)
+        r2 = co.calc_lk_gaussian(x2, x1, t[1], a[1], t[0], a[0], zmax, False, ref_sig)
+        assert rel_err(ks1, r1) < 1e-9 and rel_err(ks2, r2) < 1e-9
