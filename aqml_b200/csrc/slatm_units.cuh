@@ -6,7 +6,8 @@
 //   phase 2  work units (centre atom, many-body block) are handed out dynamically to 8-thread groups.
 //            A unit owns one output block (118 or 96 grid points): each thread keeps M consecutive grid
 //            points in registers, walks the unit's neighbours (2-body) or neighbour pairs (3-body;
-//            geometry of 8 pairs at a time is computed one pair per thread and shared by shuffles), and
+//            geometry of 8 pairs at a time is computed one pair per thread and shared through a
+//            shared-memory mailbox), and
 //            evaluates the Gaussians by the two-term recurrence  E(x+h) = E(x) R(x), R(x+h) = R(x) q
 //            from an exactly evaluated first point of its chunk: 1 exp per (entry, thread) instead of M
 //            (R at the grid start is one more exp per entry, shared).  A chunk that starts > 38 sigma
@@ -27,7 +28,38 @@ __device__ __forceinline__ double gshfl(double v, int src, unsigned gmask, int g
     return __shfl_sync(gmask, v, gbase + src);
 }
 
+// exp(x) for x <= 0 in the inner loops: k = rint(x log2 e), r = x - k ln 2 (two-term), degree-13 Taylor
+// polynomial on |r| <= 0.347 (truncation 4e-18), scaled by 2^k built from the exponent bits.  Relative error
+// <= 2 ulp; results below 2^-1021 are flushed to 0 (the library exp keeps denormals).  About half the
+// instructions of the library routine, whose constant set-up and special-case path dominate here.
+__constant__ double c_expc[12] = {1.0 / 6227020800.0, 1.0 / 479001600.0, 1.0 / 39916800.0, 1.0 / 3628800.0,
+                                  1.0 / 362880.0,     1.0 / 40320.0,     1.0 / 5040.0,     1.0 / 720.0,
+                                  1.0 / 120.0,        1.0 / 24.0,        1.0 / 6.0,        0.5};
+__device__ __forceinline__ double exp_nonpos(double x) {
+    if (x < -707.0) return 0.0;
+    const double magic = 6755399441055744.0;  // 1.5 * 2^52: adding it rounds to nearest integer
+    double t = fma(x, 1.4426950408889634, magic);
+    const int k = __double2loint(t);
+    t -= magic;
+    double r = fma(t, -6.93147180369123816490e-01, x);
+    r = fma(t, -1.90821492927058770002e-10, r);
+    double p = c_expc[0];
+#pragma unroll
+    for (int i = 1; i < 12; i++) p = fma(p, r, c_expc[i]);
+    p = fma(p, r, 1.0);
+    p = fma(p, r, 1.0);
+    return p * __hiloint2double((k + 1023) << 20, 0);
+}
+
 // GS = threads per work unit (4 or 8); M2/M3 = grid points per thread (GS*M >= nx)
+__device__ __forceinline__ int mel_of(const SlatmJob &J, const SlatmDev &T, long long atom) {
+    const int z = J.zs[atom];
+    int e = -1;
+    for (int q = 0; q < T.n_el; q++)
+        if (T.el_label[q] == z) e = q;
+    return e;
+}
+
 template <int M2, int M3, int GS>
 __global__ void __launch_bounds__(SL_THREADS, (GS == 16) ? 5 : (GS == 8) ? 4 : 3)
 slatm_units_kernel(const SlatmDev T, const SlatmJob J, const Batch *batches, int na_max, int nbn_max, int ba_max, int uc) {
@@ -41,7 +73,8 @@ slatm_units_kernel(const SlatmDev T, const SlatmJob J, const Batch *batches, int
     short *nbidx = reinterpret_cast<short *>(mel + na_max);   // [ba][na] neighbours sorted by element
     short *sstart = nbidx + nbn_max;                           // [ba][MAXEL+1]
     unsigned char *fls = reinterpret_cast<unsigned char *>(sstart + ba_max * (MAXEL + 1));  // [ba][na]
-    __shared__ int s_next;
+    __shared__ double4 s_mbox[SL_THREADS];  // per thread: the geometry of "its" entry, read by its whole group
+    __shared__ int s_next, s_next3, s_fetch[SL_THREADS / GS];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const double eps = 2.220446049250313e-16;
@@ -68,7 +101,19 @@ slatm_units_kernel(const SlatmDev T, const SlatmJob J, const Batch *batches, int
             if (T.el_label[q] == z) e = q;
         mel[i] = e;
     }
-    if (tid == 0) s_next = 0;
+    if (tid == 0) { s_next = 0; s_next3 = 0; }
+    if (J.local) for (int i = tid; i < bt.cnt * uc; i += SL_THREADS) s_norm[i] = 0.0;
+    // packed output: clear the rows too -- units without a single entry are then never visited
+    if (J.local && J.atom_prow) {
+        for (int ai = 0; ai < bt.cnt; ai++) {
+            const int e = mel_of(J, T, o + bt.a0 + ai);
+            const int pr = J.atom_prow[o + bt.a0 + ai];
+            if (e >= 0 && pr >= 0) {
+                double *row = J.px[e] + (long long)pr * T.pld[e];
+                for (int x = tid; x < T.pld[e]; x += SL_THREADS) row[x] = 0.0;
+            }
+        }
+    }
     // dense output: clear the rows, the units overwrite their blocks after the barrier
     if (J.out) {
         const int nrows = J.local ? bt.cnt : 1;
@@ -118,190 +163,248 @@ slatm_units_kernel(const SlatmDev T, const SlatmJob J, const Batch *batches, int
     }
     __syncthreads();
 
-    // ---- phase 2: work units -----------------------------------------------------------------------
-    const int ch = tid & (GS - 1), gbase = lane & ~(GS - 1);
+    // ---- phase 2: work units, executed warp-lockstep ---------------------------------------------------
+    // Every 8-thread group owns one unit at a time, but the four groups of a warp walk through the same
+    // code together: per pass each group takes the next batch of GS entries of ITS unit (geometry by one
+    // thread per entry -> mailbox), then all groups run the GS-entry accumulation loop.  Divergence is
+    // confined to unit boundaries (write-out + fetching the next non-empty unit); with independently
+    // looping groups only 46 % of the lanes were active per issued instruction.
+    constexpr unsigned FULL = 0xffffffffu;
+    const int ch = tid & (GS - 1), gbase = lane & ~(GS - 1), gtid0 = tid & ~(GS - 1), gid = tid / GS;
     const unsigned gmask = ((1u << GS) - 1u) << gbase;
     // R(x_j0) = Rg * exp(-2 j0 h^2 c): Rg (first grid point) is computed once per entry and shared
     const double qm2 = exp(-2.0 * (ch * M2) * T.h2 * T.h2 * T.cst2);
     const double qm3 = exp(-2.0 * (ch * M3) * T.h3 * T.h3 * T.cst3);
     const bool loc = J.local != 0;
-    const int nunits = (loc ? bt.cnt : T.n_el) * uc;  // global SLATM: unit = (element, block), summed over its centres
-    for (;;) {
-        int u = 0;
-        if (ch == 0) u = atomicAdd(&s_next, 1);
-        u = __shfl_sync(gmask, u, gbase);
-        if (u >= nunits) break;
-        const int ui = u / uc, ci = u - ui * uc;
-        const int ec = loc ? mel[bt.a0 + ui] : ui;
-        const int c_lo = loc ? ui : 0, c_hi = loc ? ui + 1 : bt.cnt;   // centres (batch-relative) of this unit
+    const int nown = loc ? bt.cnt : T.n_el;  // unit owners: centre atoms (aSLATM) or elements (SLATM, summed over centres)
+
+    auto group_fetch = [&](int *counter) -> int {  // one atomic per group, broadcast through shared memory
+        if (ch == 0) s_fetch[gid] = atomicAdd(counter, 1);
+        __syncwarp(gmask);
+        const int u = s_fetch[gid];
+        __syncwarp(gmask);
+        return u;
+    };
+    // store one finished block: dense row and/or packed operand row, sum of squares, k-tile mask bits
+    auto write_block = [&](const double *acc, int m, int nx, int ui, int cidx, int ec, int col, int dcol) {
         const long long orow = loc ? (long long)(o + bt.a0 + ui) : (long long)bt.mol;
-        double ssq = 0.0;  // this thread's share of the block's sum of squares
-        if (ec >= 0) {
-            const int *lay = T.lay_col + ec * T.nmb;
-            const int pr = (loc && J.atom_prow) ? J.atom_prow[o + bt.a0 + ui] : -1;
-            int col = -1, dcol = -1, nx = 0;
-            if (ci < T.n_el) {
-                const int sl = T.bop_slot[ec * MAXEL + ci];
-                if (sl >= 0) { col = lay[sl]; dcol = T.slot_col[sl]; nx = T.nx2; }
-                if (col >= 0) {
-                    const int e2 = ci, j0 = ch * M2;
-                    double a2[M2];
-#pragma unroll
-                    for (int j = 0; j < M2; j++) a2[j] = 0.0;
-                    const double xa = sx2[j0];
-                    for (int ai = c_lo; ai < c_hi; ai++) {
-                    const int c = bt.a0 + ai;
-                    if (mel[c] != ec) continue;
-                    const short *st = sstart + ai * (MAXEL + 1);
-                    const short *nb = nbidx + ai * na;
-                    const double *dr = dd + ai * na;
-                    const unsigned char *fr = fls + ai * na;
-                    for (int n0 = st[e2]; n0 < st[e2 + 1]; n0 += GS) {
-                        // my neighbour of this group-sized batch: distance and the grid-start ratio, shared by shuffles
-                        double g_r = -1.0, g_R = 0.0;
-                        if (n0 + ch < st[e2 + 1]) {
-                            const int q = nb[n0 + ch];
-                            // global SLATM counts an unordered same-element pair once (fslatm.f90:501-502)
-                            if ((fr[q] & 1) && (loc || e2 != ec || q > c)) {
-                                g_r = dr[q];
-                                g_R = exp(-(2.0 * (sx2[0] - g_r) * T.h2 + T.h2 * T.h2) * T.cst2);
-                            }
-                        }
-                        const int nt = min(GS, st[e2 + 1] - n0);
-                        for (int t = 0; t < nt; t++) {
-                            const double r = gshfl(g_r, t, gmask, gbase);
-                            if (r < 0.0) continue;  // outside the 2-body cut-off (group-uniform)
-                            const double d = xa - r;
-                            double E = exp(-(d * d) * T.cst2), R = gshfl(g_R, t, gmask, gbase) * qm2;
-#pragma unroll
-                            for (int j = 0; j < M2; j++) { a2[j] += E; E *= R; R *= T.q2; }
-                        }
-                    }
-                    }
-                    const double c0 = (loc ? 0.5 : 1.0) * (T.el_w[ec] * T.el_w[e2]) * T.coeff2;  // fslatm.f90:610-617 / :487-491
-                    unsigned bits0 = 0, bits1 = 0;
-                    const int kt0 = (col + j0) >> 4;
-#pragma unroll
-                    for (int j = 0; j < M2; j++) {
-                        const double v = a2[j] * (c0 * sinv2[j0 + j]);
-                        if (j0 + j < nx) {
-                            if (J.out) J.out[orow * J.ldo + dcol + j0 + j] = v;
-                            if (pr >= 0) J.px[ec][(long long)pr * T.pld[ec] + col + j0 + j] = v;
-                            ssq += v * v;
-                            if (v != 0.0) {
-                                int kt = ((col + j0 + j) >> 4) - kt0;
-                                if (kt == 0) bits0 = 1; else if (kt == 1) bits1 = 1; else bits1 |= 2;
-                            }
-                        }
-                    }
-                    if (pr >= 0 && J.pmask[ec]) {
-                        unsigned *mw = J.pmask[ec] + (long long)(pr >> 6) * J.maskw[ec];
-                        if (bits0) atomicOr(mw + (kt0 >> 5), 1u << (kt0 & 31));
-                        if (bits1 & 1) atomicOr(mw + ((kt0 + 1) >> 5), 1u << ((kt0 + 1) & 31));
-                        if (bits1 & 2) atomicOr(mw + ((kt0 + 2) >> 5), 1u << ((kt0 + 2) & 31));
-                    }
-                }
-            } else if (ci - T.n_el < T.nblk[ec]) {
-                const Block3 B = T.blk[ec * MAXBLK + (ci - T.n_el)];
-                col = B.col; nx = T.nx3;
-                // dense column of this block's type: find it through the slot table
-                dcol = T.slot_col[T.bot_slot[(B.e1 * MAXEL + ec) * MAXEL + B.e3] >> 1];
-                if (col >= 0) {
-                    const int j0 = ch * M3;
-                    const double xa = sx3[j0];
-                    double a3[M3];
-#pragma unroll
-                    for (int j = 0; j < M3; j++) a3[j] = 0.0;
-                    for (int ai = c_lo; ai < c_hi; ai++) {
-                    if (mel[bt.a0 + ai] != ec) continue;
-                    const short *st = sstart + ai * (MAXEL + 1);
-                    const short *nb = nbidx + ai * na;
-                    const double *dr = dd + ai * na;
-                    const unsigned char *fr = fls + ai * na;
-                    const int n1 = st[B.e1 + 1] - st[B.e1], n3 = st[B.e3 + 1] - st[B.e3];
-                    const int np = (B.e1 == B.e3) ? n1 * (n1 - 1) / 2 : n1 * n3;
-                    for (int p0 = 0; p0 < np; p0 += GS) {
-                        // my pair of this group-sized batch: geometry once, shared with the group by shuffles
-                        double g_ang = 0.0, g_A = 0.0, g_B = 0.0, g_R = 0.0;
-                        int p = p0 + ch;
-                        if (p < np) {
-                            int i, k;
-                            if (B.e1 == B.e3) {
-                                i = 0;
-                                while (p >= n1 - 1 - i) { p -= n1 - 1 - i; i++; }
-                                k = i + 1 + p;
-                            } else {
-                                i = p / n3;
-                                k = p - i * n3;
-                            }
-                            const int qi = nb[st[B.e1] + i], qk = nb[st[B.e3] + k];
-                            if ((fr[qi] & 2) && (fr[qk] & 2)) {
-                                // reference roles: "i" is the atom of the type's first element (flip swaps)
-                                const int I = B.flip ? qk : qi, K = B.flip ? qi : qk;
-                                const double wx = __dsub_rn(mx[I], mx[K]), wy = __dsub_rn(my[I], my[K]), wz = __dsub_rn(mz[I], mz[K]);
-                                const double dik = __dsqrt_rn(__dadd_rn(__dadd_rn(__dmul_rn(wx, wx), __dmul_rn(wy, wy)), __dmul_rn(wz, wz)));
-                                if (dik <= rcut) {
-                                    const double *uI = ux + ai * na, *vI = uy + ai * na, *zI = uz + ai * na;
-                                    // angle at the centre: u_I . u_K  (calc_angle(i, c, k), utils.f90:52-80)
-                                    double ca = __dadd_rn(__dadd_rn(__dmul_rn(uI[I], uI[K]), __dmul_rn(vI[I], vI[K])), __dmul_rn(zI[I], zI[K]));
-                                    ca = fmin(1.0, fmax(-1.0, ca));
-                                    g_ang = acos(ca);
-                                    // w = (I-K)/|I-K|.  cak = cos at K between I and c = w . (-u_K); cai = cos at I between K and c
-                                    // = (-w) . (-u_I): negations are exact, so these equal calc_cos_angle's values bit for bit
-                                    const double nx_ = __ddiv_rn(wx, dik), ny_ = __ddiv_rn(wy, dik), nz_ = __ddiv_rn(wz, dik);
-                                    const double cak = -__dadd_rn(__dadd_rn(__dmul_rn(nx_, uI[K]), __dmul_rn(ny_, vI[K])), __dmul_rn(nz_, zI[K]));
-                                    const double cai = __dadd_rn(__dadd_rn(__dmul_rn(nx_, uI[I]), __dmul_rn(ny_, vI[I])), __dmul_rn(nz_, zI[I]));
-                                    const double r = __dmul_rn(__dmul_rn(dr[I], dik), dr[K]);
-                                    const double rinv3 = 1.0 / (r * r * r);
-                                    g_A = B.c0 * rinv3;                  // (c0 + cos(x) c0 cak cai) / r^3
-                                    g_B = (B.c0 * cak * cai) * rinv3;
-                                    if (g_A == 0.0) g_A = 4.9e-324;      // keep "valid" distinguishable (never hit in practice)
-                                    g_R = exp(-(2.0 * (sx3[0] - g_ang) * T.h3 + T.h3 * T.h3) * T.cst3);
-                                }
-                            }
-                        }
-                        const int nt = min(GS, np - p0);
-                        for (int t = 0; t < nt; t++) {
-                            const double A0 = gshfl(g_A, t, gmask, gbase);
-                            if (A0 == 0.0) continue;  // pair failed a cut-off test (group-uniform)
-                            const double ang = gshfl(g_ang, t, gmask, gbase), B0 = gshfl(g_B, t, gmask, gbase);
-                            const double d = xa - ang;
-                            double E = exp(-(d * d) * T.cst3), R = gshfl(g_R, t, gmask, gbase) * qm3;
-#pragma unroll
-                            for (int j = 0; j < M3; j++) { a3[j] += fma(scos3[j0 + j], B0, A0) * E; E *= R; R *= T.q3; }
-                        }
-                    }
-                    }
-                    unsigned bits0 = 0, bits1 = 0;
-                    const int kt0 = (col + j0) >> 4;
-#pragma unroll
-                    for (int j = 0; j < M3; j++) {
-                        const double v = a3[j];
-                        if (j0 + j < nx) {
-                            if (J.out) J.out[orow * J.ldo + dcol + j0 + j] = v;
-                            if (pr >= 0) J.px[ec][(long long)pr * T.pld[ec] + col + j0 + j] = v;
-                            ssq += v * v;
-                            if (v != 0.0) {
-                                int kt = ((col + j0 + j) >> 4) - kt0;
-                                if (kt == 0) bits0 = 1; else if (kt == 1) bits1 = 1; else bits1 |= 2;
-                            }
-                        }
-                    }
-                    if (pr >= 0 && J.pmask[ec]) {
-                        unsigned *mw = J.pmask[ec] + (long long)(pr >> 6) * J.maskw[ec];
-                        if (bits0) atomicOr(mw + (kt0 >> 5), 1u << (kt0 & 31));
-                        if (bits1 & 1) atomicOr(mw + ((kt0 + 1) >> 5), 1u << ((kt0 + 1) & 31));
-                        if (bits1 & 2) atomicOr(mw + ((kt0 + 2) >> 5), 1u << ((kt0 + 2) & 31));
-                    }
-                }
+        const int pr = (loc && J.atom_prow) ? J.atom_prow[o + bt.a0 + ui] : -1;
+        const int j0 = ch * m, kt0 = (col + j0) >> 4;
+        unsigned bits = 0;
+        double ssq = 0.0;
+        for (int j = 0; j < m; j++) {
+            const double v = acc[j];
+            if (j0 + j < nx) {
+                if (J.out) J.out[orow * J.ldo + dcol + j0 + j] = v;
+                if (pr >= 0) J.px[ec][(long long)pr * T.pld[ec] + col + j0 + j] = v;
+                ssq += v * v;
+                if (v != 0.0) bits |= 1u << min(((col + j0 + j) >> 4) - kt0, 2);
             }
         }
-        // block's sum of squares: fixed-order tree over the 8 threads of the group
+        if (pr >= 0 && J.pmask[ec]) {
+            unsigned *mw = J.pmask[ec] + (long long)(pr >> 6) * J.maskw[ec];
+            for (int q = 0; q < 3; q++)
+                if (bits & (1u << q)) atomicOr(mw + ((kt0 + q) >> 5), 1u << ((kt0 + q) & 31));
+        }
         ssq += __shfl_xor_sync(gmask, ssq, 1);
         ssq += __shfl_xor_sync(gmask, ssq, 2);
         if (GS >= 8) ssq += __shfl_xor_sync(gmask, ssq, 4);
         if (GS >= 16) ssq += __shfl_xor_sync(gmask, ssq, 8);
-        if (ch == 0) s_norm[ui * uc + ci] = ssq;
+        if (ch == 0 && loc) s_norm[ui * uc + cidx] = ssq;
+    };
+
+    // ---------- two-body units: (owner, partner element) ----------
+    {
+        int ui = 0, e2 = 0, ec = -1, col = -1, dcol = -1, ai = 0, aiend = 0, n0 = -1, nend = 0;
+        bool active = true;
+        double a2[M2];
+        const int j0 = ch * M2;
+        const double xa = sx2[j0];
+        auto seek = [&]() -> bool {  // next centre of this unit with entries left
+            while (ai < aiend) {
+                if (mel[bt.a0 + ai] == ec) {
+                    if (n0 < 0) { n0 = sstart[ai * (MAXEL + 1) + e2]; nend = sstart[ai * (MAXEL + 1) + e2 + 1]; }
+                    if (n0 < nend) return true;
+                }
+                ai++;
+                n0 = -1;
+            }
+            return false;
+        };
+        auto fetch = [&]() {
+            for (;;) {
+                const int u = group_fetch(&s_next);
+                if (u >= nown * T.n_el) { active = false; return; }
+                ui = u / T.n_el;
+                e2 = u - ui * T.n_el;
+                ec = loc ? mel[bt.a0 + ui] : ui;
+                if (ec < 0) continue;
+                const int sl = T.bop_slot[ec * MAXEL + e2];
+                if (sl < 0) continue;
+                col = T.lay_col[ec * T.nmb + sl];  // global mode: -1 unless this element owns the block
+                if (col < 0) continue;
+                dcol = T.slot_col[sl];
+                ai = loc ? ui : 0;
+                aiend = loc ? ui + 1 : bt.cnt;
+                n0 = -1;
+                if (seek()) {
+#pragma unroll
+                    for (int j = 0; j < M2; j++) a2[j] = 0.0;
+                    return;
+                }
+            }
+        };
+        fetch();
+        while (__any_sync(FULL, active)) {
+            double4 g = make_double4(-1.0, 0.0, 0.0, 0.0);
+            if (active && n0 + ch < nend) {
+                const int q = nbidx[ai * na + n0 + ch];
+                // global SLATM counts an unordered same-element pair once (fslatm.f90:501-502)
+                if ((fls[ai * na + q] & 1) && (loc || e2 != ec || q > bt.a0 + ai)) {
+                    g.x = dd[ai * na + q];
+                    g.y = exp(-(2.0 * (sx2[0] - g.x) * T.h2 + T.h2 * T.h2) * T.cst2);
+                }
+            }
+            s_mbox[tid] = g;
+            __syncwarp();
+            if (active) {
+#pragma unroll 1
+                for (int t = 0; t < GS; t++) {
+                    const double4 mb = s_mbox[gtid0 + t];
+                    if (mb.x < 0.0) continue;  // no entry / outside the 2-body cut-off (group-uniform)
+                    const double d = xa - mb.x;
+                    double E = exp_nonpos(-(d * d) * T.cst2), R = mb.y * qm2;
+#pragma unroll
+                    for (int j = 0; j < M2; j++) { a2[j] += E; E *= R; R *= T.q2; }
+                }
+            }
+            __syncwarp();
+            if (active) {
+                n0 += GS;
+                if (!seek()) {
+                    const double c0 = (loc ? 0.5 : 1.0) * (T.el_w[ec] * T.el_w[e2]) * T.coeff2;  // fslatm.f90:610-617 / :487-491
+#pragma unroll
+                    for (int j = 0; j < M2; j++) a2[j] *= c0 * sinv2[j0 + j];
+                    write_block(a2, M2, T.nx2, ui, e2, ec, col, dcol);
+                    fetch();
+                }
+            }
+        }
+    }
+
+    // ---------- three-body units: (owner, [z1, zc, z3] block) ----------
+    {
+        int ui = 0, bi = 0, ec = -1, ai = 0, aiend = 0, p0 = -1, np = 0, n1 = 0, n3 = 0;
+        Block3 B;
+        B.col = -1;
+        bool active = true;
+        double a3[M3];
+        const int j0 = ch * M3;
+        const double xa = sx3[j0];
+        const int nbmax = uc - T.n_el;
+        auto seek = [&]() -> bool {
+            while (ai < aiend) {
+                if (mel[bt.a0 + ai] == ec) {
+                    if (p0 < 0) {
+                        const short *st = sstart + ai * (MAXEL + 1);
+                        n1 = st[B.e1 + 1] - st[B.e1];
+                        n3 = st[B.e3 + 1] - st[B.e3];
+                        np = (B.e1 == B.e3) ? n1 * (n1 - 1) / 2 : n1 * n3;
+                        p0 = 0;
+                    }
+                    if (p0 < np) return true;
+                }
+                ai++;
+                p0 = -1;
+            }
+            return false;
+        };
+        auto fetch = [&]() {
+            for (;;) {
+                const int u = group_fetch(&s_next3);
+                if (u >= nown * nbmax) { active = false; return; }
+                ui = u / nbmax;
+                bi = u - ui * nbmax;
+                ec = loc ? mel[bt.a0 + ui] : ui;
+                if (ec < 0 || bi >= T.nblk[ec]) continue;
+                B = T.blk[ec * MAXBLK + bi];
+                if (B.col < 0) continue;
+                ai = loc ? ui : 0;
+                aiend = loc ? ui + 1 : bt.cnt;
+                p0 = -1;
+                if (seek()) {
+#pragma unroll
+                    for (int j = 0; j < M3; j++) a3[j] = 0.0;
+                    return;
+                }
+            }
+        };
+        fetch();
+        while (__any_sync(FULL, active)) {
+            double4 g = make_double4(0.0, 0.0, 0.0, 0.0);  // (A0, angle, B0, Rg); A0 == 0 marks "no entry"
+            if (active && p0 + ch < np) {
+                const short *st = sstart + ai * (MAXEL + 1);
+                const short *nb = nbidx + ai * na;
+                const double *dr = dd + ai * na;
+                const unsigned char *fr = fls + ai * na;
+                int p = p0 + ch, i, k;
+                if (B.e1 == B.e3) {
+                    i = 0;
+                    while (p >= n1 - 1 - i) { p -= n1 - 1 - i; i++; }
+                    k = i + 1 + p;
+                } else {
+                    i = p / n3;
+                    k = p - i * n3;
+                }
+                const int qi = nb[st[B.e1] + i], qk = nb[st[B.e3] + k];
+                if ((fr[qi] & 2) && (fr[qk] & 2)) {
+                    // reference roles: "i" is the atom of the type's first element (flip swaps)
+                    const int I = B.flip ? qk : qi, K = B.flip ? qi : qk;
+                    const double wx = __dsub_rn(mx[I], mx[K]), wy = __dsub_rn(my[I], my[K]), wz = __dsub_rn(mz[I], mz[K]);
+                    const double dik = __dsqrt_rn(__dadd_rn(__dadd_rn(__dmul_rn(wx, wx), __dmul_rn(wy, wy)), __dmul_rn(wz, wz)));
+                    if (dik <= rcut) {
+                        const double *uI = ux + ai * na, *vI = uy + ai * na, *zI = uz + ai * na;
+                        // angle at the centre: u_I . u_K  (calc_angle(i, c, k), utils.f90:52-80)
+                        double ca = __dadd_rn(__dadd_rn(__dmul_rn(uI[I], uI[K]), __dmul_rn(vI[I], vI[K])), __dmul_rn(zI[I], zI[K]));
+                        ca = fmin(1.0, fmax(-1.0, ca));
+                        g.y = acos(ca);
+                        // w = (I-K)/|I-K|.  cak = cos at K between I and c = w . (-u_K); cai = cos at I between K and c
+                        // = (-w) . (-u_I): negations are exact, so these equal calc_cos_angle's values bit for bit
+                        const double nx_ = __ddiv_rn(wx, dik), ny_ = __ddiv_rn(wy, dik), nz_ = __ddiv_rn(wz, dik);
+                        const double cak = -__dadd_rn(__dadd_rn(__dmul_rn(nx_, uI[K]), __dmul_rn(ny_, vI[K])), __dmul_rn(nz_, zI[K]));
+                        const double cai = __dadd_rn(__dadd_rn(__dmul_rn(nx_, uI[I]), __dmul_rn(ny_, vI[I])), __dmul_rn(nz_, zI[I]));
+                        const double r = __dmul_rn(__dmul_rn(dr[I], dik), dr[K]);
+                        const double rinv3 = 1.0 / (r * r * r);
+                        g.x = B.c0 * rinv3;                  // (c0 + cos(x) c0 cak cai) / r^3
+                        g.z = (B.c0 * cak * cai) * rinv3;
+                        if (g.x == 0.0) g.x = 4.9e-324;      // keep "valid" distinguishable (never hit in practice)
+                        g.w = exp(-(2.0 * (sx3[0] - g.y) * T.h3 + T.h3 * T.h3) * T.cst3);
+                    }
+                }
+            }
+            s_mbox[tid] = g;
+            __syncwarp();
+            if (active) {
+#pragma unroll 1
+                for (int t = 0; t < GS; t++) {
+                    const double4 mb = s_mbox[gtid0 + t];
+                    if (mb.x == 0.0) continue;  // no entry / pair failed a cut-off test (group-uniform)
+                    const double d = xa - mb.y;
+                    double E = exp_nonpos(-(d * d) * T.cst3), R = mb.w * qm3;
+#pragma unroll
+                    for (int j = 0; j < M3; j++) { a3[j] += fma(scos3[j0 + j], mb.z, mb.x) * E; E *= R; R *= T.q3; }
+                }
+            }
+            __syncwarp();
+            if (active) {
+                p0 += GS;
+                if (!seek()) {
+                    const int dcol = T.slot_col[T.bot_slot[(B.e1 * MAXEL + ec) * MAXEL + B.e3] >> 1];
+                    write_block(a3, M3, T.nx3, ui, T.n_el + bi, ec, B.col, dcol);
+                    fetch();
+                }
+            }
+        }
     }
     __syncthreads();
 
@@ -329,7 +432,6 @@ slatm_units_kernel(const SlatmDev T, const SlatmJob J, const Batch *batches, int
                 double t = 0.0;
                 for (int q = 0; q < uc; q++) t += s_norm[ai * uc + q];
                 J.pnorm[ec][pr] = t;
-                for (int x = T.pdim[ec]; x < T.pld[ec]; x++) J.px[ec][(long long)pr * T.pld[ec] + x] = 0.0;
             }
         }
     }
