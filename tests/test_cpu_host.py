@@ -124,3 +124,15 @@ def test_reference_file_formats(tmp_path, monkeypatch):
     assert os.path.exists("data/g7-kernels-l.npz")
     a, b = aio.load_kernels("g7", kernel="l")
     assert np.array_equal(a, ks1) and np.array_equal(b, ks2)
+
+
+def test_block_driver_job_ids():
+    """slatm_x.py:147-184: job enumeration order and sub-job selection."""
+    from aqml_b200.representation.slatm_x import all_jobs, select_jobs, MolSet
+    assert all_jobs(2, 1) == ['11ii001001', '11ij001002', '12ij001001', '11ii002002', '12ij002001']
+    jobs, wko = select_jobs('a', 2, 1)
+    assert jobs == all_jobs(2, 1) and not wko
+    jobs, wko = select_jobs(['12ij', '11ii002002'], 2, 1)
+    assert jobs == ['12ij001001', '12ij002001', '11ii002002'] and wko
+    ms = MolSet([1, 1, 8, 6, 1, 1, 1, 1], np.zeros((8, 3)), [3, 5], 1)
+    assert ms.nzs.tolist() == [[2, 0, 1], [4, 1, 0]] and len(ms.nas1) == 1 and len(ms.nas2) == 1
