@@ -68,3 +68,152 @@ def gather_rows(K_rows, group=None):
     outs = [torch.empty_like(pad) for _ in range(world)]
     dist.all_gather(outs, pad, group=group)
     return torch.cat([o[:, :int(v.item())] for o, v in zip(outs, ns)], dim=1)
+
+
+# ----------------------------------------------------------------------------------------------------------
+# Distributed solve of (K + lambda I) alpha = y for a row-sharded K ("multi-GPU block
+# Cholesky for 100 k").  The reference solves on one host with LAPACK (`np.linalg.solve`, aqml.py:875,
+# krr.py:296); K(100k x 100k) is 80 GB per sigma, so here the matrix never leaves the GPUs that assembled it.
+#
+# Layout: row blocks of `nb` molecules dealt round-robin to the ranks (block b -> rank b % world), each rank
+# holding FULL rows of its blocks -- exactly what `fused.local_gaussian(rep, rep, row0=, nrows=)` produces, so
+# the assembly still needs no collective.  Factorisation: right-looking block Cholesky; per block column one
+# broadcast of the nb x nb diagonal factor and one exchange of the (n - k) x nb panel (the path's only "real
+# exchange steps" besides the prediction all-reduce), everything else is local cuSOLVER/cuBLAS through torch.
+
+class RowBlockCyclic(object):
+    """Which rows of an n x n matrix a rank owns: blocks of `nb` rows, block b on rank b % world."""
+
+    def __init__(self, n, nb, rank, world):
+        self.n, self.nb, self.rank, self.world = int(n), int(nb), int(rank), int(world)
+        self.nblk = (self.n + self.nb - 1) // self.nb
+        self.blocks = [b for b in range(self.nblk) if b % self.world == self.rank]
+        self.local_start = {}
+        o = 0
+        for b in self.blocks:
+            self.local_start[b] = o
+            o += self.size(b)
+        self.nloc = o
+
+    def lo(self, b):
+        return b * self.nb
+
+    def hi(self, b):
+        return min((b + 1) * self.nb, self.n)
+
+    def size(self, b):
+        return self.hi(b) - self.lo(b)
+
+    def owner(self, b):
+        return b % self.world
+
+    def rows(self):
+        """Global row indices of the local rows, in local order."""
+        return np.concatenate([np.arange(self.lo(b), self.hi(b)) for b in self.blocks]) if self.blocks else np.zeros(0, dtype=int)
+
+    def loc(self, b):
+        """Local row range of an owned block."""
+        s = self.local_start[b]
+        return s, s + self.size(b)
+
+
+def _world(group):
+    import torch.distributed as dist
+    return dist.get_world_size(group) if (dist.is_available() and dist.is_initialized()) else 1
+
+
+def cholesky_cyclic_(A_loc, layout, group=None, lam=0.0):
+    """In place: the lower triangle of the local rows of A + lam I becomes the local rows of its Cholesky
+    factor L (A = L L^T).  A_loc (layout.nloc, n); only columns <= the row's own block are read / written."""
+    import torch
+    import torch.distributed as dist
+    lay = layout
+    multi = _world(group) > 1
+    if lam:
+        for b in lay.blocks:
+            s, e = lay.loc(b)
+            A_loc[s:e, lay.lo(b):lay.hi(b)].diagonal().add_(lam)
+    for k in range(lay.nblk):
+        k0, k1 = lay.lo(k), lay.hi(k)
+        nk = k1 - k0
+        # 1. diagonal block -> L_kk on its owner, broadcast
+        Lkk = torch.empty((nk, nk), dtype=A_loc.dtype, device=A_loc.device)
+        if lay.owner(k) == lay.rank:
+            s, e = lay.loc(k)
+            Lkk, info = torch.linalg.cholesky_ex(A_loc[s:e, k0:k1])
+            A_loc[s:e, k0:k1] = Lkk
+            Lkk = Lkk.contiguous()
+            if int(info.item()) != 0:
+                Lkk.fill_(float("nan"))  # tell every rank (they all raise, nobody is left waiting in a collective)
+        if multi:
+            dist.broadcast(Lkk, src=dist.get_global_rank(group, lay.owner(k)) if group is not None else lay.owner(k), group=group)
+        if bool(torch.isnan(Lkk[0, 0])):
+            raise np.linalg.LinAlgError(f"K + lambda I is not positive definite (block column {k})")
+        if k1 >= lay.n:
+            break
+        # 2. my rows below block k: panel L[b, k] = A[b, k] L_kk^-T
+        below = [b for b in lay.blocks if b > k]
+        panel = torch.zeros((lay.n - k1, nk), dtype=A_loc.dtype, device=A_loc.device)
+        if below:
+            s = lay.loc(below[0])[0]
+            mine = torch.linalg.solve_triangular(Lkk, A_loc[s:, k0:k1].T, upper=False).T  # X L^T = A
+            A_loc[s:, k0:k1] = mine
+            for b in below:
+                bs, be = lay.loc(b)
+                panel[lay.lo(b) - k1:lay.hi(b) - k1] = mine[bs - s:be - s]
+        # 3. exchange: every rank needs the whole panel (rows of the others arrive through the sum)
+        if multi:
+            dist.all_reduce(panel, op=dist.ReduceOp.SUM, group=group)
+        # 4. trailing update of my rows, lower triangle only: A[b, j] -= L[b, k] L[j, k]^T for k < j <= b
+        for b in below:
+            bs, be = lay.loc(b)
+            A_loc[bs:be, k1:lay.hi(b)].addmm_(panel[lay.lo(b) - k1:lay.hi(b) - k1], panel[:lay.hi(b) - k1].T, alpha=-1.0)
+    return A_loc
+
+
+def cholesky_solve_cyclic(L_loc, layout, Y, group=None):
+    """alpha = (L L^T)^-1 Y with L row-block-cyclic (output of `cholesky_cyclic_`).  Y (n,) or (n, m), the same on
+    every rank; returns alpha with Y's shape on every rank."""
+    import torch
+    import torch.distributed as dist
+    lay = layout
+    multi = _world(group) > 1
+    src = (lambda r: dist.get_global_rank(group, r)) if group is not None else (lambda r: r)
+    vec = Y.dim() == 1
+    Z = (Y[:, None] if vec else Y).clone()
+    # forward: z_k = L_kk^-1 (y_k - L[k, :k] z[:k]) on the owner of block k, then broadcast
+    for k in range(lay.nblk):
+        k0, k1 = lay.lo(k), lay.hi(k)
+        zk = torch.empty((k1 - k0, Z.shape[1]), dtype=Z.dtype, device=Z.device)
+        if lay.owner(k) == lay.rank:
+            s, e = lay.loc(k)
+            rhs = Z[k0:k1] - L_loc[s:e, :k0] @ Z[:k0]
+            zk = torch.linalg.solve_triangular(L_loc[s:e, k0:k1], rhs, upper=False).contiguous()
+        if multi:
+            dist.broadcast(zk, src=src(lay.owner(k)), group=group)
+        Z[k0:k1] = zk
+    # backward: alpha_k = L_kk^-T (z_k - sum_{b>k} L[b, k]^T alpha_b); the sum runs over rows owned by all ranks
+    X = torch.zeros_like(Z)
+    acc = torch.zeros_like(Z)          # my share of  sum_b L[b, :]^T alpha_b  over my finished blocks
+    for k in range(lay.nblk - 1, -1, -1):
+        k0, k1 = lay.lo(k), lay.hi(k)
+        part = acc[k0:k1].contiguous()
+        if multi:
+            dist.all_reduce(part, op=dist.ReduceOp.SUM, group=group)
+        xk = torch.empty((k1 - k0, Z.shape[1]), dtype=Z.dtype, device=Z.device)
+        if lay.owner(k) == lay.rank:
+            s, e = lay.loc(k)
+            xk = torch.linalg.solve_triangular(L_loc[s:e, k0:k1].T, Z[k0:k1] - part, upper=True).contiguous()
+        if multi:
+            dist.broadcast(xk, src=src(lay.owner(k)), group=group)
+        X[k0:k1] = xk
+        if lay.owner(k) == lay.rank:
+            s, e = lay.loc(k)
+            acc[:k0] += L_loc[s:e, :k0].T @ xk
+    return X[:, 0] if vec else X
+
+
+def krr_solve_cyclic(K_loc, layout, Y, llambda, group=None):
+    """alpha = (K + llambda I)^-1 Y (aqml.py:874-875) for a row-block-cyclic K; K_loc is overwritten by L."""
+    cholesky_cyclic_(K_loc, layout, group=group, lam=llambda)
+    return cholesky_solve_cyclic(K_loc, layout, Y, group=group)

@@ -45,6 +45,28 @@ def _worker(rank, world, port, tmp):
         rlo, rhi = parallel.shard_range(11, rank, world)
         full = parallel.gather_rows(K[:, rlo:rhi].contiguous())
         assert torch.equal(full, K)
+        # distributed block-cyclic Cholesky solve of (K + lambda I) alpha = y, ragged last block, 1 and 3 right-hand sides
+        n = 61
+        M = torch.rand((n, n), dtype=torch.float64, generator=g)
+        A = M @ M.T / n + torch.eye(n, dtype=torch.float64)
+        Y = torch.rand((n, 3), dtype=torch.float64, generator=g)
+        ref = torch.linalg.solve(A + 1e-4 * torch.eye(n, dtype=torch.float64), Y)
+        for nb in (7, 16, 64):
+            lay = parallel.RowBlockCyclic(n, nb, rank, world)
+            assert sorted(np.concatenate([parallel.RowBlockCyclic(n, nb, r, world).rows() for r in range(world)])) == list(range(n))
+            alpha = parallel.krr_solve_cyclic(A[lay.rows()].clone(), lay, Y, 1e-4)
+            assert torch.allclose(alpha, ref, rtol=1e-11, atol=1e-13)
+            a1 = parallel.krr_solve_cyclic(A[lay.rows()].clone(), lay, Y[:, 1].contiguous(), 1e-4)
+            assert torch.allclose(a1, ref[:, 1], rtol=1e-11, atol=1e-13)
+        lay = parallel.RowBlockCyclic(n, 16, rank, world)
+        bad = A.clone()
+        bad[40, 40] = -5.0
+        try:
+            parallel.cholesky_cyclic_(bad[lay.rows()].clone(), lay)
+            raised = False
+        except np.linalg.LinAlgError:
+            raised = True
+        assert raised  # on every rank, so nobody is left waiting in a collective
         open(os.path.join(tmp, f"ok{rank}"), "w").write("ok")
     finally:
         dist.destroy_process_group()

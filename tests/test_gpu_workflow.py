@@ -121,3 +121,33 @@ def test_amons_workflow_per_query_sigmas():
         r1 = co.calc_lk_gaussian(x1, x1, a[1], a[1], a[0], a[0], zmax, False, ref_sig)
         r2 = co.calc_lk_gaussian(x2, x1, t[1], a[1], t[0], a[0], zmax, False, ref_sig)
         assert rel_err(ks1, r1) < 1e-9 and rel_err(ks2, r2) < 1e-9
+
+
+def test_sharded_krr_single_rank_matches_direct_solve():
+    """ShardedKRR (block lower-triangle assembly + block Cholesky, world 1) == full K + LU solve (aqml.py:874-876)."""
+    import torch
+    from aqml_b200 import fused
+    from aqml_b200.algo.krr_sharded import ShardedKRR
+    from aqml_b200.representation import core as rcore
+    train = synth.qm9_like(150, 6, max_heavy=6)   # seed: every element has >= 2 atoms (a single atom gives d_max = 0)
+    test = synth.qm9_like(21, 7, max_heavy=6)
+    mb = rcore.get_slatm_mbtypes(synth.split_zs(train[0], train[1]) + synth.split_zs(test[0], test[1]))
+    kw = dict(sigmas=(.05, .05), dgrids=(.08, .08), rcut=4.8)
+    zmax = 9
+    model = ShardedKRR(train[0], train[1], train[2], mb, zmax, nb=32, **kw)   # 5 blocks, ragged last one
+    rep_train = fused.PackedRep(train[2], train[1], train[0], mb, **kw)
+    rep_test = fused.PackedRep(test[2], test[1], test[0], mb, **kw)
+    dso = model.kernel_width()
+    assert rel_err(dso, fused.kernel_width(rep_train, rep_train, zmax)) < 1e-12
+    sig = dso / np.sqrt(2 * np.log(2))
+    K_loc = model.assemble(sig)
+    K = fused.local_gaussian(rep_train, rep_train, sig[None], zmax)[0]
+    low = torch.tril(torch.ones_like(K, dtype=torch.bool))
+    assert rel_err(torch.where(low, K_loc, 0).cpu().numpy(), torch.where(low, K, 0).cpu().numpy()) < 1e-12
+    y = torch.as_tensor(np.random.default_rng(0).normal(size=150), device=K.device)
+    alpha = model.fit(K_loc, y, 1e-2)
+    Kh = K.cpu().numpy() + 1e-2 * np.eye(150)
+    a_ref = np.linalg.solve(Kh, y.cpu().numpy())
+    assert rel_err(alpha.cpu().numpy(), a_ref) < 1e-9
+    y_ref = fused.local_gaussian(rep_test, rep_train, sig[None], zmax)[0].cpu().numpy() @ a_ref
+    assert rel_err(model.predict(rep_test).cpu().numpy(), y_ref) < 1e-9
