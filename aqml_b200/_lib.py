@@ -61,6 +61,7 @@ SIGNATURES = {
     "aqml_rep_local_gaussian": (_I, [_P, _P, _P, _I, _I, _I, _I, _P, _P]),
     "aqml_rep_local_gaussian_sym": (_I, [_P, _P, _I, _I, _P, _P]),
     "aqml_rep_kernel_width": (_I, [_P, _P, _I, _P, _P]),
+    "aqml_rep_kernel_width_multi": (_I, [_P, _I, _P, _I, _I, _P, _P]),
 }
 
 _lib = None

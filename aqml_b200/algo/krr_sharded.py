@@ -6,7 +6,7 @@ triangle of K_train lives on rank b % world (`parallel.RowBlockCyclic`), which b
 the triangle and the Cholesky factorisation.  Every rank packs the aSLATM of every block itself (cheap next
 to K), so kernel-width pass and kernel assembly need no data exchange at all; the collectives are
 
-  * kernel width: one all-reduce(MAX) of the (zmax,) per-element d_max vector,
+  * kernel width: none (the pruned max-distance pass is cheap enough to run redundantly on every rank),
   * Cholesky: per block column one broadcast (nb x nb) + one panel exchange ((n - k) x nb),
   * prediction: one all-reduce(SUM) of the (n_test,) partial predictions.
 
@@ -35,11 +35,9 @@ class ShardedKRR(object):
         self.lay = parallel.RowBlockCyclic(self.n, nb, rank, world)
         self.mbtypes, self.slatm_kw = mbtypes, slatm_kw
         nas, zs, coords = np.asarray(nas), np.asarray(zs), np.asarray(coords)
-        self.present = np.isin(np.arange(1, self.zmax + 1), zs % 1000)
-        last = max(self.lay.blocks) if self.lay.blocks else -1
-        # blocks 0..last are needed as column operands of my rows (lower triangle)
+        # every block on every rank: column operands of my rows, and the (pruned, hence cheap) width pass
         self.reps = []
-        for c in range(last + 1):
+        for c in range(self.lay.nblk):
             t = _take(nas, zs, coords, self.lay.lo(c), self.lay.hi(c))
             self.reps.append(fused.PackedRep(t[2], t[1], t[0], mbtypes, **slatm_kw))
         self.dso = None
@@ -50,23 +48,10 @@ class ShardedKRR(object):
         return dist.is_available() and dist.is_initialized() and dist.get_world_size(self.group) > 1
 
     def kernel_width(self):
-        """Per-element max aSLATM distance over all training atom pairs (get_kernel_width, aqml.py:204-255)."""
-        import torch
-        import torch.distributed as dist
-        dso = np.zeros(self.zmax)
-        for b in self.lay.blocks:
-            for c in range(b + 1):
-                d = fused.kernel_width(self.reps[b], self.reps[c], self.zmax)
-                dso = np.maximum(dso, np.where(d == 1.e-9, 0.0, d))  # 1e-9 marks "no such element in this block pair"
-        if self._multi():
-            t = torch.as_tensor(dso, device=self.reps[0].device if self.reps else "cuda")
-            dist.all_reduce(t, op=dist.ReduceOp.MAX, group=self.group)
-            dso = t.cpu().numpy()
-        # elements absent from the training set keep the reference's 1e-9 (aqml.py:249); an element with a single
-        # atom has d_max = 0 there as well
-        dso = np.where(self.present, dso, 1.e-9)
-        self.dso = dso
-        return dso
+        """Per-element max aSLATM distance over all training atom pairs (get_kernel_width, aqml.py:204-255).
+        The triangle-inequality pruning leaves ~1 % of the pairs, so every rank simply does the whole pass."""
+        self.dso = fused.kernel_width(self.reps, self.reps, self.zmax)
+        return self.dso
 
     def assemble(self, sigmas):
         """My rows of the lower triangle of K_train for ONE sigma set (zmax,) -> (nloc, n) device tensor

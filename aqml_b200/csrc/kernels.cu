@@ -45,8 +45,13 @@ void require_device() {
 // zero-pad to the 16-column pitch, and produce |row|^2.
 __global__ void __launch_bounds__(256) pack_rows_kernel(PackJob J) {
     const int r = blockIdx.x;
-    int src = J.rowmap ? J.rowmap[r] : (r < J.nvalid ? r : -1);
-    const double *sp = (src >= 0) ? J.src + (long long)src * J.lds : nullptr;
+    const double *sp;
+    if (J.srcrows) {
+        sp = J.srcrows[r];
+    } else {
+        int src = J.rowmap ? J.rowmap[r] : (r < J.nvalid ? r : -1);
+        sp = (src >= 0) ? J.src + (long long)src * J.lds : nullptr;
+    }
     double *dp = J.dst + (long long)r * J.ldd;
     double ss = 0.0;
     __shared__ unsigned smask[32];
@@ -98,6 +103,22 @@ __global__ void __launch_bounds__(256) colstats_kernel(const double *x, long lon
     }
     if (colsum) atomicAdd(colsum + c, s);
     if (nz) atomicOr(colnz + c, 1u);
+}
+
+// r[i] = distance of row i to the point c: Euclidean (p = 2) or sum of absolute differences (p = 1), by direct
+// differences (no cancellation).  One warp per row.
+__global__ void __launch_bounds__(256) row_dist_kernel(int p, const double *x, long long ld, int n, const double *c, int ncols,
+                                                       double *r) {
+    const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (row >= n) return;
+    const double *xr = x + (long long)row * ld;
+    double s = 0.0;
+    for (int k = lane; k < ncols; k += 32) {
+        const double d = xr[k] - c[k];
+        s += (p == 2) ? d * d : fabs(d);
+    }
+    s = warp_sum(s);
+    if (lane == 0) r[row] = (p == 2) ? sqrt(s) : s;
 }
 
 __global__ void scale_gather_kernel(const double *colsum, const int *colmap, int n, double scale, double *mean) {
@@ -306,6 +327,8 @@ static const double *column_mean(Workspace &ws, const double *x, long long ldx, 
     return mean;
 }
 
+static double pruned_max(int p, const double *A, int nA, const double *B, int nB, long long ld, bool same, Workspace &ws);
+
 static std::vector<double> inv_sigma_table(int kind, const double *sigmas, size_t n) {
     std::vector<double> t(n);
     for (size_t i = 0; i < n; i++)
@@ -329,10 +352,16 @@ static void global_pairs(int kind, int epi, const double *a, int na, long long l
     const bool same = (a == b && na == nb && lda == ldb);
     Packed pb = pack_dense(ws, b, ldb, nb, D, mean, mode == MODE_DOT);
     Packed pa = same ? pb : pack_dense(ws, a, lda, na, D, mean, mode == MODE_DOT);
+    if (epi == EPI_MAX) {
+        const double v = pruned_max(mode == MODE_DOT ? 2 : 1, pa.x, na, pb.x, nb, pa.ld, same, ws);
+        AQML_CUDA(cudaMemcpyAsync(out, &v, 8, cudaMemcpyHostToDevice, st));
+        AQML_CUDA(cudaStreamSynchronize(st));
+        return;
+    }
     PairGroup g = blank_group();
     g.A = pa.x; g.B = pb.x; g.normA = pa.norm; g.normB = pb.norm; g.ld = pa.ld;
     g.nA = na; g.nB = nb; g.tilesM = pa.rows / BM; g.tilesN = pb.rows / BN;
-    g.sym = (epi == EPI_MAX && same) ? 1 : 0;
+    g.sym = 0;
     PairParams P{};
     P.out = out; P.ldo = nb; P.slab = (long long)na * nb; P.nsig = nsig; P.zstride = 1;
     if (epi == EPI_EXP_STORE) {
@@ -560,6 +589,118 @@ static void local_laplacian(const double *x1, long long ldx1, const double *x2, 
     run_pairs(MODE_L1, EPI_LOCAL, {g}, P, ws);
 }
 
+// max_{i in A, j in B} |a_i - b_j|_p without touching most pairs (get_kernel_width / get_dsmax: the reference forms
+// the whole distance matrix, aqml.py:220-237).  d(i,j) <= r_i + r_j for the distances r to ANY common point (here
+// the column mean of B); one farthest-point sweep (the row farthest from the mean, its farthest partner, that
+// row's farthest partner) gives a pair distance L that is attained.  Only rows with r_i + max r_B >= L can take
+// part in the maximum (aSLATM: ~5 % of the H / C rows -- the norms are heavy-tailed), and among those, sorted by
+// r, whole tiles are skipped by the same test.  The surviving pairs go through the ordinary pair-tile kernel, so
+// the result is the same number the unpruned pass produces.  Operands: packed rows (pitch ld, zero padded
+// columns).  Returns d^2 (p = 2) or the L1 distance (p = 1).
+static double pruned_max_segs(int p, const std::vector<RowSeg> &SA, const std::vector<RowSeg> &SB, long long ld, bool same,
+                              Workspace &ws) {
+    cudaStream_t st = ws.stream();
+    auto total = [](const std::vector<RowSeg> &S) { long long n = 0; for (auto &s : S) n += s.n; return n; };
+    const long long nA = total(SA), nB = total(SB);
+    if (nA <= 0 || nB <= 0) return 0.0;
+    AQML_REQUIRE(nA < (1ll << 31) && nB < (1ll << 31), "too many rows");
+    const int ncols = (int)ld;
+    // reference point: column mean over B
+    double *sum = ws.zeros<double>(ncols);
+    unsigned *nzs = ws.zeros<unsigned>(ncols);
+    for (auto &sg : SB) launch_colstats(sg.x, ld, nullptr, sg.n, ncols, sum, nzs, st);
+    double *mean = ws.alloc<double>(ncols);
+    scale_gather_kernel<<<(ncols + 255) / 256, 256, 0, st>>>(sum, nullptr, ncols, 1.0 / (double)nB, mean);
+    AQML_LAUNCH_CHECK();
+    auto sweep = [&](const std::vector<RowSeg> &S, long long n, const double *c) {
+        double *r = ws.alloc<double>((size_t)n);
+        long long o = 0;
+        for (auto &sg : S) {
+            if (sg.n > 0) {
+                row_dist_kernel<<<(sg.n + 7) / 8, 256, 0, st>>>(p, sg.x, ld, sg.n, c, ncols, r + o);
+                AQML_LAUNCH_CHECK();
+            }
+            o += sg.n;
+        }
+        std::vector<double> h((size_t)n);
+        AQML_CUDA(cudaMemcpyAsync(h.data(), r, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost, st));
+        AQML_CUDA(cudaStreamSynchronize(st));
+        return h;
+    };
+    auto rowptr = [&](const std::vector<RowSeg> &S, long long i) -> const double * {
+        for (auto &sg : S) {
+            if (i < sg.n) return sg.x + i * ld;
+            i -= sg.n;
+        }
+        return nullptr;
+    };
+    auto argmax = [](const std::vector<double> &v) { return (long long)(std::max_element(v.begin(), v.end()) - v.begin()); };
+    std::vector<double> rA = sweep(SA, nA, mean);
+    std::vector<double> rB = same ? rA : sweep(SB, nB, mean);
+    for (double v : rA) if (!(v == v)) return std::numeric_limits<double>::quiet_NaN();  // NaN rows: the reference's max is NaN too
+    for (double v : rB) if (!(v == v)) return std::numeric_limits<double>::quiet_NaN();
+    const long long i0 = argmax(rA);
+    std::vector<double> t1 = sweep(SB, nB, rowptr(SA, i0));
+    const long long j1 = argmax(t1);
+    std::vector<double> t2 = sweep(SA, nA, rowptr(SB, j1));
+    const double L = std::max(t1[j1], t2[argmax(t2)]) * (1.0 - 1e-9);
+    const double rAmax = rA[i0], rBmax = rB[argmax(rB)];
+    auto select = [&](const std::vector<RowSeg> &S, const std::vector<double> &r, double partner_max, std::vector<const double *> &ptrs,
+                      std::vector<double> &bound) {
+        std::vector<long long> rows;
+        for (long long i = 0; i < (long long)r.size(); i++)
+            if (r[i] + partner_max >= L) rows.push_back(i);
+        std::sort(rows.begin(), rows.end(), [&](long long a, long long b) { return r[a] > r[b] || (r[a] == r[b] && a < b); });
+        const size_t padded = (size_t)round_up((int64_t)rows.size(), BM);
+        bound.assign(padded, -1.0);
+        ptrs.assign(padded, nullptr);
+        for (size_t k = 0; k < rows.size(); k++) { bound[k] = r[rows[k]]; ptrs[k] = rowptr(S, rows[k]); }
+        return (int)rows.size();
+    };
+    std::vector<const double *> ca, cb;
+    std::vector<double> ba, bb;
+    const int nca = select(SA, rA, rBmax, ca, ba);
+    const int ncb = same ? nca : select(SB, rB, rAmax, cb, bb);
+    if (nca == 0 || ncb == 0) return (p == 2) ? L * L : L;  // cannot happen (i0 / j1 always qualify); be safe
+    auto gather = [&](const std::vector<const double *> &ptrs, double *&px, double *&pn) {
+        px = ws.alloc<double>(ptrs.size() * (size_t)ld);
+        pn = (p == 2) ? ws.alloc<double>(ptrs.size()) : nullptr;
+        PackJob J{};
+        J.srcrows = ws.upload(ptrs); J.colmap = nullptr; J.mean = (p == 2) ? mean : nullptr;
+        J.dst = px; J.ldd = ld; J.norm = pn; J.ncols = ncols;
+        launch_pack(J, (int)ptrs.size(), st);
+    };
+    double *pa, *na_, *pb, *nb_;
+    gather(ca, pa, na_);
+    if (same) { pb = pa; nb_ = na_; } else gather(cb, pb, nb_);
+    PairGroup g = blank_group();
+    g.A = pa; g.B = pb; g.normA = na_; g.normB = nb_; g.ld = ld; g.nA = nca; g.nB = ncb;
+    g.tilesM = (int)(ca.size() / BM); g.tilesN = (int)((same ? ca.size() : cb.size()) / BN);
+    g.sym = same ? 1 : 0;
+    g.boundA = ws.upload(ba); g.boundB = same ? g.boundA : ws.upload(bb); g.bound_min = L;
+    unsigned long long *bits = ws.zeros<unsigned long long>(1);
+    PairParams P{};
+    P.out = reinterpret_cast<double *>(bits);
+    run_pairs(p == 2 ? MODE_DOT : MODE_L1, EPI_MAX, {g}, P, ws);
+    double v = 0.0;
+    AQML_CUDA(cudaMemcpyAsync(&v, bits, 8, cudaMemcpyDeviceToHost, st));
+    AQML_CUDA(cudaStreamSynchronize(st));
+    return v;
+}
+
+static double pruned_max(int p, const double *A, int nA, const double *B, int nB, long long ld, bool same, Workspace &ws) {
+    return pruned_max_segs(p, {RowSeg{A, nA}}, {RowSeg{B, nB}}, ld, same, ws);
+}
+
+double pruned_max_segs_public(int p, const std::vector<RowSeg> &SA, const std::vector<RowSeg> &SB, long long ld, bool same,
+                              Workspace &ws) {
+    return pruned_max_segs(p, SA, SB, ld, same, ws);
+}
+
+double pruned_max_public(int p, const double *A, int nA, const double *B, int nB, long long ld, bool same, Workspace &ws) {
+    return pruned_max(p, A, nA, B, nB, ld, same, ws);
+}
+
 // per-element max distance, algo/aqml.py:204-255 (cab=False)
 static void kernel_width(int p, const double *x, long long ldx, const int *zs, int A, int D, int zmax, double *dso,
                          cudaStream_t st) {
@@ -583,8 +724,7 @@ static void kernel_width(int p, const double *x, long long ldx, const int *zs, i
     std::vector<unsigned> nz((size_t)ne * D);
     AQML_CUDA(cudaMemcpyAsync(nz.data(), colnz, sizeof(unsigned) * nz.size(), cudaMemcpyDeviceToHost, st));
     AQML_CUDA(cudaStreamSynchronize(st));
-    unsigned long long *outbits = ws.zeros<unsigned long long>(ne);
-    std::vector<PairGroup> groups;
+    std::vector<double> mx(ne);
     for (int e = 0; e < ne; e++) {
         std::vector<int> colmap;
         for (int c = 0; c < D; c++) if (nz[(size_t)e * D + c]) colmap.push_back(c);
@@ -593,30 +733,15 @@ static void kernel_width(int p, const double *x, long long ldx, const int *zs, i
         long long ld = round_up(Dz, BK);
         int tiles = (n + BM - 1) / BM;
         int *d_colmap = ws.upload(colmap);
-        double *mean = nullptr;
-        if (p == 2) {
-            mean = ws.alloc<double>(Dz);
-            scale_gather_kernel<<<(Dz + 255) / 256, 256, 0, st>>>(colsum + (size_t)e * D, d_colmap, Dz, 1.0 / n, mean);
-            AQML_LAUNCH_CHECK();
-        }
         std::vector<int> rm(rz[els[e]]);
         rm.resize((size_t)tiles * BM, -1);
-        double *px = ws.alloc<double>(rm.size() * (size_t)ld), *pn = ws.alloc<double>(rm.size());
+        double *px = ws.alloc<double>(rm.size() * (size_t)ld);
         PackJob J{};
-        J.src = x; J.lds = ldx; J.rowmap = ws.upload(rm); J.colmap = d_colmap; J.mean = mean;
-        J.dst = px; J.ldd = ld; J.norm = pn; J.ncols = Dz;
+        J.src = x; J.lds = ldx; J.rowmap = ws.upload(rm); J.colmap = d_colmap; J.mean = nullptr;
+        J.dst = px; J.ldd = ld; J.norm = nullptr; J.ncols = Dz;
         launch_pack(J, (int)rm.size(), st);
-        PairGroup g = blank_group();
-        g.A = g.B = px; g.normA = g.normB = pn; g.ld = ld; g.nA = g.nB = n; g.tilesM = tiles; g.tilesN = tiles * (BM / BN);
-        g.out_slot = e; g.sym = 1;
-        groups.push_back(g);
+        mx[e] = pruned_max(p, px, n, px, n, ld, true, ws);
     }
-    PairParams P{};
-    P.out = reinterpret_cast<double *>(outbits);
-    run_pairs(p == 2 ? MODE_DOT : MODE_L1, EPI_MAX, groups, P, ws);
-    std::vector<double> mx(ne);
-    AQML_CUDA(cudaMemcpyAsync(mx.data(), outbits, sizeof(double) * ne, cudaMemcpyDeviceToHost, st));
-    AQML_CUDA(cudaStreamSynchronize(st));
     for (int z = 0; z < zmax; z++) dso[z] = 1.e-9;
     for (int e = 0; e < ne; e++) dso[els[e] - 1] = (p == 2) ? std::sqrt(mx[e]) : mx[e];
 }

@@ -18,6 +18,12 @@ struct PackJob {
     int nvalid;          // valid rows when rowmap is null
     unsigned *mask;      // [packed rows / 64][maskw] non-zero k-tile bits (pre-zeroed), or null
     int maskw;
+    const double *const *srcrows;  // if set: source row pointer per packed row (null = zero row); src/rowmap unused
+};
+
+struct RowSeg {  // n packed rows at x (one operand may consist of several allocations)
+    const double *x;
+    int n;
 };
 
 // words of k-tile mask per 64-row block for a row pitch of ld columns
@@ -31,5 +37,8 @@ void build_tiles(const std::vector<int> &rows, const std::vector<int> &mol_of_ro
 std::vector<int> class_sorted_molecules(const int *zs, const int *nas, int nm);
 void plan_sigma_chain(PairParams &P, const std::vector<double> &isig);
 void run_pairs_public(int mode, int epi, const std::vector<PairGroup> &groups, PairParams P, Workspace &ws);
+double pruned_max_public(int p, const double *A, int nA, const double *B, int nB, long long ld, bool same, Workspace &ws);
+double pruned_max_segs_public(int p, const std::vector<RowSeg> &SA, const std::vector<RowSeg> &SB, long long ld, bool same,
+                              Workspace &ws);
 
 }  // namespace aqml

@@ -72,6 +72,11 @@ struct PairGroup {
     // sum|a-b| when both are zero), so it is skipped -- bit-identical results, fewer DMMAs.  null = dense.
     const unsigned *maskA, *maskB;
     int maskw;                    // 32-bit words per 64-row block
+    // EPI_MAX pruning (triangle inequality): boundX[r] >= distance of packed row r (and of every later row of its
+    // tile -- rows are sorted by it) to a common reference point.  No pair of a tile can reach bound_min when
+    // boundA[first row] + boundB[first row] < bound_min, a value some pair is already known to attain.  null = off.
+    const double *boundA, *boundB;
+    double bound_min;
 };
 
 struct PairParams {
@@ -116,6 +121,7 @@ __global__ void __launch_bounds__(NT, CTAS_PER_SM) pair_tile_kernel(const PairPa
     const int gm = min(GM, G.tilesM - band * GM);
     const int tm = band * GM + rem % gm, tn = rem / gm;
     if ((EPI == EPI_MAX || EPI == EPI_LOCAL) && G.sym && (tn + 1) * BN <= tm * BM) return;  // tile entirely below the diagonal
+    if (EPI == EPI_MAX && G.boundA && G.boundA[tm * BM] + G.boundB[tn * BN] < G.bound_min) return;  // cannot hold the maximum
 
     // ---- de-phase the two CTAs that share an SM --------------------------------------------------
     // All tiles of a group cost the same, so the two resident CTAs would run in lockstep and reach

@@ -935,26 +935,44 @@ int aqml_rep_local_gaussian_sym(const aqml_rep *r, const double *sigmas, int nsi
     });
 }
 
-int aqml_rep_kernel_width(const aqml_rep *r1, const aqml_rep *r2, int zmax, double *dso, void *stream) {
+int aqml_rep_kernel_width_multi(const aqml_rep *const *reps1, int n1, const aqml_rep *const *reps2, int n2, int zmax, double *dso,
+                                void *stream) {
     return guarded([&] {
-        AQML_REQUIRE(r1 && r2 && dso && zmax >= 1, "bad argument");
+        AQML_REQUIRE(reps1 && reps2 && n1 >= 1 && n2 >= 1 && dso && zmax >= 1, "bad argument");
         require_device();
         cudaStream_t st = (cudaStream_t)stream;
         Workspace ws(st);
-        std::vector<PairGroup> groups;
-        std::vector<int> labels;
-        rep_groups(r1, r2, zmax, groups, labels);
-        unsigned long long *bits = ws.zeros<unsigned long long>(groups.size() + 1);
-        for (size_t i = 0; i < groups.size(); i++) { groups[i].out_slot = (int)i; groups[i].sym = (r1 == r2); }
-        PairParams P{};
-        P.out = reinterpret_cast<double *>(bits);
-        run_pairs_public(MODE_DOT, EPI_MAX, groups, P, ws);
-        std::vector<double> mx(groups.size() + 1);
-        AQML_CUDA(cudaMemcpyAsync(mx.data(), bits, sizeof(double) * groups.size(), cudaMemcpyDeviceToHost, st));
-        AQML_CUDA(cudaStreamSynchronize(st));
+        bool same = (n1 == n2);
+        for (int i = 0; same && i < n1; i++) same = (reps1[i] == reps2[i]);
+        // element label -> row segments of every representation that holds atoms of it
+        std::map<int, std::pair<std::vector<RowSeg>, std::vector<RowSeg>>> segs;
+        std::map<int, long long> lds;
+        auto collect = [&](const aqml_rep *const *reps, int n, bool second) {
+            for (int i = 0; i < n; i++) {
+                AQML_REQUIRE(reps[i], "null representation");
+                for (const auto &e : reps[i]->els) {
+                    if (e.n == 0) continue;
+                    int z = e.label % 1000;
+                    AQML_REQUIRE(z >= 1 && z <= zmax, "element %d outside 1..zmax=%d", z, zmax);
+                    auto it = lds.find(e.label);
+                    if (it == lds.end()) lds[e.label] = e.ld;
+                    else AQML_REQUIRE(it->second == e.ld, "representations were built with different many-body types");
+                    (second ? segs[e.label].second : segs[e.label].first).push_back(RowSeg{e.x, e.n});
+                }
+            }
+        };
+        collect(reps1, n1, false);
+        collect(reps2, n2, true);
         for (int z = 0; z < zmax; z++) dso[z] = 1.e-9;
-        for (size_t i = 0; i < groups.size(); i++) dso[labels[i] % 1000 - 1] = std::sqrt(mx[i]);
+        for (auto &kv : segs) {
+            if (kv.second.first.empty() || kv.second.second.empty()) continue;
+            dso[kv.first % 1000 - 1] = std::sqrt(pruned_max_segs_public(2, kv.second.first, kv.second.second, lds[kv.first], same, ws));
+        }
     });
+}
+
+int aqml_rep_kernel_width(const aqml_rep *r1, const aqml_rep *r2, int zmax, double *dso, void *stream) {
+    return aqml_rep_kernel_width_multi(&r1, 1, &r2, 1, zmax, dso, stream);
 }
 
 }  // extern "C"

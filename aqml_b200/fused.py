@@ -75,9 +75,14 @@ def local_gaussian(rep1, rep2, sigmas, zmax, row0=0, nrows=None, out=None, symme
 
 
 def kernel_width(rep1, rep2, zmax):
-    """Per-element max L2 distance between rep1 and rep2 atoms (get_kernel_width, aqml.py:204-255)."""
+    """Per-element max L2 distance between rep1 and rep2 atoms (get_kernel_width, aqml.py:204-255).
+    ``rep1`` / ``rep2`` may be lists of PackedRep (a data set packed in blocks): the maximum runs over all of them."""
     import torch
+    l1 = list(rep1) if isinstance(rep1, (list, tuple)) else [rep1]
+    l2 = list(rep2) if isinstance(rep2, (list, tuple)) else [rep2]
     dso = np.zeros(zmax)
-    with torch.cuda.device(rep1.device):
-        L.call("aqml_rep_kernel_width", rep1._h, rep2._h, int(zmax), L.ptr(dso), L.current_stream())
+    h1 = (C.c_void_p * len(l1))(*[r._h for r in l1])
+    h2 = h1 if (len(l1) == len(l2) and all(a is b for a, b in zip(l1, l2))) else (C.c_void_p * len(l2))(*[r._h for r in l2])
+    with torch.cuda.device(l1[0].device):
+        L.call("aqml_rep_kernel_width_multi", h1, len(l1), h2, len(l2), int(zmax), L.ptr(dso), L.current_stream())
     return dso

@@ -184,6 +184,12 @@ int aqml_rep_local_gaussian(const aqml_rep *r1, const aqml_rep *r2, const double
 int aqml_rep_local_gaussian_sym(const aqml_rep *r, const double *sigmas, int nsigmas, int zmax, double *K, void *stream);
 /* per-element max L2 distance over r1 x r2 atoms (get_kernel_width on packed rows); dso HOST (zmax) */
 int aqml_rep_kernel_width(const aqml_rep *r1, const aqml_rep *r2, int zmax, double *dso, void *stream);
+/* same over the union of several representations on each side (a data set packed in blocks): the maximum over
+ * ALL atom pairs of reps1[*] x reps2[*].  The pass is pruned by the triangle inequality (distances to a common
+ * reference point + one attained pair distance as lower bound), so only the rows that can take part in the
+ * maximum are contracted -- the reference forms the whole distance matrix (aqml.py:220-237). */
+int aqml_rep_kernel_width_multi(const aqml_rep *const *reps1, int n1, const aqml_rep *const *reps2, int n2, int zmax, double *dso,
+                                void *stream);
 
 /* counters for bench.py: number of device kernels this library launched since load */
 int64_t aqml_launch_count(void);

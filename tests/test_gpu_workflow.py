@@ -145,8 +145,10 @@ def test_sharded_krr_single_rank_matches_direct_solve():
     low = torch.tril(torch.ones_like(K, dtype=torch.bool))
     assert rel_err(torch.where(low, K_loc, 0).cpu().numpy(), torch.where(low, K, 0).cpu().numpy()) < 1e-12
     y = torch.as_tensor(np.random.default_rng(0).normal(size=150), device=K.device)
-    alpha = model.fit(K_loc, y, 1e-2)
-    Kh = K.cpu().numpy() + 1e-2 * np.eye(150)
+    # lambda = 10 keeps cond(K + lambda I) ~ 1e4, so that rounding-order noise in K (FP64 atomics, ~1e-16) stays
+    # far below the tolerance in alpha
+    alpha = model.fit(K_loc, y, 10.0)
+    Kh = K.cpu().numpy() + 10.0 * np.eye(150)
     a_ref = np.linalg.solve(Kh, y.cpu().numpy())
     assert rel_err(alpha.cpu().numpy(), a_ref) < 1e-9
     y_ref = fused.local_gaussian(rep_test, rep_train, sig[None], zmax)[0].cpu().numpy() @ a_ref
