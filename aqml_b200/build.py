@@ -8,7 +8,7 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = [os.path.join(HERE, "csrc", f) for f in ("kernels.cu", "slatm.cu")]
-HDR = [os.path.join(HERE, "csrc", f) for f in ("common.cuh", "pairtile.cuh", "packing.cuh")] + \
+HDR = sorted(os.path.join(HERE, "csrc", f) for f in os.listdir(os.path.join(HERE, "csrc")) if f.endswith(".cuh")) + \
       [os.path.join(os.path.dirname(HERE), "include", "aqml_b200.h")]
 OUT = os.path.join(HERE, "lib", "libaqml_b200.so")
 

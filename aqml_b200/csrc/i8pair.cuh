@@ -1,0 +1,441 @@
+// Local Gaussian kernel on the 5th-generation tensor cores: FP64-accurate a.b from exact int8 slice products
+// (tcgen05.mma kind::i8, accumulators in TMEM) -- the B200-native engine of calc_lk_gaussian (fkernels.f90:23-93).
+//
+// FP64 DMMA peaks at 37 TF on this chip; the int8 pipe does 4.1 POP/s (profiles/r01_micro_i8_umma.txt).  An FP64
+// row x is split once, when the representation is packed, into S = 7 signed 7-bit digits of a per-row fixed
+// point number:  x[k] = 2^e * sum_{s=1..7} q_s[k] 128^-s + r,  |q_s| <= 64,  |r| <= 2^(e-50)  (e = exponent of the
+// row maximum + 1).  Then
+//     a.b = 2^(ea+eb) * sum_{g=0..6} 128^-(g+2) * P_g,      P_g = sum_{i+j=g} q^a_i . q^b_j    (28 products)
+// and every P_g is an EXACT int32 (<= 7 * 4401 * 64^2 < 2^31): the only errors are the dropped digit pairs
+// (i+j >= 7) and the digits beyond 7, both <= 2^-48 of max|a| max|b| per column -- below what the FP64 DMMA path
+// loses to cancellation in |a|^2 + |b|^2 - 2 a.b.  Parity with the oracle is asserted at the same 1e-10.
+//
+// Kernel: one CTA per 128 x 64 tile of atom pairs (A rows = TMEM lanes), 6 warps:
+//   warp 0 (one lane)  producer: per stage two active 16-column k-chunks of all 7 digit planes of A (2 x 14 KB,
+//                      contiguous in the pre-tiled slice buffer) and of B (2 x 7 x 1 KB) by cp.async.bulk onto an
+//                      mbarrier (4 stages x 42 KB);
+//   warp 1 (one lane)  issues the 28 UTCIMMA (M 128, N 64, K 32 = two k-chunks via the descriptor's leading
+//                      byte offset, so the exact 16-column block sparsity of the DMMA engine carries over) into 7
+//                      accumulators (7 x 64 = 448 TMEM columns); tcgen05.commit frees the stage / signals the end;
+//   warps 2-17         epilogue (4 per TMEM lane quarter, 16 columns each): tcgen05.ld of the 7 accumulators, Horner in FP64, d^2 = |a|^2+|b|^2-2a.b, exp per
+//                      sigma (squaring chain), sum over the atoms of a molecule pair (column runs in registers,
+//                      row runs by segmented shuffles), one RED.F64 per (sigma, molecule pair, warp).
+// Operands are staged in the canonical K-major no-swizzle core-matrix layout (8 rows x 16 B), which is exactly how
+// the slice buffer is written, so a stage is filled by plain 1-D bulk copies (no tensor maps).
+#pragma once
+
+namespace aqml {
+
+constexpr int I8_S = 7;                          // digit planes
+constexpr int I8_BM = 128, I8_BN = 64;           // tile: A rows x B rows
+constexpr int I8_STAGES = 3;
+constexpr int I8_A_CHUNK = I8_S * 2048;          // bytes of one k-chunk (16 columns) of an A tile, all planes
+constexpr int I8_B_CHUNK = I8_S * 1024;
+constexpr int I8_STAGE_BYTES = 2 * (I8_A_CHUNK + I8_B_CHUNK);  // 43008
+constexpr int I8_THREADS = 576;               // producer warp, MMA warp, 16 epilogue warps
+constexpr int I8_MAXSIG = 8;
+
+struct I8Group {
+    const int8_t *slA, *slB;      // [row block of 128][KT + 1][plane][128 rows x 16 B]; k-chunk KT is all zero
+    const int *expA, *expB;       // per packed row: exponent e
+    const double *normA, *normB;  // |row|^2 (FP64)
+    const int *segA, *segB;       // molecule per packed row, -1 = padding
+    int nrA, nrB;                 // packed rows covered by seg / norm / exp
+    const unsigned *maskA, *maskB;
+    int maskw;
+    int KT;
+    int tilesM, tilesN, tile_begin;
+    int zcol, segA_off, segA_n, sym;
+};
+
+struct I8Params {
+    const I8Group *groups;
+    int ngroups;
+    const double *isig;
+    int nsig, zstride;
+    double *out;
+    long long ldo, slab;
+    unsigned long long *stats;
+    int chain, order[16], nsq[16];
+    int debug;  // AQML_I8_DEBUG: phase timers into stats[2..6]
+};
+
+struct I8Smem {
+    unsigned long long full[I8_STAGES], empty[I8_STAGES], accum;
+    unsigned tmem_base;
+    int nact;
+    int segA[I8_BM], expA[I8_BM];
+    double normA[I8_BM];
+    int segB[I8_BN], expB[I8_BN];
+    double normB[I8_BN];
+    unsigned short kt[KT_LIST_MAX + 2];
+};
+
+namespace i8 {
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long *b, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(b)), "r"(count));
+}
+__device__ __forceinline__ bool mbar_try_wait(unsigned long long *b, unsigned phase) {
+    unsigned ok;
+    asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+                 : "=r"(ok) : "r"(smem_u32(b)), "r"(phase) : "memory");
+    return ok != 0;
+}
+// bounded: a protocol bug becomes a launch failure, never a hung GPU
+__device__ __forceinline__ void mbar_wait(unsigned long long *b, unsigned phase) {
+    for (long long it = 0; !mbar_try_wait(b, phase); it++)
+        if (it > 400000000ll) __trap();
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *b, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(b)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, unsigned bytes, unsigned long long *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+// K-major, no swizzle: 8 rows x 16 B core matrices; sbo = byte stride between 8-row groups, lbo = between the two
+// 16-byte k-chunks of one MMA (checked bit-exactly by tools/micro/i8_umma.cu)
+__device__ __forceinline__ unsigned long long smem_desc(unsigned addr, unsigned lbo, unsigned sbo) {
+    return (unsigned long long)((addr & 0x3FFFF) >> 4) | ((unsigned long long)(lbo >> 4) << 16) |
+           ((unsigned long long)(sbo >> 4) << 32) | (1ull << 46);
+}
+__device__ __forceinline__ void umma(unsigned tmem_d, unsigned long long da, unsigned long long db, unsigned idesc, unsigned accumulate) {
+    asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n}"
+                 ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(unsigned long long *bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// s32 accumulate, s8 x s8, both K-major, N >> 3 at bit 17, M >> 4 at bit 24
+__host__ __device__ constexpr unsigned idesc(int M, int N) { return (2u << 4) | (1u << 7) | (1u << 10) | ((unsigned)(N >> 3) << 17) | ((unsigned)(M >> 4) << 24); }
+__device__ __forceinline__ double pow2(int e) {  // 2^e, clamped to the normal range
+    e = max(-1022, min(1023, e));
+    return __hiloint2double((e + 1023) << 20, 0);
+}
+}  // namespace i8
+
+// exp(x), x <= 0 (or -inf), without a branch so that the 32 independent evaluations of a lane interleave
+__device__ __forceinline__ double i8_exp(double x) {
+    const double xc = fmax(x, -708.0);
+    const double magic = 6755399441055744.0;
+    double t = fma(xc, 1.4426950408889634, magic);
+    const int k = __double2loint(t);
+    t -= magic;
+    double r = fma(t, -6.93147180369123816490e-01, xc);
+    r = fma(t, -1.90821492927058770002e-10, r);
+    double p = c_expc[0];
+#pragma unroll
+    for (int i = 1; i < 12; i++) p = fma(p, r, c_expc[i]);
+    p = fma(p, r, 1.0);
+    p = fma(p, r, 1.0);
+    const double v = p * __hiloint2double((k + 1023) << 20, 0);
+    return (x < -707.0) ? 0.0 : v;
+}
+
+// sum the lanes of each A molecule (contiguous lanes, last lane run_end) and add the heads' totals into K
+__device__ __noinline__ void i8_flush(double r, int lane, int run_end, bool head, double *dst) {
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const double u = __shfl_down_sync(0xffffffffu, r, o);
+        if (lane + o <= run_end) r += u;
+    }
+    if (head) atomicAdd(dst, r);
+}
+
+// ---- slicing -------------------------------------------------------------------------------------------------
+// exponent per row: |x| * 2^-e <= 1/2
+__global__ void __launch_bounds__(256) i8_rowexp_kernel(const double *x, long long ld, int nrows, int *expo, int *nonfinite) {
+    const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (row >= nrows) return;
+    const double *xr = x + (long long)row * ld;
+    double m = 0.0;
+    bool bad = false;
+    for (int k = lane; k < ld; k += 32) {
+        const double v = fabs(xr[k]);
+        bad |= !(v <= 1.7976931348623157e308);
+        m = fmax(m, v);
+    }
+    m = warp_max(m);
+    bad = __any_sync(0xffffffffu, bad);
+    if (lane == 0) {
+        int e = 0;
+        if (m > 0.0) { frexp(m, &e); e += 1; }
+        if (e > 1000) bad = true;   // > 1e301: leave such data to the FP64 engine
+        expo[row] = max(e, -1000);  // tinier rows keep |x| 2^-e <= 1/2 and only lose (irrelevant) digits
+        if (bad) atomicOr(nonfinite, 1);
+    }
+}
+
+// thread = one row of a 128-row block; per 16-column chunk: 7 planes x 16 B
+__global__ void __launch_bounds__(128) i8_slice_kernel(const double *x, long long ld, int nrows, const int *expo, int KT, int kt_per_block,
+                                                       int8_t *sl) {
+    const int rb = blockIdx.x, r = threadIdx.x, row = rb * 128 + r;
+    const int kt0 = blockIdx.y * kt_per_block, kt1 = min(KT, kt0 + kt_per_block);
+    const bool valid = row < nrows;
+    const double sc = valid ? i8::pow2(-expo[row]) : 0.0;  // |e| <= 1000: exact power of two
+    const double *xr = x + (long long)(valid ? row : 0) * ld;
+    for (int kt = kt0; kt < kt1; kt++) {
+        double t[16];
+#pragma unroll
+        for (int c = 0; c < 16; c += 2) {
+            const double2 v = valid ? *reinterpret_cast<const double2 *>(xr + kt * 16 + c) : make_double2(0.0, 0.0);
+            t[c] = v.x * sc;
+            t[c + 1] = v.y * sc;
+        }
+        int8_t *dst = sl + (((long long)rb * (KT + 1) + kt) * I8_S) * 2048 + r * 16;
+#pragma unroll
+        for (int s = 0; s < I8_S; s++) {
+            unsigned w[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+            for (int c = 0; c < 16; c++) {
+                const double u = t[c] * 128.0;   // exact
+                const double q = rint(u);        // |q| <= 64
+                t[c] = u - q;                    // exact, |.| <= 1/2
+                w[c >> 2] |= ((unsigned)(int)q & 0xffu) << ((c & 3) * 8);
+            }
+            *reinterpret_cast<uint4 *>(dst + s * 2048) = make_uint4(w[0], w[1], w[2], w[3]);
+        }
+    }
+}
+
+// ---- the pair kernel -----------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(I8_THREADS, 1) i8_pair_kernel(const I8Params P) {
+    extern __shared__ __align__(1024) unsigned char i8_smem[];
+    unsigned char *stages = i8_smem;
+    I8Smem &S = *reinterpret_cast<I8Smem *>(i8_smem + I8_STAGES * I8_STAGE_BYTES);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+    int gi = 0;
+    while (gi + 1 < P.ngroups && (int)blockIdx.x >= P.groups[gi + 1].tile_begin) gi++;
+    const I8Group G = P.groups[gi];
+    const int t = blockIdx.x - G.tile_begin;
+    constexpr int GM = 16;  // tile rows per raster band (A planes stay L2 resident while B streams)
+    const int band = t / (GM * G.tilesN), rem = t % (GM * G.tilesN);
+    const int gm = min(GM, G.tilesM - band * GM);
+    const int tm = band * GM + rem % gm, tn = rem / gm;
+    if (G.sym && (tn + 1) * I8_BN <= tm * I8_BM) return;  // entirely below the diagonal
+
+    const long long T0 = clock64();
+    int any = 0;
+    for (int i = tid; i < I8_BM + I8_BN; i += I8_THREADS) {
+        if (i < I8_BM) {
+            const int r = tm * I8_BM + i;
+            int s = (r < G.nrA) ? G.segA[r] : -1;
+            s = (s >= G.segA_off && s - G.segA_off < G.segA_n) ? s - G.segA_off : -1;
+            S.segA[i] = s;
+            any |= (s >= 0);
+            S.normA[i] = (r < G.nrA) ? G.normA[r] : 0.0;
+            S.expA[i] = (r < G.nrA) ? G.expA[r] : 0;
+        } else {
+            const int c = i - I8_BM, r = tn * I8_BN + c;
+            S.segB[c] = (r < G.nrB) ? G.segB[r] : -1;
+            S.normB[c] = (r < G.nrB) ? G.normB[r] : 0.0;
+            S.expB[c] = (r < G.nrB) ? G.expB[r] : 0;
+        }
+    }
+    if (!__syncthreads_or(any)) return;  // no wanted row in this tile (row-block sharding)
+
+    // active 16-column k-chunks: both operands have a non-zero there (exact: a zero chunk adds 0 to a.b)
+    if (warp == 0) {
+        int n = 0;
+        const bool masked = G.maskA && G.maskB && G.maskw <= 32 && G.KT <= KT_LIST_MAX;
+        if (masked) {
+            unsigned bits = 0;
+            if (lane < G.maskw) {
+                const int nb64A = (G.nrA + 63) / 64;
+                unsigned a = G.maskA[(long long)(2 * tm) * G.maskw + lane];
+                if (2 * tm + 1 < nb64A) a |= G.maskA[(long long)(2 * tm + 1) * G.maskw + lane];
+                bits = a & G.maskB[(long long)tn * G.maskw + lane];
+            }
+            for (int w = 0; w < G.maskw; w++) {
+                unsigned b = __shfl_sync(0xffffffffu, bits, w);
+                const int cnt = __popc(b);
+                if (lane < cnt) {
+                    for (int q = 0; q < lane; q++) b &= b - 1;
+                    S.kt[n + lane] = (unsigned short)(w * 32 + __ffs(b) - 1);
+                }
+                n += cnt;
+            }
+        } else {
+            for (int k = lane; k < G.KT; k += 32) S.kt[k] = (unsigned short)k;
+            n = G.KT;
+        }
+        if (lane == 0) {
+            if (n & 1) S.kt[n] = (unsigned short)G.KT;  // pad the last stage with the all-zero chunk
+            S.nact = n;
+            if (P.stats) {  // in units of 64 x 64 x 16 k-tiles, like the DMMA engine
+                atomicAdd(P.stats, 2ull * (unsigned long long)n);
+                atomicAdd(P.stats + 1, 2ull * (unsigned long long)G.KT);
+            }
+        }
+    }
+    if (tid == 0) {
+        for (int s = 0; s < I8_STAGES; s++) { i8::mbar_init(&S.full[s], 1); i8::mbar_init(&S.empty[s], 1); }
+        i8::mbar_init(&S.accum, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(i8::smem_u32(&S.tmem_base)), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const unsigned tb = S.tmem_base;
+    const int nst = (S.nact + 1) >> 1;
+    const long long T1 = clock64();
+
+    if (warp == 0) {
+        if (lane == 0) {
+            const int8_t *srcA = G.slA + (long long)tm * (G.KT + 1) * I8_A_CHUNK;
+            const int8_t *srcB = G.slB + (long long)(tn >> 1) * (G.KT + 1) * I8_A_CHUNK + (tn & 1) * 1024;
+            for (int it = 0; it < nst; it++) {
+                const int s = it % I8_STAGES;
+                if (it >= I8_STAGES) i8::mbar_wait(&S.empty[s], ((it / I8_STAGES) - 1) & 1);
+                unsigned char *st = stages + s * I8_STAGE_BYTES;
+                i8::mbar_expect_tx(&S.full[s], I8_STAGE_BYTES);
+#pragma unroll
+                for (int c = 0; c < 2; c++) {
+                    const int kt = S.kt[2 * it + c];
+                    i8::bulk_g2s(st + c * I8_A_CHUNK, srcA + (long long)kt * I8_A_CHUNK, I8_A_CHUNK, &S.full[s]);
+                    unsigned char *db = st + 2 * I8_A_CHUNK + c * I8_B_CHUNK;
+                    const int8_t *sb = srcB + (long long)kt * I8_A_CHUNK;
+#pragma unroll
+                    for (int p = 0; p < I8_S; p++) i8::bulk_g2s(db + p * 1024, sb + p * 2048, 1024, &S.full[s]);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0 && nst > 0) {
+            constexpr unsigned ID = i8::idesc(I8_BM, I8_BN);
+            for (int it = 0; it < nst; it++) {
+                const int s = it % I8_STAGES;
+                i8::mbar_wait(&S.full[s], (it / I8_STAGES) & 1);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const unsigned a0 = i8::smem_u32(stages + s * I8_STAGE_BYTES), b0 = a0 + 2 * I8_A_CHUNK;
+                const unsigned long long da = i8::smem_desc(a0, I8_A_CHUNK, 128), db = i8::smem_desc(b0, I8_B_CHUNK, 128);
+#pragma unroll
+                for (int i = 0; i < I8_S; i++)
+#pragma unroll
+                    for (int j = 0; j < I8_S; j++)
+                        if (i + j < I8_S)  // the first product of accumulator g = i + j is (0, g)
+                            i8::umma(tb + (i + j) * I8_BN, da + (unsigned long long)(i * 2048 >> 4), db + (unsigned long long)(j * 1024 >> 4), ID,
+                                     (it > 0 || i > 0) ? 1u : 0u);
+                i8::umma_commit(&S.empty[s]);  // stage reusable once these MMAs have read it
+            }
+            i8::umma_commit(&S.accum);
+        }
+    } else {
+        // ---- epilogue: 16 warps; warp (q, h) owns TMEM lanes / tile rows 32q .. 32q+31 and columns 16h .. 16h+15 ----
+        // (many warps with little state each: the exp / Horner chains are latency bound, not issue bound)
+        constexpr int EC = I8_BN / 4;  // 16 columns per warp
+        const int q = warp & 3, cbase = ((warp - 2) >> 2) * EC, row = q * 32 + lane;
+        const int sr = S.segA[row];
+        // lanes of one molecule are contiguous: head lane and last lane of my run
+        const int prev = __shfl_up_sync(0xffffffffu, sr, 1);
+        const bool head = ((lane == 0) || (prev != sr)) && sr >= 0;
+        const unsigned heads = __ballot_sync(0xffffffffu, (lane == 0) || (prev != sr));
+        const unsigned above = (lane == 31) ? 0u : (heads >> (lane + 1));
+        const int run_end = above ? (lane + __ffs(above) - 1) : 31;
+        const double na = S.normA[row];
+        const double sa = i8::pow2(S.expA[row] - 7);
+        const int growA = tm * I8_BM + row;
+        const unsigned lastmask = __ballot_sync(0xffffffffu, lane < EC && (lane == EC - 1 || S.segB[cbase + lane + 1] != S.segB[cbase + lane]));
+        if (nst > 0) {
+            i8::mbar_wait(&S.accum, 0);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        }
+        const long long T2 = clock64();
+        if (P.debug && warp == 2 && lane == 0) {
+            atomicAdd(P.stats + 2, (unsigned long long)(T1 - T0));
+            atomicAdd(P.stats + 3, (unsigned long long)(T2 - T1));
+            atomicAdd(P.stats + 5, (unsigned long long)nst);
+            atomicAdd(P.stats + 6, 1ull);
+        }
+        // phase 1: d^2 of my 16 pairs per lane -> registers
+        double x[EC];
+        if (!(P.debug & 4)) {
+        const unsigned trow = tb + ((unsigned)(q * 32) << 16) + cbase;
+#pragma unroll
+        for (int cc = 0; cc < EC / 4; cc++) {
+            unsigned v[I8_S][4];
+            if (nst > 0) {
+#pragma unroll
+                for (int g = 0; g < I8_S; g++)
+                    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];"
+                                 : "=r"(v[g][0]), "=r"(v[g][1]), "=r"(v[g][2]), "=r"(v[g][3]) : "r"(trow + g * I8_BN + cc * 4));
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            } else {
+#pragma unroll
+                for (int g = 0; g < I8_S; g++)
+#pragma unroll
+                    for (int j = 0; j < 4; j++) v[g][j] = 0u;
+            }
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const int col = cbase + cc * 4 + j;
+                // sum_g P_g 128^-g, exactly: the three heavy and the four light accumulators as two 64-bit integers
+                const long long hi = ((long long)(int)v[0][j] << 14) + ((long long)(int)v[1][j] << 7) + (long long)(int)v[2][j];
+                const long long lo = ((long long)(int)v[3][j] << 21) + ((long long)(int)v[4][j] << 14) + ((long long)(int)v[5][j] << 7) +
+                                     (long long)(int)v[6][j];
+                const double d = fma((double)lo, 2.2737367544323206e-13 /* 2^-42 */, (double)hi * 6.103515625e-05 /* 2^-14 */);
+                const double dot = d * sa * i8::pow2(S.expB[col] - 7);
+                double xx = fmax(na + S.normB[col] - 2.0 * dot, 0.0);
+                // pairs that do not count: on / below the diagonal of a symmetric kernel, padding rows / columns
+                if ((G.sym && tn * I8_BN + col <= growA) || sr < 0 || S.segB[col] < 0) xx = __longlong_as_double(0x7ff0000000000000LL);
+                x[cc * 4 + j] = xx;
+            }
+        }
+        const long long T3 = clock64();
+        if (P.debug && warp == 2 && lane == 0) atomicAdd(P.stats + 7, (unsigned long long)(T3 - T2));
+        if (!(P.debug & 2)) {
+        // phase 2: per sigma exp (chain: squarings of the previous sigma's values, in place), then the sums over molecule
+        // pairs: column runs sequentially in registers, row runs by a segmented shuffle reduction, one RED per head lane
+#pragma unroll 1
+        for (int si = 0; si < P.nsig; si++) {
+            const int s = P.chain ? P.order[si] : si;
+            double *outS = P.out + (long long)s * P.slab + (long long)max(sr, 0) * P.ldo;
+            double run = 0.0;
+            if (P.chain) {
+                if (si == 0) {
+                    const double f = P.isig[s * P.zstride + G.zcol];
+#pragma unroll
+                    for (int j = 0; j < EC; j++) x[j] = i8_exp(x[j] * f);  // +inf * f = -inf -> 0
+                } else {
+                    for (int k = 0; k < P.nsq[si]; k++)
+#pragma unroll
+                        for (int j = 0; j < EC; j++) x[j] *= x[j];
+                }
+#pragma unroll
+                for (int j = 0; j < EC; j++) {
+                    run += x[j];
+                    if ((lastmask >> j) & 1u) {  // warp-uniform: column cbase + j closes a molecule of B
+                        const int sc = S.segB[cbase + j];
+                        if (sc >= 0) i8_flush(run, lane, run_end, head, outS + sc);
+                        run = 0.0;
+                    }
+                }
+            } else {
+                const double f = P.isig[s * P.zstride + G.zcol];
+#pragma unroll
+                for (int j = 0; j < EC; j++) {
+                    run += i8_exp(x[j] * f);
+                    if ((lastmask >> j) & 1u) {
+                        const int sc = S.segB[cbase + j];
+                        if (sc >= 0) i8_flush(run, lane, run_end, head, outS + sc);
+                        run = 0.0;
+                    }
+                }
+            }
+        }
+        }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (P.debug && tid == 0) atomicAdd(P.stats + 4, (unsigned long long)(clock64() - T1));
+    if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tb), "r"(512u) : "memory");
+}
+
+}  // namespace aqml

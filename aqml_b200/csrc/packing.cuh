@@ -36,6 +36,7 @@ void build_tiles(const std::vector<int> &rows, const std::vector<int> &mol_of_ro
                  std::vector<int> &seg);
 std::vector<int> class_sorted_molecules(const int *zs, const int *nas, int nm);
 void plan_sigma_chain(PairParams &P, const std::vector<double> &isig);
+unsigned long long *pair_stats_buffer();
 void run_pairs_public(int mode, int epi, const std::vector<PairGroup> &groups, PairParams P, Workspace &ws);
 double pruned_max_public(int p, const double *A, int nA, const double *B, int nB, long long ld, bool same, Workspace &ws);
 double pruned_max_segs_public(int p, const std::vector<RowSeg> &SA, const std::vector<RowSeg> &SB, long long ld, bool same,

@@ -381,6 +381,7 @@ __global__ void __launch_bounds__(SL_THREADS) slatm_kernel(const SlatmDev T, con
 
 }  // namespace aqml
 #include "slatm_units.cuh"
+#include "i8pair.cuh"
 namespace aqml {
 
 // K <- Kc + Kc^T (+ diag), in place, one 32x32 tile pair per block: Kc holds, for every unordered atom pair,
@@ -686,13 +687,71 @@ struct aqml_rep {
         int *seg;
         unsigned *mask;
         int maskw;
+        int8_t *sl = nullptr;  // int8 digit planes for the tcgen05 engine (i8pair.cuh), null = not built
+        int *expo = nullptr;   // per packed row exponent
+        int nr = 0;            // packed rows (multiple of 64)
     };
+    bool i8_ready = false;     // every element has digit planes and all values are finite
     std::vector<El> els;
     std::vector<int> nas;
     std::vector<std::vector<int>> cnt;  // [el][mol]
 };
 
 namespace aqml {
+
+// AQML_PAIR_ENGINE=dmma keeps the FP64 DMMA engine for the fused local kernel; default: int8 digit planes on tcgen05
+static bool i8_engine_enabled() {
+    const char *e = getenv("AQML_PAIR_ENGINE");
+    return !(e && (!strcmp(e, "dmma") || !strcmp(e, "fp64")));
+}
+
+static void run_pairs_i8(const aqml_rep *r1, const aqml_rep *r2, int zmax, int row0, int nrows, bool sym, PairParams PP, Workspace &ws) {
+    std::vector<I8Group> gs;
+    int total = 0;
+    for (const auto &a : r1->els)
+        for (const auto &b : r2->els) {
+            if (a.label != b.label || a.n == 0 || b.n == 0) continue;
+            AQML_REQUIRE(a.ld == b.ld, "representations were built with different many-body types");
+            const int z = a.label % 1000;
+            AQML_REQUIRE(z >= 1 && z <= zmax, "element %d outside 1..zmax=%d", z, zmax);
+            I8Group g;
+            memset(&g, 0, sizeof(g));
+            g.slA = a.sl; g.slB = b.sl; g.expA = a.expo; g.expB = b.expo; g.normA = a.norm; g.normB = b.norm;
+            g.segA = a.seg; g.segB = b.seg; g.nrA = a.nr; g.nrB = b.nr;
+            g.maskA = a.mask; g.maskB = b.mask; g.maskw = a.maskw;
+            g.KT = a.ld / 16;
+            g.tilesM = (a.nr + I8_BM - 1) / I8_BM; g.tilesN = (b.nr + I8_BN - 1) / I8_BN;
+            g.tile_begin = total; total += g.tilesM * g.tilesN;
+            g.zcol = z - 1; g.segA_off = row0; g.segA_n = nrows; g.sym = sym ? 1 : 0;
+            gs.push_back(g);
+        }
+    if (total == 0) return;
+    I8Params P;
+    memset(&P, 0, sizeof(P));
+    P.groups = ws.upload(gs); P.ngroups = (int)gs.size();
+    P.isig = PP.isig; P.nsig = PP.nsig; P.zstride = PP.zstride; P.out = PP.out; P.ldo = PP.ldo; P.slab = PP.slab;
+    P.stats = pair_stats_buffer();
+    P.chain = PP.chain;
+    for (int i = 0; i < 16; i++) { P.order[i] = PP.order[i]; P.nsq[i] = PP.nsq[i]; }
+    const int smem = I8_STAGES * I8_STAGE_BYTES + (int)sizeof(I8Smem);
+    AQML_CUDA(cudaFuncSetAttribute(i8_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    P.debug = getenv("AQML_I8_DEBUG") ? atoi(getenv("AQML_I8_DEBUG")) : 0;
+    if (P.debug) AQML_CUDA(cudaMemsetAsync(P.stats + 2, 0, 48, ws.stream()));
+    i8_pair_kernel<<<total, I8_THREADS, smem, ws.stream()>>>(P);
+    AQML_LAUNCH_CHECK();
+    if (P.debug) {
+        unsigned long long h[6];
+        AQML_CUDA(cudaMemcpyAsync(h, P.stats + 2, 48, cudaMemcpyDeviceToHost, ws.stream()));
+        AQML_CUDA(cudaStreamSynchronize(ws.stream()));
+        double n = (double)std::max<unsigned long long>(h[4], 1);
+        fprintf(stderr, "[i8] tiles %llu (grid %d): setup %.0f clk, mainloop %.0f clk, mainloop+epilogue %.0f clk, stages/tile %.1f, epilogue phase 1 %.0f clk\n", h[4], total,
+                h[0] / n, h[1] / n, h[2] / n, h[3] / n, h[5] / n);
+    }
+}
+
+static bool use_i8(const aqml_rep *r1, const aqml_rep *r2, int nsigmas) {
+    return i8_engine_enabled() && r1->i8_ready && r2->i8_ready && nsigmas <= I8_MAXSIG;
+}
 
 static void rep_create(const double *coords, int on_dev, const int *zs, const int *nas, int nmol,
                        const aqml_slatm_params *p, cudaStream_t st, aqml_rep **out) {
@@ -745,6 +804,7 @@ static void rep_create(const double *coords, int on_dev, const int *zs, const in
             zero_rows_kernel<<<(unsigned)pad.size(), 128, 0, st>>>(el.x, el.ld, ws.upload(pad), (int)pad.size(), el.norm);
             AQML_LAUNCH_CHECK();
         }
+        el.nr = (int)nr;
         J.px[e] = el.x; J.pnorm[e] = el.norm; J.pmask[e] = el.mask; J.maskw[e] = el.maskw;
         rep->els.push_back(el);
     }
@@ -753,6 +813,29 @@ static void rep_create(const double *coords, int on_dev, const int *zs, const in
     J.coords = dcoords; J.zs = ws.upload(zs, mi.A); J.mol_off = ws.upload(mi.off); J.atom_mol = ws.upload(mi.atom_mol);
     J.nmol = nmol; J.A = mi.A; J.local = 1; J.out = nullptr; J.ldo = 0; J.atom_prow = ws.upload(atom_prow);
     launch_slatm(t, J, mi, ws);
+    if (i8_engine_enabled()) {
+        // digit planes of every packed operand (7 bytes per element next to the 8 of the FP64 copy)
+        int *flag = ws.zeros<int>(1);
+        for (auto &el : rep->els) {
+            if (el.n == 0) continue;
+            const int KT = el.ld / 16, rb = (el.nr + 127) / 128;
+            const size_t bytes = (size_t)rb * (KT + 1) * I8_A_CHUNK;
+            el.sl = keep.alloc<int8_t>(bytes);
+            el.expo = keep.alloc<int>(el.nr);
+            rep->bytes += (int64_t)bytes + 4 * el.nr;
+            AQML_CUDA(cudaMemsetAsync(el.sl, 0, bytes, st));
+            i8_rowexp_kernel<<<(el.nr + 7) / 8, 256, 0, st>>>(el.x, el.ld, el.nr, el.expo, flag);
+            AQML_LAUNCH_CHECK();
+            const int split = std::max(1, std::min(KT, 2048 / std::max(rb, 1)));
+            const int per = (KT + split - 1) / split;
+            i8_slice_kernel<<<dim3(rb, (KT + per - 1) / per), 128, 0, st>>>(el.x, el.ld, el.nr, el.expo, KT, per, el.sl);
+            AQML_LAUNCH_CHECK();
+        }
+        int bad = 0;
+        AQML_CUDA(cudaMemcpyAsync(&bad, flag, sizeof(int), cudaMemcpyDeviceToHost, st));
+        AQML_CUDA(cudaStreamSynchronize(st));
+        rep->i8_ready = (bad == 0);  // NaN / Inf rows (coincident atoms): the FP64 engine reproduces the reference's NaNs
+    }
     rep->owned = keep.pointers();
     keep.release_all();
     *out = rep.release();
@@ -893,7 +976,8 @@ int aqml_rep_local_gaussian(const aqml_rep *r1, const aqml_rep *r2, const double
         P.isig = ws.upload(isig); P.nsig = nsigmas; P.zstride = zmax;
         plan_sigma_chain(P, isig);
         P.out = K; P.ldo = r2->nmol; P.slab = (long long)nrows * r2->nmol;
-        run_pairs_public(MODE_DOT, EPI_LOCAL, groups, P, ws);
+        if (use_i8(r1, r2, nsigmas)) run_pairs_i8(r1, r2, zmax, row0, nrows, false, P, ws);
+        else run_pairs_public(MODE_DOT, EPI_LOCAL, groups, P, ws);
     });
 }
 
@@ -928,7 +1012,8 @@ int aqml_rep_local_gaussian_sym(const aqml_rep *r, const double *sigmas, int nsi
         P.isig = ws.upload(isig); P.nsig = nsigmas; P.zstride = zmax;
         plan_sigma_chain(P, isig);
         P.out = K; P.ldo = n; P.slab = (long long)n * n;
-        run_pairs_public(MODE_DOT, EPI_LOCAL, groups, P, ws);
+        if (use_i8(r, r, nsigmas)) run_pairs_i8(r, r, zmax, 0, n, true, P, ws);
+        else run_pairs_public(MODE_DOT, EPI_LOCAL, groups, P, ws);
         dim3 grid((n + 31) / 32, (n + 31) / 32, nsigmas);
         symmetrize_kernel<<<grid, 256, 0, st>>>(K, n, nsigmas, ws.upload(diag));
         AQML_LAUNCH_CHECK();
