@@ -10,14 +10,15 @@
 // (i+j >= 7) and the digits beyond 7, both <= 2^-48 of max|a| max|b| per column -- below what the FP64 DMMA path
 // loses to cancellation in |a|^2 + |b|^2 - 2 a.b.  Parity with the oracle is asserted at the same 1e-10.
 //
-// Kernel: one CTA per 128 x 64 tile of atom pairs (A rows = TMEM lanes), 6 warps:
+// Kernel: persistent, one CTA per SM walking the 128 x 64 tiles of atom pairs (A rows = TMEM lanes):
 //   warp 0 (one lane)  producer: per stage two active 16-column k-chunks of all 7 digit planes of A (2 x 14 KB,
 //                      contiguous in the pre-tiled slice buffer) and of B (2 x 7 x 1 KB) by cp.async.bulk onto an
 //                      mbarrier (4 stages x 42 KB);
 //   warp 1 (one lane)  issues the 28 UTCIMMA (M 128, N 64, K 32 = two k-chunks via the descriptor's leading
 //                      byte offset, so the exact 16-column block sparsity of the DMMA engine carries over) into 7
 //                      accumulators (7 x 64 = 448 TMEM columns); tcgen05.commit frees the stage / signals the end;
-//   warps 2-17         epilogue (4 per TMEM lane quarter, 16 columns each): tcgen05.ld of the 7 accumulators, Horner in FP64, d^2 = |a|^2+|b|^2-2a.b, exp per
+//   warp 2             tile metadata one tile ahead (double buffered);
+//   warps 3-18         epilogue (4 per TMEM lane quarter, 16 columns each): tcgen05.ld of the 7 accumulators, Horner in FP64, d^2 = |a|^2+|b|^2-2a.b, exp per
 //                      sigma (squaring chain), sum over the atoms of a molecule pair (column runs in registers,
 //                      row runs by segmented shuffles), one RED.F64 per (sigma, molecule pair, warp).
 // Operands are staged in the canonical K-major no-swizzle core-matrix layout (8 rows x 16 B), which is exactly how
@@ -28,11 +29,17 @@ namespace aqml {
 
 constexpr int I8_S = 7;                          // digit planes
 constexpr int I8_BM = 128, I8_BN = 64;           // tile: A rows x B rows
-constexpr int I8_STAGES = 3;
+constexpr int I8_STAGES = 4;
 constexpr int I8_A_CHUNK = I8_S * 2048;          // bytes of one k-chunk (16 columns) of an A tile, all planes
 constexpr int I8_B_CHUNK = I8_S * 1024;
 constexpr int I8_STAGE_BYTES = 2 * (I8_A_CHUNK + I8_B_CHUNK);  // 43008
-constexpr int I8_THREADS = 576;               // producer warp, MMA warp, 16 epilogue warps
+constexpr int I8_EPI_WARPS = 16;
+// FP64 arithmetic and the tensor pipe exclude each other on this chip (tools/micro/i8_umma.cu: dense FP64 + UTCIMMA take the
+// sum of their times; FP32 overlaps fully).  Measured: overlapping the epilogue's exp / sums with the next tile's MMAs (0)
+// still beats running them strictly after each other (1): 331 vs 353 ms per step.
+constexpr int I8_SERIAL_EPILOGUE = 0;
+constexpr int I8_META = 3;                       // tile metadata buffers (prepared up to two tiles ahead)
+constexpr int I8_THREADS = 32 * (3 + I8_EPI_WARPS);  // producer, MMA issuer, tile metadata, 16 epilogue warps
 constexpr int I8_MAXSIG = 8;
 
 struct I8Group {
@@ -57,19 +64,26 @@ struct I8Params {
     long long ldo, slab;
     unsigned long long *stats;
     int chain, order[16], nsq[16];
-    int debug;  // AQML_I8_DEBUG: phase timers into stats[2..6]
+    int debug;  // AQML_I8_DEBUG: MMA-thread wait timers into stats[2..6]
+};
+
+struct I8Meta {  // everything the roles need to know about one tile
+    int tm, tn, nact, KT, zcol, sym;
+    const int8_t *srcA, *srcB;
+    int segA[I8_BM], expA[I8_BM];
+    double normA[I8_BM];
+    int segB[I8_BN + 1];
+    double normB[I8_BN], m2sB[I8_BN];  // |b|^2, -2 * 2^(e_b - 7)
+    unsigned short kt[KT_LIST_MAX + 2];
 };
 
 struct I8Smem {
-    unsigned long long full[I8_STAGES], empty[I8_STAGES], accum;
+    unsigned long long full[I8_STAGES], empty[I8_STAGES], accum, tmem_free, meta_full[I8_META], meta_empty[I8_META];
     unsigned tmem_base;
-    int nact;
-    int segA[I8_BM], expA[I8_BM];
-    double normA[I8_BM];
-    int segB[I8_BN], expB[I8_BN];
-    double normB[I8_BN];
-    unsigned short kt[KT_LIST_MAX + 2];
+    double exptab[256];  // 2^(j/128), 2^(j/16384)
+    I8Meta meta[I8_META];
 };
+
 
 namespace i8 {
 __device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
@@ -85,7 +99,10 @@ __device__ __forceinline__ bool mbar_try_wait(unsigned long long *b, unsigned ph
 // bounded: a protocol bug becomes a launch failure, never a hung GPU
 __device__ __forceinline__ void mbar_wait(unsigned long long *b, unsigned phase) {
     for (long long it = 0; !mbar_try_wait(b, phase); it++)
-        if (it > 400000000ll) __trap();
+        if (it > 30000000ll) __trap();
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long *b) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(b)) : "memory");
 }
 __device__ __forceinline__ void mbar_expect_tx(unsigned long long *b, unsigned bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(b)), "r"(bytes) : "memory");
@@ -115,22 +132,25 @@ __device__ __forceinline__ double pow2(int e) {  // 2^e, clamped to the normal r
 }
 }  // namespace i8
 
-// exp(x), x <= 0 (or -inf), without a branch so that the 32 independent evaluations of a lane interleave
-__device__ __forceinline__ double i8_exp(double x) {
+// exp(x), x <= 0 (or -inf): x log2(e) = k + j1/128 + j2/16384 + rho;  exp(x) = 2^k T[j1] U[j2] exp(r), |r| <= 2.2e-5, cubic
+// polynomial.  9 FP64 instructions instead of the 18 of a polynomial-only evaluation: on this chip FP64 arithmetic and
+// the tensor pipe exclude each other (profiles/r01_micro_dmma_dfma.txt, r01_i8_pair_kernel_ncu.txt), so every FP64
+// instruction of the epilogue is time taken from the MMAs.  tab: 128 entries 2^(j/128), then 128 entries 2^(j/16384).
+__device__ __forceinline__ double i8_exp(double x, const double *tab) {
     const double xc = fmax(x, -708.0);
     const double magic = 6755399441055744.0;
-    double t = fma(xc, 1.4426950408889634, magic);
-    const int k = __double2loint(t);
+    double t = fma(xc, 23637.115549924776 /* 2^14 log2(e) */, magic);
+    const int n = __double2loint(t);
     t -= magic;
-    double r = fma(t, -6.93147180369123816490e-01, xc);
-    r = fma(t, -1.90821492927058770002e-10, r);
-    double p = c_expc[0];
-#pragma unroll
-    for (int i = 1; i < 12; i++) p = fma(p, r, c_expc[i]);
+    double r = fma(t, -4.2306346131226746e-05 /* ln2 / 2^14, upper 27 bits: t * hi is exact */, xc);
+    r = fma(t, -3.384964780863074e-13, r);
+    double p = fma(r, 1.0 / 6.0, 0.5);
     p = fma(p, r, 1.0);
     p = fma(p, r, 1.0);
-    const double v = p * __hiloint2double((k + 1023) << 20, 0);
-    return (x < -707.0) ? 0.0 : v;
+    const double w = tab[(n >> 7) & 127] * tab[128 + (n & 127)];
+    const double v = w * p;
+    const double sc = __hiloint2double(((n >> 14) + 1023) << 20, 0);
+    return (x < -707.0) ? 0.0 : v * sc;
 }
 
 // sum the lanes of each A molecule (contiguous lanes, last lane run_end) and add the heads' totals into K
@@ -200,80 +220,27 @@ __global__ void __launch_bounds__(128) i8_slice_kernel(const double *x, long lon
 }
 
 // ---- the pair kernel -----------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(I8_THREADS, 1) i8_pair_kernel(const I8Params P) {
+// Persistent: one CTA per SM walks the tile list (tile = blockIdx.x + k gridDim.x, same raster order as a plain grid).
+// Roles: warp 0 producer, warp 1 MMA issuer, warp 2 tile metadata (segments, norms, exponents, active k-chunk list,
+// one tile ahead, double buffered), warps 3-18 epilogue.  The epilogue first drains TMEM into registers (phase 1),
+// hands TMEM back (the next tile's MMAs start while exp / sums / REDs of this tile run), and the operand ring
+// keeps filling across tile boundaries.
+__global__ void __launch_bounds__(I8_THREADS, 1) i8_pair_kernel(const I8Params P, int total_tiles) {
     extern __shared__ __align__(1024) unsigned char i8_smem[];
     unsigned char *stages = i8_smem;
     I8Smem &S = *reinterpret_cast<I8Smem *>(i8_smem + I8_STAGES * I8_STAGE_BYTES);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
-    int gi = 0;
-    while (gi + 1 < P.ngroups && (int)blockIdx.x >= P.groups[gi + 1].tile_begin) gi++;
-    const I8Group G = P.groups[gi];
-    const int t = blockIdx.x - G.tile_begin;
-    constexpr int GM = 16;  // tile rows per raster band (A planes stay L2 resident while B streams)
-    const int band = t / (GM * G.tilesN), rem = t % (GM * G.tilesN);
-    const int gm = min(GM, G.tilesM - band * GM);
-    const int tm = band * GM + rem % gm, tn = rem / gm;
-    if (G.sym && (tn + 1) * I8_BN <= tm * I8_BM) return;  // entirely below the diagonal
-
-    const long long T0 = clock64();
-    int any = 0;
-    for (int i = tid; i < I8_BM + I8_BN; i += I8_THREADS) {
-        if (i < I8_BM) {
-            const int r = tm * I8_BM + i;
-            int s = (r < G.nrA) ? G.segA[r] : -1;
-            s = (s >= G.segA_off && s - G.segA_off < G.segA_n) ? s - G.segA_off : -1;
-            S.segA[i] = s;
-            any |= (s >= 0);
-            S.normA[i] = (r < G.nrA) ? G.normA[r] : 0.0;
-            S.expA[i] = (r < G.nrA) ? G.expA[r] : 0;
-        } else {
-            const int c = i - I8_BM, r = tn * I8_BN + c;
-            S.segB[c] = (r < G.nrB) ? G.segB[r] : -1;
-            S.normB[c] = (r < G.nrB) ? G.normB[r] : 0.0;
-            S.expB[c] = (r < G.nrB) ? G.expB[r] : 0;
-        }
-    }
-    if (!__syncthreads_or(any)) return;  // no wanted row in this tile (row-block sharding)
-
-    // active 16-column k-chunks: both operands have a non-zero there (exact: a zero chunk adds 0 to a.b)
-    if (warp == 0) {
-        int n = 0;
-        const bool masked = G.maskA && G.maskB && G.maskw <= 32 && G.KT <= KT_LIST_MAX;
-        if (masked) {
-            unsigned bits = 0;
-            if (lane < G.maskw) {
-                const int nb64A = (G.nrA + 63) / 64;
-                unsigned a = G.maskA[(long long)(2 * tm) * G.maskw + lane];
-                if (2 * tm + 1 < nb64A) a |= G.maskA[(long long)(2 * tm + 1) * G.maskw + lane];
-                bits = a & G.maskB[(long long)tn * G.maskw + lane];
-            }
-            for (int w = 0; w < G.maskw; w++) {
-                unsigned b = __shfl_sync(0xffffffffu, bits, w);
-                const int cnt = __popc(b);
-                if (lane < cnt) {
-                    for (int q = 0; q < lane; q++) b &= b - 1;
-                    S.kt[n + lane] = (unsigned short)(w * 32 + __ffs(b) - 1);
-                }
-                n += cnt;
-            }
-        } else {
-            for (int k = lane; k < G.KT; k += 32) S.kt[k] = (unsigned short)k;
-            n = G.KT;
-        }
-        if (lane == 0) {
-            if (n & 1) S.kt[n] = (unsigned short)G.KT;  // pad the last stage with the all-zero chunk
-            S.nact = n;
-            if (P.stats) {  // in units of 64 x 64 x 16 k-tiles, like the DMMA engine
-                atomicAdd(P.stats, 2ull * (unsigned long long)n);
-                atomicAdd(P.stats + 1, 2ull * (unsigned long long)G.KT);
-            }
-        }
-    }
     if (tid == 0) {
         for (int s = 0; s < I8_STAGES; s++) { i8::mbar_init(&S.full[s], 1); i8::mbar_init(&S.empty[s], 1); }
         i8::mbar_init(&S.accum, 1);
+        i8::mbar_init(&S.tmem_free, I8_EPI_WARPS);
+        for (int b = 0; b < I8_META; b++) { i8::mbar_init(&S.meta_full[b], 1); i8::mbar_init(&S.meta_empty[b], I8_EPI_WARPS); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (tid >= 64 && tid < 64 + 256) {
+        const int j = tid - 64;
+        S.exptab[j] = (j < 128) ? exp2((double)j / 128.0) : exp2((double)(j - 128) / 16384.0);
     }
     if (warp == 1) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(i8::smem_u32(&S.tmem_base)), "r"(512u) : "memory");
@@ -283,158 +250,278 @@ __global__ void __launch_bounds__(I8_THREADS, 1) i8_pair_kernel(const I8Params P
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const unsigned tb = S.tmem_base;
-    const int nst = (S.nact + 1) >> 1;
-    const long long T1 = clock64();
 
-    if (warp == 0) {
+    if (warp == 2) {
+        // ---- tile metadata, one tile ahead ----
+        int tl = 0;
+        for (int tile = blockIdx.x;; tile += gridDim.x) {
+            const int b = tl % I8_META;
+            I8Meta &M = S.meta[b];
+            if (tl >= I8_META) i8::mbar_wait(&S.meta_empty[b], ((tl / I8_META) - 1) & 1);
+            if (tile >= total_tiles) {  // sentinel: every role stops here
+                if (lane == 0) M.tm = -1;
+                __syncwarp();
+                if (lane == 0) i8::mbar_arrive(&S.meta_full[b]);
+                break;
+            }
+            int gi = 0;
+            while (gi + 1 < P.ngroups && tile >= P.groups[gi + 1].tile_begin) gi++;
+            const I8Group G = P.groups[gi];
+            const int t = tile - G.tile_begin;
+            constexpr int GM = 16;  // tile rows per raster band (A planes stay L2 resident while B streams)
+            const int band = t / (GM * G.tilesN), rem = t % (GM * G.tilesN);
+            const int gm = min(GM, G.tilesM - band * GM);
+            const int tm = band * GM + rem % gm, tn = rem / gm;
+            if (G.sym && (tn + 1) * I8_BN <= tm * I8_BM) continue;  // entirely below the diagonal
+            int any = 0;
+            for (int i = lane; i < I8_BM + I8_BN; i += 32) {
+                if (i < I8_BM) {
+                    const int r = tm * I8_BM + i;
+                    int sg = (r < G.nrA) ? G.segA[r] : -1;
+                    sg = (sg >= G.segA_off && sg - G.segA_off < G.segA_n) ? sg - G.segA_off : -1;
+                    M.segA[i] = sg;
+                    any |= (sg >= 0);
+                    M.normA[i] = (r < G.nrA) ? G.normA[r] : 0.0;
+                    M.expA[i] = (r < G.nrA) ? G.expA[r] : 0;
+                } else {
+                    const int c = i - I8_BM, r = tn * I8_BN + c;
+                    M.segB[c] = (r < G.nrB) ? G.segB[r] : -1;
+                    M.normB[c] = (r < G.nrB) ? G.normB[r] : 0.0;
+                    M.m2sB[c] = -2.0 * i8::pow2(((r < G.nrB) ? G.expB[r] : 0) - 7);
+                }
+            }
+            if (!__any_sync(0xffffffffu, any)) continue;  // no wanted row in this tile (row-block sharding)
+            // active 16-column k-chunks: both operands have a non-zero there (exact: a zero chunk adds 0 to a.b)
+            int n = 0;
+            const bool masked = G.maskA && G.maskB && G.maskw <= 32 && G.KT <= KT_LIST_MAX;
+            if (masked) {
+                unsigned bits = 0;
+                if (lane < G.maskw) {
+                    const int nb64A = (G.nrA + 63) / 64;
+                    unsigned am = G.maskA[(long long)(2 * tm) * G.maskw + lane];
+                    if (2 * tm + 1 < nb64A) am |= G.maskA[(long long)(2 * tm + 1) * G.maskw + lane];
+                    bits = am & G.maskB[(long long)tn * G.maskw + lane];
+                }
+                for (int w = 0; w < G.maskw; w++) {
+                    unsigned bb = __shfl_sync(0xffffffffu, bits, w);
+                    const int cnt = __popc(bb);
+                    if (lane < cnt) {
+                        for (int k = 0; k < lane; k++) bb &= bb - 1;
+                        M.kt[n + lane] = (unsigned short)(w * 32 + __ffs(bb) - 1);
+                    }
+                    n += cnt;
+                }
+            } else {
+                for (int k = lane; k < G.KT; k += 32) M.kt[k] = (unsigned short)k;
+                n = G.KT;
+            }
+            if (lane == 0) {
+                if (n & 1) M.kt[n] = (unsigned short)G.KT;  // pad the last stage with the all-zero chunk
+                M.nact = n; M.tm = tm; M.tn = tn; M.KT = G.KT; M.zcol = G.zcol; M.sym = G.sym;
+                M.srcA = G.slA + (long long)tm * (G.KT + 1) * I8_A_CHUNK;
+                M.srcB = G.slB + (long long)(tn >> 1) * (G.KT + 1) * I8_A_CHUNK + (tn & 1) * 1024;
+                if (P.stats) {  // in units of 64 x 64 x 16 k-tiles, like the DMMA engine
+                    atomicAdd(P.stats, 2ull * (unsigned long long)n);
+                    atomicAdd(P.stats + 1, 2ull * (unsigned long long)G.KT);
+                }
+            }
+            __syncwarp();
+            if (lane == 0) i8::mbar_arrive(&S.meta_full[b]);
+            tl++;
+        }
+    } else if (warp == 0) {
+        // ---- producer ----
         if (lane == 0) {
-            const int8_t *srcA = G.slA + (long long)tm * (G.KT + 1) * I8_A_CHUNK;
-            const int8_t *srcB = G.slB + (long long)(tn >> 1) * (G.KT + 1) * I8_A_CHUNK + (tn & 1) * 1024;
-            for (int it = 0; it < nst; it++) {
-                const int s = it % I8_STAGES;
-                if (it >= I8_STAGES) i8::mbar_wait(&S.empty[s], ((it / I8_STAGES) - 1) & 1);
-                unsigned char *st = stages + s * I8_STAGE_BYTES;
-                i8::mbar_expect_tx(&S.full[s], I8_STAGE_BYTES);
+            int it = 0;  // position in the stage ring, continues across tiles
+            for (int tl = 0;; tl++) {
+                const int b = tl % I8_META;
+                const I8Meta &M = S.meta[b];
+                i8::mbar_wait(&S.meta_full[b], (tl / I8_META) & 1);
+                if (M.tm < 0) break;
+                const int nst = (M.nact + 1) >> 1;
+                const int8_t *srcA = M.srcA, *srcB = M.srcB;
+                for (int k = 0; k < nst; k++, it++) {
+                    const int s = it % I8_STAGES;
+                    if (it >= I8_STAGES) i8::mbar_wait(&S.empty[s], ((it / I8_STAGES) - 1) & 1);
+                    unsigned char *st = stages + s * I8_STAGE_BYTES;
+                    i8::mbar_expect_tx(&S.full[s], I8_STAGE_BYTES);
 #pragma unroll
-                for (int c = 0; c < 2; c++) {
-                    const int kt = S.kt[2 * it + c];
-                    i8::bulk_g2s(st + c * I8_A_CHUNK, srcA + (long long)kt * I8_A_CHUNK, I8_A_CHUNK, &S.full[s]);
-                    unsigned char *db = st + 2 * I8_A_CHUNK + c * I8_B_CHUNK;
-                    const int8_t *sb = srcB + (long long)kt * I8_A_CHUNK;
+                    for (int c = 0; c < 2; c++) {
+                        const int kt = M.kt[2 * k + c];
+                        i8::bulk_g2s(st + c * I8_A_CHUNK, srcA + (long long)kt * I8_A_CHUNK, I8_A_CHUNK, &S.full[s]);
+                        unsigned char *db = st + 2 * I8_A_CHUNK + c * I8_B_CHUNK;
+                        const int8_t *sb = srcB + (long long)kt * I8_A_CHUNK;
 #pragma unroll
-                    for (int p = 0; p < I8_S; p++) i8::bulk_g2s(db + p * 1024, sb + p * 2048, 1024, &S.full[s]);
+                        for (int p = 0; p < I8_S; p++) i8::bulk_g2s(db + p * 1024, sb + p * 2048, 1024, &S.full[s]);
+                    }
                 }
             }
         }
     } else if (warp == 1) {
-        if (lane == 0 && nst > 0) {
+        // ---- MMA issuer ----
+        if (lane == 0) {
             constexpr unsigned ID = i8::idesc(I8_BM, I8_BN);
-            for (int it = 0; it < nst; it++) {
-                const int s = it % I8_STAGES;
-                i8::mbar_wait(&S.full[s], (it / I8_STAGES) & 1);
+            int it = 0;
+            long long w_meta = 0, w_tmem = 0, w_full = 0;
+            const long long t_begin = clock64();
+            for (int tl = 0;; tl++) {
+                const int b = tl % I8_META;
+                long long c0 = clock64();
+                i8::mbar_wait(&S.meta_full[b], (tl / I8_META) & 1);
+                w_meta += clock64() - c0;
+                if (S.meta[b].tm < 0) {
+                    if (P.debug) {
+                        atomicAdd(P.stats + 2, (unsigned long long)(clock64() - t_begin));
+                        atomicAdd(P.stats + 3, (unsigned long long)w_meta);
+                        atomicAdd(P.stats + 4, (unsigned long long)w_tmem);
+                        atomicAdd(P.stats + 5, (unsigned long long)w_full);
+                        atomicAdd(P.stats + 6, (unsigned long long)it);
+                    }
+                    break;
+                }
+                const int nst = (S.meta[b].nact + 1) >> 1;
+                c0 = clock64();
+                if (tl > 0) i8::mbar_wait(&S.tmem_free, (tl - 1) & 1);  // the previous tile's accumulators are in registers
+                w_tmem += clock64() - c0;
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const unsigned a0 = i8::smem_u32(stages + s * I8_STAGE_BYTES), b0 = a0 + 2 * I8_A_CHUNK;
-                const unsigned long long da = i8::smem_desc(a0, I8_A_CHUNK, 128), db = i8::smem_desc(b0, I8_B_CHUNK, 128);
+                for (int k = 0; k < nst; k++, it++) {
+                    const int s = it % I8_STAGES;
+                    c0 = clock64();
+                    i8::mbar_wait(&S.full[s], (it / I8_STAGES) & 1);
+                    w_full += clock64() - c0;
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const unsigned a0 = i8::smem_u32(stages + s * I8_STAGE_BYTES), b0 = a0 + 2 * I8_A_CHUNK;
+                    const unsigned long long da = i8::smem_desc(a0, I8_A_CHUNK, 128), db = i8::smem_desc(b0, I8_B_CHUNK, 128);
 #pragma unroll
-                for (int i = 0; i < I8_S; i++)
+                    for (int i = 0; i < I8_S; i++)
 #pragma unroll
-                    for (int j = 0; j < I8_S; j++)
-                        if (i + j < I8_S)  // the first product of accumulator g = i + j is (0, g)
-                            i8::umma(tb + (i + j) * I8_BN, da + (unsigned long long)(i * 2048 >> 4), db + (unsigned long long)(j * 1024 >> 4), ID,
-                                     (it > 0 || i > 0) ? 1u : 0u);
-                i8::umma_commit(&S.empty[s]);  // stage reusable once these MMAs have read it
+                        for (int j = 0; j < I8_S; j++)
+                            if (i + j < I8_S)  // the first product of accumulator g = i + j is (0, g)
+                                i8::umma(tb + (i + j) * I8_BN, da + (unsigned long long)(i * 2048 >> 4), db + (unsigned long long)(j * 1024 >> 4), ID,
+                                         (k > 0 || i > 0) ? 1u : 0u);
+                    i8::umma_commit(&S.empty[s]);  // stage reusable once these MMAs have read it
+                }
+                if (nst > 0) i8::umma_commit(&S.accum);
+                else i8::mbar_arrive(&S.accum);
             }
-            i8::umma_commit(&S.accum);
         }
     } else {
         // ---- epilogue: 16 warps; warp (q, h) owns TMEM lanes / tile rows 32q .. 32q+31 and columns 16h .. 16h+15 ----
         // (many warps with little state each: the exp / Horner chains are latency bound, not issue bound)
         constexpr int EC = I8_BN / 4;  // 16 columns per warp
-        const int q = warp & 3, cbase = ((warp - 2) >> 2) * EC, row = q * 32 + lane;
-        const int sr = S.segA[row];
-        // lanes of one molecule are contiguous: head lane and last lane of my run
-        const int prev = __shfl_up_sync(0xffffffffu, sr, 1);
-        const bool head = ((lane == 0) || (prev != sr)) && sr >= 0;
-        const unsigned heads = __ballot_sync(0xffffffffu, (lane == 0) || (prev != sr));
-        const unsigned above = (lane == 31) ? 0u : (heads >> (lane + 1));
-        const int run_end = above ? (lane + __ffs(above) - 1) : 31;
-        const double na = S.normA[row];
-        const double sa = i8::pow2(S.expA[row] - 7);
-        const int growA = tm * I8_BM + row;
-        const unsigned lastmask = __ballot_sync(0xffffffffu, lane < EC && (lane == EC - 1 || S.segB[cbase + lane + 1] != S.segB[cbase + lane]));
-        if (nst > 0) {
-            i8::mbar_wait(&S.accum, 0);
+        const int q = warp & 3, cbase = ((warp - 3) >> 2) * EC, row = q * 32 + lane;
+        for (int tl = 0;; tl++) {
+            const int b = tl % I8_META;
+            const I8Meta &M = S.meta[b];
+            i8::mbar_wait(&S.meta_full[b], (tl / I8_META) & 1);
+            if (M.tm < 0) break;
+            const int nst = (M.nact + 1) >> 1;
+            const int sr = M.segA[row];
+            // lanes of one molecule are contiguous: head lane and last lane of my run
+            const int prev = __shfl_up_sync(0xffffffffu, sr, 1);
+            const bool head = ((lane == 0) || (prev != sr)) && sr >= 0;
+            const unsigned heads = __ballot_sync(0xffffffffu, (lane == 0) || (prev != sr));
+            const unsigned above = (lane == 31) ? 0u : (heads >> (lane + 1));
+            const int run_end = above ? (lane + __ffs(above) - 1) : 31;
+            const double na = M.normA[row];
+            const double sa = i8::pow2(M.expA[row] - 7);
+            const int growA = M.tm * I8_BM + row;
+            const unsigned lastmask = __ballot_sync(0xffffffffu, lane < EC && (lane == EC - 1 || M.segB[cbase + lane + 1] != M.segB[cbase + lane]));
+            const long long e0 = clock64();
+            i8::mbar_wait(&S.accum, tl & 1);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        }
-        const long long T2 = clock64();
-        if (P.debug && warp == 2 && lane == 0) {
-            atomicAdd(P.stats + 2, (unsigned long long)(T1 - T0));
-            atomicAdd(P.stats + 3, (unsigned long long)(T2 - T1));
-            atomicAdd(P.stats + 5, (unsigned long long)nst);
-            atomicAdd(P.stats + 6, 1ull);
-        }
-        // phase 1: d^2 of my 16 pairs per lane -> registers
-        double x[EC];
-        if (!(P.debug & 4)) {
-        const unsigned trow = tb + ((unsigned)(q * 32) << 16) + cbase;
+            const long long e1 = clock64();
+            // phase 1: drain my 16 columns of the 7 accumulators into two exact 64-bit integers per pair (integer pipe
+            // only), then hand TMEM back: the next tile's MMAs run while everything below happens
+            long long hi[EC], lo[EC];
 #pragma unroll
-        for (int cc = 0; cc < EC / 4; cc++) {
-            unsigned v[I8_S][4];
+            for (int j = 0; j < EC; j++) hi[j] = lo[j] = 0;
             if (nst > 0) {
+                const unsigned trow = tb + ((unsigned)(q * 32) << 16) + cbase;
 #pragma unroll
-                for (int g = 0; g < I8_S; g++)
-                    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];"
-                                 : "=r"(v[g][0]), "=r"(v[g][1]), "=r"(v[g][2]), "=r"(v[g][3]) : "r"(trow + g * I8_BN + cc * 4));
-                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-            } else {
+                for (int g = 0; g < I8_S; g++) {
+                    unsigned v[EC];
+                    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+                                   "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+                                 : "r"(trow + g * I8_BN));
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                    // sum_g P_g 128^-g = 2^-14 hi + 2^-42 lo with hi = P0 2^14 + P1 2^7 + P2, lo = P3 2^21 + ... + P6
 #pragma unroll
-                for (int g = 0; g < I8_S; g++)
-#pragma unroll
-                    for (int j = 0; j < 4; j++) v[g][j] = 0u;
+                    for (int j = 0; j < EC; j++) {
+                        const long long pv = (long long)(int)v[j];
+                        if (g < 3) hi[j] += pv << (7 * (2 - g));
+                        else lo[j] += pv << (7 * (6 - g));
+                    }
+                }
             }
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncwarp();
+            if (!I8_SERIAL_EPILOGUE && lane == 0) i8::mbar_arrive(&S.tmem_free);
+            const long long e2 = clock64();
+            // d^2 of my 16 pairs
+            double x[EC];
 #pragma unroll
-            for (int j = 0; j < 4; j++) {
-                const int col = cbase + cc * 4 + j;
-                // sum_g P_g 128^-g, exactly: the three heavy and the four light accumulators as two 64-bit integers
-                const long long hi = ((long long)(int)v[0][j] << 14) + ((long long)(int)v[1][j] << 7) + (long long)(int)v[2][j];
-                const long long lo = ((long long)(int)v[3][j] << 21) + ((long long)(int)v[4][j] << 14) + ((long long)(int)v[5][j] << 7) +
-                                     (long long)(int)v[6][j];
-                const double d = fma((double)lo, 2.2737367544323206e-13 /* 2^-42 */, (double)hi * 6.103515625e-05 /* 2^-14 */);
-                const double dot = d * sa * i8::pow2(S.expB[col] - 7);
-                double xx = fmax(na + S.normB[col] - 2.0 * dot, 0.0);
+            for (int j = 0; j < EC; j++) {
+                const int col = cbase + j;
+                const double d = fma((double)lo[j], 2.2737367544323206e-13 /* 2^-42 */, (double)hi[j] * 6.103515625e-05 /* 2^-14 */);
+                double xx = fmax(fma(d * sa, M.m2sB[col], na + M.normB[col]), 0.0);  // |a|^2 + |b|^2 - 2 a.b
                 // pairs that do not count: on / below the diagonal of a symmetric kernel, padding rows / columns
-                if ((G.sym && tn * I8_BN + col <= growA) || sr < 0 || S.segB[col] < 0) xx = __longlong_as_double(0x7ff0000000000000LL);
-                x[cc * 4 + j] = xx;
+                if ((M.sym && M.tn * I8_BN + col <= growA) || sr < 0 || M.segB[col] < 0) xx = __longlong_as_double(0x7ff0000000000000LL);
+                x[j] = xx;
             }
-        }
-        const long long T3 = clock64();
-        if (P.debug && warp == 2 && lane == 0) atomicAdd(P.stats + 7, (unsigned long long)(T3 - T2));
-        if (!(P.debug & 2)) {
-        // phase 2: per sigma exp (chain: squarings of the previous sigma's values, in place), then the sums over molecule
-        // pairs: column runs sequentially in registers, row runs by a segmented shuffle reduction, one RED per head lane
+            // phase 2: per sigma exp (chain: squarings of the previous sigma's values, in place), then the sums over
+            // molecule pairs: column runs sequentially in registers, row runs by a segmented shuffle reduction, one RED
+            // per head lane
 #pragma unroll 1
-        for (int si = 0; si < P.nsig; si++) {
-            const int s = P.chain ? P.order[si] : si;
-            double *outS = P.out + (long long)s * P.slab + (long long)max(sr, 0) * P.ldo;
-            double run = 0.0;
-            if (P.chain) {
-                if (si == 0) {
-                    const double f = P.isig[s * P.zstride + G.zcol];
+            for (int si = 0; si < P.nsig; si++) {
+                const int s = P.chain ? P.order[si] : si;
+                double *outS = P.out + (long long)s * P.slab + (long long)max(sr, 0) * P.ldo;
+                double run = 0.0;
+                if (P.chain) {
+                    if (si == 0) {
+                        const double f = P.isig[s * P.zstride + M.zcol];
 #pragma unroll
-                    for (int j = 0; j < EC; j++) x[j] = i8_exp(x[j] * f);  // +inf * f = -inf -> 0
-                } else {
-                    for (int k = 0; k < P.nsq[si]; k++)
+                        for (int j = 0; j < EC; j++) x[j] = i8_exp(x[j] * f, S.exptab);  // +inf * f = -inf -> 0
+                    } else {
+                        for (int k = 0; k < P.nsq[si]; k++)
 #pragma unroll
-                        for (int j = 0; j < EC; j++) x[j] *= x[j];
-                }
-#pragma unroll
-                for (int j = 0; j < EC; j++) {
-                    run += x[j];
-                    if ((lastmask >> j) & 1u) {  // warp-uniform: column cbase + j closes a molecule of B
-                        const int sc = S.segB[cbase + j];
-                        if (sc >= 0) i8_flush(run, lane, run_end, head, outS + sc);
-                        run = 0.0;
+                            for (int j = 0; j < EC; j++) x[j] *= x[j];
                     }
-                }
-            } else {
-                const double f = P.isig[s * P.zstride + G.zcol];
 #pragma unroll
-                for (int j = 0; j < EC; j++) {
-                    run += i8_exp(x[j] * f);
-                    if ((lastmask >> j) & 1u) {
-                        const int sc = S.segB[cbase + j];
-                        if (sc >= 0) i8_flush(run, lane, run_end, head, outS + sc);
-                        run = 0.0;
+                    for (int j = 0; j < EC; j++) {
+                        run += x[j];
+                        if ((lastmask >> j) & 1u) {  // warp-uniform: column cbase + j closes a molecule of B
+                            const int sc = M.segB[cbase + j];
+                            if (sc >= 0) i8_flush(run, lane, run_end, head, outS + sc);
+                            run = 0.0;
+                        }
+                    }
+                } else {
+                    const double f = P.isig[s * P.zstride + M.zcol];
+#pragma unroll
+                    for (int j = 0; j < EC; j++) {
+                        run += i8_exp(x[j] * f, S.exptab);
+                        if ((lastmask >> j) & 1u) {
+                            const int sc = M.segB[cbase + j];
+                            if (sc >= 0) i8_flush(run, lane, run_end, head, outS + sc);
+                            run = 0.0;
+                        }
                     }
                 }
             }
-        }
-        }
+            __syncwarp();
+            if (I8_SERIAL_EPILOGUE && lane == 0) i8::mbar_arrive(&S.tmem_free);
+            if (P.debug && warp == 3 && lane == 0) {
+                atomicAdd(P.stats + 7, (unsigned long long)(e1 - e0));
+                atomicAdd(P.stats + 8, (unsigned long long)(e2 - e1));
+                atomicAdd(P.stats + 9, (unsigned long long)(clock64() - e2));
+            }
+            if (lane == 0) i8::mbar_arrive(&S.meta_empty[b]);  // this tile's metadata buffer may be refilled
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
-    if (P.debug && tid == 0) atomicAdd(P.stats + 4, (unsigned long long)(clock64() - T1));
     if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tb), "r"(512u) : "memory");
 }
 

@@ -735,17 +735,22 @@ static void run_pairs_i8(const aqml_rep *r1, const aqml_rep *r2, int zmax, int r
     for (int i = 0; i < 16; i++) { P.order[i] = PP.order[i]; P.nsq[i] = PP.nsq[i]; }
     const int smem = I8_STAGES * I8_STAGE_BYTES + (int)sizeof(I8Smem);
     AQML_CUDA(cudaFuncSetAttribute(i8_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    P.debug = getenv("AQML_I8_DEBUG") ? atoi(getenv("AQML_I8_DEBUG")) : 0;
-    if (P.debug) AQML_CUDA(cudaMemsetAsync(P.stats + 2, 0, 48, ws.stream()));
-    i8_pair_kernel<<<total, I8_THREADS, smem, ws.stream()>>>(P);
+    int dev = 0, sms = 0;
+    AQML_CUDA(cudaGetDevice(&dev));
+    AQML_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    P.debug = getenv("AQML_I8_DEBUG") ? 1 : 0;
+    if (P.debug) AQML_CUDA(cudaMemsetAsync(P.stats + 2, 0, 64, ws.stream()));
+    i8_pair_kernel<<<std::min(total, sms), I8_THREADS, smem, ws.stream()>>>(P, total);
     AQML_LAUNCH_CHECK();
     if (P.debug) {
-        unsigned long long h[6];
-        AQML_CUDA(cudaMemcpyAsync(h, P.stats + 2, 48, cudaMemcpyDeviceToHost, ws.stream()));
+        unsigned long long h[8];
+        AQML_CUDA(cudaMemcpyAsync(h, P.stats + 2, 64, cudaMemcpyDeviceToHost, ws.stream()));
         AQML_CUDA(cudaStreamSynchronize(ws.stream()));
-        double n = (double)std::max<unsigned long long>(h[4], 1);
-        fprintf(stderr, "[i8] tiles %llu (grid %d): setup %.0f clk, mainloop %.0f clk, mainloop+epilogue %.0f clk, stages/tile %.1f, epilogue phase 1 %.0f clk\n", h[4], total,
-                h[0] / n, h[1] / n, h[2] / n, h[3] / n, h[5] / n);
+        const double n = std::min(total, sms), st = (double)std::max<unsigned long long>(h[4], 1);
+        fprintf(stderr, "[i8] %d tiles, %.0f stages; MMA thread per CTA: total %.0f clk = %.0f clk/stage; waiting for metadata %.1f%%, TMEM %.1f%%, operands %.1f%%\n",
+                total, st, h[0] / n, (double)h[0] / st, 100.0 * h[1] / h[0], 100.0 * h[2] / h[0], 100.0 * h[3] / h[0]);
+        fprintf(stderr, "[i8] epilogue warp per tile: waiting for accumulators %.0f clk, TMEM drain %.0f clk, exp + sums %.0f clk\n", (double)h[5] / total,
+                (double)h[6] / total, (double)h[7] / total);
     }
 }
 

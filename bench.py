@@ -359,14 +359,48 @@ def run_ours(args):
         except Exception:
             pass
         hbm_peak = peaks.get("hbm_gbs", 6650.0)
+        slatm_bytes = float(rep_bytes)
+        engine = "dmma" if os.environ.get("AQML_PAIR_ENGINE", "") in ("dmma", "fp64") else "i8"
+        exec_flops = kt_exec * ktile_flops  # FP64-equivalent flops of the k-tiles actually contracted
         traffic = None
         try:  # dram__bytes_read+write of one launch, from the committed ncu --set full capture of this command
-            tr = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))["pair_tile_kernel<MODE_DOT,EPI_LOCAL>"]
+            key = "pair_tile_kernel<MODE_DOT,EPI_LOCAL>" if engine == "dmma" else "i8_pair_kernel"
+            tr = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))[key]
             if args.n_train == 20000 and args.n_test == 2000:
                 traffic = float(tr["dram_bytes_read"] + tr["dram_bytes_write"])
         except Exception:
             pass
-        slatm_bytes = float(rep_bytes)
+        roofline = {"bound": "tensor", "achieved": ach_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach_tf / peak_tf,
+                    "traffic": traffic, "traffic_unit": "bytes of DRAM per launch (profiles/r01_traffic.json)",
+                    "algorithmic_flops_per_launch": flops,
+                    # all-zero 16-column k-tiles are skipped exactly: the work actually issued,
+                    # incl. row/column padding, and its share of the dense sweep
+                    "executed_flops_per_launch": exec_flops,
+                    "executed_tflops": exec_flops / (t_kernel_ms * 1e-3) / 1e12,
+                    "executed_frac_of_peak": exec_flops / (t_kernel_ms * 1e-3) / 1e12 / peak_tf,
+                    "ktiles_executed_over_dense": kt_exec / max(kt_dense, 1.0),
+                    "peak_source": "cuBLAS DGEMM 8192^3 best of 10 measured in this run (MEASURED_PEAKS.json has no FP64 entry)"}
+        if engine == "dmma":
+            roofline["kernel"] = "pair_tile_kernel<MODE_DOT,EPI_LOCAL> (FP64 DMMA.8x8x4)"
+            roofline["note"] = ("achieved/frac use the SURVEY 8(d) algorithmic flop count 2*sum_z D_z*n1_z*n2_z; frac > 1 because "
+                                "16-column k-tiles that are all-zero in either 64-row operand block are skipped (exact, "
+                                "bit-identical; counted on the device). Hardware utilisation = executed_frac_of_peak; the FP64 "
+                                "DMMA/DFMA ceiling of the chip is 37.0 TF (profiles/r01_micro_dmma_dfma.txt)")
+        else:
+            int8_ops = exec_flops * 28.0  # 28 digit-plane products per FP64 product
+            int8_peak = 4.13  # POP/s, tcgen05 kind::i8 at N >= 128 measured on this pool (profiles/r01_micro_i8_umma.txt)
+            roofline["kernel"] = "i8_pair_kernel (tcgen05.mma kind::i8, 7 x 7-bit digit planes, 28 exact int32 products in TMEM)"
+            roofline["int8_pops"] = int8_ops / (t_kernel_ms * 1e-3) / 1e15
+            roofline["int8_peak_pops"] = int8_peak
+            roofline["int8_frac_of_peak"] = roofline["int8_pops"] / int8_peak
+            roofline["int8_frac_of_n64_rate"] = roofline["int8_pops"] / 2.9
+            roofline["note"] = ("FP64-accurate contraction from exact int8 digit-plane products on the 5th-generation tensor "
+                                "cores (DESIGN.md 4.1b): achieved/frac are FP64-EQUIVALENT flops (SURVEY 8(d) count "
+                                "2*sum_z D_z*n1_z*n2_z) against the measured cuBLAS DGEMM peak, so frac > 1 is the point of the "
+                                "design (plus exact skipping of all-zero 16-column k-tiles). Hardware utilisation = "
+                                "int8_frac_of_peak (28 int8 MMAs per FP64 k-tile; an N=64 UTCIMMA is capped at 2.9 POP/s by "
+                                "shared-memory operand bandwidth, int8_frac_of_n64_rate). Same results to <= 1e-10 as the "
+                                "FP64 DMMA engine (AQML_PAIR_ENGINE=dmma), asserted in tests/")
         line = {
             "metric": "local_gaussian_kernel_elements_per_sec",
             "value": world * elems_rank / (ms_per_step * 1e-3), "unit": "kernel elements/s",
@@ -382,23 +416,7 @@ def run_ours(args):
             "phases_ms": {"aslatm": t_slatm_ms, "kernel": t_kernel_ms},
             "gpu_launches": launches,
             "clocks": clocks,
-            "roofline": {"bound": "tensor", "kernel": "pair_tile_kernel<MODE_DOT,EPI_LOCAL> (FP64 DMMA.8x8x4)",
-                         "achieved": ach_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach_tf / peak_tf,
-                         "traffic": traffic, "traffic_unit": "bytes of DRAM per launch (profiles/r01_traffic.json)",
-                         "algorithmic_flops_per_launch": flops,
-                         # all-zero 16-column k-tiles are skipped exactly: the DMMA work
-                         # actually issued, incl. row/column padding, and its share of the dense sweep
-                         "executed_flops_per_launch": kt_exec * ktile_flops,
-                         "executed_tflops": kt_exec * ktile_flops / (t_kernel_ms * 1e-3) / 1e12,
-                         "executed_frac_of_peak": kt_exec * ktile_flops / (t_kernel_ms * 1e-3) / 1e12 / peak_tf,
-                         "ktiles_executed_over_dense": kt_exec / max(kt_dense, 1.0),
-                         "note": "achieved/frac use the SURVEY 8(d) algorithmic flop count 2*sum_z D_z*n1_z*n2_z; frac > 1 "
-                                 "because 16-column k-tiles that are all-zero in either 64-row operand block are skipped "
-                                 "(exact, bit-identical; counted on the device). Hardware utilisation = "
-                                 "executed_frac_of_peak; the FP64 DMMA/DFMA ceiling of the chip is 37.0 TF "
-                                 "(profiles/r01_micro_dmma_dfma.txt)",
-                         "peak_source": "cuBLAS DGEMM 8192^3 best of 10 measured in this run "
-                                        "(MEASURED_PEAKS.json has no FP64 entry)"},
+            "roofline": roofline,
             "roofline_aslatm": {"bound": "hbm", "kernel": "slatm_kernel (packed output)",
                                 "achieved": slatm_bytes / (t_slatm_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
                                 "frac": slatm_bytes / (t_slatm_ms * 1e-3) / 1e9 / hbm_peak,

@@ -81,3 +81,40 @@ def test_demo_learning_curve_through_gpu(demo):
     rows_ref = o.learning_curve(demo["k1"][1], demo["k2"][1], ngs, ys, nheav, zsu)
     for r, rr in zip(rows, rows_ref):
         assert np.max(np.abs(r[5] - rr[5])) < 1e-8 * o.H2KC
+
+
+def test_int8_tensor_engine_equals_fp64_engine_and_oracle():
+    """The tcgen05 int8 digit-plane engine (default) and the FP64 DMMA engine (AQML_PAIR_ENGINE=dmma) on the SAME packed
+    representation: both within 1e-10 of the oracle, each other within 1e-11; arbitrary (non power-of-two) sigma ratios,
+    row ranges and the symmetric path included; values spanning many orders of magnitude (narrow sigma)."""
+    import os
+    nas, zs, coords = synth.qm9_like(90, 55)
+    n1 = 64
+    off = np.concatenate(([0], np.cumsum(nas)))
+    A1 = off[n1]
+    mb = o.get_slatm_mbtypes(synth.split_zs(nas, zs))
+    kw = dict(sigmas=(.05, .05), dgrids=(.04, .04), rcut=4.8)
+    xl = co.generate_slatm_batch(coords, zs, nas, mb, True, **kw)
+    zmax = 9
+    dso = co.get_kernel_width(nas, zs, xl)
+    dso = np.concatenate((dso, np.full(zmax - len(dso), 1e-9)))
+    for coeffs in ((0.5, 1.0, 2.0, 4.0), (0.05, 0.3, 1.7)):
+        sig = np.array([c * dso / np.sqrt(2 * np.log(2)) for c in coeffs])
+        ref = co.calc_lk_gaussian(xl[A1:], xl[:A1], zs[A1:], zs[:A1], nas[n1:], nas[:n1], zmax, False, sig)
+        ref11 = co.calc_lk_gaussian(xl[:A1], xl[:A1], zs[:A1], zs[:A1], nas[:n1], nas[:n1], zmax, False, sig)
+        train = fused.PackedRep(coords[:A1], zs[:A1], nas[:n1], mb, **kw)
+        test = fused.PackedRep(coords[A1:], zs[A1:], nas[n1:], mb, **kw)
+        out = {}
+        for engine in ("i8", "dmma"):
+            os.environ["AQML_PAIR_ENGINE"] = engine
+            try:
+                out[engine] = (fused.local_gaussian(test, train, sig, zmax).cpu().numpy(),
+                               fused.local_gaussian(test, train, sig, zmax, row0=3, nrows=11).cpu().numpy(),
+                               fused.local_gaussian(train, train, sig, zmax, symmetric=True).cpu().numpy())
+            finally:
+                del os.environ["AQML_PAIR_ENGINE"]
+            assert rel_err(out[engine][0], ref) < TOL
+            assert rel_err(out[engine][1], ref[:, 3:14]) < TOL
+            assert rel_err(out[engine][2], ref11) < TOL
+        for a, b in zip(out["i8"], out["dmma"]):
+            assert rel_err(a, b) < 1e-11
