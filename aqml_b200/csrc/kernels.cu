@@ -506,6 +506,7 @@ static void local_gaussian(const double *x1, long long ldx1, const double *x2, l
     AQML_CUDA(cudaMemcpyAsync(nz.data(), colnz, sizeof(unsigned) * nz.size(), cudaMemcpyDeviceToHost, st));
     AQML_CUDA(cudaStreamSynchronize(st));
 
+    std::vector<I8Pair> i8pairs;
     for (int e = 0; e < ne; e++) {
         int z = els[e];
         std::vector<int> colmap;
@@ -548,8 +549,14 @@ static void local_gaussian(const double *x1, long long ldx1, const double *x2, l
         g.segA = ws.upload(sg1); g.segB = ws.upload(sg2); g.zA = nullptr; g.zcol = z - 1;
         g.tilesM = (int)rm1.size() / BM; g.tilesN = (int)rm2.size() / BN;
         groups.push_back(g);
+        I8Pair pr;
+        pr.a = I8Side{p1, n1, g.segA, k1, mw, (int)rm1.size(), ld};
+        pr.b = I8Side{p2, n2, g.segB, k2, mw, (int)rm2.size(), ld};
+        pr.zcol = z - 1;
+        i8pairs.push_back(pr);
     }
-    run_pairs(MODE_DOT, EPI_LOCAL, groups, P, ws);
+    // default engine: int8 digit planes on the tcgen05 tensor cores; FP64 DMMA when disabled / not applicable
+    if (!i8_local_pairs(i8pairs, P, ws)) run_pairs(MODE_DOT, EPI_LOCAL, groups, P, ws);
 }
 
 static void local_laplacian(const double *x1, long long ldx1, const double *x2, long long ldx2, const int *nas1,

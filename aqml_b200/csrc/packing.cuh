@@ -37,6 +37,23 @@ void build_tiles(const std::vector<int> &rows, const std::vector<int> &mol_of_ro
 std::vector<int> class_sorted_molecules(const int *zs, const int *nas, int nm);
 void plan_sigma_chain(PairParams &P, const std::vector<double> &isig);
 unsigned long long *pair_stats_buffer();
+
+// int8 digit-plane engine (i8pair.cuh, compiled in slatm.cu) for element-matched local Gaussian groups given as packed
+// FP64 operands.  Slices both sides into temporary digit planes, launches the tcgen05 kernel and returns true; returns
+// false without launching anything when the engine is disabled (AQML_PAIR_ENGINE=dmma), more than 8 sigmas are asked
+// for, or an operand holds a non-finite value (the FP64 engine then reproduces the reference's NaNs).
+struct I8Side {
+    const double *x, *norm;   // packed rows (pitch ld, multiple of 16), |row|^2
+    const int *seg;           // molecule per packed row, -1 = padding
+    const unsigned *mask;     // k-tile masks per 64-row block, or null
+    int maskw, nr;            // mask words per block, packed rows (multiple of 64)
+    long long ld;
+};
+struct I8Pair {
+    I8Side a, b;
+    int zcol;
+};
+bool i8_local_pairs(const std::vector<I8Pair> &pairs, const PairParams &P, Workspace &ws);
 void run_pairs_public(int mode, int epi, const std::vector<PairGroup> &groups, PairParams P, Workspace &ws);
 double pruned_max_public(int p, const double *A, int nA, const double *B, int nB, long long ld, bool same, Workspace &ws);
 double pruned_max_segs_public(int p, const std::vector<RowSeg> &SA, const std::vector<RowSeg> &SB, long long ld, bool same,

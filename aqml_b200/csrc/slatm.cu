@@ -699,32 +699,34 @@ struct aqml_rep {
 
 namespace aqml {
 
+
 // AQML_PAIR_ENGINE=dmma keeps the FP64 DMMA engine for the fused local kernel; default: int8 digit planes on tcgen05
 static bool i8_engine_enabled() {
     const char *e = getenv("AQML_PAIR_ENGINE");
     return !(e && (!strcmp(e, "dmma") || !strcmp(e, "fp64")));
 }
 
-static void run_pairs_i8(const aqml_rep *r1, const aqml_rep *r2, int zmax, int row0, int nrows, bool sym, PairParams PP, Workspace &ws) {
-    std::vector<I8Group> gs;
+// digit planes + row exponents of a packed operand (i8pair.cuh); `flag` is set on the device when a value is not finite
+template <class Alloc>
+static void i8_make_planes(const double *x, long long ld, int nr, Alloc &mem, int *flag, cudaStream_t st, int8_t *&sl, int *&expo,
+                           size_t *bytes_out = nullptr) {
+    const int KT = (int)(ld / 16), rb = (nr + 127) / 128;
+    const size_t bytes = (size_t)rb * (KT + 1) * I8_A_CHUNK;
+    sl = mem.template alloc<int8_t>(bytes);
+    expo = mem.template alloc<int>(nr);
+    if (bytes_out) *bytes_out = bytes;
+    AQML_CUDA(cudaMemsetAsync(sl, 0, bytes, st));
+    i8_rowexp_kernel<<<(nr + 7) / 8, 256, 0, st>>>(x, ld, nr, expo, flag);
+    AQML_LAUNCH_CHECK();
+    const int split = std::max(1, std::min(KT, 2048 / std::max(rb, 1)));
+    const int per = (KT + split - 1) / split;
+    i8_slice_kernel<<<dim3(rb, (KT + per - 1) / per), 128, 0, st>>>(x, ld, nr, expo, KT, per, sl);
+    AQML_LAUNCH_CHECK();
+}
+
+static void launch_i8(std::vector<I8Group> &gs, const PairParams &PP, Workspace &ws) {
     int total = 0;
-    for (const auto &a : r1->els)
-        for (const auto &b : r2->els) {
-            if (a.label != b.label || a.n == 0 || b.n == 0) continue;
-            AQML_REQUIRE(a.ld == b.ld, "representations were built with different many-body types");
-            const int z = a.label % 1000;
-            AQML_REQUIRE(z >= 1 && z <= zmax, "element %d outside 1..zmax=%d", z, zmax);
-            I8Group g;
-            memset(&g, 0, sizeof(g));
-            g.slA = a.sl; g.slB = b.sl; g.expA = a.expo; g.expB = b.expo; g.normA = a.norm; g.normB = b.norm;
-            g.segA = a.seg; g.segB = b.seg; g.nrA = a.nr; g.nrB = b.nr;
-            g.maskA = a.mask; g.maskB = b.mask; g.maskw = a.maskw;
-            g.KT = a.ld / 16;
-            g.tilesM = (a.nr + I8_BM - 1) / I8_BM; g.tilesN = (b.nr + I8_BN - 1) / I8_BN;
-            g.tile_begin = total; total += g.tilesM * g.tilesN;
-            g.zcol = z - 1; g.segA_off = row0; g.segA_n = nrows; g.sym = sym ? 1 : 0;
-            gs.push_back(g);
-        }
+    for (auto &g : gs) { g.tile_begin = total; total += g.tilesM * g.tilesN; }
     if (total == 0) return;
     I8Params P;
     memset(&P, 0, sizeof(P));
@@ -753,6 +755,63 @@ static void run_pairs_i8(const aqml_rep *r1, const aqml_rep *r2, int zmax, int r
                 (double)h[6] / total, (double)h[7] / total);
     }
 }
+
+// fused path: the representations carry their digit planes
+static void run_pairs_i8(const aqml_rep *r1, const aqml_rep *r2, int zmax, int row0, int nrows, bool sym, const PairParams &PP, Workspace &ws) {
+    std::vector<I8Group> gs;
+    for (const auto &a : r1->els)
+        for (const auto &b : r2->els) {
+            if (a.label != b.label || a.n == 0 || b.n == 0) continue;
+            AQML_REQUIRE(a.ld == b.ld, "representations were built with different many-body types");
+            const int z = a.label % 1000;
+            AQML_REQUIRE(z >= 1 && z <= zmax, "element %d outside 1..zmax=%d", z, zmax);
+            I8Group g;
+            memset(&g, 0, sizeof(g));
+            g.slA = a.sl; g.slB = b.sl; g.expA = a.expo; g.expB = b.expo; g.normA = a.norm; g.normB = b.norm;
+            g.segA = a.seg; g.segB = b.seg; g.nrA = a.nr; g.nrB = b.nr;
+            g.maskA = a.mask; g.maskB = b.mask; g.maskw = a.maskw;
+            g.KT = a.ld / 16;
+            g.tilesM = (a.nr + I8_BM - 1) / I8_BM; g.tilesN = (b.nr + I8_BN - 1) / I8_BN;
+            g.zcol = z - 1; g.segA_off = row0; g.segA_n = nrows; g.sym = sym ? 1 : 0;
+            gs.push_back(g);
+        }
+    launch_i8(gs, PP, ws);
+}
+
+}  // namespace aqml
+
+// packed FP64 operands from the dense API (kernels.cu): temporary digit planes
+bool aqml::i8_local_pairs(const std::vector<I8Pair> &pairs, const PairParams &PP, Workspace &ws) {
+    if (!i8_engine_enabled() || PP.nsig > I8_MAXSIG) return false;
+    cudaStream_t st = ws.stream();
+    int *flag = ws.zeros<int>(1);
+    std::vector<I8Group> gs;
+    for (const auto &pr : pairs) {
+        if (pr.a.nr == 0 || pr.b.nr == 0) continue;
+        I8Group g;
+        memset(&g, 0, sizeof(g));
+        int8_t *sa, *sb;
+        int *ea, *eb;
+        i8_make_planes(pr.a.x, pr.a.ld, pr.a.nr, ws, flag, st, sa, ea);
+        if (pr.b.x == pr.a.x && pr.b.nr == pr.a.nr) { sb = sa; eb = ea; }
+        else i8_make_planes(pr.b.x, pr.b.ld, pr.b.nr, ws, flag, st, sb, eb);
+        g.slA = sa; g.slB = sb; g.expA = ea; g.expB = eb; g.normA = pr.a.norm; g.normB = pr.b.norm;
+        g.segA = pr.a.seg; g.segB = pr.b.seg; g.nrA = pr.a.nr; g.nrB = pr.b.nr;
+        g.maskA = pr.a.mask; g.maskB = pr.b.mask; g.maskw = pr.a.maskw;
+        g.KT = (int)(pr.a.ld / 16);
+        g.tilesM = (pr.a.nr + I8_BM - 1) / I8_BM; g.tilesN = (pr.b.nr + I8_BN - 1) / I8_BN;
+        g.zcol = pr.zcol; g.segA_off = 0; g.segA_n = 0x7fffffff; g.sym = 0;
+        gs.push_back(g);
+    }
+    int bad = 0;
+    AQML_CUDA(cudaMemcpyAsync(&bad, flag, sizeof(int), cudaMemcpyDeviceToHost, st));
+    AQML_CUDA(cudaStreamSynchronize(st));
+    if (bad) return false;
+    launch_i8(gs, PP, ws);
+    return true;
+}
+
+namespace aqml {
 
 static bool use_i8(const aqml_rep *r1, const aqml_rep *r2, int nsigmas) {
     return i8_engine_enabled() && r1->i8_ready && r2->i8_ready && nsigmas <= I8_MAXSIG;
@@ -823,18 +882,9 @@ static void rep_create(const double *coords, int on_dev, const int *zs, const in
         int *flag = ws.zeros<int>(1);
         for (auto &el : rep->els) {
             if (el.n == 0) continue;
-            const int KT = el.ld / 16, rb = (el.nr + 127) / 128;
-            const size_t bytes = (size_t)rb * (KT + 1) * I8_A_CHUNK;
-            el.sl = keep.alloc<int8_t>(bytes);
-            el.expo = keep.alloc<int>(el.nr);
+            size_t bytes = 0;
+            i8_make_planes(el.x, el.ld, el.nr, keep, flag, st, el.sl, el.expo, &bytes);
             rep->bytes += (int64_t)bytes + 4 * el.nr;
-            AQML_CUDA(cudaMemsetAsync(el.sl, 0, bytes, st));
-            i8_rowexp_kernel<<<(el.nr + 7) / 8, 256, 0, st>>>(el.x, el.ld, el.nr, el.expo, flag);
-            AQML_LAUNCH_CHECK();
-            const int split = std::max(1, std::min(KT, 2048 / std::max(rb, 1)));
-            const int per = (KT + split - 1) / split;
-            i8_slice_kernel<<<dim3(rb, (KT + per - 1) / per), 128, 0, st>>>(el.x, el.ld, el.nr, el.expo, KT, per, el.sl);
-            AQML_LAUNCH_CHECK();
         }
         int bad = 0;
         AQML_CUDA(cudaMemcpyAsync(&bad, flag, sizeof(int), cudaMemcpyDeviceToHost, st));
