@@ -715,7 +715,8 @@ static void i8_make_planes(const double *x, long long ld, int nr, Alloc &mem, in
     sl = mem.template alloc<int8_t>(bytes);
     expo = mem.template alloc<int>(nr);
     if (bytes_out) *bytes_out = bytes;
-    AQML_CUDA(cudaMemsetAsync(sl, 0, bytes, st));
+    // only the trailing all-zero k-chunk of every row block needs clearing: the slice kernel writes everything else
+    AQML_CUDA(cudaMemset2DAsync(sl + (size_t)KT * I8_A_CHUNK, (size_t)(KT + 1) * I8_A_CHUNK, 0, I8_A_CHUNK, rb, st));
     i8_rowexp_kernel<<<(nr + 7) / 8, 256, 0, st>>>(x, ld, nr, expo, flag);
     AQML_LAUNCH_CHECK();
     const int split = std::max(1, std::min(KT, 2048 / std::max(rb, 1)));
