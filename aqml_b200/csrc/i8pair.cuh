@@ -65,6 +65,7 @@ struct I8Params {
     unsigned long long *stats;
     int chain, order[16], nsq[16];
     int debug;  // AQML_I8_DEBUG: MMA-thread wait timers into stats[2..6]
+    int store;  // 0: sum exp over the atoms of each molecule pair (local kernels); 1: K[s][seg_a][seg_b] = exp (global kernels)
 };
 
 struct I8Meta {  // everything the roles need to know about one tile
@@ -478,7 +479,28 @@ __global__ void __launch_bounds__(I8_THREADS, 1) i8_pair_kernel(const I8Params P
                 const int s = P.chain ? P.order[si] : si;
                 double *outS = P.out + (long long)s * P.slab + (long long)max(sr, 0) * P.ldo;
                 double run = 0.0;
-                if (P.chain) {
+                if (P.store) {
+                    // global kernel (fkernels.f90:344-355): every pair is one element of K; 16 consecutive columns per lane
+                    if (!P.chain || si == 0) {
+                        const double f = P.isig[s * P.zstride + M.zcol];
+#pragma unroll
+                        for (int j = 0; j < EC; j++) {
+                            const double e = i8_exp(x[j] * f, S.exptab);
+                            if (P.chain) x[j] = e;
+                            const int sc = M.segB[cbase + j];
+                            if (sr >= 0 && sc >= 0) outS[sc] = e;
+                        }
+                    } else {
+                        for (int k = 0; k < P.nsq[si]; k++)
+#pragma unroll
+                            for (int j = 0; j < EC; j++) x[j] *= x[j];
+#pragma unroll
+                        for (int j = 0; j < EC; j++) {
+                            const int sc = M.segB[cbase + j];
+                            if (sr >= 0 && sc >= 0) outS[sc] = x[j];
+                        }
+                    }
+                } else if (P.chain) {
                     if (si == 0) {
                         const double f = P.isig[s * P.zstride + M.zcol];
 #pragma unroll

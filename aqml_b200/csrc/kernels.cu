@@ -371,6 +371,11 @@ static void global_pairs(int kind, int epi, const double *a, int na, long long l
         P.isig = ws.upload(tab);
         plan_sigma_chain(P, tab);
     }
+    if (epi == EPI_EXP_STORE && mode == MODE_DOT) {
+        // default engine for the Gaussian kernel: int8 digit planes on the tcgen05 tensor cores (i8pair.cuh)
+        I8Side sa{pa.x, pa.norm, nullptr, nullptr, 0, pa.rows, pa.ld}, sb{pb.x, pb.norm, nullptr, nullptr, 0, pb.rows, pb.ld};
+        if (i8_global_pair(sa, na, sb, nb, P, ws)) return;
+    }
     run_pairs(mode, epi, {g}, P, ws);
 }
 

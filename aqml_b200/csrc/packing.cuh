@@ -54,6 +54,9 @@ struct I8Pair {
     int zcol;
 };
 bool i8_local_pairs(const std::vector<I8Pair> &pairs, const PairParams &P, Workspace &ws);
+// global Gaussian kernel K[s][i][j] = exp(d2_ij * isig[s]) for packed operands a (na valid rows) and b (nb valid rows):
+// seg is ignored (identity).  Same fallback rules as above.
+bool i8_global_pair(const I8Side &a, int na, const I8Side &b, int nb, const PairParams &P, Workspace &ws);
 void run_pairs_public(int mode, int epi, const std::vector<PairGroup> &groups, PairParams P, Workspace &ws);
 double pruned_max_public(int p, const double *A, int nA, const double *B, int nB, long long ld, bool same, Workspace &ws);
 double pruned_max_segs_public(int p, const std::vector<RowSeg> &SA, const std::vector<RowSeg> &SB, long long ld, bool same,

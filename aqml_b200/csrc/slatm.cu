@@ -699,7 +699,6 @@ struct aqml_rep {
 
 namespace aqml {
 
-
 // AQML_PAIR_ENGINE=dmma keeps the FP64 DMMA engine for the fused local kernel; default: int8 digit planes on tcgen05
 static bool i8_engine_enabled() {
     const char *e = getenv("AQML_PAIR_ENGINE");
@@ -725,7 +724,7 @@ static void i8_make_planes(const double *x, long long ld, int nr, Alloc &mem, in
     AQML_LAUNCH_CHECK();
 }
 
-static void launch_i8(std::vector<I8Group> &gs, const PairParams &PP, Workspace &ws) {
+static void launch_i8(std::vector<I8Group> &gs, const PairParams &PP, Workspace &ws, int store = 0) {
     int total = 0;
     for (auto &g : gs) { g.tile_begin = total; total += g.tilesM * g.tilesN; }
     if (total == 0) return;
@@ -742,6 +741,7 @@ static void launch_i8(std::vector<I8Group> &gs, const PairParams &PP, Workspace 
     AQML_CUDA(cudaGetDevice(&dev));
     AQML_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     P.debug = getenv("AQML_I8_DEBUG") ? 1 : 0;
+    P.store = store;
     if (P.debug) AQML_CUDA(cudaMemsetAsync(P.stats + 2, 0, 64, ws.stream()));
     i8_pair_kernel<<<std::min(total, sms), I8_THREADS, smem, ws.stream()>>>(P, total);
     AQML_LAUNCH_CHECK();
@@ -809,6 +809,38 @@ bool aqml::i8_local_pairs(const std::vector<I8Pair> &pairs, const PairParams &PP
     AQML_CUDA(cudaStreamSynchronize(st));
     if (bad) return false;
     launch_i8(gs, PP, ws);
+    return true;
+}
+
+bool aqml::i8_global_pair(const I8Side &a, int na, const I8Side &b, int nb, const PairParams &PP, Workspace &ws) {
+    if (!i8_engine_enabled() || PP.nsig > I8_MAXSIG || na <= 0 || nb <= 0) return false;
+    cudaStream_t st = ws.stream();
+    int *flag = ws.zeros<int>(1);
+    I8Group g;
+    memset(&g, 0, sizeof(g));
+    int8_t *sa, *sb;
+    int *ea, *eb;
+    i8_make_planes(a.x, a.ld, a.nr, ws, flag, st, sa, ea);
+    const bool same = (b.x == a.x && b.nr == a.nr);
+    if (same) { sb = sa; eb = ea; }
+    else i8_make_planes(b.x, b.ld, b.nr, ws, flag, st, sb, eb);
+    auto ident = [&](int nr, int n) {
+        std::vector<int> v(nr, -1);
+        for (int i = 0; i < n && i < nr; i++) v[i] = i;
+        return ws.upload(v);
+    };
+    g.slA = sa; g.slB = sb; g.expA = ea; g.expB = eb; g.normA = a.norm; g.normB = b.norm;
+    g.segA = ident(a.nr, na); g.segB = ident(b.nr, nb); g.nrA = a.nr; g.nrB = b.nr;
+    g.maskA = a.mask; g.maskB = b.mask; g.maskw = a.maskw;
+    g.KT = (int)(a.ld / 16);
+    g.tilesM = (a.nr + I8_BM - 1) / I8_BM; g.tilesN = (b.nr + I8_BN - 1) / I8_BN;
+    g.zcol = 0; g.segA_off = 0; g.segA_n = 0x7fffffff; g.sym = 0;
+    int bad = 0;
+    AQML_CUDA(cudaMemcpyAsync(&bad, flag, sizeof(int), cudaMemcpyDeviceToHost, st));
+    AQML_CUDA(cudaStreamSynchronize(st));
+    if (bad) return false;
+    std::vector<I8Group> gs{g};
+    launch_i8(gs, PP, ws, 1);
     return true;
 }
 
