@@ -98,7 +98,7 @@ __global__ void __launch_bounds__(256) colstats_kernel(const double *x, long lon
     for (int i = r0; i < r1; i++) {
         int r = rows ? rows[i] : i;
         double v = x[(long long)r * ldx + c];
-        s += v;
+        if (fabs(v) <= 1.7976931348623157e308) s += v;  // a NaN / Inf must stay in its own row (centring is only a shift)
         nz |= (v != 0.0);
     }
     if (colsum) atomicAdd(colsum + c, s);

@@ -300,7 +300,8 @@ __global__ void __launch_bounds__(NT, CTAS_PER_SM) pair_tile_kernel(const PairPa
 #pragma unroll
                 for (int e = 0; e < 2; e++) {
                     double nb = sNB[wn * 32 + ni * 8 + 2 * t4 + e];
-                    acc[mi][ni][e] = fmax(na + nb - 2.0 * acc[mi][ni][e], 0.0);
+                    const double d2 = na + nb - 2.0 * acc[mi][ni][e];
+                    acc[mi][ni][e] = (d2 < 0.0) ? 0.0 : d2;  // clamp the cancellation noise, keep NaN (the reference propagates it)
                 }
         }
     }

@@ -242,3 +242,51 @@ def test_vector_kernels_on_padded_arrays(slatm_set):
     assert rel_err(Kg, ref) < TOL
     Kl = kernels.calc_vector_kernels_laplacian(p1, p2, nas1, nas2, [500., 900.])
     assert rel_err(Kl, co.calc_lk_laplacian(x1, x2, nas1, nas2, [500., 900.])) < TOL
+
+
+def test_int8_engine_hostile_rows():
+    """Rows that stress the digit-plane representation of the tcgen05 engine: 16 orders of magnitude inside one row,
+    rows of very different scale, denormal-sized and exactly-zero rows, negative values, exact powers of two and
+    half-integers at digit boundaries, duplicated rows (d2 = 0).  Global and local kernels, both engines vs the oracle."""
+    import os
+    rng = np.random.default_rng(99)
+    n1, n2, D = 70, 150, 300
+    def rows(n):
+        X = rng.normal(size=(n, D)) * 10.0 ** rng.integers(-8, 3, size=(n, D))        # wide dynamic range within rows
+        X[:, ::7] = 0.0
+        X[1] *= 1e-6; X[2] *= 1e5; X[3] = 0.0; X[4] = 1e-310; X[5, :40] = 2.0 ** rng.integers(-30, 10, size=40)
+        X[6, :40] = (rng.integers(-64, 65, size=40) + 0.5) / 128.0                      # ties in the first digit
+        return X
+    A, B = rows(n1), rows(n2)
+    B[10] = A[0]; B[11] = A[2]
+    dmax = co.l2_distance(A, B).max()
+    for sig in (0.05 * dmax, dmax):
+        ref = co.gaussian_kernel(A, B, sig)
+        for engine in ("i8", "dmma"):
+            os.environ["AQML_PAIR_ENGINE"] = engine
+            try:
+                K = kernels.gaussian_kernel(A, B, sig)
+            finally:
+                del os.environ["AQML_PAIR_ENGINE"]
+            assert rel_err(K, ref) < TOL, (engine, sig)
+    # local kernel on the same rows: 3 "elements", ragged molecules
+    zs1 = rng.choice([1, 6, 8], size=n1); zs2 = rng.choice([1, 6, 8], size=n2)
+    nas1 = np.array([3, 7, 1, 9, 20, 30]); nas2 = np.array([50, 1, 2, 40, 57])
+    sigmas = np.array([[c * dmax] * 8 for c in (0.07, 0.5, 3.0)])
+    ref = co.calc_lk_gaussian(A, B, zs1, zs2, nas1, nas2, 8, False, sigmas)
+    for engine in ("i8", "dmma"):
+        os.environ["AQML_PAIR_ENGINE"] = engine
+        try:
+            K = kernels.get_local_kernels_gaussian(A, B, zs1, zs2, nas1, nas2, False, 8, sigmas)
+            K0 = kernels.get_local_kernels_gaussian(A, B, zs1, zs2, nas1, nas2, False, 8, sigmas, center=False)
+        finally:
+            del os.environ["AQML_PAIR_ENGINE"]
+        assert rel_err(K, ref) < TOL and rel_err(K0, ref) < TOL, engine
+    # more than 8 sigmas: served by the FP64 engine automatically
+    many = np.array([[c * dmax] * 8 for c in np.linspace(0.1, 2.0, 11)])
+    K = kernels.get_local_kernels_gaussian(A, B, zs1, zs2, nas1, nas2, False, 8, many)
+    assert rel_err(K, co.calc_lk_gaussian(A, B, zs1, zs2, nas1, nas2, 8, False, many)) < TOL
+    # NaN / Inf inputs fall back to the FP64 engine and propagate as in the reference
+    A2 = A.copy(); A2[7, 3] = np.nan
+    K = kernels.gaussian_kernel(A2, B, dmax)
+    assert np.isnan(K[7]).all() and not np.isnan(np.delete(K, 7, axis=0)).any()
