@@ -118,3 +118,23 @@ def test_int8_tensor_engine_equals_fp64_engine_and_oracle():
             assert rel_err(out[engine][2], ref11) < TOL
         for a, b in zip(out["i8"], out["dmma"]):
             assert rel_err(a, b) < 1e-11
+
+
+def test_chunked_host_delivery_equals_one_shot():
+    """fused.local_gaussian_to_host (row blocks, D2H overlapped on a second stream) == one contraction + one copy."""
+    import torch
+    nas, zs, coords = synth.qm9_like(83, 77)
+    n1 = 50
+    off = np.concatenate(([0], np.cumsum(nas)))
+    A1 = off[n1]
+    mb = o.get_slatm_mbtypes(synth.split_zs(nas, zs))
+    kw = dict(sigmas=(.05, .05), dgrids=(.04, .04), rcut=4.8)
+    train = fused.PackedRep(coords[:A1], zs[:A1], nas[:n1], mb, **kw)
+    test = fused.PackedRep(coords[A1:], zs[A1:], nas[n1:], mb, **kw)
+    sig = np.array([[c * 12.0] * 9 for c in (0.5, 1.0, 2.0)])
+    ref = fused.local_gaussian(test, train, sig, 9).cpu()
+    for chunks in (1, 4, 5, 200):
+        out = torch.full((3, 83 - n1, n1), -1.0, dtype=torch.float64).pin_memory()
+        fused.local_gaussian_to_host(coords[A1:], zs[A1:], nas[n1:], train, mb, sig, 9, out, chunks=chunks, **kw)
+        torch.cuda.synchronize()
+        assert rel_err(out.numpy(), ref.numpy()) < 1e-12
