@@ -151,7 +151,7 @@ __device__ __forceinline__ double i8_exp(double x, const double *tab) {
     const double w = tab[(n >> 7) & 127] * tab[128 + (n & 127)];
     const double v = w * p;
     const double sc = __hiloint2double(((n >> 14) + 1023) << 20, 0);
-    return (x < -707.0) ? 0.0 : v * sc;
+    return (x < -707.0) ? 0.0 : ((x != x) ? x : v * sc);  // NaN in, NaN out
 }
 
 // sum the lanes of each A molecule (contiguous lanes, last lane run_end) and add the heads' totals into K
@@ -165,26 +165,23 @@ __device__ __noinline__ void i8_flush(double r, int lane, int run_end, bool head
 }
 
 // ---- slicing -------------------------------------------------------------------------------------------------
-// exponent per row: |x| * 2^-e <= 1/2
-__global__ void __launch_bounds__(256) i8_rowexp_kernel(const double *x, long long ld, int nrows, int *expo, int *nonfinite) {
+// exponent per row: |x| * 2^-e <= 1/2.  Non-finite or absurdly large (> 1e301) values need no special path: such a row has
+// |row|^2 = NaN / Inf, which reaches K through d^2 = |a|^2 + |b|^2 - 2 a.b exactly as in the reference (NaN stays NaN,
+// Inf gives exp(-Inf) = 0); whatever digits the row gets are irrelevant.
+__global__ void __launch_bounds__(256) i8_rowexp_kernel(const double *x, long long ld, int nrows, int *expo) {
     const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (row >= nrows) return;
     const double *xr = x + (long long)row * ld;
     double m = 0.0;
-    bool bad = false;
     for (int k = lane; k < ld; k += 32) {
         const double v = fabs(xr[k]);
-        bad |= !(v <= 1.7976931348623157e308);
-        m = fmax(m, v);
+        if (v <= 1.7976931348623157e308) m = fmax(m, v);
     }
     m = warp_max(m);
-    bad = __any_sync(0xffffffffu, bad);
     if (lane == 0) {
         int e = 0;
         if (m > 0.0) { frexp(m, &e); e += 1; }
-        if (e > 1000) bad = true;   // > 1e301: leave such data to the FP64 engine
-        expo[row] = max(e, -1000);  // tinier rows keep |x| 2^-e <= 1/2 and only lose (irrelevant) digits
-        if (bad) atomicOr(nonfinite, 1);
+        expo[row] = max(min(e, 1000), -1000);  // tinier rows keep |x| 2^-e <= 1/2 and only lose (irrelevant) digits
     }
 }
 
@@ -203,6 +200,8 @@ __global__ void __launch_bounds__(128) i8_slice_kernel(const double *x, long lon
             const double2 v = valid ? *reinterpret_cast<const double2 *>(xr + kt * 16 + c) : make_double2(0.0, 0.0);
             t[c] = v.x * sc;
             t[c + 1] = v.y * sc;
+            if (!(fabs(t[c]) <= 0.5)) t[c] = 0.0;          // NaN / Inf / > 1e301: see i8_rowexp_kernel
+            if (!(fabs(t[c + 1]) <= 0.5)) t[c + 1] = 0.0;
         }
         int8_t *dst = sl + (((long long)rb * (KT + 1) + kt) * I8_S) * 2048 + r * 16;
 #pragma unroll
@@ -466,7 +465,8 @@ __global__ void __launch_bounds__(I8_THREADS, 1) i8_pair_kernel(const I8Params P
             for (int j = 0; j < EC; j++) {
                 const int col = cbase + j;
                 const double d = fma((double)lo[j], 2.2737367544323206e-13 /* 2^-42 */, (double)hi[j] * 6.103515625e-05 /* 2^-14 */);
-                double xx = fmax(fma(d * sa, M.m2sB[col], na + M.normB[col]), 0.0);  // |a|^2 + |b|^2 - 2 a.b
+                double xx = fma(d * sa, M.m2sB[col], na + M.normB[col]);  // |a|^2 + |b|^2 - 2 a.b
+                xx = (xx < 0.0) ? 0.0 : xx;                                   // clamp rounding noise, keep NaN
                 // pairs that do not count: on / below the diagonal of a symmetric kernel, padding rows / columns
                 if ((M.sym && M.tn * I8_BN + col <= growA) || sr < 0 || M.segB[col] < 0) xx = __longlong_as_double(0x7ff0000000000000LL);
                 x[j] = xx;

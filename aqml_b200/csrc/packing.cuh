@@ -40,8 +40,8 @@ unsigned long long *pair_stats_buffer();
 
 // int8 digit-plane engine (i8pair.cuh, compiled in slatm.cu) for element-matched local Gaussian groups given as packed
 // FP64 operands.  Slices both sides into temporary digit planes, launches the tcgen05 kernel and returns true; returns
-// false without launching anything when the engine is disabled (AQML_PAIR_ENGINE=dmma), more than 8 sigmas are asked
-// for, or an operand holds a non-finite value (the FP64 engine then reproduces the reference's NaNs).
+// false without launching anything when the engine is disabled (AQML_PAIR_ENGINE=dmma) or more than 8 sigmas are asked
+// for.  NaN / Inf rows need no fallback: they reach K through |row|^2 as in the reference.
 struct I8Side {
     const double *x, *norm;   // packed rows (pitch ld, multiple of 16), |row|^2
     const int *seg;           // molecule per packed row, -1 = padding

@@ -691,7 +691,7 @@ struct aqml_rep {
         int *expo = nullptr;   // per packed row exponent
         int nr = 0;            // packed rows (multiple of 64)
     };
-    bool i8_ready = false;     // every element has digit planes and all values are finite
+    bool i8_ready = false;     // every element has digit planes
     std::vector<El> els;
     std::vector<int> nas;
     std::vector<std::vector<int>> cnt;  // [el][mol]
@@ -705,9 +705,9 @@ static bool i8_engine_enabled() {
     return !(e && (!strcmp(e, "dmma") || !strcmp(e, "fp64")));
 }
 
-// digit planes + row exponents of a packed operand (i8pair.cuh); `flag` is set on the device when a value is not finite
+// digit planes + row exponents of a packed operand (i8pair.cuh)
 template <class Alloc>
-static void i8_make_planes(const double *x, long long ld, int nr, Alloc &mem, int *flag, cudaStream_t st, int8_t *&sl, int *&expo,
+static void i8_make_planes(const double *x, long long ld, int nr, Alloc &mem, cudaStream_t st, int8_t *&sl, int *&expo,
                            size_t *bytes_out = nullptr) {
     const int KT = (int)(ld / 16), rb = (nr + 127) / 128;
     const size_t bytes = (size_t)rb * (KT + 1) * I8_A_CHUNK;
@@ -716,7 +716,7 @@ static void i8_make_planes(const double *x, long long ld, int nr, Alloc &mem, in
     if (bytes_out) *bytes_out = bytes;
     // only the trailing all-zero k-chunk of every row block needs clearing: the slice kernel writes everything else
     AQML_CUDA(cudaMemset2DAsync(sl + (size_t)KT * I8_A_CHUNK, (size_t)(KT + 1) * I8_A_CHUNK, 0, I8_A_CHUNK, rb, st));
-    i8_rowexp_kernel<<<(nr + 7) / 8, 256, 0, st>>>(x, ld, nr, expo, flag);
+    i8_rowexp_kernel<<<(nr + 7) / 8, 256, 0, st>>>(x, ld, nr, expo);
     AQML_LAUNCH_CHECK();
     const int split = std::max(1, std::min(KT, 2048 / std::max(rb, 1)));
     const int per = (KT + split - 1) / split;
@@ -785,7 +785,6 @@ static void run_pairs_i8(const aqml_rep *r1, const aqml_rep *r2, int zmax, int r
 bool aqml::i8_local_pairs(const std::vector<I8Pair> &pairs, const PairParams &PP, Workspace &ws) {
     if (!i8_engine_enabled() || PP.nsig > I8_MAXSIG) return false;
     cudaStream_t st = ws.stream();
-    int *flag = ws.zeros<int>(1);
     std::vector<I8Group> gs;
     for (const auto &pr : pairs) {
         if (pr.a.nr == 0 || pr.b.nr == 0) continue;
@@ -793,9 +792,9 @@ bool aqml::i8_local_pairs(const std::vector<I8Pair> &pairs, const PairParams &PP
         memset(&g, 0, sizeof(g));
         int8_t *sa, *sb;
         int *ea, *eb;
-        i8_make_planes(pr.a.x, pr.a.ld, pr.a.nr, ws, flag, st, sa, ea);
+        i8_make_planes(pr.a.x, pr.a.ld, pr.a.nr, ws, st, sa, ea);
         if (pr.b.x == pr.a.x && pr.b.nr == pr.a.nr) { sb = sa; eb = ea; }
-        else i8_make_planes(pr.b.x, pr.b.ld, pr.b.nr, ws, flag, st, sb, eb);
+        else i8_make_planes(pr.b.x, pr.b.ld, pr.b.nr, ws, st, sb, eb);
         g.slA = sa; g.slB = sb; g.expA = ea; g.expB = eb; g.normA = pr.a.norm; g.normB = pr.b.norm;
         g.segA = pr.a.seg; g.segB = pr.b.seg; g.nrA = pr.a.nr; g.nrB = pr.b.nr;
         g.maskA = pr.a.mask; g.maskB = pr.b.mask; g.maskw = pr.a.maskw;
@@ -804,10 +803,6 @@ bool aqml::i8_local_pairs(const std::vector<I8Pair> &pairs, const PairParams &PP
         g.zcol = pr.zcol; g.segA_off = 0; g.segA_n = 0x7fffffff; g.sym = 0;
         gs.push_back(g);
     }
-    int bad = 0;
-    AQML_CUDA(cudaMemcpyAsync(&bad, flag, sizeof(int), cudaMemcpyDeviceToHost, st));
-    AQML_CUDA(cudaStreamSynchronize(st));
-    if (bad) return false;
     launch_i8(gs, PP, ws);
     return true;
 }
@@ -815,15 +810,14 @@ bool aqml::i8_local_pairs(const std::vector<I8Pair> &pairs, const PairParams &PP
 bool aqml::i8_global_pair(const I8Side &a, int na, const I8Side &b, int nb, const PairParams &PP, Workspace &ws) {
     if (!i8_engine_enabled() || PP.nsig > I8_MAXSIG || na <= 0 || nb <= 0) return false;
     cudaStream_t st = ws.stream();
-    int *flag = ws.zeros<int>(1);
     I8Group g;
     memset(&g, 0, sizeof(g));
     int8_t *sa, *sb;
     int *ea, *eb;
-    i8_make_planes(a.x, a.ld, a.nr, ws, flag, st, sa, ea);
+    i8_make_planes(a.x, a.ld, a.nr, ws, st, sa, ea);
     const bool same = (b.x == a.x && b.nr == a.nr);
     if (same) { sb = sa; eb = ea; }
-    else i8_make_planes(b.x, b.ld, b.nr, ws, flag, st, sb, eb);
+    else i8_make_planes(b.x, b.ld, b.nr, ws, st, sb, eb);
     auto ident = [&](int nr, int n) {
         std::vector<int> v(nr, -1);
         for (int i = 0; i < n && i < nr; i++) v[i] = i;
@@ -835,10 +829,6 @@ bool aqml::i8_global_pair(const I8Side &a, int na, const I8Side &b, int nb, cons
     g.KT = (int)(a.ld / 16);
     g.tilesM = (a.nr + I8_BM - 1) / I8_BM; g.tilesN = (b.nr + I8_BN - 1) / I8_BN;
     g.zcol = 0; g.segA_off = 0; g.segA_n = 0x7fffffff; g.sym = 0;
-    int bad = 0;
-    AQML_CUDA(cudaMemcpyAsync(&bad, flag, sizeof(int), cudaMemcpyDeviceToHost, st));
-    AQML_CUDA(cudaStreamSynchronize(st));
-    if (bad) return false;
     std::vector<I8Group> gs{g};
     launch_i8(gs, PP, ws, 1);
     return true;
@@ -911,18 +901,15 @@ static void rep_create(const double *coords, int on_dev, const int *zs, const in
     J.nmol = nmol; J.A = mi.A; J.local = 1; J.out = nullptr; J.ldo = 0; J.atom_prow = ws.upload(atom_prow);
     launch_slatm(t, J, mi, ws);
     if (i8_engine_enabled()) {
-        // digit planes of every packed operand (7 bytes per element next to the 8 of the FP64 copy)
-        int *flag = ws.zeros<int>(1);
+        // digit planes of every packed operand (7 bytes per element next to the 8 of the FP64 copy); stream ordered,
+        // no host synchronisation (NaN rows from coincident atoms travel through |row|^2, see i8_rowexp_kernel)
         for (auto &el : rep->els) {
             if (el.n == 0) continue;
             size_t bytes = 0;
-            i8_make_planes(el.x, el.ld, el.nr, keep, flag, st, el.sl, el.expo, &bytes);
+            i8_make_planes(el.x, el.ld, el.nr, keep, st, el.sl, el.expo, &bytes);
             rep->bytes += (int64_t)bytes + 4 * el.nr;
         }
-        int bad = 0;
-        AQML_CUDA(cudaMemcpyAsync(&bad, flag, sizeof(int), cudaMemcpyDeviceToHost, st));
-        AQML_CUDA(cudaStreamSynchronize(st));
-        rep->i8_ready = (bad == 0);  // NaN / Inf rows (coincident atoms): the FP64 engine reproduces the reference's NaNs
+        rep->i8_ready = true;
     }
     rep->owned = keep.pointers();
     keep.release_all();
