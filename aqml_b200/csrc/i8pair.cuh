@@ -65,6 +65,7 @@ struct I8Params {
     unsigned long long *stats;
     int chain, order[16], nsq[16];
     int debug;  // AQML_I8_DEBUG: MMA-thread wait timers into stats[2..6]
+    int gm;     // tile rows per raster band
     int store;  // 0: sum exp over the atoms of each molecule pair (local kernels); 1: K[s][seg_a][seg_b] = exp (global kernels)
 };
 
@@ -268,7 +269,7 @@ __global__ void __launch_bounds__(I8_THREADS, 1) i8_pair_kernel(const I8Params P
             while (gi + 1 < P.ngroups && tile >= P.groups[gi + 1].tile_begin) gi++;
             const I8Group G = P.groups[gi];
             const int t = tile - G.tile_begin;
-            constexpr int GM = 16;  // tile rows per raster band (A planes stay L2 resident while B streams)
+            const int GM = P.gm;  // tile rows per raster band (A planes stay L2 resident while B streams)
             const int band = t / (GM * G.tilesN), rem = t % (GM * G.tilesN);
             const int gm = min(GM, G.tilesM - band * GM);
             const int tm = band * GM + rem % gm, tn = rem / gm;
