@@ -134,26 +134,9 @@ __device__ __forceinline__ double pow2(int e) {  // 2^e, clamped to the normal r
 }
 }  // namespace i8
 
-// exp(x), x <= 0 (or -inf): x log2(e) = k + j1/128 + j2/16384 + rho;  exp(x) = 2^k T[j1] U[j2] exp(r), |r| <= 2.2e-5, cubic
-// polynomial.  9 FP64 instructions instead of the 18 of a polynomial-only evaluation: on this chip FP64 arithmetic and
-// the tensor pipe exclude each other (profiles/r01_micro_dmma_dfma.txt, r01_i8_pair_kernel_ncu.txt), so every FP64
-// instruction of the epilogue is time taken from the MMAs.  tab: 128 entries 2^(j/128), then 128 entries 2^(j/16384).
-__device__ __forceinline__ double i8_exp(double x, const double *tab) {
-    const double xc = fmax(x, -708.0);
-    const double magic = 6755399441055744.0;
-    double t = fma(xc, 23637.115549924776 /* 2^14 log2(e) */, magic);
-    const int n = __double2loint(t);
-    t -= magic;
-    double r = fma(t, -4.2306346131226746e-05 /* ln2 / 2^14, upper 27 bits: t * hi is exact */, xc);
-    r = fma(t, -3.384964780863074e-13, r);
-    double p = fma(r, 1.0 / 6.0, 0.5);
-    p = fma(p, r, 1.0);
-    p = fma(p, r, 1.0);
-    const double w = tab[(n >> 7) & 127] * tab[128 + (n & 127)];
-    const double v = w * p;
-    const double sc = __hiloint2double(((n >> 14) + 1023) << 20, 0);
-    return (x < -707.0) ? 0.0 : ((x != x) ? x : v * sc);  // NaN in, NaN out
-}
+// exp: the table-based exp_tab of slatm_units.cuh (9 FP64 instructions).  On this chip FP64 arithmetic and the tensor pipe
+// exclude each other (profiles/r01_micro_i8_umma.txt), so every FP64 instruction of the epilogue is time taken from the MMAs.
+__device__ __forceinline__ double i8_exp(double x, const double *tab) { return exp_tab(x, tab); }
 
 // sum the lanes of each A molecule (contiguous lanes, last lane run_end) and add the heads' totals into K
 __device__ __noinline__ void i8_flush(double r, int lane, int run_end, bool head, double *dst) {
@@ -239,10 +222,7 @@ __global__ void __launch_bounds__(I8_THREADS, 1) i8_pair_kernel(const I8Params P
         for (int b = 0; b < I8_META; b++) { i8::mbar_init(&S.meta_full[b], 1); i8::mbar_init(&S.meta_empty[b], I8_EPI_WARPS); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (tid >= 64 && tid < 64 + 256) {
-        const int j = tid - 64;
-        S.exptab[j] = (j < 128) ? exp2((double)j / 128.0) : exp2((double)(j - 128) / 16384.0);
-    }
+    fill_exp_table(S.exptab, tid, I8_THREADS);
     if (warp == 1) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(i8::smem_u32(&S.tmem_base)), "r"(512u) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");

@@ -52,6 +52,29 @@ __device__ __forceinline__ double exp_nonpos(double x) {
 }
 
 // GS = threads per work unit (4 or 8); M2/M3 = grid points per thread (GS*M >= nx)
+// exp(x), x <= 0 (or -inf; NaN in, NaN out), from two 128-entry tables in shared memory: x log2(e) = k + j1/128 + j2/16384 +
+// rho; exp(x) = 2^k T[j1] U[j2] exp(r), |r| <= 2.2e-5, cubic polynomial.  9 FP64 instructions (exp_nonpos: 18), 5e-16.
+// tab[0..127] = 2^(j/128), tab[128..255] = 2^(j/16384)  (fill_exp_table).
+__device__ __forceinline__ double exp_tab(double x, const double *tab) {
+    const double xc = fmax(x, -708.0);
+    const double magic = 6755399441055744.0;
+    double t = fma(xc, 23637.115549924776 /* 2^14 log2(e) */, magic);
+    const int n = __double2loint(t);
+    t -= magic;
+    double r = fma(t, -4.2306346131226746e-05 /* ln2 / 2^14, upper 27 bits: t * hi is exact */, xc);
+    r = fma(t, -3.384964780863074e-13, r);
+    double p = fma(r, 1.0 / 6.0, 0.5);
+    p = fma(p, r, 1.0);
+    p = fma(p, r, 1.0);
+    const double w = tab[(n >> 7) & 127] * tab[128 + (n & 127)];
+    const double v = w * p;
+    const double sc = __hiloint2double(((n >> 14) + 1023) << 20, 0);
+    return (x < -707.0) ? 0.0 : ((x != x) ? x : v * sc);
+}
+__device__ __forceinline__ void fill_exp_table(double *tab, int tid, int nthreads) {
+    for (int j = tid; j < 256; j += nthreads) tab[j] = (j < 128) ? exp2((double)j / 128.0) : exp2((double)(j - 128) / 16384.0);
+}
+
 __device__ __forceinline__ int mel_of(const SlatmJob &J, const SlatmDev &T, long long atom) {
     const int z = J.zs[atom];
     int e = -1;
@@ -75,6 +98,7 @@ slatm_units_kernel(const SlatmDev T, const SlatmJob J, const Batch *batches, int
     unsigned char *fls = reinterpret_cast<unsigned char *>(sstart + ba_max * (MAXEL + 1));  // [ba][na]
     __shared__ double4 s_mbox[SL_THREADS];  // per thread: the geometry of "its" entry, read by its whole group
     __shared__ int s_next, s_next3, s_fetch[SL_THREADS / GS];
+    __shared__ double s_exptab[256];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const double eps = 2.220446049250313e-16;
@@ -82,6 +106,7 @@ slatm_units_kernel(const SlatmDev T, const SlatmJob J, const Batch *batches, int
     const Batch bt = batches[blockIdx.x];
     const int o = J.mol_off[bt.mol], na = J.mol_off[bt.mol + 1] - o;
 
+    fill_exp_table(s_exptab, tid, SL_THREADS);
     for (int i = tid; i < GS * M2; i += SL_THREADS) {
         int q = min(i, T.nx2 - 1);
         sx2[i] = T.xs2[q];
@@ -273,7 +298,7 @@ slatm_units_kernel(const SlatmDev T, const SlatmJob J, const Batch *batches, int
                     const double4 mb = s_mbox[gtid0 + t];
                     if (mb.x < 0.0) continue;  // no entry / outside the 2-body cut-off (group-uniform)
                     const double d = xa - mb.x;
-                    double E = exp_nonpos(-(d * d) * T.cst2), R = mb.y * qm2;
+                    double E = exp_tab(-(d * d) * T.cst2, s_exptab), R = mb.y * qm2;
 #pragma unroll
                     for (int j = 0; j < M2; j++) { a2[j] += E; E *= R; R *= T.q2; }
                 }
@@ -390,7 +415,7 @@ slatm_units_kernel(const SlatmDev T, const SlatmJob J, const Batch *batches, int
                     const double4 mb = s_mbox[gtid0 + t];
                     if (mb.x == 0.0) continue;  // no entry / pair failed a cut-off test (group-uniform)
                     const double d = xa - mb.y;
-                    double E = exp_nonpos(-(d * d) * T.cst3), R = mb.w * qm3;
+                    double E = exp_tab(-(d * d) * T.cst3, s_exptab), R = mb.w * qm3;
 #pragma unroll
                     for (int j = 0; j < M3; j++) { a3[j] += fma(scos3[j0 + j], mb.z, mb.x) * E; E *= R; R *= T.q3; }
                 }

@@ -423,6 +423,9 @@ def run_ours(args):
             roofline["int8_peak_pops"] = int8_peak
             roofline["int8_frac_of_peak"] = roofline["int8_pops"] / int8_peak
             roofline["int8_frac_of_n64_rate"] = roofline["int8_pops"] / 2.9
+            if peaks.get("bf16_tflops"):  # MEASURED_PEAKS.json: cuBLAS bf16 dense; the int8 pipe does twice that per clock
+                roofline["measured_bf16_tflops"] = peaks["bf16_tflops"]
+                roofline["int8_frac_of_2x_measured_bf16"] = roofline["int8_pops"] * 1e3 / (2.0 * peaks["bf16_tflops"])
             roofline["note"] = ("FP64-accurate contraction from exact int8 digit-plane products on the 5th-generation tensor "
                                 "cores (DESIGN.md 4.1b): achieved/frac are FP64-EQUIVALENT flops (SURVEY 8(d) count "
                                 "2*sum_z D_z*n1_z*n2_z) against the measured cuBLAS DGEMM peak, so frac > 1 is the point of the "
