@@ -70,7 +70,7 @@ struct I8Params {
 };
 
 struct I8Meta {  // everything the roles need to know about one tile
-    int tm, tn, nact, KT, zcol, sym;
+    int tm, tn, nact, KT, zcol, sym, dense;  // dense: every k-chunk 0 .. KT-1 is active (no list)
     const int8_t *srcA, *srcB;
     int segA[I8_BM], expA[I8_BM];
     double normA[I8_BM];
@@ -293,12 +293,11 @@ __global__ void __launch_bounds__(I8_THREADS, 1) i8_pair_kernel(const I8Params P
                     n += cnt;
                 }
             } else {
-                for (int k = lane; k < G.KT; k += 32) M.kt[k] = (unsigned short)k;
-                n = G.KT;
+                n = G.KT;  // no masks (or more chunks than the list holds): all of them, generated by the producer
             }
             if (lane == 0) {
-                if (n & 1) M.kt[n] = (unsigned short)G.KT;  // pad the last stage with the all-zero chunk
-                M.nact = n; M.tm = tm; M.tn = tn; M.KT = G.KT; M.zcol = G.zcol; M.sym = G.sym;
+                if (masked && (n & 1)) M.kt[n] = (unsigned short)G.KT;  // pad the last stage with the all-zero chunk
+                M.nact = n; M.tm = tm; M.tn = tn; M.KT = G.KT; M.zcol = G.zcol; M.sym = G.sym; M.dense = masked ? 0 : 1;
                 M.srcA = G.slA + (long long)tm * (G.KT + 1) * I8_A_CHUNK;
                 M.srcB = G.slB + (long long)(tn >> 1) * (G.KT + 1) * I8_A_CHUNK + (tn & 1) * 1024;
                 if (P.stats) {  // in units of 64 x 64 x 16 k-tiles, like the DMMA engine
@@ -328,7 +327,7 @@ __global__ void __launch_bounds__(I8_THREADS, 1) i8_pair_kernel(const I8Params P
                     i8::mbar_expect_tx(&S.full[s], I8_STAGE_BYTES);
 #pragma unroll
                     for (int c = 0; c < 2; c++) {
-                        const int kt = M.kt[2 * k + c];
+                        const int kt = M.dense ? min(2 * k + c, M.KT) : (int)M.kt[2 * k + c];
                         i8::bulk_g2s(st + c * I8_A_CHUNK, srcA + (long long)kt * I8_A_CHUNK, I8_A_CHUNK, &S.full[s]);
                         unsigned char *db = st + 2 * I8_A_CHUNK + c * I8_B_CHUNK;
                         const int8_t *sb = srcB + (long long)kt * I8_A_CHUNK;
@@ -440,6 +439,11 @@ __global__ void __launch_bounds__(I8_THREADS, 1) i8_pair_kernel(const I8Params P
             __syncwarp();
             if (!I8_SERIAL_EPILOGUE && lane == 0) i8::mbar_arrive(&S.tmem_free);
             const long long e2 = clock64();
+            if (P.debug & 2) {  // measurement only: no exp / sums (how much of the tile time is the FP64 epilogue?)
+                __syncwarp();
+                if (lane == 0) i8::mbar_arrive(&S.meta_empty[b]);
+                continue;
+            }
             // d^2 of my 16 pairs
             double x[EC];
 #pragma unroll

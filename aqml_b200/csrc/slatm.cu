@@ -740,7 +740,7 @@ static void launch_i8(std::vector<I8Group> &gs, const PairParams &PP, Workspace 
     int dev = 0, sms = 0;
     AQML_CUDA(cudaGetDevice(&dev));
     AQML_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    P.debug = getenv("AQML_I8_DEBUG") ? 1 : 0;
+    P.debug = getenv("AQML_I8_DEBUG") ? atoi(getenv("AQML_I8_DEBUG")) : 0;
     P.store = store;
     P.gm = getenv("AQML_I8_GM") ? std::max(1, atoi(getenv("AQML_I8_GM"))) : 16;
     if (P.debug) AQML_CUDA(cudaMemsetAsync(P.stats + 2, 0, 64, ws.stream()));

@@ -290,3 +290,11 @@ def test_int8_engine_hostile_rows():
     A2 = A.copy(); A2[7, 3] = np.nan
     K = kernels.gaussian_kernel(A2, B, dmax)
     assert np.isnan(K[7]).all() and not np.isnan(np.delete(K, 7, axis=0)).any()
+
+
+def test_global_gaussian_very_long_rows():
+    """More 16-column k-chunks than the tile metadata's chunk list holds (D > 16384): the int8 engine walks them all."""
+    rng = np.random.default_rng(5)
+    A, B = rng.random((70, 20011)), rng.random((45, 20011))
+    sigma = 0.4 * np.sqrt(20011)
+    assert rel_err(kernels.gaussian_kernel(A, B, sigma), co.gaussian_kernel(A, B, sigma)) < TOL
