@@ -41,6 +41,7 @@ constexpr int I8_SERIAL_EPILOGUE = 0;
 constexpr int I8_META = 3;                       // tile metadata buffers (prepared up to two tiles ahead)
 constexpr int I8_THREADS = 32 * (3 + I8_EPI_WARPS);  // producer, MMA issuer, tile metadata, 16 epilogue warps
 constexpr int I8_MAXSIG = 8;
+constexpr int I8_MAX_LD = 65536;                 // int32 accumulators: 7 * ld * 64^2 < 2^31 (longer rows: FP64 engine)
 
 struct I8Group {
     const int8_t *slA, *slB;      // [row block of 128][KT + 1][plane][128 rows x 16 B]; k-chunk KT is all zero

@@ -785,6 +785,8 @@ static void run_pairs_i8(const aqml_rep *r1, const aqml_rep *r2, int zmax, int r
 // packed FP64 operands from the dense API (kernels.cu): temporary digit planes
 bool aqml::i8_local_pairs(const std::vector<I8Pair> &pairs, const PairParams &PP, Workspace &ws) {
     if (!i8_engine_enabled() || PP.nsig > I8_MAXSIG) return false;
+    for (const auto &pr : pairs)
+        if (pr.a.ld > I8_MAX_LD) return false;
     cudaStream_t st = ws.stream();
     std::vector<I8Group> gs;
     for (const auto &pr : pairs) {
@@ -809,7 +811,7 @@ bool aqml::i8_local_pairs(const std::vector<I8Pair> &pairs, const PairParams &PP
 }
 
 bool aqml::i8_global_pair(const I8Side &a, int na, const I8Side &b, int nb, const PairParams &PP, Workspace &ws) {
-    if (!i8_engine_enabled() || PP.nsig > I8_MAXSIG || na <= 0 || nb <= 0) return false;
+    if (!i8_engine_enabled() || PP.nsig > I8_MAXSIG || na <= 0 || nb <= 0 || a.ld > I8_MAX_LD) return false;
     cudaStream_t st = ws.stream();
     I8Group g;
     memset(&g, 0, sizeof(g));
@@ -838,6 +840,8 @@ bool aqml::i8_global_pair(const I8Side &a, int na, const I8Side &b, int nb, cons
 namespace aqml {
 
 static bool use_i8(const aqml_rep *r1, const aqml_rep *r2, int nsigmas) {
+    for (const auto &e : r1->els)
+        if (e.ld > I8_MAX_LD) return false;
     return i8_engine_enabled() && r1->i8_ready && r2->i8_ready && nsigmas <= I8_MAXSIG;
 }
 
