@@ -88,7 +88,7 @@ def kernel_width(rep1, rep2, zmax):
     return dso
 
 
-def local_gaussian_to_host(coordinates, nuclear_charges, nas, rep_train, mbtypes, kernel_sigmas, zmax, out_host, chunks=4,
+def local_gaussian_to_host(coordinates, nuclear_charges, nas, rep_train, mbtypes, kernel_sigmas, zmax, out_host, chunks=2,
                            **slatm_kw):
     """K[k, a, b] between HOST-resident query molecules (coordinates (A,3), nuclear_charges (A,), nas) and a packed
     training set, delivered into the pinned host tensor ``out_host`` (nsigmas, len(nas), rep_train.nmol).
@@ -96,8 +96,8 @@ def local_gaussian_to_host(coordinates, nuclear_charges, nas, rep_train, mbtypes
     The queries are processed in ``chunks`` row blocks: block c is packed and contracted on the current stream while
     block c-1 travels device -> host on a second stream (two device buffers), so the 8 bytes per kernel element of the
     result leave the GPU behind the compute instead of after it, and K never has to fit in device memory (two block
-    buffers).  For a K that does fit, one contraction + one copy is faster (bench.py e2e: 346 vs 357 ms with 4 blocks:
-    per-block packing and the persistent kernel's tail cost more than the hidden copy).  Returns after everything has
+    buffers).  Two blocks are the sweet spot on the bench workload (e2e 343 ms against 351 ms for one contraction + one
+    copy; every further block adds packing and a kernel tail).  Returns after everything has
     been enqueued; the current stream is made to wait for the copies (synchronise it before reading ``out_host``)."""
     import torch
     nas = np.asarray(nas)
