@@ -294,6 +294,138 @@ static void run_overlap() {
     cudaFree(dsink);
 }
 
+// cta_group::2: a pair of CTAs (cluster of 2) shares one MMA of M = 256 (128 rows per CTA), N = 64: each CTA stages its own
+// 128 rows of A and HALF of B (32 rows); D (128 lanes x 64 columns per accumulator) lands in each CTA's own TMEM.
+// Rate of the 28-product schedule, issued by the leader CTA only.
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128) rate2_kernel(int rounds, long long *cycles, int32_t *sink, const int8_t *A,
+                                                                             const int8_t *B, int32_t *C) {
+    extern __shared__ __align__(128) int8_t sm[];
+    int8_t *sA = sm;                  // 7 planes x 4 KB (my 128 rows)
+    int8_t *sB = sm + 7 * 4096;       // 7 planes x 32 rows x 32 B = 1 KB (my half of B)
+    __shared__ __align__(8) uint64_t bar;
+    __shared__ uint32_t tmem_base;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    unsigned rank;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
+    if (A) {  // correctness mode: plane 0 only, A (256 x 32), B (64 x 32) row-major int8
+        for (int i = tid; i < 128 * 32; i += 128) sA[canon_off(i / 32, i % 32)] = A[(rank * 128 + i / 32) * 32 + i % 32];
+        for (int i = tid; i < 32 * 32; i += 128) sB[canon_off(i / 32, i % 32)] = B[(rank * 32 + i / 32) * 32 + i % 32];
+    } else {
+        for (int i = tid; i < 7 * 4096 + 7 * 1024; i += 128) sm[i] = (int8_t)((i * 37 + 11) % 127 - 63);
+    }
+    if (tid == 0) { mbar_init(&bar, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base)), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tb = tmem_base;
+    long long t0 = clock64();
+    if (rank == 0 && tid == 0) {
+        const uint32_t idesc = make_idesc(256, 64);
+        const uint64_t da0 = smem_desc(smem_u32(sA), 128, 256), db0 = smem_desc(smem_u32(sB), 128, 256);
+        if (A) {
+            asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::2.kind::i8 [%0], %1, %2, %3, p;\n}"
+                         ::"r"(tb), "l"(da0), "l"(db0), "r"(idesc), "r"(0u) : "memory");
+        } else {
+            for (int r = 0; r < rounds; r++) {
+#pragma unroll
+                for (int i = 0; i < 7; i++)
+#pragma unroll
+                    for (int j = 0; j < 7; j++)
+                        if (i + j < 7)
+                            asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::2.kind::i8 [%0], %1, %2, %3, p;\n}"
+                                         ::"r"(tb + (i + j) * 64), "l"(da0 + (uint64_t)(i * 4096 >> 4)), "l"(db0 + (uint64_t)(j * 1024 >> 4)), "r"(idesc), "r"(1u) : "memory");
+            }
+        }
+        // arrive on the barrier of BOTH CTAs (same shared-memory offset in each)
+        asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                     ::"r"(smem_u32(&bar)), "h"((unsigned short)3) : "memory");
+    }
+    mbar_wait(&bar, 0);
+    long long t1 = clock64();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    if (A) {
+        for (int c0 = 0; c0 < 64; c0 += 8) {
+            uint32_t v[8];
+            asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                         : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+                         : "r"(tb + ((uint32_t)(warp * 32) << 16) + c0));
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            for (int j = 0; j < 8; j++) C[(rank * 128 + tid) * 64 + c0 + j] = (int32_t)v[j];
+        }
+    } else {
+        uint32_t v[4];
+        asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]) : "r"(tb + ((uint32_t)(warp * 32) << 16)));
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        if (v[0] == 0x12345678u) sink[0] = (int32_t)v[1];
+    }
+    if (tid == 0) cycles[blockIdx.x] = t1 - t0;
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tb), "r"(512u) : "memory");
+}
+
+static void run_rate2() {
+    int dev = 0, sms = 0;
+    CK(cudaGetDevice(&dev));
+    CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    sms &= ~1;
+    long long *dcy; int32_t *dsink;
+    CK(cudaMalloc(&dcy, sms * 8)); CK(cudaMalloc(&dsink, 64));
+    const int smem = 7 * 4096 + 7 * 1024;
+    CK(cudaFuncSetAttribute(rate2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    // correctness: one MMA, M = 256, N = 64, K = 32
+    {
+        std::vector<int8_t> A(256 * 32), B(64 * 32);
+        srand(3);
+        for (auto &v : A) v = (int8_t)(rand() % 255 - 127);
+        for (auto &v : B) v = (int8_t)(rand() % 255 - 127);
+        int8_t *dA, *dB; int32_t *dC;
+        CK(cudaMalloc(&dA, A.size())); CK(cudaMalloc(&dB, B.size())); CK(cudaMalloc(&dC, 256 * 64 * 4));
+        CK(cudaMemcpy(dA, A.data(), A.size(), cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(dB, B.data(), B.size(), cudaMemcpyHostToDevice));
+        CK(cudaMemset(dC, 0xff, 256 * 64 * 4));
+        rate2_kernel<<<2, 128, smem>>>(1, dcy, dsink, dA, dB, dC);
+        cudaError_t e = cudaDeviceSynchronize();
+        if (e != cudaSuccess) { printf("cta_group::2 check: CUDA error %s\n", cudaGetErrorString(e)); return; }
+        std::vector<int32_t> Cc(256 * 64);
+        CK(cudaMemcpy(Cc.data(), dC, Cc.size() * 4, cudaMemcpyDeviceToHost));
+        int bad = 0;
+        for (int i = 0; i < 256; i++)
+            for (int j = 0; j < 64; j++) {
+                int32_t s = 0;
+                for (int k = 0; k < 32; k++) s += (int32_t)A[i * 32 + k] * (int32_t)B[j * 32 + k];
+                if (s != Cc[i * 64 + j]) { if (bad < 3) printf("  mismatch (%d,%d): got %d want %d\n", i, j, Cc[i * 64 + j], s); bad++; }
+            }
+        printf("check cta_group::2 256x64x32 int8 UMMA: %s (%d mismatches)\n", bad ? "FAIL" : "OK", bad);
+        cudaFree(dA); cudaFree(dB); cudaFree(dC);
+        if (bad) return;
+    }
+    const int rounds = 4000;
+    rate2_kernel<<<sms, 128, smem>>>(10, dcy, dsink, nullptr, nullptr, nullptr);
+    CK(cudaDeviceSynchronize());
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+    CK(cudaEventRecord(e0));
+    rate2_kernel<<<sms, 128, smem>>>(rounds, dcy, dsink, nullptr, nullptr, nullptr);
+    CK(cudaEventRecord(e1));
+    CK(cudaDeviceSynchronize());
+    float ms = 0;
+    CK(cudaEventElapsedTime(&ms, e0, e1));
+    std::vector<long long> cy(sms);
+    CK(cudaMemcpy(cy.data(), dcy, sms * 8, cudaMemcpyDeviceToHost));
+    double ops = 2.0 * 256 * 64 * 32 * 28.0 * rounds * (sms / 2);
+    printf("cta_group::2, M=256 (2 x 128), N=64, 7 accumulators: %.3f ms, %.2f POPS, %.1f clk per MMA (pair 0), FP64-equivalent %.1f TF\n", ms,
+           ops / (ms * 1e-3) / 1e15, (double)cy[0] / (28.0 * rounds), ops / 28.0 / (ms * 1e-3) / 1e12);
+    cudaFree(dcy); cudaFree(dsink);
+}
+
 template <int N>
 static int run_check_ts(int mode) {
     std::vector<int8_t> A(128 * 32), B(N * 32);
@@ -441,6 +573,7 @@ int main() {
     if (bad) { printf("descriptor interpretation A failed; trying swapped LBO/SBO\n"); run_check<64>(256, 128); }
     run_check_ts<64>(0);
     run_check_ts<64>(1);
+    run_rate2();
     run_overlap<0>();
     run_overlap<1>();
     run_rate_ts(0);
