@@ -93,11 +93,11 @@ def local_gaussian_to_host(coordinates, nuclear_charges, nas, rep_train, mbtypes
     """K[k, a, b] between HOST-resident query molecules (coordinates (A,3), nuclear_charges (A,), nas) and a packed
     training set, delivered into the pinned host tensor ``out_host`` (nsigmas, len(nas), rep_train.nmol).
 
-    The queries are processed in ``chunks`` row blocks: block c is packed and contracted on the current stream while
+    The queries are processed in ``chunks`` row blocks (an int, or a tuple of relative block sizes): block c is packed and contracted on the current stream while
     block c-1 travels device -> host on a second stream (two device buffers), so the 8 bytes per kernel element of the
     result leave the GPU behind the compute instead of after it, and K never has to fit in device memory (two block
-    buffers).  Two blocks are the sweet spot on the bench workload (e2e 343 ms against 351 ms for one contraction + one
-    copy; every further block adds packing and a kernel tail).  Returns after everything has
+    buffers).  Two unequal blocks, (0.75, 0.25), are the sweet spot on the bench workload: e2e 338 ms against 351 ms for
+    one contraction + one copy (only the last block's copy is exposed; every further block adds packing and a kernel tail).  Returns after everything has
     been enqueued; the current stream is made to wait for the copies (synchronise it before reading ``out_host``)."""
     import torch
     nas = np.asarray(nas)
@@ -107,7 +107,11 @@ def local_gaussian_to_host(coordinates, nuclear_charges, nas, rep_train, mbtypes
     sig = sig.reshape(len(sig), -1)
     nq, nsig = len(nas), sig.shape[0]
     off = np.concatenate(([0], np.cumsum(nas)))
-    bounds = np.linspace(0, nq, min(max(int(chunks), 1), max(nq, 1)) + 1).astype(int)
+    if isinstance(chunks, (list, tuple)):  # relative block sizes, e.g. (0.7, 0.2, 0.1): only the last block's copy is exposed
+        fr = np.cumsum(np.asarray(chunks, dtype=np.float64))
+        bounds = np.unique(np.concatenate(([0], np.rint(fr / fr[-1] * nq).astype(int))))
+    else:
+        bounds = np.linspace(0, nq, min(max(int(chunks), 1), max(nq, 1)) + 1).astype(int)
     dev = rep_train.device
     with torch.cuda.device(dev):
         cur = torch.cuda.current_stream()

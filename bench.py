@@ -338,11 +338,12 @@ def run_ours(args):
         pc1 = torch.as_tensor(train[2]).pin_memory().numpy()
         pc2 = torch.as_tensor(test[2]).pin_memory().numpy()
 
-        e2e_chunks = int(os.environ.get("AQML_E2E_CHUNKS", "2"))  # measured: 1 -> 350.5, 2 -> 342.8, 3 -> 343.4 ms
+        e2e_chunks = os.environ.get("AQML_E2E_CHUNKS", "0.75,0.25")  # measured: 1 -> 350.5, 2 -> 345.1, 0.75,0.25 -> 337.6, 0.7,0.2,0.1 -> 340.3 ms
+        e2e_chunks = tuple(float(v) for v in e2e_chunks.split(",")) if "," in e2e_chunks else int(e2e_chunks)
 
         def e2e_step():
             r1 = fused.PackedRep(pc1, train[1], train[0], mb, **SLATM_KW)   # coords H2D inside
-            if e2e_chunks > 1:  # queries in row blocks, D2H of block c-1 behind the contraction of block c
+            if e2e_chunks != 1:  # queries in row blocks, D2H of block c-1 behind the contraction of block c
                 fused.local_gaussian_to_host(pc2, test[1], test[0], r1, mb, sig, ZMAX, kh, chunks=e2e_chunks, **SLATM_KW)
                 r1.close()
                 return
