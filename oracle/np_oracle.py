@@ -458,6 +458,34 @@ def learning_curve(ks1, ks2, ngs, ys, nheav1, zsu, llambda=1e-4):
     return rows
 
 
+
+def calc_ka(x2, x1, zs2, zs1, nas2, nas1, zmax, sigmas, kernel='g'):
+    """aqml.py:258-309 (cab=False, zaq=None): atomic kernel matrix, summed over the atoms of each training molecule.
+    Returns ks (nsigmas, A2, N1): ks[k, j, m] = sum_{i in molecule m, Z_i == Z_j} exp(-0.5 (d_ij / sigmas[k, Z_j-1])^2)."""
+    zs1, zs2 = np.asarray(zs1), np.asarray(zs2)
+    nsg, na1, na2, n1 = len(sigmas), len(zs1), len(zs2), len(nas1)
+    ksa = np.zeros((nsg, na2, na1))
+    for zi in np.unique(zs2):
+        ias1 = np.nonzero(zs1 == zi)[0]
+        ias2 = np.nonzero(zs2 == zi)[0]
+        if len(ias1) == 0:
+            continue
+        ds = fl2_distance(x2[ias2], x1[ias1]) if kernel[0] == 'g' else fl1_distance(x2[ias2], x1[ias1])
+        for k in range(nsg):
+            ksa[k][np.ix_(ias2, ias1)] = np.exp(-0.5 * (ds / sigmas[k][zi - 1]) ** 2)
+    off = np.concatenate(([0], np.cumsum(nas1)))
+    return np.stack([ksa[:, :, off[i]:off[i + 1]].sum(axis=2) for i in range(n1)], axis=2)
+
+
+def atomic_energies(ksa21, alphas, zs2, zsu, esb, free_atom=ORCA_B3LYPVDZ):
+    """aqml.py:903-930 (``-ieaq -prog orca``): per-atom contribution of the query molecule,
+    E_A[j] = (ksa21 . alphas)[j] + esb[Z_j] - H2KC * E_free_atom[Z_j]   (kcal/mol).
+    ksa21 (A2, N1) for one sigma, alphas (N1,), esb = dressed-atom energies in the order of zsu."""
+    easq = np.dot(ksa21, alphas)
+    edct = dict(zip([int(z) for z in zsu], esb))
+    return np.array([easq[j] + edct[int(z)] - H2KC * free_atom[int(z)] for j, z in enumerate(zs2)]), easq
+
+
 def read_xyz(path, prop='b3lypvdz'):
     """cheminfo/rw/xyz.py:10-80 (geometry + one 'key=value' property on line 2)."""
     sym2z = {'H': 1, 'C': 6, 'N': 7, 'O': 8, 'F': 9, 'P': 15, 'S': 16, 'Cl': 17}

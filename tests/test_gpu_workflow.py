@@ -153,3 +153,36 @@ def test_sharded_krr_single_rank_matches_direct_solve():
     assert rel_err(alpha.cpu().numpy(), a_ref) < 1e-9
     y_ref = fused.local_gaussian(rep_test, rep_train, sig[None], zmax)[0].cpu().numpy() @ a_ref
     assert rel_err(model.predict(rep_test).cpu().numpy(), y_ref) < 1e-9
+
+
+def test_readme_atomic_energies_through_gpu(demo):
+    """The reference's second KAT (demo/example/README.md:75-94, `-ieaq -prog orca`) with every kernel on the GPU:
+    aSLATM -> widths -> K_train -> alphas (host LAPACK as upstream) -> calc_ka -> per-atom energies, two printed decimals."""
+    import torch
+    from aqml_b200.representation import core as rcore
+    from conftest import mbtypes_from_array
+    readme = [-163.80, -163.55, -163.57, -163.55, -163.77, -163.42, -159.70, -161.60, -90.76, -59.83, -59.98, -59.99,
+              -59.98, -59.78, -64.12, -63.75, -60.70]
+    n1 = int(demo["n1"])
+    nas, zs, coords = demo["nas"], demo["zs"], demo["coords"]
+    mb = mbtypes_from_array(demo["mbtypes"])
+    off = np.concatenate(([0], np.cumsum(nas)))
+    A1 = off[n1]
+    x = rcore.generate_slatm_batch(torch.as_tensor(coords, device="cuda"), zs, nas, mb, local=True, sigmas=[.05, .05],
+                                   dgrids=[.04, .04], rcut=4.8)
+    dso = algo.get_kernel_width(nas, zs, x)
+    sig = (dso / np.sqrt(2 * np.log(2)))[None, :]
+    k1 = kernels.get_local_kernels_gaussian(x[:A1], x[:A1], zs[:A1], zs[:A1], nas[:n1], nas[:n1], False, 8, sig)[0].cpu().numpy()
+    zs_list = synth.split_zs(nas, zs)
+    zsu = np.unique(zs)
+    ngs = np.array([[(z == zz).sum() for zz in zsu] for z in zs_list])
+    ys = demo["energies"] * krr.H2KC
+    free = np.array([krr.H2KC * o.ORCA_B3LYPVDZ[int(z)] for z in zsu])
+    _, ys1, ys2, esb = krr.calc_ae_dressed(ngs, ys, np.arange(n1), np.arange(n1, n1 + 1), free)
+    alphas = krr.solve(k1, ys1, 1e-4)
+    ksa21 = algo.calc_ka(x[A1:], x[:A1], zs[A1:], zs[:A1], nas[n1:], nas[:n1], False, 8, sig)[0].cpu().numpy()
+    easq = ksa21 @ alphas
+    edct = dict(zip([int(z) for z in zsu], esb))
+    fdct = dict(zip([int(z) for z in zsu], free))
+    ea = np.array([easq[j] + edct[int(z)] - fdct[int(z)] for j, z in enumerate(zs[A1:])])
+    assert np.all(np.abs(ea - np.array(readme)) < 5.1e-3), ea

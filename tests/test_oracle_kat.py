@@ -105,3 +105,35 @@ def test_c_vs_np_on_synthetic():
     kc = co.calc_lk_laplacian(xl_c[A1:], xl_c[:A1], nas[n1:], nas[:n1], [50., 200.])
     kn = o.calc_lk_laplacian(xl_c[A1:], xl_c[:A1], nas[n1:], nas[:n1], [50., 200.])
     assert rel_err(kc, kn) < 1e-12
+
+
+# demo/example/README.md:75-94  (`aqml -train g7 -test target -p b3lypvdz -ieaq -prog orca`): atom, Z, E_A in kcal/mol
+README_ATOMIC = [(6, -163.80), (6, -163.55), (6, -163.57), (6, -163.55), (6, -163.77), (6, -163.42), (6, -159.70),
+                 (6, -161.60), (8, -90.76), (1, -59.83), (1, -59.98), (1, -59.99), (1, -59.98), (1, -59.78),
+                 (1, -64.12), (1, -63.75), (1, -60.70)]
+
+
+def test_readme_atomic_energies(demo):
+    """The reference's second known-answer test: atomic contributions to the atomisation energy of the target molecule
+    after training on all 16 amons (README two decimals).  Pins calc_ka (aqml.py:258-309), the dressed-atom baseline
+    and the free-atom table on top of the aSLATM / width / KRR chain pinned by the learning curve."""
+    n1 = int(demo["n1"])
+    nas, zs, x = demo["nas"], demo["zs"], demo["x_local"]
+    off = np.concatenate(([0], np.cumsum(nas)))
+    A1 = off[n1]
+    zs_list = [zs[off[i]:off[i + 1]] for i in range(len(nas))]
+    zsu = np.unique(zs)
+    ngs = np.array([[(z == zz).sum() for zz in zsu] for z in zs_list])
+    ys = demo["energies"] * o.H2KC
+    sig = demo["sigmas"][1:2]                                   # coefficient 1.0, as in the README run
+    idx1, idx2 = np.arange(n1), np.arange(n1, n1 + 1)
+    ys1, ys2, esb = o.calc_ae_dressed(ngs, ys, idx1, idx2, zsu)
+    k1 = demo["k1"][1].copy()
+    k1[np.diag_indices_from(k1)] += 1e-4
+    alphas = np.linalg.solve(k1, ys1)
+    ksa21 = o.calc_ka(x[A1:], x[:A1], zs[A1:], zs[:A1], nas[n1:], nas[:n1], 8, sig)[0]
+    ea, easq = o.atomic_energies(ksa21, alphas, zs[A1:], zsu, esb)
+    # aqml.py:909-910: the atomic contributions add up to the molecular prediction
+    assert abs(easq.sum() - np.dot(demo["k2"][1], alphas)[0]) < 1e-9
+    assert [int(z) for z in zs[A1:]] == [z for z, _ in README_ATOMIC]
+    assert np.all(np.abs(ea - np.array([e for _, e in README_ATOMIC])) < 5.1e-3), ea
