@@ -137,3 +137,10 @@ def test_readme_atomic_energies(demo):
     assert abs(easq.sum() - np.dot(demo["k2"][1], alphas)[0]) < 1e-9
     assert [int(z) for z in zs[A1:]] == [z for z, _ in README_ATOMIC]
     assert np.all(np.abs(ea - np.array([e for _, e in README_ATOMIC])) < 5.1e-3), ea
+
+
+def test_docs_unit_conversion(demo):
+    """docs/source/users_guide/amons_qml.rst:81,97-105: the b3lypvdz energies of the first five g7 amons in kcal/mol
+    (Hartree x io2.Units().h2kc), as the reference's own reader prints them."""
+    doc = np.array([-25401.85283769, -49280.26416003, -71817.46145015, -73935.93419366, -96479.43688458])
+    assert np.allclose(demo["energies"][:5] * o.H2KC, doc, rtol=0, atol=5e-9)
