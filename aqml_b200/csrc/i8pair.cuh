@@ -66,6 +66,7 @@ struct I8Params {
     unsigned long long *stats;
     int chain, order[16], nsq[16];
     int debug;  // AQML_I8_DEBUG: MMA-thread wait timers into stats[2..6]
+    int *counter;  // zeroed before the launch: next tile to hand out
     int gm;     // tile rows per raster band
     int store;  // 0: sum exp over the atoms of each molecule pair (local kernels); 1: K[s][seg_a][seg_b] = exp (global kernels)
 };
@@ -205,9 +206,9 @@ __global__ void __launch_bounds__(128) i8_slice_kernel(const double *x, long lon
 }
 
 // ---- the pair kernel -----------------------------------------------------------------------------------------
-// Persistent: one CTA per SM walks the tile list (tile = blockIdx.x + k gridDim.x, same raster order as a plain grid).
+// Persistent: one CTA per SM; tiles are handed out in raster order by an atomic counter.
 // Roles: warp 0 producer, warp 1 MMA issuer, warp 2 tile metadata (segments, norms, exponents, active k-chunk list,
-// one tile ahead, double buffered), warps 3-18 epilogue.  The epilogue first drains TMEM into registers (phase 1),
+// two tiles ahead, triple buffered), warps 3-18 epilogue.  The epilogue first drains TMEM into registers (phase 1),
 // hands TMEM back (the next tile's MMAs start while exp / sums / REDs of this tile run), and the operand ring
 // keeps filling across tile boundaries.
 __global__ void __launch_bounds__(I8_THREADS, 1) i8_pair_kernel(const I8Params P, int total_tiles) {
@@ -235,8 +236,13 @@ __global__ void __launch_bounds__(I8_THREADS, 1) i8_pair_kernel(const I8Params P
 
     if (warp == 2) {
         // ---- tile metadata, one tile ahead ----
+        // tiles are handed out dynamically (one atomic per tile): the tiles in flight are always consecutive in the raster
+        // order, so the CTAs that share a B tile read it within one L2 residency and the tail is balanced
         int tl = 0;
-        for (int tile = blockIdx.x;; tile += gridDim.x) {
+        for (;;) {
+            int tile = 0;
+            if (lane == 0) tile = atomicAdd(P.counter, 1);
+            tile = __shfl_sync(0xffffffffu, tile, 0);
             const int b = tl % I8_META;
             I8Meta &M = S.meta[b];
             if (tl >= I8_META) i8::mbar_wait(&S.meta_empty[b], ((tl / I8_META) - 1) & 1);

@@ -742,6 +742,7 @@ static void launch_i8(std::vector<I8Group> &gs, const PairParams &PP, Workspace 
     AQML_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     P.debug = getenv("AQML_I8_DEBUG") ? atoi(getenv("AQML_I8_DEBUG")) : 0;
     P.store = store;
+    P.counter = ws.zeros<int>(1);
     P.gm = getenv("AQML_I8_GM") ? std::max(1, atoi(getenv("AQML_I8_GM"))) : 16;
     if (P.debug) AQML_CUDA(cudaMemsetAsync(P.stats + 2, 0, 64, ws.stream()));
     i8_pair_kernel<<<std::min(total, sms), I8_THREADS, smem, ws.stream()>>>(P, total);
