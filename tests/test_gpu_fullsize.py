@@ -87,3 +87,28 @@ def test_rotation_invariance_at_scale():
     summed.index_add_(0, torch.as_tensor(mol, device="cuda"), x0)
     n1 = sum(1 for t in mb if len(t) == 1)
     assert float((summed[:, n1:] - g0[:, n1:]).abs().max()) < 1e-11 * scale  # SLATM == sum of aSLATM rows
+
+
+def test_symmetric_multi_tile_both_engines():
+    """K(X, X) at a size where every element group spans many 128 x 64 tiles (diagonal-crossing tiles, ragged last tiles):
+    the symmetric route of the int8 engine == its rectangular route == the FP64 engine."""
+    import os
+    from aqml_b200 import fused
+    from aqml_b200.representation import core as rcore
+    nas, zs, coords = synth.qm9_like_fast(700, 9, pool=256)
+    mb = rcore.get_slatm_mbtypes(synth.split_zs(nas, zs))
+    kw = dict(sigmas=(.05, .05), dgrids=(.04, .04), rcut=4.8)
+    rep = fused.PackedRep(coords, zs, nas, mb, **kw)
+    dso = fused.kernel_width(rep, rep, 9)
+    sig = np.array([c * dso / np.sqrt(2 * np.log(2)) for c in (0.5, 1.0, 2.0, 4.0)])
+    Ks = fused.local_gaussian(rep, rep, sig, 9, symmetric=True)
+    Kr = fused.local_gaussian(rep, rep, sig, 9)
+    assert float((Ks - Kr).abs().max() / Kr.abs().max()) < 1e-12
+    assert bool((Ks == Ks.transpose(1, 2)).all())
+    os.environ["AQML_PAIR_ENGINE"] = "dmma"
+    try:
+        Kd = fused.local_gaussian(rep, rep, sig, 9, symmetric=True)
+    finally:
+        del os.environ["AQML_PAIR_ENGINE"]
+    rel = ((Ks - Kd).abs() / Kd.abs().clamp_min(1e-10 * float(Kd.abs().max()))).max()
+    assert float(rel) < 1e-11
