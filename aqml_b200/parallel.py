@@ -70,6 +70,31 @@ def gather_rows(K_rows, group=None):
     return torch.cat([o[:, :int(v.item())] for o, v in zip(outs, ns)], dim=1)
 
 
+def allgather_rows(x_local, counts, group=None):
+    """Row blocks of a 2-D tensor from all ranks, concatenated in rank order on every rank (rank r contributes
+    ``counts[r]`` rows; ``counts`` is known everywhere).  SURVEY 8e: SLATM generation is sharded by molecules, then ONE
+    all-gather gives every GPU the full column-side representation (7.2 GB for 100 k x 8975 over NVLink) -- the only
+    collective of the global-kernel path."""
+    import torch
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return x_local
+    world = dist.get_world_size(group)
+    counts = [int(c) for c in counts]
+    assert len(counts) == world and x_local.shape[0] == counts[dist.get_rank(group)]
+    nmax, D = max(counts), x_local.shape[1]
+    out = torch.empty((world * nmax, D), dtype=x_local.dtype, device=x_local.device)
+    mine = x_local.contiguous()
+    if mine.shape[0] != nmax:
+        pad = torch.zeros((nmax, D), dtype=x_local.dtype, device=x_local.device)
+        pad[:mine.shape[0]] = mine
+        mine = pad
+    dist.all_gather([out[r * nmax:(r + 1) * nmax] for r in range(world)], mine, group=group)
+    if all(c == nmax for c in counts):
+        return out
+    return torch.cat([out[r * nmax:r * nmax + counts[r]] for r in range(world)], dim=0)
+
+
 # ----------------------------------------------------------------------------------------------------------
 # Distributed solve of (K + lambda I) alpha = y for a row-sharded K (SURVEY 8f row 2: "multi-GPU block
 # Cholesky for 100 k").  The reference solves on one host with LAPACK (`np.linalg.solve`, aqml.py:875,

@@ -517,10 +517,23 @@ def run_config3(args):
     D = int(L.load().aqml_slatm_dim(L.slatm_params(mb, **SLATM_KW)))
     ev = lambda: torch.cuda.Event(enable_timing=True)  # noqa: E731
 
+    # SLATM of the column molecules is sharded by molecules over the ranks, then one all-gather
+    from aqml_b200 import parallel
+    shard = world > 1 and not os.environ.get("AQML_NO_SLATM_SHARD")
+    if shard:
+        parts = [parallel.shard_range(args.n_cols, r, world) for r in range(world)]
+        clo, chi = parts[rank]
+        coff = np.concatenate(([0], np.cumsum(cols[0])))
+        cc_loc, zs_loc, nas_loc = cc[coff[clo]:coff[chi]], cols[1][coff[clo]:coff[chi]], cols[0][clo:chi]
+        counts = [h - l for l, h in parts]
+
     def step(tm=None):
         e = [ev() for _ in range(3)]
         e[0].record()
-        xc = rcore.generate_slatm_batch(cc, cols[1], cols[0], mb, local=False, **kw)
+        if shard:
+            xc = parallel.allgather_rows(rcore.generate_slatm_batch(cc_loc, zs_loc, nas_loc, mb, local=False, **kw), counts)
+        else:
+            xc = rcore.generate_slatm_batch(cc, cols[1], cols[0], mb, local=False, **kw)
         xr = rcore.generate_slatm_batch(cr, rows[1], rows[0], mb, local=False, **kw)
         e[1].record()
         K = kernels.global_kernels(xr, xc, sig, args.kernel)
@@ -558,7 +571,9 @@ def run_config3(args):
             "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": "config3: global SLATM %s kernel, 4 sigmas, %d rows per GPU x %d columns, D=%d; "
-                                   "row-block sharded, no collective" % (args.kernel, args.rows_per_gpu, args.n_cols, D)},
+                                   "K row-block sharded%s" % (args.kernel, args.rows_per_gpu, args.n_cols, D,
+                                                           "; column SLATM generated 1/N per rank + one NCCL all-gather" if shard
+                                                           else ", no collective")},
             "phases_ms": {"slatm": t_sl, "kernel_incl_pack": t_k},
             "slatm_molecules_per_sec": world * (args.n_cols + args.rows_per_gpu) / (t_sl * 1e-3),
             "kernel_tera_ops": ops / (t_k * 1e-3) / 1e12}))

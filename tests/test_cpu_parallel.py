@@ -45,6 +45,12 @@ def _worker(rank, world, port, tmp):
         rlo, rhi = parallel.shard_range(11, rank, world)
         full = parallel.gather_rows(K[:, rlo:rhi].contiguous())
         assert torch.equal(full, K)
+        # representation row blocks: equal and ragged contributions
+        X = torch.rand((23, 5), dtype=torch.float64, generator=g)
+        for counts in ([12, 11], [20, 3]):
+            lo2 = sum(counts[:rank])
+            got = parallel.allgather_rows(X[lo2:lo2 + counts[rank]].contiguous(), counts)
+            assert torch.equal(got, X)
         # distributed block-cyclic Cholesky solve of (K + lambda I) alpha = y, ragged last block, 1 and 3 right-hand sides
         n = 61
         M = torch.rand((n, n), dtype=torch.float64, generator=g)
