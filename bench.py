@@ -444,7 +444,11 @@ def run_ours(args):
             "metric": "local_gaussian_kernel_elements_per_sec",
             "value": world * elems_rank / (ms_per_step * 1e-3), "unit": "kernel elements/s",
             "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "dtype_detail": ("FP64 in, FP64 out, <= 1e-10 vs the FP64 oracle; default engine: a.b from exact int8 digit-plane products "
+                             "(int32 accumulators) on the tcgen05 tensor cores, norms / exp / sums in FP64; AQML_PAIR_ENGINE=dmma: "
+                             "FP64 DMMA throughout") if engine == "i8" else "FP64 DMMA throughout",
+            "data": "synthetic",
             "config": {"workload": "config2: 20k train x 2k test QM9-shaped molecules, local aSLATM element-matched "
                                    "Gaussian kernel, FP64, 4 sigmas; step = coords -> aSLATM(train+test) -> K",
                        "n_train": args.n_train, "n_test_per_gpu": args.n_test, "atoms_per_gpu": atoms_rank,
