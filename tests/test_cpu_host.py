@@ -136,3 +136,39 @@ def test_block_driver_job_ids():
     assert jobs == ['12ij001001', '12ij002001', '11ii002002'] and wko
     ms = MolSet([1, 1, 8, 6, 1, 1, 1, 1], np.zeros((8, 3)), [3, 5], 1)
     assert ms.nzs.tolist() == [[2, 0, 1], [4, 1, 0]] and len(ms.nas1) == 1 and len(ms.nas2) == 1
+
+
+def test_digit_plane_algebra():
+    """The arithmetic behind the int8 tensor engine (aqml_b200/csrc/i8pair.cuh), restated in NumPy: 7 signed 7-bit digit
+    planes per row, 28 plane products, exact integer accumulation, Horner recombination -- against the FP64 dot product."""
+    rng = np.random.default_rng(11)
+    n, D = 40, 1500
+    X = rng.normal(size=(n, D)) * 10.0 ** rng.integers(-6, 2, size=(n, D))
+    X[:, ::5] = 0.0
+    X[3] = 0.0
+
+    def planes(X):
+        m = np.abs(X).max(axis=1)
+        e = np.where(m > 0, np.frexp(m)[1] + 1, 0)                 # |x| 2^-e <= 1/2
+        t = X * np.exp2(-e.astype(float))[:, None]
+        qs = []
+        for _ in range(7):
+            u = t * 128.0
+            q = np.rint(u)
+            t = u - q                                              # exact, |t| <= 1/2
+            qs.append(q.astype(np.int64))
+        return qs, e, t
+
+    qs, e, resid = planes(X)
+    assert all(np.abs(q).max() <= 64 for q in qs)                   # fits int8 with room to spare
+    recon = sum(q * 128.0 ** -(s + 1) for s, q in enumerate(qs)) * np.exp2(e.astype(float))[:, None]
+    assert np.all(np.abs(recon - X) <= np.exp2(e.astype(float) - 50)[:, None])
+    # P_g = sum_{i+j=g} q_i q_j^T, exact in int32 for rows of this length
+    P = [sum(qs[i] @ qs[g - i].T for i in range(g + 1)) for g in range(7)]
+    assert all(np.abs(p).max() < 2 ** 31 for p in P)
+    hi = (P[0] << 14) + (P[1] << 7) + P[2]
+    lo = (P[3] << 21) + (P[4] << 14) + (P[5] << 7) + P[6]
+    dot = (hi * 2.0 ** -14 + lo * 2.0 ** -42) * np.exp2((e[:, None] + e[None, :] - 14).astype(float))
+    exact = X @ X.T
+    scale = np.sqrt(np.outer((X * X).sum(1), (X * X).sum(1)))       # |a||b|
+    assert np.all(np.abs(dot - exact) <= 1e-13 * np.maximum(scale, 1e-300))
