@@ -10,17 +10,20 @@
 // (i+j >= 7) and the digits beyond 7, both <= 2^-48 of max|a| max|b| per column -- below what the FP64 DMMA path
 // loses to cancellation in |a|^2 + |b|^2 - 2 a.b.  Parity with the oracle is asserted at the same 1e-10.
 //
-// Kernel: persistent, one CTA per SM walking the 128 x 64 tiles of atom pairs (A rows = TMEM lanes):
+// Kernel: persistent, one CTA per SM; 128 x 64 tiles of atom pairs (A rows = TMEM lanes) handed out in raster order by an
+// atomic counter; roles synchronised by mbarriers only:
 //   warp 0 (one lane)  producer: per stage two active 16-column k-chunks of all 7 digit planes of A (2 x 14 KB,
 //                      contiguous in the pre-tiled slice buffer) and of B (2 x 7 x 1 KB) by cp.async.bulk onto an
 //                      mbarrier (4 stages x 42 KB);
 //   warp 1 (one lane)  issues the 28 UTCIMMA (M 128, N 64, K 32 = two k-chunks via the descriptor's leading
 //                      byte offset, so the exact 16-column block sparsity of the DMMA engine carries over) into 7
 //                      accumulators (7 x 64 = 448 TMEM columns); tcgen05.commit frees the stage / signals the end;
-//   warp 2             tile metadata one tile ahead (double buffered);
-//   warps 3-18         epilogue (4 per TMEM lane quarter, 16 columns each): tcgen05.ld of the 7 accumulators, Horner in FP64, d^2 = |a|^2+|b|^2-2a.b, exp per
-//                      sigma (squaring chain), sum over the atoms of a molecule pair (column runs in registers,
-//                      row runs by segmented shuffles), one RED.F64 per (sigma, molecule pair, warp).
+//   warp 2             tile metadata (segments, norms, exponents, active k-chunk list) two tiles ahead, triple buffered;
+//   warps 3-18         epilogue (4 per TMEM lane quarter, 16 columns each): tcgen05.ld of the 7 accumulators into two exact
+//                      64-bit integers per pair, TMEM handed back (the next tile's MMAs start), then FP64:
+//                      d^2 = |a|^2+|b|^2-2a.b, table-based exp, squaring chain over the sigmas, sum over the atoms of a
+//                      molecule pair (column runs in registers, row runs by segmented shuffles), one RED.F64 per
+//                      (sigma, molecule pair, warp); or K[s][i][j] = exp for the global kernel (store epilogue).
 // Operands are staged in the canonical K-major no-swizzle core-matrix layout (8 rows x 16 B), which is exactly how
 // the slice buffer is written, so a stage is filled by plain 1-D bulk copies (no tensor maps).
 #pragma once
