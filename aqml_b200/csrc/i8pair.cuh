@@ -414,7 +414,7 @@ __global__ void __launch_bounds__(I8_THREADS, 1) i8_pair_kernel(const I8Params P
             const unsigned above = (lane == 31) ? 0u : (heads >> (lane + 1));
             const int run_end = above ? (lane + __ffs(above) - 1) : 31;
             const double na = M.normA[row];
-            const double sa = i8::pow2(M.expA[row] - 7);
+            const double sa = i8::pow2(M.expA[row] - 21);  // 2^(e_a - 7) * 2^-14 (the scale of `hi` below)
             const int growA = M.tm * I8_BM + row;
             const unsigned lastmask = __ballot_sync(0xffffffffu, lane < EC && (lane == EC - 1 || M.segB[cbase + lane + 1] != M.segB[cbase + lane]));
             const long long e0 = clock64();
@@ -459,7 +459,7 @@ __global__ void __launch_bounds__(I8_THREADS, 1) i8_pair_kernel(const I8Params P
 #pragma unroll
             for (int j = 0; j < EC; j++) {
                 const int col = cbase + j;
-                const double d = fma((double)lo[j], 2.2737367544323206e-13 /* 2^-42 */, (double)hi[j] * 6.103515625e-05 /* 2^-14 */);
+                const double d = fma((double)lo[j], 3.725290298461914e-09 /* 2^-28 */, (double)hi[j]);  // 2^14 sum_g P_g 128^-g
                 double xx = fma(d * sa, M.m2sB[col], na + M.normB[col]);  // |a|^2 + |b|^2 - 2 a.b
                 xx = (xx < 0.0) ? 0.0 : xx;                                   // clamp rounding noise, keep NaN
                 // pairs that do not count: on / below the diagonal of a symmetric kernel, padding rows / columns
