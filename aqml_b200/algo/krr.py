@@ -101,3 +101,149 @@ def multi_fidelity_predict(ks1, ks2, ys, n1s, nzs1, nzs2, llambda=1e-10, device=
         alphas = solve(ks1[ims][:, ims], y1, llambda, device)
         pred += np.dot(ks2[:, ims], alphas) + base2
     return pred
+
+
+class krr(object):
+    """The reference's KRR driver object (coreml/cml/algo/krr.py:21-325), host NumPy as upstream: holds the labels and
+    the molecule bookkeeping, fixes train / test indices (`get_idx`) and runs the learning curve on precomputed kernel
+    matrices (`run`).  After `get_idx` the instance has the fields the block driver reads
+    (`cml.representation.slatm_x.slatm(obj, ...)`: zs, coords, nas, nas1, nas2, nzs), so
+    ``obj = krr(ys); obj.init_m(mols); obj.get_idx(...); mk = slatm(obj, ck=True, ...); obj.run([mk.mk1[i], mk.mk2[i]])``
+    works as in algo/qml.py:362-372.  ``mols`` needs zs, nas, nsheav, coords, nzs and (optionally) imcs."""
+
+    def __init__(self, ys):
+        _ys = np.array(ys)
+        if len(_ys.shape) == 2:
+            nr, nc = _ys.shape
+            assert nr > nc, '#ERROR: each column of `ys should correspond to one property!!'
+        assert np.logical_not(np.any(np.isnan(_ys))), '#ERROR: property is NaN, check your sdf file'
+        self._ys = _ys
+        self._nm = len(ys)
+        self.n2 = 0
+
+    def init_m(self, obj, nbody=1, icn=False, nproc=1):
+        if nbody != 1 or icn:
+            raise NotImplementedError('many-body / coordination-number baselines need cheminfo graphs (krr.py:153-161)')
+        self.obj = obj
+        self._zs = np.asarray(obj.zs)
+        self._zsu = np.unique(self._zs)
+        self._nas = np.asarray(obj.nas)
+        self._nsheav = np.asarray(obj.nsheav)
+        self._coords = np.asarray(obj.coords)
+        self._ias2 = np.cumsum(self._nas)
+        self._ias1 = np.concatenate(([0], self._ias2[:-1])).astype(int)
+        self._imcs = np.asarray(getattr(obj, 'imcs', np.zeros(len(self._nas), dtype=bool)))
+        self._nzs = np.asarray(obj.nzs)
+        if self._nm != len(self._nas):
+            raise Exception('#ERROR: len(ys)!= len(_nas)??')
+
+    def get_idx(self, idx=1, n2=None, n1s=None, iaml=True, seed1=1, namin=1, namax=7):
+        """krr.py:56-151.  iaml: the last |idx| molecules are the test set, training sets grow with the number of heavy
+        atoms; otherwise a seeded random permutation."""
+        self.iaml = iaml
+        assert isinstance(idx, (int, np.integer)), '#ERROR: idx should be a int'
+        idx = abs(int(idx))
+        n1s = [] if n1s is None else list(n1s)   # (upstream's mutable default argument accumulates across calls)
+        if iaml:
+            tidxs = np.arange(self._nm)
+            tidx1, idx2 = tidxs[:-idx], tidxs[-idx:]
+        else:
+            np.random.seed(seed1)
+            _tidx = np.random.permutation(self._nm)
+            tidx1 = _tidx[:-idx]
+            idx2 = _tidx[-n2:] if n2 else _tidx[-idx:]
+        self.nm = self._nm
+        nsu_heav = np.unique(self._nsheav)
+        self.nsu_heav = nsu_heav
+        if len(n1s) == 0:
+            tidx1_sorted, cnt = [], 0
+            t = self._nsheav[tidx1]
+            for na in range(namin, namax + 1):
+                if np.any(na == nsu_heav):
+                    i = tidx1[t == na]
+                    tidx1_sorted += list(i)
+                    cnt += len(i)
+                    n1s.append(cnt)
+                else:
+                    n1s.append(np.nan if cnt == 0 else cnt)
+            tidx1 = np.array(tidx1_sorted, dtype=int)
+        self.n1s = n1s
+        tidx = np.concatenate((tidx1, idx2)).astype(int)
+        n1, n2 = len(tidx1), len(idx2)
+        self.n2 = n2
+        self.ys = self._ys[tidx]
+        _nas = self._nas[tidx]
+        self.coords = np.concatenate([self._coords[self._ias1[i]:self._ias2[i]] for i in tidx])
+        self.zs = np.concatenate([self._zs[self._ias1[i]:self._ias2[i]] for i in tidx]).astype(int)
+        self.nas1 = _nas[:n1]
+        self.nas2 = _nas[n1:] if n2 else np.array([], dtype=int)
+        self.nas = np.concatenate((self.nas1, self.nas2))
+        self.nzs = self._nzs[tidx]
+        self.imcs = self._imcs[tidx]
+        self.nsheav = self._nsheav[tidx]
+        self.nat1, self.nat2 = int(self.nas1.sum()), int(self.nas2.sum())
+        self.zs1, self.zs2 = self.zs[:self.nat1], self.zs[self.nat1:]
+        self.ias2 = np.cumsum(self.nas)
+        self.ias1 = np.concatenate(([0], self.ias2[:-1])).astype(int)
+
+    @staticmethod
+    def calc_ae_dressed(imcs1, ns1, ys1, ns2, ys2):
+        """krr.py:163-183: dressed-atom baseline from the molecules that are not complexes."""
+        flt = np.logical_not(imcs1)
+        esb, _, rank, _ = np.linalg.lstsq(ns1[flt], ys1[flt], rcond=None)
+        ys2_base = np.zeros(np.array(ys2).shape)
+        if rank < len(ns1[0]):
+            return ys1, ys2, ys2_base
+        ys2_base = np.dot(ns2, esb)
+        return ys1 - np.dot(ns1, esb), ys2 - ys2_base, ys2_base
+
+    def run(self, mks, exclude=None, usebl=True, llambda=1e-10, iprt=True, device=False):
+        """krr.py:185-325 for a fixed test set (``usek1o=False``): one KRR model per training-set size in `n1s`.
+        mks = [k1 (N1,N1), k2 (N2,N1)] or a .npz with keys k1, k2.  Sets maes, rmses, errsmax, dys, n1so."""
+        if isinstance(mks, str):
+            dic = np.load(mks)
+            mks = [dic['k1'].copy(), dic['k2'].copy()]
+        mk1, mk2 = np.array(mks[0], dtype=np.float64), np.array(mks[1], dtype=np.float64)
+        assert mk1.shape[0] <= self.nm
+        if self.n2 == 0:
+            raise NotImplementedError('usek1o=T (random test sets out of k1) is not supported; call get_idx with a test set')
+        n2 = self.n2
+        tidx = np.arange(self.nm)
+        idx1, idx2 = tidx[:-n2], tidx[-n2:]
+        _ys1, _ys2 = self.ys[idx1], self.ys[idx2]
+        n1so, maes, rmses, dys, errsmax = [], [], [], [], []
+        for n1 in self.n1s:
+            if n1 is None or (isinstance(n1, float) and np.isnan(n1)):
+                if iprt: print('%6s' % 'None')
+                maes.append(np.nan); rmses.append(np.nan)
+                continue
+            _idx1 = np.setdiff1d(np.arange(int(n1)), exclude) if exclude else np.arange(int(n1))
+            if len(_idx1) == 0:
+                continue
+            ys1i, ys2i = _ys1[_idx1], _ys2
+            if usebl:
+                ns1 = self.nzs[idx1][_idx1]
+                rank1 = np.linalg.matrix_rank(ns1)
+                if rank1 < len(ns1[0]):
+                    if iprt: print('%6s # rank(ns1)=%d less than len(nzu)=%d' % ('None', rank1, len(ns1[0])))
+                    maes.append(np.nan); rmses.append(np.nan)
+                    continue
+                if not np.all([si > 1 for si in ns1.shape]):
+                    continue
+                ys1i, ys2i, _ = krr.calc_ae_dressed(self.imcs[idx1][_idx1], ns1, ys1i, self.nzs[idx2], ys2i)
+            n1so.append(len(_idx1))
+            alphas = solve(mk1[_idx1][:, _idx1], ys1i, llambda, device)
+            dys2i = np.dot(mk2[:, _idx1], alphas) - ys2i
+            dys.append(dys2i)
+            a = np.abs(dys2i)
+            errmax = np.unique(dys2i[np.max(a) == a])[0]
+            if n2 == 1:
+                mae = dys2i[0]; rmse = abs(mae)
+            else:
+                mae = np.sum(a) / n2
+                rmse = np.sqrt(np.sum(dys2i * dys2i) / n2)
+            if iprt: print('%6d %12.4f %12.4f %12.4f' % (len(_idx1), mae, rmse, errmax))
+            maes.append(mae); rmses.append(rmse); errsmax.append(errmax)
+        self.dys, self.errsmax = dys, errsmax
+        self.maes, self.rmses = np.array(maes), np.array(rmses)
+        self.n1so = np.array(n1so, dtype=int)

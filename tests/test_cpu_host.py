@@ -172,3 +172,37 @@ def test_digit_plane_algebra():
     exact = X @ X.T
     scale = np.sqrt(np.outer((X * X).sum(1), (X * X).sum(1)))       # |a||b|
     assert np.all(np.abs(dot - exact) <= 1e-13 * np.maximum(scale, 1e-300))
+
+
+def test_krr_driver_object_reproduces_readme_rows(demo):
+    """`cml.algo.krr.krr` (krr.py:21-325): init_m / get_idx / run on the golden demo kernels reproduce the README learning
+    curve wherever krr.run's own baseline is defined (it prints None for the rank-deficient N_I = 1, 2 rows, krr.py:262-266;
+    aqml.py falls back to free-atom energies there)."""
+    from cml.algo.krr import krr
+    n1 = int(demo["n1"])
+    nas, zs = demo["nas"], demo["zs"]
+    zs_list = synth.split_zs(nas, zs)
+    zsu = np.unique(zs)
+
+    class Mols:
+        pass
+    m = Mols()
+    m.zs, m.nas, m.coords = zs, nas, demo["coords"]
+    m.nsheav = np.array([(z > 1).sum() for z in zs_list])
+    m.nzs = np.array([[(z == zz).sum() for zz in zsu] for z in zs_list])
+    # the demo's amons are stored sorted by file name, not by size: krr.get_idx sorts the training set by heavy atoms
+    obj = krr(demo["energies"] * 627.5094738898777)
+    obj.init_m(m)
+    obj.get_idx(idx=1, iaml=True, namin=1, namax=7)
+    assert obj.n2 == 1 and len(obj.nas1) == n1 and obj.n1s == [1, 3, 5, 6, 10, 11, 16]
+    order = np.argsort(m.nsheav[:n1], kind='stable')
+    assert np.array_equal(obj.nas1, nas[:n1][order])
+    k1 = demo["k1"][1][order][:, order]
+    k2 = demo["k2"][1][:, order]
+    obj.run([k1, k2], llambda=1e-4, iprt=False)
+    readme = demo["readme_curve"]
+    assert np.isnan(obj.maes[0])                                       # N_I = 1: one molecule, three elements
+    ok = ~np.isnan(obj.maes)
+    assert ok[2:].all()
+    assert np.all(np.abs(obj.maes[ok] - readme[ok, 3]) < 5.1e-5)       # signed error of the single test molecule
+    assert list(obj.n1so) == [int(v) for v in readme[ok, 1]]
