@@ -247,3 +247,132 @@ class krr(object):
         self.dys, self.errsmax = dys, errsmax
         self.maes, self.rmses = np.array(maes), np.array(rmses)
         self.n1so = np.array(n1so, dtype=int)
+
+
+class rkrr(object):
+    """The reference's recursive / multi-fidelity KRR driver object (coreml/cml/algo/rkrr.py:18-267).  ``ys`` (nm, nl): one
+    column per level of theory, cheapest first.  `run` trains levels 0 .. nl-2 on the nested prefixes ``n1s[::-1]`` (level 0
+    learns y_0, level l learns y_l - y_{l-1}) and the last level for every size in ``n1s`` (NaN labels skipped); the
+    prediction is the sum over levels plus the dressed-atom baselines.  Host NumPy as upstream; kernels come from the GPU."""
+
+    def __init__(self, ys):
+        self._ys = np.array(ys, dtype=np.float64)
+        self.nm = len(ys)
+        self.nl = len(ys[0])
+        self.n2 = 0
+
+    def init_m(self, obj):
+        self._zs = np.asarray(obj.zs)
+        self._zsu = np.unique(self._zs)
+        self._nas = np.asarray(obj.nas)
+        self._nsheav = np.asarray(obj.nsheav)
+        self._coords = np.asarray(obj.coords)
+        self._ias2 = np.cumsum(self._nas)
+        self._ias1 = np.concatenate(([0], self._ias2[:-1])).astype(int)
+        # rkrr.py:38-42 get_nzs: element counts per molecule
+        self._nzs = np.array([[int((self._zs[b:e] == z).sum()) for z in self._zsu] for b, e in zip(self._ias1, self._ias2)])
+
+    def get_idx(self, idx=-1, n1s=None, n1max=-1, seed1=1, namin=1, namax=7):
+        """rkrr.py:45-158: idx = -n (the last n molecules are the targets), idx > 0 (seeded random split), or a list of
+        training indices; namax = 0 (one training set or the given n1s), < 0 (all amons with N_I <= -namax), > 0 (one
+        training set per heavy-atom count)."""
+        n1s = [] if n1s is None else list(n1s)
+        tidxs = np.arange(self.nm)
+        if isinstance(idx, (int, np.integer)):
+            if idx == 0:
+                _idx1, idx2 = np.arange(self.nm), np.array([], dtype=int)
+            elif idx > 0:
+                np.random.seed(seed1)
+                tidxs = np.random.permutation(self.nm)
+                _idx1, idx2 = tidxs[:-idx], tidxs[-idx:]
+                if n1max > 0:
+                    _idx1 = _idx1[:n1max]
+            else:
+                _idx1, idx2 = tidxs[:idx], tidxs[idx:]
+        elif isinstance(idx, (list, tuple, np.ndarray)):
+            _idx1 = np.array(idx, dtype=int)
+            idx2 = np.setdiff1d(tidxs, _idx1)
+        else:
+            raise TypeError('#ERROR: unsupported type of `idx')
+        self.nsu_heav = np.unique(self._nsheav)
+        idx1 = _idx1
+        aml = True
+        if namax == 0:
+            aml = False
+            if len(n1s) == 0:
+                n1s = [len(_idx1)]
+        elif namax < 0:
+            idx1 = _idx1[np.logical_and(self._nsheav[_idx1] >= namin, self._nsheav[_idx1] <= -namax)]
+            idx2 = np.setdiff1d(tidxs, idx1)
+            n1s = [len(idx1)]
+        else:
+            n1s, idx1_sorted, cnt = [], [], 0
+            t = self._nsheav[_idx1]
+            for na in range(namin, namax + 1):
+                if np.any(na == self.nsu_heav):
+                    idx_i = _idx1[t == na]
+                    idx1_sorted += list(idx_i)
+                    cnt += len(idx_i)
+                    n1s.append(cnt)
+                else:
+                    n1s.append(np.nan if cnt == 0 else cnt)
+            idx1 = np.array(idx1_sorted, dtype=int)
+        self.aml, self.n1s = aml, n1s
+        self.n2 = len(idx2)
+        tidx = np.concatenate((idx1, idx2)).astype(int)
+        n1 = len(idx1)
+        self.ys = self._ys[tidx]
+        _nas = self._nas[tidx]
+        self.coords = np.concatenate([self._coords[self._ias1[i]:self._ias2[i]] for i in tidx])
+        self.zs = np.concatenate([self._zs[self._ias1[i]:self._ias2[i]] for i in tidx]).astype(int)
+        self.nas1, self.nas2, self.nas = _nas[:n1], _nas[n1:], _nas
+        self.nzs = self._nzs[tidx]
+        self.nsheav = self._nsheav[tidx]
+        self.nat1, self.nat2 = int(self.nas1.sum()), int(self.nas2.sum())
+        self.zs1, self.zs2 = self.zs[:self.nat1], self.zs[self.nat1:]
+
+    @staticmethod
+    def calc_e_base(nzs1, ys1, nzs2):
+        return e_base(nzs1, ys1, nzs2)  # rkrr.py:171-177
+
+    def run(self, mks, usebl=True, llambda=1e-10, iprt=True, device=False):
+        """rkrr.py:179-267.  Sets maes (signed error of the first target per training-set size) and n1s."""
+        if isinstance(mks, str):
+            dic = np.load(mks)
+            mks = [dic['k1'].copy(), dic['k2'].copy()]
+        mk1, mk2 = np.array(mks[0], dtype=np.float64), np.array(mks[1], dtype=np.float64)
+        n2, nl = self.n2, self.nl
+        idxs2 = np.arange(self.nm)[-n2:]
+        sizes = [n for n in self.n1s if not (n is None or (isinstance(n, float) and np.isnan(n)))]
+        n1sr = sizes[::-1]
+        ys2p = np.zeros(n2)
+        ns_nested = []
+        for l in range(nl - 1):
+            ims1 = np.arange(int(n1sr[l]))
+            ns_nested.append(len(ims1))
+            tgt = self.ys[ims1, l] if l == 0 else self.ys[ims1, l] - self.ys[ims1, l - 1]
+            ys1, ys2_base = e_base(self.nzs[ims1], tgt, self.nzs[idxs2])
+            alphas = solve(mk1[ims1][:, ims1], ys1, llambda, device)
+            ys2p += np.dot(mk2[:, ims1], alphas) + ys2_base
+        if iprt: print(' ** ns_nested = ', ns_nested)
+        l = nl - 1
+        maes, n1s = [], []
+        for _n1 in self.n1s:
+            if _n1 is None or (isinstance(_n1, float) and np.isnan(_n1)):
+                maes.append(np.nan); n1s.append(np.nan)
+                continue
+            _ims1 = np.arange(int(_n1))
+            ims1 = _ims1[np.logical_not(np.isnan(self.ys[_ims1, l]))]
+            nzs1, nzs2 = self.nzs[ims1], self.nzs[idxs2]
+            if len(ims1) == 0 or np.linalg.matrix_rank(nzs1) < len(nzs1[0]):
+                if iprt: print('%6s' % 'None')
+                n1s.append(np.nan); maes.append(np.nan)
+                continue
+            tgt = self.ys[ims1, l] - self.ys[ims1, l - 1] if nl > 1 else self.ys[ims1, l]
+            ys1, ys2_base = e_base(nzs1, tgt, nzs2)
+            alphas = solve(mk1[ims1][:, ims1], ys1, llambda, device)
+            dys = ys2p + np.dot(mk2[:, ims1], alphas) + ys2_base - self.ys[idxs2, l]
+            if iprt: print('%6d %.2f' % (len(ims1), dys[0]))
+            maes.append(dys[0]); n1s.append(len(ims1))
+        self.maes, self.n1s_run = maes, n1s
+        self.ys2p_low = ys2p
