@@ -169,6 +169,12 @@ int aqml_generate_slatm_batch_dev(const double *coords, const int *zs_dev, const
  * ---------------------------------------------------------------------------------------- */
 typedef struct aqml_rep aqml_rep; /* aSLATM rows grouped by element, columns restricted to the element's support */
 
+/* Contraction engines of the Gaussian kernels (calc_lk_gaussian, fgaussian_kernel and the fused path below).  Default:
+ * FP64-accurate a.b from exact int8 digit-plane products on the tcgen05 tensor cores (28 UTCIMMA per FP64 k-tile, int32
+ * accumulators in TMEM, i8pair.cuh); the representation then also holds 7 bytes of digit planes per packed element.
+ * Environment AQML_PAIR_ENGINE=dmma selects the FP64 DMMA engine (no digit planes are built).  More than 8 sigmas or rows
+ * longer than 65536 columns use the FP64 engine automatically.  Both agree with the reference to <= 1e-10 per element. */
+
 /* coords: DEVICE if coords_on_device else HOST; zs, nas HOST.  Asynchronous on `stream`. */
 int aqml_rep_create(const double *coords, int coords_on_device, const int *zs, const int *nas, int nmol,
                     const aqml_slatm_params *p, void *stream, aqml_rep **out);
