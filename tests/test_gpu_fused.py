@@ -138,3 +138,23 @@ def test_chunked_host_delivery_equals_one_shot():
         fused.local_gaussian_to_host(coords[A1:], zs[A1:], nas[n1:], train, mb, sig, 9, out, chunks=chunks, **kw)
         torch.cuda.synchronize()
         assert rel_err(out.numpy(), ref.numpy()) < 1e-12
+
+
+def test_eight_sigmas_on_the_int8_engine():
+    """The int8 engine's limit of 8 sigmas per launch, as a power-of-two ladder (squaring chain) and as arbitrary widths."""
+    nas, zs, coords = synth.qm9_like(40, 91)
+    n1 = 28
+    off = np.concatenate(([0], np.cumsum(nas)))
+    A1 = off[n1]
+    mb = o.get_slatm_mbtypes(synth.split_zs(nas, zs))
+    kw = dict(sigmas=(.05, .05), dgrids=(.04, .04), rcut=4.8)
+    xl = co.generate_slatm_batch(coords, zs, nas, mb, True, **kw)
+    dso = co.get_kernel_width(nas, zs, xl)
+    dso = np.concatenate((dso, np.full(9 - len(dso), 1e-9)))
+    train = fused.PackedRep(coords[:A1], zs[:A1], nas[:n1], mb, **kw)
+    test = fused.PackedRep(coords[A1:], zs[A1:], nas[n1:], mb, **kw)
+    for coeffs in ([2.0 ** k for k in range(-3, 5)], [0.11, 0.37, 0.5, 0.93, 1.4, 2.2, 3.1, 5.0]):
+        sig = np.array([c * dso / np.sqrt(2 * np.log(2)) for c in coeffs])
+        ref = co.calc_lk_gaussian(xl[A1:], xl[:A1], zs[A1:], zs[:A1], nas[n1:], nas[:n1], 9, False, sig)
+        K = fused.local_gaussian(test, train, sig, 9).cpu().numpy()
+        assert K.shape == ref.shape and rel_err(K, ref) < TOL
