@@ -37,6 +37,7 @@ SIGNATURES = {
     "aqml_launch_count": (_L, []),
     "aqml_pair_stats": (_I, [_P, _P, _I]),
     "aqml_tile_shape": (None, [_P, _P, _P]),
+    "aqml_measure_i8_peak": (_I, [_P, _P]),
     "aqml_fgaussian_kernel": (_I, [_P, _I, _P, _I, _I, _P, _D]),
     "aqml_flaplacian_kernel": (_I, [_P, _I, _P, _I, _I, _P, _D]),
     "aqml_fl2_distance": (_I, [_P, _P, _I, _I, _I, _P]),
@@ -56,6 +57,8 @@ SIGNATURES = {
     "aqml_generate_slatm_batch": (_I, [_P, _P, _P, _I, C.POINTER(SlatmParams), _I, _P]),
     "aqml_generate_slatm_batch_dev": (_I, [_P, _P, _P, _I, C.POINTER(SlatmParams), _I, _P, _L, _P]),
     "aqml_rep_create": (_I, [_P, _I, _P, _P, _I, C.POINTER(SlatmParams), _P, C.POINTER(_P)]),
+    "aqml_rep_create_ex": (_I, [_P, _I, _P, _P, _I, C.POINTER(SlatmParams), _I, _P, C.POINTER(_P)]),
+    "aqml_rep_slab": (_I, [_P, C.POINTER(_P), C.POINTER(_L)]),
     "aqml_rep_destroy": (None, [_P]),
     "aqml_rep_bytes": (_L, [_P]),
     "aqml_rep_local_gaussian": (_I, [_P, _P, _P, _I, _I, _I, _I, _P, _P]),

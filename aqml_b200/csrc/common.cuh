@@ -84,10 +84,30 @@ class Workspace {
     T *alloc(size_t n) {
         void *p = nullptr;
         size_t bytes = (n ? n : 1) * sizeof(T);
+        if (slab_) {  // carve from the slab reserved up front (256-byte aligned pieces, same order on every rank)
+            const size_t o = slab_aligned(slab_used_);
+            if (o + bytes > slab_bytes_) fail(AQML_EINVAL, "internal: slab of %zu bytes too small (%zu + %zu)", slab_bytes_, o, bytes);
+            slab_used_ = o + bytes;
+            return reinterpret_cast<T *>(slab_ + o);
+        }
         AQML_CUDA(cudaMallocAsync(&p, bytes, stream_));
         ptrs_.push_back(p);
         return reinterpret_cast<T *>(p);
     }
+    // one allocation that every following alloc() is carved from: the owner's storage becomes a single contiguous
+    // buffer that can be sent to another GPU as it is (aqml_rep_slab)
+    void reserve(size_t bytes) {
+        void *p = nullptr;
+        AQML_CUDA(cudaMallocAsync(&p, bytes ? bytes : 1, stream_));
+        ptrs_.push_back(p);
+        slab_ = reinterpret_cast<unsigned char *>(p);
+        slab_bytes_ = bytes;
+        slab_used_ = 0;
+    }
+    static size_t slab_aligned(size_t v) { return (v + 255) / 256 * 256; }
+    static size_t slab_piece(size_t bytes) { return slab_aligned(bytes ? bytes : 1); }
+    unsigned char *slab() const { return slab_; }
+    size_t slab_bytes() const { return slab_bytes_; }
     template <class T>
     T *upload(const T *host, size_t n) {
         T *d = alloc<T>(n);
@@ -112,6 +132,8 @@ class Workspace {
   private:
     cudaStream_t stream_;
     std::vector<void *> ptrs_;
+    unsigned char *slab_ = nullptr;
+    size_t slab_bytes_ = 0, slab_used_ = 0;
 };
 
 inline int64_t round_up(int64_t v, int64_t m) { return (v + m - 1) / m * m; }

@@ -2,20 +2,33 @@
 // (tcgen05.mma kind::i8, accumulators in TMEM) -- the B200-native engine of calc_lk_gaussian (fkernels.f90:23-93).
 //
 // FP64 DMMA peaks at 37 TF on this chip; the int8 pipe does 4.1 POP/s (profiles/r01_micro_i8_umma.txt).  An FP64
-// row x is split once, when the representation is packed, into S = 7 signed 7-bit digits of a per-row fixed
-// point number:  x[k] = 2^e * sum_{s=1..7} q_s[k] 128^-s + r,  |q_s| <= 64,  |r| <= 2^(e-50)  (e = exponent of the
-// row maximum + 1).  Then
-//     a.b = 2^(ea+eb) * sum_{g=0..6} 128^-(g+2) * P_g,      P_g = sum_{i+j=g} q^a_i . q^b_j    (28 products)
-// and every P_g is an EXACT int32 (<= 7 * 4401 * 64^2 < 2^31): the only errors are the dropped digit pairs
-// (i+j >= 7) and the digits beyond 7, both <= 2^-48 of max|a| max|b| per column -- below what the FP64 DMMA path
-// loses to cancellation in |a|^2 + |b|^2 - 2 a.b.  Parity with the oracle is asserted at the same 1e-10.
+// row x is split once, when the representation is packed, into S = 6 signed 8-bit digits of a per-row fixed
+// point number:  x[k] = 2^e * sum_{s=0..5} q_s[k] 256^-(s+1) + r,  -128 <= q_s <= 127,  |r| <= 0.502 * 2^(e-48)
+// (e: |x| 2^-e < 0.498 for the row maximum).  A digit is q = floor(u + 128/255), which keeps every remainder in
+// [-128/255, 127/255) and therefore every following digit inside the int8 range (a plain round-to-nearest digit can
+// be +128).  Then
+//     a.b = 2^(ea+eb) * sum_g 256^-(g+2) * P_g,      P_g = sum_{i+j=g} q^a_i . q^b_j
+// over the products with i + j <= 5 PLUS (3,3) -- 22 products (variant 0) -- or every product with i + j <= 6 -- 26
+// (variant 1, AQML_I8_PRODUCTS=26).  Every P_g is an EXACT int32 (<= 6 products: 6 * ld * 128^2 < 2^31 for ld <= 21840).  Why (3,3):
+// the dropped level i + j = 6 contains the square q_3 . q_3, which does not average out for a ~ b (exactly the
+// pairs with a large kernel value): without it the error of a.b is 6 x larger (tests/test_cpu_host.py::test_digit_plane_algebra).  Errors
+// left: 22 products: the four mixed pairs of level 6, <= 2^-48 of 2^(ea+eb) per column, and the digits beyond the
+// 6th, 2^-49 of 2^ea per element -- measured on aSLATM rows 1e-13 .. 1e-12 relative per exp term at sigma = dmax/2.4
+// (the 7 x 7-bit / 28-product scheme of round 1: 2e-13 .. 6e-13); 26 products: 1e-14 .. 3e-14.
+//
+// The products are issued as 8 (10) MMAs: A plane i meets the B planes 0 .. n-1, which lie one behind the other in
+// the stage buffer, as ONE instruction with N = 64 n stacked rows (split at 256) whose 64-column output slices are
+// the consecutive accumulators g = i .. i+n-1.  N >= 128 runs at the full UTCIMMA rate (64 clk per 128 columns; a
+// single N = 64 product takes 48 clk, not 32: tools/micro/i8_umma.cu), so a stage costs ~720 (832) clk instead of
+// the 28 x 48 = 1344 of round 1's one-MMA-per-product schedule.  Accumulator 6 is not touched by plane 0 (whose
+// MMAs clear the others at the first stage of a tile): the epilogue zeroes it with tcgen05.st after draining it.
 //
 // Kernel: persistent, one CTA per SM; 128 x 64 tiles of atom pairs (A rows = TMEM lanes) handed out in raster order by an
 // atomic counter; roles synchronised by mbarriers only:
-//   warp 0 (one lane)  producer: per stage two active 16-column k-chunks of all 7 digit planes of A (2 x 14 KB,
-//                      contiguous in the pre-tiled slice buffer) and of B (2 x 7 x 1 KB) by cp.async.bulk onto an
-//                      mbarrier (4 stages x 42 KB);
-//   warp 1 (one lane)  issues the 28 UTCIMMA (M 128, N 64, K 32 = two k-chunks via the descriptor's leading
+//   warp 0 (one lane)  producer: per stage two active 16-column k-chunks of all 6 digit planes of A (2 x 12 KB,
+//                      contiguous in the pre-tiled slice buffer) and of B (2 x 6 x 1 KB) by cp.async.bulk onto an
+//                      mbarrier (4 stages x 36 KB);
+//   warp 1 (one lane)  issues the 8 UTCIMMA (M 128, N 64..256, K 32 = two k-chunks via the descriptor's leading
 //                      byte offset, so the exact 16-column block sparsity of the DMMA engine carries over) into 7
 //                      accumulators (7 x 64 = 448 TMEM columns); tcgen05.commit frees the stage / signals the end;
 //   warp 2             tile metadata (segments, norms, exponents, active k-chunk list) two tiles ahead, triple buffered;
@@ -30,7 +43,7 @@
 
 namespace aqml {
 
-constexpr int I8_S = 7;                          // digit planes
+constexpr int I8_S = 6;                          // digit planes (8 bits each)
 constexpr int I8_BM = 128, I8_BN = 64;           // tile: A rows x B rows
 constexpr int I8_STAGES = 4;
 constexpr int I8_A_CHUNK = I8_S * 2048;          // bytes of one k-chunk (16 columns) of an A tile, all planes
@@ -44,7 +57,8 @@ constexpr int I8_SERIAL_EPILOGUE = 0;
 constexpr int I8_META = 3;                       // tile metadata buffers (prepared up to two tiles ahead)
 constexpr int I8_THREADS = 32 * (3 + I8_EPI_WARPS);  // producer, MMA issuer, tile metadata, 16 epilogue warps
 constexpr int I8_MAXSIG = 8;
-constexpr int I8_MAX_LD = 65536;                 // int32 accumulators: 7 * ld * 64^2 < 2^31 (longer rows: FP64 engine)
+constexpr int I8_NACC = 7;                       // accumulators: levels i + j = 0 .. 6
+constexpr int I8_MAX_LD = 21840;                 // int32 accumulators: <= 6 products each, 6 * ld * 128^2 < 2^31 (longer rows: FP64 engine)
 
 struct I8Group {
     const int8_t *slA, *slB;      // [row block of 128][KT + 1][plane][128 rows x 16 B]; k-chunk KT is all zero
@@ -80,7 +94,7 @@ struct I8Meta {  // everything the roles need to know about one tile
     int segA[I8_BM], expA[I8_BM];
     double normA[I8_BM];
     int segB[I8_BN + 1];
-    double normB[I8_BN], m2sB[I8_BN];  // |b|^2, -2 * 2^(e_b - 7)
+    double normB[I8_BN], m2sB[I8_BN];  // |b|^2, -2 * 2^(e_b - 8)
     unsigned short kt[KT_LIST_MAX + 2];
 };
 
@@ -154,7 +168,7 @@ __device__ __noinline__ void i8_flush(double r, int lane, int run_end, bool head
 }
 
 // ---- slicing -------------------------------------------------------------------------------------------------
-// exponent per row: |x| * 2^-e <= 1/2.  Non-finite or absurdly large (> 1e301) values need no special path: such a row has
+// exponent per row: |x| * 2^-e < 0.498 (the first digit floor(256 t + 128/255) must not exceed 127).  Non-finite or absurdly large (> 1e301) values need no special path: such a row has
 // |row|^2 = NaN / Inf, which reaches K through d^2 = |a|^2 + |b|^2 - 2 a.b exactly as in the reference (NaN stays NaN,
 // Inf gives exp(-Inf) = 0); whatever digits the row gets are irrelevant.
 __global__ void __launch_bounds__(256) i8_rowexp_kernel(const double *x, long long ld, int nrows, int *expo) {
@@ -169,12 +183,25 @@ __global__ void __launch_bounds__(256) i8_rowexp_kernel(const double *x, long lo
     m = warp_max(m);
     if (lane == 0) {
         int e = 0;
-        if (m > 0.0) { frexp(m, &e); e += 1; }
-        expo[row] = max(min(e, 1000), -1000);  // tinier rows keep |x| 2^-e <= 1/2 and only lose (irrelevant) digits
+        if (m > 0.0) {
+            const double f = frexp(m, &e);  // m = f 2^e, f in [1/2, 1)
+            e += (f < 0.996) ? 1 : 2;
+        }
+        expo[row] = max(min(e, 1000), -990);  // tinier rows keep |x| 2^-e < 0.498 and only lose (irrelevant) digits
     }
 }
 
-// thread = one row of a 128-row block; per 16-column chunk: 7 planes x 16 B
+// 8-bit digits of t, |t| < 0.498: q = floor(256 t + 128/255) in [-128, 127], remainder in [-128/255, 127/255) -- the one
+// interval that maps onto itself, so every digit fits an int8 (the clamp only acts when the rounding of u + c crosses
+// the interval's end; the remainder stays exact and the following digits absorb it)
+__device__ __forceinline__ int i8_digit(double &t) {
+    const double u = t * 256.0;                                       // exact
+    const double q = fmin(fmax(floor(u + 128.0 / 255.0), -128.0), 127.0);
+    t = u - q;                                                        // exact
+    return (int)q;
+}
+
+// thread = one row of a 128-row block; per 16-column chunk: 6 planes x 16 B
 __global__ void __launch_bounds__(128) i8_slice_kernel(const double *x, long long ld, int nrows, const int *expo, int KT, int kt_per_block,
                                                        int8_t *sl) {
     const int rb = blockIdx.x, r = threadIdx.x, row = rb * 128 + r;
@@ -197,15 +224,45 @@ __global__ void __launch_bounds__(128) i8_slice_kernel(const double *x, long lon
         for (int s = 0; s < I8_S; s++) {
             unsigned w[4] = {0u, 0u, 0u, 0u};
 #pragma unroll
-            for (int c = 0; c < 16; c++) {
-                const double u = t[c] * 128.0;   // exact
-                const double q = rint(u);        // |q| <= 64
-                t[c] = u - q;                    // exact, |.| <= 1/2
-                w[c >> 2] |= ((unsigned)(int)q & 0xffu) << ((c & 3) * 8);
-            }
+            for (int c = 0; c < 16; c++) w[c >> 2] |= ((unsigned)i8_digit(t[c]) & 0xffu) << ((c & 3) * 8);
             *reinterpret_cast<uint4 *>(dst + s * 2048) = make_uint4(w[0], w[1], w[2], w[3]);
         }
     }
+}
+
+// ---- peak of the pipe, measured where the bench runs (aqml_measure_i8_peak) -----------------------------------------
+// One CTA per SM, one thread issues `rounds` x 2 UTCIMMA of M 128, N 256, K 32 into the two halves of TMEM from operands
+// that stay in shared memory: the best rate kind::i8 reaches on this chip (profiles/r01_micro_i8_umma.txt: 128 clk per MMA).
+__global__ void __launch_bounds__(128) i8_peak_kernel(int rounds) {
+    __shared__ __align__(1024) int8_t sA[128 * 32], sB[256 * 32];
+    __shared__ __align__(8) unsigned long long bar;
+    __shared__ unsigned tmem_base;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    for (int i = tid; i < 128 * 32; i += 128) sA[i] = (int8_t)((i * 37 + 11) % 255 - 127);
+    for (int i = tid; i < 256 * 32; i += 128) sB[i] = (int8_t)((i * 53 + 7) % 255 - 127);
+    if (tid == 0) { i8::mbar_init(&bar, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(i8::smem_u32(&tmem_base)), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const unsigned tb = tmem_base;
+    if (tid == 0) {
+        const unsigned long long da = i8::smem_desc(i8::smem_u32(sA), 2048, 128), db = i8::smem_desc(i8::smem_u32(sB), 4096, 128);
+        constexpr unsigned ID = i8::idesc(128, 256);
+        for (int r = 0; r < rounds; r++) {
+            i8::umma(tb, da, db, ID, 1u);
+            i8::umma(tb + 256, da, db, ID, 1u);
+        }
+        i8::umma_commit(&bar);
+        i8::mbar_wait(&bar, 0);
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tb), "r"(512u) : "memory");
 }
 
 // ---- the pair kernel -----------------------------------------------------------------------------------------
@@ -214,6 +271,8 @@ __global__ void __launch_bounds__(128) i8_slice_kernel(const double *x, long lon
 // two tiles ahead, triple buffered), warps 3-18 epilogue.  The epilogue first drains TMEM into registers (phase 1),
 // hands TMEM back (the next tile's MMAs start while exp / sums / REDs of this tile run), and the operand ring
 // keeps filling across tile boundaries.
+// VAR 0: 22 products (i + j <= 5 and (3,3)); VAR 1: 26 products (i + j <= 6)
+template <int VAR>
 __global__ void __launch_bounds__(I8_THREADS, 1) i8_pair_kernel(const I8Params P, int total_tiles) {
     extern __shared__ __align__(1024) unsigned char i8_smem[];
     unsigned char *stages = i8_smem;
@@ -278,7 +337,7 @@ __global__ void __launch_bounds__(I8_THREADS, 1) i8_pair_kernel(const I8Params P
                     const int c = i - I8_BM, r = tn * I8_BN + c;
                     M.segB[c] = (r < G.nrB) ? G.segB[r] : -1;
                     M.normB[c] = (r < G.nrB) ? G.normB[r] : 0.0;
-                    M.m2sB[c] = -2.0 * i8::pow2(((r < G.nrB) ? G.expB[r] : 0) - 7);
+                    M.m2sB[c] = -2.0 * i8::pow2(((r < G.nrB) ? G.expB[r] : 0) - 8);
                 }
             }
             if (!__any_sync(0xffffffffu, any)) continue;  // no wanted row in this tile (row-block sharding)
@@ -350,7 +409,11 @@ __global__ void __launch_bounds__(I8_THREADS, 1) i8_pair_kernel(const I8Params P
     } else if (warp == 1) {
         // ---- MMA issuer ----
         if (lane == 0) {
-            constexpr unsigned ID = i8::idesc(I8_BM, I8_BN);
+            // A plane i against the stacked B planes j0 .. j0 + n - 1 (N = 64 n) -> accumulators i + j0 .. i + j0 + n - 1
+            constexpr int NMMA = VAR ? 9 : 8;
+            constexpr int mi[9] = {0, 0, 1, 1, 2, VAR ? 2 : 3, VAR ? 3 : 4, VAR ? 4 : 5, 5};
+            constexpr int mj[9] = {0, 4, 0, VAR ? 4 : 3, 0, VAR ? 3 : 0, 0, 0, 0};
+            constexpr int mn[9] = {4, 2, VAR ? 4 : 3, 2, VAR ? 3 : 4, VAR ? 2 : 4, VAR ? 4 : 2, VAR ? 3 : 1, 2};
             int it = 0;
             long long w_meta = 0, w_tmem = 0, w_full = 0;
             const long long t_begin = clock64();
@@ -371,7 +434,7 @@ __global__ void __launch_bounds__(I8_THREADS, 1) i8_pair_kernel(const I8Params P
                 }
                 const int nst = (S.meta[b].nact + 1) >> 1;
                 c0 = clock64();
-                if (tl > 0) i8::mbar_wait(&S.tmem_free, (tl - 1) & 1);  // the previous tile's accumulators are in registers
+                i8::mbar_wait(&S.tmem_free, tl & 1);  // accumulator 6 cleared (tl = 0) / the previous tile's accumulators are in registers
                 w_tmem += clock64() - c0;
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 for (int k = 0; k < nst; k++, it++) {
@@ -383,12 +446,9 @@ __global__ void __launch_bounds__(I8_THREADS, 1) i8_pair_kernel(const I8Params P
                     const unsigned a0 = i8::smem_u32(stages + s * I8_STAGE_BYTES), b0 = a0 + 2 * I8_A_CHUNK;
                     const unsigned long long da = i8::smem_desc(a0, I8_A_CHUNK, 128), db = i8::smem_desc(b0, I8_B_CHUNK, 128);
 #pragma unroll
-                    for (int i = 0; i < I8_S; i++)
-#pragma unroll
-                        for (int j = 0; j < I8_S; j++)
-                            if (i + j < I8_S)  // the first product of accumulator g = i + j is (0, g)
-                                i8::umma(tb + (i + j) * I8_BN, da + (unsigned long long)(i * 2048 >> 4), db + (unsigned long long)(j * 1024 >> 4), ID,
-                                         (k > 0 || i > 0) ? 1u : 0u);
+                    for (int m = 0; m < NMMA; m++)  // plane 0 comes first and clears accumulators 0 .. 5 at k = 0 (6: the epilogue)
+                        i8::umma(tb + (mi[m] + mj[m]) * I8_BN, da + (unsigned long long)(mi[m] * 2048 >> 4),
+                                 db + (unsigned long long)(mj[m] * 1024 >> 4), i8::idesc(I8_BM, I8_BN * mn[m]), (k > 0 || mi[m] > 0) ? 1u : 0u);
                     i8::umma_commit(&S.empty[s]);  // stage reusable once these MMAs have read it
                 }
                 if (nst > 0) i8::umma_commit(&S.accum);
@@ -400,6 +460,16 @@ __global__ void __launch_bounds__(I8_THREADS, 1) i8_pair_kernel(const I8Params P
         // (many warps with little state each: the exp / Horner chains are latency bound, not issue bound)
         constexpr int EC = I8_BN / 4;  // 16 columns per warp
         const int q = warp & 3, cbase = ((warp - 3) >> 2) * EC, row = q * 32 + lane;
+        const unsigned trow = tb + ((unsigned)(q * 32) << 16) + cbase;
+        auto clear_acc6 = [&]() {  // plane 0's MMAs never touch level 6: it accumulates from zero
+            asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1};"
+                         ::"r"(trow + 6 * I8_BN), "r"(0u) : "memory");
+            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        };
+        clear_acc6();
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) i8::mbar_arrive(&S.tmem_free);
         for (int tl = 0;; tl++) {
             const int b = tl % I8_META;
             const I8Meta &M = S.meta[b];
@@ -414,36 +484,36 @@ __global__ void __launch_bounds__(I8_THREADS, 1) i8_pair_kernel(const I8Params P
             const unsigned above = (lane == 31) ? 0u : (heads >> (lane + 1));
             const int run_end = above ? (lane + __ffs(above) - 1) : 31;
             const double na = M.normA[row];
-            const double sa = i8::pow2(M.expA[row] - 21);  // 2^(e_a - 7) * 2^-14 (the scale of `hi` below)
+            const double sa = i8::pow2(M.expA[row] - 24);  // 2^(e_a - 8) * 2^-16 (the scale of `hi` below)
             const int growA = M.tm * I8_BM + row;
             const unsigned lastmask = __ballot_sync(0xffffffffu, lane < EC && (lane == EC - 1 || M.segB[cbase + lane + 1] != M.segB[cbase + lane]));
             const long long e0 = clock64();
             i8::mbar_wait(&S.accum, tl & 1);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const long long e1 = clock64();
-            // phase 1: drain my 16 columns of the 7 accumulators into two exact 64-bit integers per pair (integer pipe
+            // phase 1: drain my 16 columns of the 6 accumulators into two exact 64-bit integers per pair (integer pipe
             // only), then hand TMEM back: the next tile's MMAs run while everything below happens
             long long hi[EC], lo[EC];
 #pragma unroll
             for (int j = 0; j < EC; j++) hi[j] = lo[j] = 0;
             if (nst > 0) {
-                const unsigned trow = tb + ((unsigned)(q * 32) << 16) + cbase;
 #pragma unroll
-                for (int g = 0; g < I8_S; g++) {
+                for (int g = 0; g < I8_NACC; g++) {
                     unsigned v[EC];
                     asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
                                  : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
                                    "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
                                  : "r"(trow + g * I8_BN));
                     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                    // sum_g P_g 128^-g = 2^-14 hi + 2^-42 lo with hi = P0 2^14 + P1 2^7 + P2, lo = P3 2^21 + ... + P6
+                    // sum_g P_g 256^-g = 2^-16 hi + 2^-48 lo with hi = P0 2^16 + P1 2^8 + P2, lo = P3 2^24 + P4 2^16 + P5 2^8 + P6
 #pragma unroll
                     for (int j = 0; j < EC; j++) {
                         const long long pv = (long long)(int)v[j];
-                        if (g < 3) hi[j] += pv << (7 * (2 - g));
-                        else lo[j] += pv << (7 * (6 - g));
+                        if (g < 3) hi[j] += pv << (8 * (2 - g));
+                        else lo[j] += pv << (8 * (6 - g));
                     }
                 }
+                clear_acc6();
             }
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             __syncwarp();
@@ -459,7 +529,7 @@ __global__ void __launch_bounds__(I8_THREADS, 1) i8_pair_kernel(const I8Params P
 #pragma unroll
             for (int j = 0; j < EC; j++) {
                 const int col = cbase + j;
-                const double d = fma((double)lo[j], 3.725290298461914e-09 /* 2^-28 */, (double)hi[j]);  // 2^14 sum_g P_g 128^-g
+                const double d = fma((double)lo[j], 2.3283064365386963e-10 /* 2^-32 */, (double)hi[j]);  // 2^16 sum_g P_g 256^-g
                 double xx = fma(d * sa, M.m2sB[col], na + M.normB[col]);  // |a|^2 + |b|^2 - 2 a.b
                 xx = (xx < 0.0) ? 0.0 : xx;                                   // clamp rounding noise, keep NaN
                 // pairs that do not count: on / below the diagonal of a symmetric kernel, padding rows / columns

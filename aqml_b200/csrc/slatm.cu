@@ -692,6 +692,9 @@ struct aqml_rep {
         int nr = 0;            // packed rows (multiple of 64)
     };
     bool i8_ready = false;     // every element has digit planes
+    unsigned char *slab = nullptr;  // the one allocation everything above lives in
+    int64_t slab_bytes = 0;
+    mutable std::vector<std::pair<cudaStream_t, cudaEvent_t>> uses;  // last consumer launch per foreign stream (aqml_rep_destroy waits)
     std::vector<El> els;
     std::vector<int> nas;
     std::vector<std::vector<int>> cnt;  // [el][mol]
@@ -706,6 +709,7 @@ static bool i8_engine_enabled() {
 }
 
 // digit planes + row exponents of a packed operand (i8pair.cuh)
+static void i8_fill_planes(const double *x, long long ld, int nr, cudaStream_t st, int8_t *sl, int *expo);
 template <class Alloc>
 static void i8_make_planes(const double *x, long long ld, int nr, Alloc &mem, cudaStream_t st, int8_t *&sl, int *&expo,
                            size_t *bytes_out = nullptr) {
@@ -714,6 +718,10 @@ static void i8_make_planes(const double *x, long long ld, int nr, Alloc &mem, cu
     sl = mem.template alloc<int8_t>(bytes);
     expo = mem.template alloc<int>(nr);
     if (bytes_out) *bytes_out = bytes;
+    i8_fill_planes(x, ld, nr, st, sl, expo);
+}
+static void i8_fill_planes(const double *x, long long ld, int nr, cudaStream_t st, int8_t *sl, int *expo) {
+    const int KT = (int)(ld / 16), rb = (nr + 127) / 128;
     // only the trailing all-zero k-chunk of every row block needs clearing: the slice kernel writes everything else
     AQML_CUDA(cudaMemset2DAsync(sl + (size_t)KT * I8_A_CHUNK, (size_t)(KT + 1) * I8_A_CHUNK, 0, I8_A_CHUNK, rb, st));
     i8_rowexp_kernel<<<(nr + 7) / 8, 256, 0, st>>>(x, ld, nr, expo);
@@ -736,7 +744,10 @@ static void launch_i8(std::vector<I8Group> &gs, const PairParams &PP, Workspace 
     P.chain = PP.chain;
     for (int i = 0; i < 16; i++) { P.order[i] = PP.order[i]; P.nsq[i] = PP.nsq[i]; }
     const int smem = I8_STAGES * I8_STAGE_BYTES + (int)sizeof(I8Smem);
-    AQML_CUDA(cudaFuncSetAttribute(i8_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    // AQML_I8_PRODUCTS=26: every digit product with i + j <= 6 (10 x lower truncation error, ~15 % more tensor work)
+    static const bool full6 = getenv("AQML_I8_PRODUCTS") && atoi(getenv("AQML_I8_PRODUCTS")) >= 26;
+    auto kern = full6 ? i8_pair_kernel<1> : i8_pair_kernel<0>;
+    AQML_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     int dev = 0, sms = 0;
     AQML_CUDA(cudaGetDevice(&dev));
     AQML_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
@@ -745,7 +756,7 @@ static void launch_i8(std::vector<I8Group> &gs, const PairParams &PP, Workspace 
     P.counter = ws.zeros<int>(1);
     P.gm = getenv("AQML_I8_GM") ? std::max(1, atoi(getenv("AQML_I8_GM"))) : 16;
     if (P.debug) AQML_CUDA(cudaMemsetAsync(P.stats + 2, 0, 64, ws.stream()));
-    i8_pair_kernel<<<std::min(total, sms), I8_THREADS, smem, ws.stream()>>>(P, total);
+    kern<<<std::min(total, sms), I8_THREADS, smem, ws.stream()>>>(P, total);
     AQML_LAUNCH_CHECK();
     if (P.debug) {
         unsigned long long h[8];
@@ -840,15 +851,29 @@ bool aqml::i8_global_pair(const I8Side &a, int na, const I8Side &b, int nb, cons
 
 namespace aqml {
 
+// a kernel on `st` reads the rep: remember it if `st` is not the stream the rep's memory is freed on
+static void mark_use(const aqml_rep *r, cudaStream_t st) {
+    if (!r || st == r->stream) return;
+    for (auto &u : r->uses)
+        if (u.first == st) { cudaEventRecord(u.second, st); return; }
+    cudaEvent_t ev;
+    if (cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) != cudaSuccess) return;
+    cudaEventRecord(ev, st);
+    r->uses.push_back({st, ev});
+}
+
 static bool use_i8(const aqml_rep *r1, const aqml_rep *r2, int nsigmas) {
     for (const auto &e : r1->els)
         if (e.ld > I8_MAX_LD) return false;
     return i8_engine_enabled() && r1->i8_ready && r2->i8_ready && nsigmas <= I8_MAXSIG;
 }
 
+// flags bit 0: layout only -- allocate the storage exactly as a computing call would, launch nothing: the contents
+// arrive from the rank that computed them (aqml_rep_slab + a broadcast; the layout depends only on zs / nas / p)
 static void rep_create(const double *coords, int on_dev, const int *zs, const int *nas, int nmol,
-                       const aqml_slatm_params *p, cudaStream_t st, aqml_rep **out) {
-    AQML_REQUIRE(coords && zs && nas && out && nmol >= 1, "bad argument");
+                       const aqml_slatm_params *p, int flags, cudaStream_t st, aqml_rep **out) {
+    const bool compute = !(flags & 1);
+    AQML_REQUIRE((coords || !compute) && zs && nas && out && nmol >= 1, "bad argument");
     require_device();
     Workspace ws(st);     // temporaries
     Workspace keep(st);   // becomes the rep's storage
@@ -873,50 +898,71 @@ static void rep_create(const double *coords, int on_dev, const int *zs, const in
             mols[e].push_back(m);
             rep->cnt[e][m]++;
         }
+    const bool planes = i8_engine_enabled();
+    // pass 1: packed row maps and the size of the storage (one slab, so that a rep can travel as one buffer)
+    std::vector<std::vector<int>> rms(ne), sgs(ne);
+    size_t total = 0;
+    auto add = [&](size_t n, size_t elem) { total = Workspace::slab_aligned(total) + (n ? n : 1) * elem; };  // = Workspace::alloc
+    for (int e = 0; e < ne; e++) {
+        build_tiles(rows[e], mols[e], rms[e], sgs[e]);
+        const size_t nr = rms[e].size(), ld = (size_t)t.dev.pld[e];
+        const int mw = mask_words((long long)ld);
+        add(nr * ld, 8); add(nr, 8); add(nr, 4);
+        if (mw <= 32 && nr) add(nr / 64 * (size_t)mw, 4);
+        if (planes && !rows[e].empty()) { add((size_t)((nr + 127) / 128) * (ld / 16 + 1) * I8_A_CHUNK, 1); add(nr, 4); }
+    }
+    keep.reserve(total);
+    // pass 2: carve (same order)
     std::vector<int> atom_prow(mi.A, -1);
     SlatmJob J;
     memset(&J, 0, sizeof(J));
     for (int e = 0; e < ne; e++) {
-        std::vector<int> rm, sg;
-        build_tiles(rows[e], mols[e], rm, sg);
+        const std::vector<int> &rm = rms[e], &sg = sgs[e];
         aqml_rep::El el;
         el.label = t.labels[e]; el.n = (int)rows[e].size(); el.tiles = (int)rm.size() / BM; el.ld = t.dev.pld[e];
         size_t nr = rm.size();
         el.x = keep.alloc<double>(nr * (size_t)el.ld);
         el.norm = keep.alloc<double>(nr);
-        el.seg = keep.upload(sg);
+        el.seg = keep.alloc<int>(nr);
+        if (compute && nr) AQML_CUDA(cudaMemcpyAsync(el.seg, sg.data(), nr * sizeof(int), cudaMemcpyHostToDevice, st));
         el.maskw = mask_words(el.ld);
-        el.mask = (el.maskw <= 32 && nr) ? keep.zeros<unsigned>(nr / 64 * (size_t)el.maskw) : nullptr;
+        el.mask = nullptr;
+        if (el.maskw <= 32 && nr) {
+            el.mask = keep.alloc<unsigned>(nr / 64 * (size_t)el.maskw);
+            if (compute) AQML_CUDA(cudaMemsetAsync(el.mask, 0, nr / 64 * (size_t)el.maskw * sizeof(unsigned), st));
+        }
         rep->bytes += (int64_t)(nr * (size_t)el.ld * 8 + nr * 12);
         std::vector<int> pad;
         for (size_t r = 0; r < nr; r++) {
             if (rm[r] >= 0) atom_prow[rm[r]] = (int)r;
             else pad.push_back((int)r);
         }
-        if (!pad.empty()) {
+        if (compute && !pad.empty()) {
             zero_rows_kernel<<<(unsigned)pad.size(), 128, 0, st>>>(el.x, el.ld, ws.upload(pad), (int)pad.size(), el.norm);
             AQML_LAUNCH_CHECK();
         }
         el.nr = (int)nr;
+        if (planes && el.n) {  // digit planes + row exponents (6 bytes per element next to the 8 of the FP64 copy)
+            const size_t bytes = (size_t)((nr + 127) / 128) * (el.ld / 16 + 1) * I8_A_CHUNK;
+            el.sl = keep.alloc<int8_t>(bytes);
+            el.expo = keep.alloc<int>(nr);
+            rep->bytes += (int64_t)bytes + 4 * el.nr;
+        }
         J.px[e] = el.x; J.pnorm[e] = el.norm; J.pmask[e] = el.mask; J.maskw[e] = el.maskw;
         rep->els.push_back(el);
     }
     rep->ne = ne;
-    const double *dcoords = on_dev ? coords : ws.upload(coords, (size_t)mi.A * 3);
-    J.coords = dcoords; J.zs = ws.upload(zs, mi.A); J.mol_off = ws.upload(mi.off); J.atom_mol = ws.upload(mi.atom_mol);
-    J.nmol = nmol; J.A = mi.A; J.local = 1; J.out = nullptr; J.ldo = 0; J.atom_prow = ws.upload(atom_prow);
-    launch_slatm(t, J, mi, ws);
-    if (i8_engine_enabled()) {
-        // digit planes of every packed operand (7 bytes per element next to the 8 of the FP64 copy); stream ordered,
-        // no host synchronisation (NaN rows from coincident atoms travel through |row|^2, see i8_rowexp_kernel)
-        for (auto &el : rep->els) {
-            if (el.n == 0) continue;
-            size_t bytes = 0;
-            i8_make_planes(el.x, el.ld, el.nr, keep, st, el.sl, el.expo, &bytes);
-            rep->bytes += (int64_t)bytes + 4 * el.nr;
-        }
-        rep->i8_ready = true;
+    if (compute) {
+        const double *dcoords = on_dev ? coords : ws.upload(coords, (size_t)mi.A * 3);
+        J.coords = dcoords; J.zs = ws.upload(zs, mi.A); J.mol_off = ws.upload(mi.off); J.atom_mol = ws.upload(mi.atom_mol);
+        J.nmol = nmol; J.A = mi.A; J.local = 1; J.out = nullptr; J.ldo = 0; J.atom_prow = ws.upload(atom_prow);
+        launch_slatm(t, J, mi, ws);
+        if (planes)  // stream ordered, no host synchronisation (NaN rows from coincident atoms travel through |row|^2)
+            for (auto &el : rep->els)
+                if (el.n) i8_fill_planes(el.x, el.ld, el.nr, st, el.sl, el.expo);
     }
+    rep->i8_ready = planes;
+    rep->slab = keep.slab(); rep->slab_bytes = (int64_t)keep.slab_bytes();
     rep->owned = keep.pointers();
     keep.release_all();
     *out = rep.release();
@@ -1013,13 +1059,61 @@ int aqml_calc_sbot(const double *coords, const int *zs, int na, int ia, int izef
     return single_type(coords, zs, na, ia, izeff, mb, rcut, nx, dgrid, sigma, coeff, 6.0, ys);
 }
 
+int aqml_measure_i8_peak(double *ops_per_s, void *stream) {
+    return guarded([&] {
+        AQML_REQUIRE(ops_per_s, "bad argument");
+        require_device();
+        cudaStream_t st = (cudaStream_t)stream;
+        int dev = 0, sms = 0;
+        AQML_CUDA(cudaGetDevice(&dev));
+        AQML_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        cudaEvent_t e0, e1;
+        AQML_CUDA(cudaEventCreate(&e0));
+        AQML_CUDA(cudaEventCreate(&e1));
+        const int rounds = 20000;  // x 2 MMAs x 128 clk = 2.6 ms at 1.965 GHz
+        double best = 0.0;
+        for (int rep = 0; rep < 4; rep++) {  // first pass warms up
+            AQML_CUDA(cudaEventRecord(e0, st));
+            i8_peak_kernel<<<sms, 128, 0, st>>>(rounds);
+            AQML_LAUNCH_CHECK();
+            AQML_CUDA(cudaEventRecord(e1, st));
+            AQML_CUDA(cudaEventSynchronize(e1));
+            float ms = 0.f;
+            AQML_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+            if (rep > 0) best = std::max(best, 2.0 * 128 * 256 * 32 * 2.0 * rounds * sms / (ms * 1e-3));
+        }
+        cudaEventDestroy(e0);
+        cudaEventDestroy(e1);
+        *ops_per_s = best;
+    });
+}
+
 int aqml_rep_create(const double *coords, int coords_on_device, const int *zs, const int *nas, int nmol,
                     const aqml_slatm_params *p, void *stream, aqml_rep **out) {
-    return guarded([&] { rep_create(coords, coords_on_device, zs, nas, nmol, p, (cudaStream_t)stream, out); });
+    return guarded([&] { rep_create(coords, coords_on_device, zs, nas, nmol, p, 0, (cudaStream_t)stream, out); });
+}
+
+int aqml_rep_create_ex(const double *coords, int coords_on_device, const int *zs, const int *nas, int nmol,
+                       const aqml_slatm_params *p, int flags, void *stream, aqml_rep **out) {
+    return guarded([&] { rep_create(coords, coords_on_device, zs, nas, nmol, p, flags, (cudaStream_t)stream, out); });
+}
+
+int aqml_rep_slab(const aqml_rep *r, void **ptr, int64_t *bytes) {
+    return guarded([&] {
+        AQML_REQUIRE(r && ptr && bytes, "bad argument");
+        *ptr = r->slab;
+        *bytes = r->slab_bytes;
+    });
 }
 
 void aqml_rep_destroy(aqml_rep *r) {
     if (!r) return;
+    // kernels that read the rep on another stream than the one it was created on must finish before the memory goes
+    // back to the pool
+    for (auto &u : r->uses) {
+        cudaStreamWaitEvent(r->stream, u.second, 0);
+        cudaEventDestroy(u.second);
+    }
     for (void *p : r->owned) cudaFreeAsync(p, r->stream);
     delete r;
 }
@@ -1059,6 +1153,8 @@ int aqml_rep_local_gaussian(const aqml_rep *r1, const aqml_rep *r2, const double
         P.out = K; P.ldo = r2->nmol; P.slab = (long long)nrows * r2->nmol;
         if (use_i8(r1, r2, nsigmas)) run_pairs_i8(r1, r2, zmax, row0, nrows, false, P, ws);
         else run_pairs_public(MODE_DOT, EPI_LOCAL, groups, P, ws);
+        mark_use(r1, st);
+        mark_use(r2, st);
     });
 }
 
@@ -1098,6 +1194,7 @@ int aqml_rep_local_gaussian_sym(const aqml_rep *r, const double *sigmas, int nsi
         dim3 grid((n + 31) / 32, (n + 31) / 32, nsigmas);
         symmetrize_kernel<<<grid, 256, 0, st>>>(K, n, nsigmas, ws.upload(diag));
         AQML_LAUNCH_CHECK();
+        mark_use(r, st);
     });
 }
 
@@ -1134,6 +1231,8 @@ int aqml_rep_kernel_width_multi(const aqml_rep *const *reps1, int n1, const aqml
             if (kv.second.first.empty() || kv.second.second.empty()) continue;
             dso[kv.first % 1000 - 1] = std::sqrt(pruned_max_segs_public(2, kv.second.first, kv.second.second, lds[kv.first], same, ws));
         }
+        for (int i = 0; i < n1; i++) mark_use(reps1[i], st);
+        for (int i = 0; i < n2; i++) mark_use(reps2[i], st);
     });
 }
 

@@ -15,23 +15,49 @@ import numpy as np
 from . import _lib as L
 
 
+class _DeviceBytes:
+    """CUDA array interface over a raw device allocation (torch.as_tensor wraps it without a copy)."""
+
+    def __init__(self, ptr, nbytes):
+        self.__cuda_array_interface__ = {"shape": (int(nbytes),), "typestr": "|u1", "data": (int(ptr), False), "version": 2}
+
+
 class PackedRep:
-    """aSLATM of a set of molecules, packed by element on the current CUDA device."""
+    """aSLATM of a set of molecules, packed by element on the current CUDA device.
+
+    ``compute=False`` only lays out the storage (``coordinates`` may be None): the contents are then received
+    from the rank that computed them (``slab_tensor`` + a broadcast, ``parallel.share_reps``)."""
 
     def __init__(self, coordinates, nuclear_charges, nas, mbtypes, izeff=False, sigmas=(0.05, 0.05),
-                 dgrids=(0.03, 0.03), rcut=4.8, rpower=6):
+                 dgrids=(0.03, 0.03), rcut=4.8, rpower=6, compute=True):
         import torch
         self._h = C.c_void_p()
         self.nas = L.i32(nas)
         self.zs = L.i32(nuclear_charges)
         self.nmol = len(self.nas)
+        if len(self.zs) != int(self.nas.sum()):
+            raise ValueError(f"nuclear_charges has {len(self.zs)} entries, nas sums to {int(self.nas.sum())}")
         p = L.slatm_params(mbtypes, izeff, sigmas, dgrids, rcut, rpower)
         on_dev = L.is_tensor(coordinates)
-        coords = L.dev_f64(coordinates).contiguous() if on_dev else L.f64(coordinates)
+        if coordinates is None:
+            if compute:
+                raise ValueError("coordinates are required unless compute=False")
+            coords = None
+        else:
+            coords = L.dev_f64(coordinates).contiguous() if on_dev else L.f64(coordinates)
+            if tuple(coords.shape) != (len(self.zs), 3):
+                raise ValueError(f"coordinates must have shape ({len(self.zs)}, 3), got {tuple(coords.shape)}")
         self.device = coords.device if on_dev else torch.device("cuda", torch.cuda.current_device())
         with torch.cuda.device(self.device):
-            L.call("aqml_rep_create", L.ptr(coords), int(on_dev), L.ptr(self.zs), L.ptr(self.nas), self.nmol, p,
-                   L.current_stream(), C.byref(self._h))
+            L.call("aqml_rep_create_ex", L.ptr(coords), int(on_dev), L.ptr(self.zs), L.ptr(self.nas), self.nmol, p,
+                   0 if compute else 1, L.current_stream(), C.byref(self._h))
+
+    def slab_tensor(self):
+        """The representation's storage as one uint8 CUDA tensor (a view: valid while this object lives)."""
+        import torch
+        ptr, nb = C.c_void_p(), C.c_int64()
+        L.call("aqml_rep_slab", self._h, C.byref(ptr), C.byref(nb))
+        return torch.as_tensor(_DeviceBytes(ptr.value, nb.value), device=self.device)
 
     @property
     def nbytes(self):

@@ -95,6 +95,22 @@ def allgather_rows(x_local, counts, group=None):
     return torch.cat([out[r * nmax:r * nmax + counts[r]] for r in range(world)], dim=0)
 
 
+def share_reps(reps, owners, group=None):
+    """Packed representations computed 1/N per rank, made complete on every rank ("SLATM: molecules are
+    independent -> ranges per GPU, then one all-gather so every GPU holds the full column-side representation").
+    reps[b] is a PackedRep on every rank -- computed where owners[b] == rank, laid out only (compute=False) elsewhere;
+    its storage is one buffer whose layout depends only on the molecules, so block b is one broadcast from its owner.
+    The broadcasts are enqueued together (NCCL runs them back to back on its stream) and waited for at the end."""
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return
+    src = (lambda r: dist.get_global_rank(group, r)) if group is not None else (lambda r: r)
+    views = [r.slab_tensor() for r in reps]   # keep the views alive until the collectives have been waited for
+    works = [dist.broadcast(v, src=src(o), group=group, async_op=True) for v, o in zip(views, owners)]
+    for w in works:
+        w.wait()
+
+
 # ----------------------------------------------------------------------------------------------------------
 # Distributed solve of (K + lambda I) alpha = y for a row-sharded K (SURVEY 8f row 2: "multi-GPU block
 # Cholesky for 100 k").  The reference solves on one host with LAPACK (`np.linalg.solve`, aqml.py:875,

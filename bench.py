@@ -1,21 +1,29 @@
 #!/usr/bin/env python
 """Benchmark of the AQML hot path on B200 (contract: see the task prompt / DESIGN.md section 6).
 
-Workload (BASELINE.json configs[1]): 20k train x 2k test QM9-shaped molecules, local aSLATM
-element-matched Gaussian kernel, FP64, 4 sigmas.  One *step* = the whole hot path for one batch:
+Workload (BASELINE.json configs[1]): 20k train x 2k test QM9-shaped molecules, local aSLATM element-matched
+Gaussian kernel, FP64, 4 sigmas -- as the KRR feed the reference builds it for (algo/aqml.py:711-789, 876).
+One *step* = the whole hot path for that ONE fixed problem, cut over the N ranks (aqml_b200/sharded.py):
 
-    coordinates -> aSLATM (train + test, written element-packed) -> K[4, n_test, n_train]
+    coordinates -> aSLATM (train blocks 1/N per rank + test)              phase aslatm
+                -> every block's packed operands to every rank             phase allgather  (NCCL, N > 1)
+                -> kernel width over all train + test atoms                phase width      (+ all-reduce MAX)
+                -> ks1 = K(train, train): lower block triangle, 4 sigmas   phase k_train
+                -> ks2 = K(test, train), sharded by training columns       phase k_test
+                -> y = ks2 . alpha                                         phase predict    (+ all-reduce SUM)
 
-`value`  : kernel elements/s with coordinates already resident in HBM (device timed, CUDA events).
-`e2e`    : same metric through the C ABI with HOST buffers (coords H2D, K D2H inside the timing).
-N > 1    : weak scaling -- every rank owns its own 2k test molecules (a row block of K) against
-           the same 20k training molecules; no data-path collective.
-`--impl reference`: the restated reference loops (C/OpenMP, oracle/c_oracle.c -- the Fortran cannot
-           be compiled in this image) on the host cores, bounded sample of the same workload.
+`value`  : UNIQUE kernel elements delivered per second, whole job: 4 * (n_train (n_train + 1) / 2 + n_test n_train) per
+           step, coordinates already resident in HBM (device timed with CUDA events, max over ranks).
+`e2e`    : same metric through the public API with HOST buffers: coordinates H2D from pinned memory, every K tile and
+           the predictions D2H into pinned memory, all inside the timed region.
+N > 1    : strong scaling of the fixed problem; collectives inside the timed region (see phases_ms).
+`--impl reference`: the restated reference loops (C/OpenMP, oracle/c_oracle.c -- the Fortran cannot be compiled in
+           this image) on the host cores, the same phases on a bounded sample of the same workload.
 """
 from __future__ import annotations
 
 import argparse
+import ctypes as C
 import json
 import os
 import subprocess
@@ -32,6 +40,10 @@ SEED = 20251019 + 2
 COEFFS = (0.5, 1.0, 2.0, 4.0)
 SLATM_KW = dict(sigmas=(.05, .05), dgrids=(.04, .04), rcut=4.8)
 ZMAX = 9
+METRIC = "local_gaussian_kernel_elements_per_sec"
+WORKLOAD = ("config2 as KRR feed: 20k train x 2k test QM9-shaped molecules, local aSLATM element-matched Gaussian "
+            "kernel, FP64, 4 sigmas; step = coords -> aSLATM(train+test) -> kernel width -> K(train,train) "
+            "[lower block triangle] -> K(test,train) -> K(test,train).alpha")
 
 
 def init_nccl(local_rank):
@@ -54,13 +66,13 @@ def init_nccl(local_rank):
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--n-train", type=int, default=20000)
     ap.add_argument("--n-test", type=int, default=2000)
-    ap.add_argument("--cpu-train", type=int, default=256, help="CPU-baseline sample: training molecules")
-    ap.add_argument("--cpu-test", type=int, default=48, help="CPU-baseline sample: test molecules")
+    ap.add_argument("--cpu-train", type=int, default=96, help="CPU-baseline sample: training molecules")
+    ap.add_argument("--cpu-test", type=int, default=24, help="CPU-baseline sample: test molecules")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-fp64-engine", action="store_true", help="skip the extra FP64 DMMA engine measurement")
@@ -73,10 +85,10 @@ def parse():
     return ap.parse_args()
 
 
-def make_sets(n_train, n_test, rank):
+def make_sets(n_train, n_test):
     from aqml_b200 import synth
     train = synth.qm9_like_fast(n_train, SEED, pool=512)
-    test = synth.qm9_like_fast(n_test, SEED + 1000 * (rank + 1), pool=256)
+    test = synth.qm9_like_fast(n_test, SEED + 1000, pool=256)
     return train, test
 
 
@@ -88,6 +100,11 @@ def mbtypes_for(train, test):
     # all five QM9 elements with full multiplicity (n1/n2/n3 = 5/15/75, D = 8975 at dgrid 0.04)
     zl.append(np.array([1, 1, 1, 6, 6, 6, 7, 7, 7, 8, 8, 8, 9, 9, 9]))
     return rcore.get_slatm_mbtypes(zl)
+
+
+def sigmas_from(dso):
+    """aqml.py:195,775: sigma = coeff * dmax / sqrt(2 ln 2) per element (absent elements keep 1e-9)."""
+    return np.array([c * np.asarray(dso) / np.sqrt(2 * np.log(2)) for c in COEFFS])
 
 
 # ------------------------------------------------------------------------------------------------
@@ -141,44 +158,50 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------
-# CPU arm (restated reference loops)
+# CPU arm (restated reference loops): the same phases on a bounded sample
 # ------------------------------------------------------------------------------------------------
 def cpu_sample(args, steps=1, warmup=0):
-    """Time molecules -> aSLATM -> local Gaussian kernel on the host cores for a bounded sample."""
-    from aqml_b200 import synth
+    """molecules -> aSLATM -> kernel width -> K(train, train) -> K(test, train) on the host cores, as the reference does
+    it: dense (atoms, D) rows, the width from full per-element distance matrices (aqml.py:220-237), ks1 as a full
+    n x n call of calc_lk_gaussian (aqml.py:788; the reference does not use its symmetry)."""
     from oracle import c_oracle as co
-    train, test = make_sets(args.cpu_train, args.cpu_test, 0)
-    mb = mbtypes_for(*make_sets(2000, 500, 0))
-    sig = np.array([c * np.full(ZMAX, 16.0) / np.sqrt(2 * np.log(2)) for c in COEFFS])
+    train, test = make_sets(args.cpu_train, args.cpu_test)
+    mb = mbtypes_for(*make_sets(2000, 500))
     co.load(fast=True)
     co.set_num_threads(len(os.sched_getaffinity(0)), fast=True)  # torchrun exports OMP_NUM_THREADS=1
     cores = co.num_threads(fast=True)
+    nas = np.concatenate((train[0], test[0]))
+    zs = np.concatenate((train[1], test[1]))
 
     def one():
-        t0 = time.perf_counter()
+        t = [time.perf_counter()]
         x1 = co.generate_slatm_batch(train[2], train[1], train[0], mb, True, fast=True, **SLATM_KW)
         x2 = co.generate_slatm_batch(test[2], test[1], test[0], mb, True, fast=True, **SLATM_KW)
-        t1 = time.perf_counter()
-        K = co.calc_lk_gaussian(x2, x1, test[1], train[1], test[0], train[0], ZMAX, False, sig, fast=True)
-        t2 = time.perf_counter()
-        return t1 - t0, t2 - t1, K
+        t.append(time.perf_counter())
+        dso = co.get_kernel_width(nas, zs, np.concatenate((x1, x2)), fast=True)
+        dso = np.concatenate((dso, np.full(ZMAX - len(dso), 1e-9)))
+        sig = sigmas_from(dso)
+        t.append(time.perf_counter())
+        co.calc_lk_gaussian(x1, x1, train[1], train[1], train[0], train[0], ZMAX, False, sig, fast=True)
+        t.append(time.perf_counter())
+        co.calc_lk_gaussian(x2, x1, test[1], train[1], test[0], train[0], ZMAX, False, sig, fast=True)
+        t.append(time.perf_counter())
+        return np.diff(t)
 
     for _ in range(warmup):
         one()
-    ts, tk = [], []
-    for _ in range(max(steps, 1)):
-        a, b, K = one()
-        ts.append(a)
-        tk.append(b)
-    t_slatm, t_kernel = float(np.median(ts)), float(np.median(tk))
-    elems = len(COEFFS) * args.cpu_test * args.cpu_train
-    atoms = int(train[0].sum() + test[0].sum())
-    return dict(value=elems / (t_slatm + t_kernel), unit="kernel elements/s", cores=cores, kind="port",
-                sample=f"{args.cpu_test} test x {args.cpu_train} train QM9-shaped molecules ({atoms} atoms, D=8975, "
-                       f"4 sigmas), molecules->aSLATM->K; restated reference loops (C/OpenMP -O3 -march=native), "
-                       f"not gfortran",
-                aslatm_atoms_per_sec=atoms / t_slatm, seconds=t_slatm + t_kernel,
-                seconds_slatm=t_slatm, seconds_kernel=t_kernel)
+    ph = np.median(np.array([one() for _ in range(max(steps, 1))]), axis=0)
+    total = float(ph.sum())
+    S, n, nt = len(COEFFS), args.cpu_train, args.cpu_test
+    elems = S * (n * n + nt * n)          # what the reference computes: the full ks1 and ks2
+    atoms = int(nas.sum())
+    return dict(value=elems / total, unit="kernel elements/s", cores=cores, kind="port",
+                sample=f"{n} train + {nt} test QM9-shaped molecules ({atoms} atoms, D=8975, 4 sigmas): molecules -> aSLATM "
+                       f"-> kernel width -> K(train,train) [full {n}x{n}, as aqml.py:788] -> K(test,train); restated "
+                       f"reference loops (C/OpenMP -O3 -march=native), not gfortran; value counts every element "
+                       f"computed ({elems}), {S * (n * (n + 1) // 2 + nt * n) / total:.4g} unique elements/s",
+                aslatm_atoms_per_sec=atoms / float(ph[0]), seconds=total,
+                phases_ms={k: float(v) * 1e3 for k, v in zip(("aslatm", "width", "k_train", "k_test"), ph)})
 
 
 def run_reference(args):
@@ -188,12 +211,12 @@ def run_reference(args):
     t0 = time.perf_counter()
     r = cpu_sample(args, steps=args.steps, warmup=min(args.warmup, 1))
     ms = r["seconds"] * 1e3
-    line = {"impl": "reference", "metric": "local_gaussian_kernel_elements_per_sec", "value": r["value"],
-            "unit": "kernel elements/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+    line = {"impl": "reference", "metric": METRIC, "value": r["value"],
+            "unit": "kernel elements/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": min(args.warmup, 1),
+            "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic",
-            "config": {"workload": "config2: 20k train x 2k test QM9-shaped, local aSLATM element-matched Gaussian "
-                                   "kernel, 4 sigmas (CPU arm: bounded sample of it)", "sample": r["sample"]},
+            "config": {"workload": WORKLOAD + " (CPU arm: bounded sample of it)", "sample": r["sample"]},
+            "phases_ms": r["phases_ms"],
             "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
             "aslatm_atoms_per_sec": r["aslatm_atoms_per_sec"],
             "e2e": {"value": r["value"], "unit": "kernel elements/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -227,7 +250,7 @@ def run_ours(args):
     import torch
     import torch.distributed as dist
     from aqml_b200 import _lib as L
-    from aqml_b200 import fused
+    from aqml_b200 import sharded
 
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -237,41 +260,42 @@ def run_ours(args):
         init_nccl(local_rank)
     lib = L.load()
 
-    train, test = make_sets(args.n_train, args.n_test, rank)
+    train, test = make_sets(args.n_train, args.n_test)   # the same fixed problem on every rank
     mb = mbtypes_for(train, test)
     S = len(COEFFS)
     dev = torch.device("cuda", local_rank)
+    sk = sharded.ShardedKernels((train[0], train[1]), (test[0], test[1]), mb, ZMAX, rank, world, **SLATM_KW)
     c1 = torch.as_tensor(train[2], device=dev)
     c2 = torch.as_tensor(test[2], device=dev)
-    K = torch.empty((S, args.n_test, args.n_train), dtype=torch.float64, device=dev)
-
-    # sigmas from the per-element dmax of a training subsample (width heuristic, aqml.py:204-255,775)
-    nsub = min(args.n_train, 400)
-    asub = int(train[0][:nsub].sum())
-    sub = fused.PackedRep(train[2][:asub], train[1][:asub], train[0][:nsub], mb, **SLATM_KW)
-    dso = fused.kernel_width(sub, sub, ZMAX)
-    sub.close()
-    sig = np.array([c * dso / np.sqrt(2 * np.log(2)) for c in COEFFS])
+    rng = np.random.Generator(np.random.PCG64(SEED))
+    alpha = torch.as_tensor(rng.standard_normal((S, args.n_train)) / args.n_train, device=dev)  # stands in for the solver's output
+    PH = ("aslatm", "allgather", "width", "k_train", "k_test", "predict")
+    out = {}
 
     def ev():
         return torch.cuda.Event(enable_timing=True)
 
-    def step(timing=None):
-        e = [ev() for _ in range(3)] if timing is not None else None
-        if e:
-            e[0].record()
-        r1 = fused.PackedRep(c1, train[1], train[0], mb, **SLATM_KW)
-        r2 = fused.PackedRep(c2, test[1], test[0], mb, **SLATM_KW)
-        if e:
-            e[1].record()
-        fused.local_gaussian(r2, r1, sig, ZMAX, out=K)
-        if e:
-            e[2].record()
+    def step(timing=None, coords=None, after=None):
+        e = [ev() for _ in range(len(PH) + 1)] if timing is not None else None
+        mark = (lambda i: e[i].record()) if e else (lambda i: None)
+        mark(0)
+        sk.pack(*(coords or (c1, c2)))
+        if not out:
+            out["kt"], out["ks"] = sk.alloc_out(S)
+        mark(1)
+        sk.share()
+        mark(2)
+        sig = sigmas_from(sk.width())
+        mark(3)
+        sk.k_train(sig, out["kt"], after)
+        mark(4)
+        sk.k_test(sig, out["ks"], after)
+        mark(5)
+        y = sk.predict(out["ks"], alpha)
+        mark(6)
+        if timing is not None:
             timing.append(e)
-        nbytes = r1.nbytes + r2.nbytes
-        r1.close()
-        r2.close()
-        return nbytes
+        return y, sig
 
     def barrier():
         torch.cuda.synchronize()
@@ -279,224 +303,223 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(max(args.warmup, 3)):
-        rep_bytes = step()
+    warm = max(args.warmup, 3)
+    for _ in range(warm):
+        step()
     barrier()
+    rep_bytes = sum(r.nbytes for r in sk.reps) + sk.test.nbytes
     sampler = ClockSampler(local_rank) if rank == 0 else None
-    import ctypes as C
-    L.call("aqml_pair_stats", None, None, 1)  # reset the executed / dense k-tile counters
     launches0 = lib.aqml_launch_count()
     timing = []
     w0 = time.time()
     e_start, e_end = ev(), ev()
     e_start.record()
     for _ in range(args.steps):
-        step(timing)
+        y, sig = step(timing)
     e_end.record()
     barrier()
     w1 = time.time()
     launches = int(lib.aqml_launch_count() - launches0)
+    t_total_ms = e_start.elapsed_time(e_end)
+    phases = [float(np.mean([e[i].elapsed_time(e[i + 1]) for e in timing])) for i in range(len(PH))]
+    clocks = sampler.stop(w0, w1) if sampler else None
+    y_host = y.cpu().numpy()
+
+    # ---- untimed: k-tiles the contraction executed in one step (device counters; reading them synchronises) -----
+    L.call("aqml_pair_stats", None, None, 1)
+    sk.k_train(sig, out["kt"])
+    sk.k_test(sig, out["ks"])
     kt_exec, kt_dense = C.c_int64(0), C.c_int64(0)
     L.call("aqml_pair_stats", C.c_void_p(C.addressof(kt_exec)), C.c_void_p(C.addressof(kt_dense)), 1)
-    kt_exec, kt_dense = kt_exec.value / args.steps, kt_dense.value / args.steps  # per launch
+    kt_exec, kt_dense = float(kt_exec.value), float(kt_dense.value)
     bm, bn, bk = C.c_int(0), C.c_int(0), C.c_int(0)
     lib.aqml_tile_shape(C.c_void_p(C.addressof(bm)), C.c_void_p(C.addressof(bn)), C.c_void_p(C.addressof(bk)))
     ktile_flops = 2.0 * bm.value * bn.value * bk.value
-    t_total_ms = e_start.elapsed_time(e_end)
-    t_slatm_ms = float(np.mean([e[0].elapsed_time(e[1]) for e in timing]))
-    t_kernel_ms = float(np.mean([e[1].elapsed_time(e[2]) for e in timing]))
-    clocks = sampler.stop(w0, w1) if sampler else None
 
-    # ---- the FP64 DMMA engine on the same inputs (reported next to the default int8 tensor engine) --------------
+    # ---- untimed: the FP64 DMMA engine on the K(test, train) phase of the same inputs ---------------------------
     fp64_engine = None
-    if rank == 0 and world == 1 and not args.no_fp64_engine and os.environ.get("AQML_PAIR_ENGINE", "") not in ("dmma", "fp64"):
+    engine = "dmma" if os.environ.get("AQML_PAIR_ENGINE", "") in ("dmma", "fp64") else "i8"
+    if rank == 0 and world == 1 and not args.no_fp64_engine and engine == "i8":
         os.environ["AQML_PAIR_ENGINE"] = "dmma"
         try:
-            for it in range(3):  # last pass timed: aSLATM alone (no digit planes are built for the FP64 engine)
-                if it:
-                    r1.close()
-                    r2.close()
-                torch.cuda.synchronize()
-                s0, s1 = ev(), ev()
-                s0.record()
-                r1 = fused.PackedRep(c1, train[1], train[0], mb, **SLATM_KW)
-                r2 = fused.PackedRep(c2, test[1], test[0], mb, **SLATM_KW)
-                s1.record()
-                torch.cuda.synchronize()
-                t_slatm_only = s0.elapsed_time(s1)
-            fused.local_gaussian(r2, r1, sig, ZMAX, out=K)
+            sk.k_test(sig, out["ks"])
             torch.cuda.synchronize()
             L.call("aqml_pair_stats", None, None, 1)
             a, b = ev(), ev()
             a.record()
-            for _ in range(2):
-                fused.local_gaussian(r2, r1, sig, ZMAX, out=K)
+            sk.k_test(sig, out["ks"])
             b.record()
             torch.cuda.synchronize()
             ke, kd = C.c_int64(0), C.c_int64(0)
             L.call("aqml_pair_stats", C.c_void_p(C.addressof(ke)), C.c_void_p(C.addressof(kd)), 1)
-            fp64_engine = {"kernel_ms": a.elapsed_time(b) / 2, "ktiles_executed": ke.value / 2, "aslatm_ms": t_slatm_only}
-            r1.close()
-            r2.close()
+            fp64_engine = {"k_test_ms": a.elapsed_time(b), "ktiles_executed": float(ke.value)}
         finally:
             del os.environ["AQML_PAIR_ENGINE"]
 
-    # ---- end-to-end through the C ABI with host buffers -----------------------------------------
-    e2e_ms = None
+    # ---- end to end through the public API with host buffers ----------------------------------------------------
+    e2e_ms, h2d, d2h = None, 0, 0
     if not args.no_e2e:
-        kh = torch.empty((S, args.n_test, args.n_train), dtype=torch.float64, pin_memory=True)
         pc1 = torch.as_tensor(train[2]).pin_memory().numpy()
         pc2 = torch.as_tensor(test[2]).pin_memory().numpy()
+        host = {k: torch.empty(v.shape, dtype=torch.float64, pin_memory=True) for k, v in list(out["kt"].items()) + list(out["ks"].items())}
+        yh = torch.empty((S, args.n_test), dtype=torch.float64, pin_memory=True)
+        side = torch.cuda.Stream()
+        cur = torch.cuda.current_stream()
 
-        e2e_chunks = os.environ.get("AQML_E2E_CHUNKS", "0.75,0.25")  # measured: 1 -> 350.5, 2 -> 345.1, 0.75,0.25 -> 337.6, 0.7,0.2,0.1 -> 340.3 ms
-        e2e_chunks = tuple(float(v) for v in e2e_chunks.split(",")) if "," in e2e_chunks else int(e2e_chunks)
+        def to_host(key, t):  # D2H of a finished tile on a second stream, behind the next tile's contraction
+            ready = torch.cuda.Event()
+            ready.record(cur)
+            side.wait_event(ready)
+            with torch.cuda.stream(side):
+                host[key].copy_(t, non_blocking=True)
 
         def e2e_step():
-            r1 = fused.PackedRep(pc1, train[1], train[0], mb, **SLATM_KW)   # coords H2D inside
-            if e2e_chunks != 1:  # queries in row blocks, D2H of block c-1 behind the contraction of block c
-                fused.local_gaussian_to_host(pc2, test[1], test[0], r1, mb, sig, ZMAX, kh, chunks=e2e_chunks, **SLATM_KW)
-                r1.close()
-                return
-            r2 = fused.PackedRep(pc2, test[1], test[0], mb, **SLATM_KW)
-            fused.local_gaussian(r2, r1, sig, ZMAX, out=K)
-            kh.copy_(K, non_blocking=True)                                    # K D2H
-            r1.close()
-            r2.close()
+            cur.wait_stream(side)            # the previous step's copies have left the tile buffers
+            y, _ = step(coords=(pc1, pc2), after=to_host)
+            yh.copy_(y, non_blocking=True)
+            cur.wait_stream(side)
         for _ in range(2):
             e2e_step()
         barrier()
         a, b = ev(), ev()
-        a.record()
         n_e2e = max(2, min(args.steps, 3))
+        a.record()
         for _ in range(n_e2e):
             e2e_step()
         b.record()
         barrier()
         e2e_ms = a.elapsed_time(b) / n_e2e
-        h2d = int(train[2].nbytes + test[2].nbytes + 4 * (len(train[1]) + len(test[1])) + sig.nbytes)
-        d2h = int(K.numel() * 8)
+        atoms_mine = sum(int(sk.nas1[lo:hi].sum()) for lo, hi in (sk.bounds[b] for b in sk.mine)) + int(sk.nas2.sum())
+        h2d = atoms_mine * (24 + 4) + sig.nbytes
+        d2h = sum(int(v.numel()) * 8 for v in host.values()) + yh.numel() * 8
+        del host
 
-    # ---- reduce over ranks ---------------------------------------------------------------------
-    vals = torch.tensor([t_total_ms, t_slatm_ms, t_kernel_ms, e2e_ms or 0.0], dtype=torch.float64, device=dev)
+    # ---- reduce over ranks ----------------------------------------------------------------------------------------
+    vals = torch.tensor([t_total_ms, e2e_ms or 0.0] + phases, dtype=torch.float64, device=dev)
+    sums = torch.tensor([float(h2d), float(d2h), float(sk.unique_elements(S)), kt_exec, float(launches)], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(vals, op=dist.ReduceOp.MAX)
-    t_total_ms, t_slatm_ms, t_kernel_ms, e2e_max = [float(v) for v in vals.cpu()]
+        dist.all_reduce(sums, op=dist.ReduceOp.SUM)
+    vals = [float(v) for v in vals.cpu()]
+    t_total_ms, e2e_max, phases = vals[0], vals[1], vals[2:]
+    h2d_all, d2h_all, elems_all, kt_exec_all, launches_all = [float(v) for v in sums.cpu()]
     ms_per_step = t_total_ms / args.steps
-    elems_rank = S * args.n_test * args.n_train
-    atoms_rank = int(train[0].sum() + test[0].sum())
+    ph = dict(zip(PH, phases))
+    atoms_all = int(train[0].sum() + test[0].sum())
 
     if rank == 0:
-        # algorithmic work of the dominant kernel (pair_tile_kernel<DOT,LOCAL>): 2 * sum_z D_z n1_z n2_z
         p = L.slatm_params(mb, **{k: SLATM_KW[k] for k in SLATM_KW})
         nel = 5
         d_z = {z: nel * p.nx2 + (nel * (nel + 1) // 2) * p.nx3 for z in (1, 6, 7, 8, 9)}
+        # algorithmic FP64 flops of the contraction: 2 sum_z D_z n1_z n2_z; symmetric K(train, train): half
         flops = 0.0
         for z in d_z:
-            flops += 2.0 * d_z[z] * float((test[1] == z).sum()) * float((train[1] == z).sum())
-        peak_tf = fp64_peak_tflops(torch)
-        ach_tf = flops / (t_kernel_ms * 1e-3) / 1e12
+            n1z, n2z = float((train[1] == z).sum()), float((test[1] == z).sum())
+            flops += 2.0 * d_z[z] * (n1z * (n1z + 1) / 2 + n2z * n1z)
         peaks = {}
         try:
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
         except Exception:
             pass
         hbm_peak = peaks.get("hbm_gbs", 6650.0)
-        # algorithmic bytes of the aSLATM phase: the packed FP64 operand 8 * sum_z D_z(padded to 16) * A_z; the
-        # int8 digit planes written next to it (7 B per element) are an implementation detail of the default engine
-        slatm_bytes = 0.0
-        for z in d_z:
-            slatm_bytes += 8.0 * (-(-d_z[z] // 16) * 16) * float((test[1] == z).sum() + (train[1] == z).sum())
-        engine = "dmma" if os.environ.get("AQML_PAIR_ENGINE", "") in ("dmma", "fp64") else "i8"
-        exec_flops = kt_exec * ktile_flops  # FP64-equivalent flops of the k-tiles actually contracted
+        t_k_ms = ph["k_train"] + ph["k_test"]     # the contraction phases (i8_pair_kernel + a memset / mirror kernel per tile)
+        nprod = 26 if int(os.environ.get("AQML_I8_PRODUCTS", "22") or 22) >= 26 else 22
+        exec_flops = kt_exec * ktile_flops        # rank 0: FP64-equivalent flops of the k-tiles actually contracted
+        dgemm_tf = fp64_peak_tflops(torch)
         traffic = None
-        try:  # dram__bytes_read+write of one launch, from the committed ncu --set full capture of this command
-            key = "pair_tile_kernel<MODE_DOT,EPI_LOCAL>" if engine == "dmma" else "i8_pair_kernel"
-            tr = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))[key]
-            if args.n_train == 20000 and args.n_test == 2000:
+        try:  # dram__bytes_read+write of the step's i8_pair_kernel launches, from the committed ncu --set full capture
+            tr = json.load(open(os.path.join(ROOT, "profiles", "r02_traffic.json")))["i8_pair_kernel"]
+            if args.n_train == 20000 and args.n_test == 2000 and world == 1:
                 traffic = float(tr["dram_bytes_read"] + tr["dram_bytes_write"])
         except Exception:
             pass
-        roofline = {"bound": "tensor", "achieved": ach_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach_tf / peak_tf,
-                    "traffic": traffic, "traffic_unit": "bytes of DRAM per launch (profiles/r01_traffic.json)",
-                    "algorithmic_flops_per_launch": flops,
-                    # all-zero 16-column k-tiles are skipped exactly: the work actually issued,
-                    # incl. row/column padding, and its share of the dense sweep
-                    "executed_flops_per_launch": exec_flops,
-                    "executed_tflops": exec_flops / (t_kernel_ms * 1e-3) / 1e12,
-                    "executed_frac_of_peak": exec_flops / (t_kernel_ms * 1e-3) / 1e12 / peak_tf,
-                    "ktiles_executed_over_dense": kt_exec / max(kt_dense, 1.0),
-                    "peak_source": "cuBLAS DGEMM 8192^3 best of 10 measured in this run (MEASURED_PEAKS.json has no FP64 entry)"}
-        if engine == "dmma":
-            roofline["kernel"] = "pair_tile_kernel<MODE_DOT,EPI_LOCAL> (FP64 DMMA.8x8x4)"
-            roofline["note"] = ("achieved/frac use the SURVEY 8(d) algorithmic flop count 2*sum_z D_z*n1_z*n2_z; frac > 1 because "
-                                "16-column k-tiles that are all-zero in either 64-row operand block are skipped (exact, "
-                                "bit-identical; counted on the device). Hardware utilisation = executed_frac_of_peak; the FP64 "
-                                "DMMA/DFMA ceiling of the chip is 37.0 TF (profiles/r01_micro_dmma_dfma.txt)")
+        if engine == "i8":
+            pk = C.c_double(0.0)
+            L.call("aqml_measure_i8_peak", C.c_void_p(C.addressof(pk)), L.current_stream())
+            i8_peak = pk.value / 1e12
+            ach = exec_flops * nprod / (t_k_ms * 1e-3) / 1e12
+            roofline = {
+                "bound": "tensor", "achieved": ach, "peak": i8_peak, "unit": "TOP/s (int8 multiply-adds x 2, executed, per GPU)",
+                "frac": ach / i8_peak, "traffic": traffic,
+                "traffic_unit": "bytes of DRAM per step over the i8_pair_kernel launches (profiles/r02_traffic.json)",
+                "kernel": "i8_pair_kernel (tcgen05.mma kind::i8: six 8-bit digit planes, %d exact int32 plane products in TMEM "
+                          "per FP64 product, issued as stacked-N UTCIMMA)" % nprod,
+                "peak_source": "aqml_measure_i8_peak(): UTCIMMA M128 N256 K32, operands resident in shared memory, measured in "
+                               "this run on this GPU (best of 3)",
+                "kernel_ms_per_step": t_k_ms,
+                "int8_ops_per_step": exec_flops * nprod,
+                "ktiles_executed_over_dense": kt_exec / max(kt_dense, 1.0),
+                "algorithmic_fp64_flops_per_step": flops, "executed_fp64_equiv_flops_per_step": exec_flops,
+                "fp64_equiv_tflops": flops / world / (t_k_ms * 1e-3) / 1e12,
+                "dgemm_peak_tflops": dgemm_tf,
+                "fp64_equiv_over_dgemm_peak": flops / world / (t_k_ms * 1e-3) / 1e12 / dgemm_tf,
+                "note": "frac = int8 operations the tensor pipe executed / the pipe's peak measured in this run (<= 1). "
+                        "fp64_equiv_* is a speed-up figure, not a utilisation: SURVEY 8(d) flop count 2*sum_z D_z*n1_z*n2_z "
+                        "(halved for the symmetric K(train,train)) per GPU over the same time, against cuBLAS DGEMM 8192^3 "
+                        "measured in this run; all-zero 16-column k-tiles are skipped exactly (ktiles_executed_over_dense)"}
+            if peaks.get("bf16_tflops"):
+                roofline["frac_of_2x_measured_bf16_burst"] = ach / (2.0 * peaks["bf16_tflops"])
         else:
-            int8_ops = exec_flops * 28.0  # 28 digit-plane products per FP64 product
-            int8_peak = 4.13  # POP/s, tcgen05 kind::i8 at N >= 128 measured on this pool (profiles/r01_micro_i8_umma.txt)
-            roofline["kernel"] = "i8_pair_kernel (tcgen05.mma kind::i8, 7 x 7-bit digit planes, 28 exact int32 products in TMEM)"
-            roofline["int8_pops"] = int8_ops / (t_kernel_ms * 1e-3) / 1e15
-            roofline["int8_peak_pops"] = int8_peak
-            roofline["int8_frac_of_peak"] = roofline["int8_pops"] / int8_peak
-            roofline["int8_frac_of_n64_rate"] = roofline["int8_pops"] / 2.9
-            if peaks.get("bf16_tflops"):  # MEASURED_PEAKS.json: cuBLAS bf16 dense; the int8 pipe does twice that per clock
-                roofline["measured_bf16_tflops"] = peaks["bf16_tflops"]
-                roofline["int8_frac_of_2x_measured_bf16"] = roofline["int8_pops"] * 1e3 / (2.0 * peaks["bf16_tflops"])
-            roofline["note"] = ("FP64-accurate contraction from exact int8 digit-plane products on the 5th-generation tensor "
-                                "cores (DESIGN.md 4.1b): achieved/frac are FP64-EQUIVALENT flops (SURVEY 8(d) count "
-                                "2*sum_z D_z*n1_z*n2_z) against the measured cuBLAS DGEMM peak, so frac > 1 is the point of the "
-                                "design (plus exact skipping of all-zero 16-column k-tiles). Hardware utilisation = "
-                                "int8_frac_of_peak (28 int8 MMAs per FP64 k-tile; an N=64 UTCIMMA is capped at 2.9 POP/s by "
-                                "shared-memory operand bandwidth, int8_frac_of_n64_rate). Same results to <= 1e-10 as the "
-                                "FP64 DMMA engine (AQML_PAIR_ENGINE=dmma), asserted in tests/")
+            ach = exec_flops / (t_k_ms * 1e-3) / 1e12
+            roofline = {"bound": "tensor", "achieved": ach, "peak": dgemm_tf, "unit": "TFLOP/s", "frac": ach / dgemm_tf,
+                        "traffic": None, "kernel": "pair_tile_kernel<MODE_DOT,EPI_LOCAL> (FP64 DMMA.8x8x4), executed flops",
+                        "peak_source": "cuBLAS DGEMM 8192^3 best of 10 measured in this run",
+                        "algorithmic_fp64_flops_per_step": flops, "kernel_ms_per_step": t_k_ms}
+        # aSLATM phase: bytes the kernel has to write -- packed FP64 operand 8 * sum_z D_z(padded to 16) * A_z and,
+        # for the int8 engine, 6 more bytes of digit planes per element; per GPU this is 1/N of the training set + the test set
+        el_all = sum((-(-d_z[z] // 16) * 16) * float((test[1] == z).sum() + (train[1] == z).sum()) for z in d_z)
+        el_rank = sum((-(-d_z[z] // 16) * 16) * float((test[1] == z).sum() + (train[1] == z).sum() / world) for z in d_z)
+        slatm_bytes = 8.0 * el_rank
         line = {
-            "metric": "local_gaussian_kernel_elements_per_sec",
-            "value": world * elems_rank / (ms_per_step * 1e-3), "unit": "kernel elements/s",
-            "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
-            "dtype_detail": ("FP64 in, FP64 out, <= 1e-10 vs the FP64 oracle; default engine: a.b from exact int8 digit-plane products "
-                             "(int32 accumulators) on the tcgen05 tensor cores, norms / exp / sums in FP64; AQML_PAIR_ENGINE=dmma: "
+            "metric": METRIC,
+            "value": elems_all / (ms_per_step * 1e-3), "unit": "kernel elements/s",
+            "n_gpus": world, "steps": args.steps, "warmup": warm, "ms_per_step": ms_per_step,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+            "dtype_detail": ("FP64 in, FP64 out, <= 1e-10 vs the FP64 oracle; a.b from exact int8 digit-plane products (int32 "
+                             "accumulators) on the tcgen05 tensor cores, norms / exp / sums in FP64; AQML_PAIR_ENGINE=dmma: "
                              "FP64 DMMA throughout") if engine == "i8" else "FP64 DMMA throughout",
             "data": "synthetic",
-            "config": {"workload": "config2: 20k train x 2k test QM9-shaped molecules, local aSLATM element-matched "
-                                   "Gaussian kernel, FP64, 4 sigmas; step = coords -> aSLATM(train+test) -> K",
-                       "n_train": args.n_train, "n_test_per_gpu": args.n_test, "atoms_per_gpu": atoms_rank,
+            "config": {"workload": WORKLOAD, "n_train": args.n_train, "n_test": args.n_test, "atoms": atoms_all,
                        "D": int(lib.aqml_slatm_dim(p)), "D_z": d_z[6], "nsigmas": S,
-                       "sharding": "row blocks of K (test molecules) per GPU, no collective",
-                       "l2": "inputs larger than L2 (packed operands + digit planes %.1f GB per step)" % (rep_bytes / 1e9)},
-            "aslatm_atoms_per_sec": world * atoms_rank / (t_slatm_ms * 1e-3),
-            "phases_ms": {"aslatm": t_slatm_ms, "kernel": t_kernel_ms},
-            "gpu_launches": launches,
+                       "elements_per_step": int(elems_all),
+                       "elements_counted": "unique elements: lower triangle (incl. diagonal) of K(train,train) + K(test,train), "
+                                           "x 4 sigmas; diagonal tiles are delivered mirrored",
+                       "sharding": "2N training blocks, rank r owns blocks r and 2N-1-r: its aSLATM, its block rows of the lower "
+                                   "triangle of K(train,train), its columns of K(test,train); NCCL: one broadcast per block "
+                                   "(packed operands), all-reduce MAX (width), all-reduce SUM (prediction)",
+                       "l2": "inputs larger than L2 (packed operands + digit planes %.1f GB per GPU and step)" % (rep_bytes / 1e9)},
+            "aslatm_atoms_per_sec": atoms_all / (ph["aslatm"] * 1e-3),
+            "phases_ms": ph,
+            "gpu_launches": int(launches_all),
             "clocks": clocks,
             "roofline": roofline,
-            "roofline_aslatm": {"bound": "hbm", "kernel": "slatm_units_kernel (packed output) + digit-plane split",
-                                "achieved": slatm_bytes / (t_slatm_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
-                                "frac": slatm_bytes / (t_slatm_ms * 1e-3) / 1e9 / hbm_peak,
-                                "algorithmic_bytes_per_step": slatm_bytes,
+            "roofline_aslatm": {"bound": "hbm", "kernel": "slatm_units_kernel (packed FP64 output) + digit-plane split",
+                                "achieved": slatm_bytes / (ph["aslatm"] * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                                "frac": slatm_bytes / (ph["aslatm"] * 1e-3) / 1e9 / hbm_peak,
+                                "algorithmic_bytes_per_step": slatm_bytes, "digit_plane_bytes_per_step": 6.0 * el_rank,
+                                "whole_problem_bytes": 8.0 * el_all,
                                 "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650"},
+            "prediction_checksum": float(np.abs(y_host).sum()),
         }
         if fp64_engine is not None:
             ef = fp64_engine["ktiles_executed"] * ktile_flops
-            ms = fp64_engine["kernel_ms"]
+            ms = fp64_engine["k_test_ms"]
             line["roofline_fp64_engine"] = {
-                "kernel": "pair_tile_kernel<MODE_DOT,EPI_LOCAL> (FP64 DMMA.8x8x4), AQML_PAIR_ENGINE=dmma, same inputs, kernel only",
-                "kernel_ms": ms, "bound": "tensor", "achieved": flops / (ms * 1e-3) / 1e12, "peak": peak_tf, "unit": "TFLOP/s",
-                "frac": flops / (ms * 1e-3) / 1e12 / peak_tf, "executed_tflops": ef / (ms * 1e-3) / 1e12,
-                "executed_frac_of_peak": ef / (ms * 1e-3) / 1e12 / peak_tf,
-                "speedup_of_default_engine": ms / t_kernel_ms,
-                "aslatm_ms_without_digit_planes": fp64_engine["aslatm_ms"],
-                "aslatm_atoms_per_sec_without_digit_planes": atoms_rank / (fp64_engine["aslatm_ms"] * 1e-3),
-                "note": "the north_star's literal design point (FP64 DMMA tiles): 88 % of the cuBLAS DGEMM peak, tensor pipe 84 % "
-                        "active (profiles/r01_pair_tile_kernel_ncu.txt); kept as the fallback engine"}
+                "kernel": "pair_tile_kernel<MODE_DOT,EPI_LOCAL> (FP64 DMMA.8x8x4), AQML_PAIR_ENGINE=dmma, K(test,train) phase of the "
+                          "same inputs", "k_test_ms": ms, "bound": "tensor", "achieved": ef / (ms * 1e-3) / 1e12, "peak": dgemm_tf,
+                "unit": "TFLOP/s", "frac": ef / (ms * 1e-3) / 1e12 / dgemm_tf,
+                "speedup_of_default_engine": ms / ph["k_test"],
+                "note": "the north_star's literal design point (FP64 DMMA tiles), kept as the fallback engine"}
         if e2e_ms is not None:
-            line["e2e"] = {"value": world * elems_rank / (e2e_max * 1e-3), "unit": "kernel elements/s",
-                           "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": e2e_max}
+            line["e2e"] = {"value": elems_all / (e2e_max * 1e-3), "unit": "kernel elements/s",
+                           "h2d_bytes_per_step": int(h2d_all), "d2h_bytes_per_step": int(d2h_all), "ms_per_step": e2e_max}
         if world == 1 and not args.no_cpu_baseline:
             r = cpu_sample(args, steps=1, warmup=0)
             line["cpu_baseline"] = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}
             line["cpu_baseline"]["aslatm_atoms_per_sec"] = r["aslatm_atoms_per_sec"]
+            line["cpu_baseline"]["phases_ms"] = r["phases_ms"]
         print(json.dumps(line))
+    sk.close()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

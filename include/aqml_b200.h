@@ -170,14 +170,26 @@ int aqml_generate_slatm_batch_dev(const double *coords, const int *zs_dev, const
 typedef struct aqml_rep aqml_rep; /* aSLATM rows grouped by element, columns restricted to the element's support */
 
 /* Contraction engines of the Gaussian kernels (calc_lk_gaussian, fgaussian_kernel and the fused path below).  Default:
- * FP64-accurate a.b from exact int8 digit-plane products on the tcgen05 tensor cores (28 UTCIMMA per FP64 k-tile, int32
- * accumulators in TMEM, i8pair.cuh); the representation then also holds 7 bytes of digit planes per packed element.
+ * FP64-accurate a.b from exact int8 digit-plane products on the tcgen05 tensor cores (six 8-bit digit planes per row, 22
+ * exact int32 plane products in TMEM issued as 8 stacked-N UTCIMMA per 32 columns, i8pair.cuh; AQML_I8_PRODUCTS=26 adds
+ * the rest of the seventh product level); the representation then also holds 6 bytes of digit planes per packed element.
  * Environment AQML_PAIR_ENGINE=dmma selects the FP64 DMMA engine (no digit planes are built).  More than 8 sigmas or rows
- * longer than 65536 columns use the FP64 engine automatically.  Both agree with the reference to <= 1e-10 per element. */
+ * longer than 21840 columns use the FP64 engine automatically.  Both agree with the reference to <= 1e-10 per element. */
 
 /* coords: DEVICE if coords_on_device else HOST; zs, nas HOST.  Asynchronous on `stream`. */
 int aqml_rep_create(const double *coords, int coords_on_device, const int *zs, const int *nas, int nmol,
                     const aqml_slatm_params *p, void *stream, aqml_rep **out);
+/* Same with flags.  Bit 0 (AQML_REP_LAYOUT_ONLY): allocate the representation's storage exactly as a computing call
+ * would but launch nothing (coords may be NULL) -- the contents are then received from the GPU that computed them.
+ * The storage of a representation is ONE device allocation whose layout depends only on (zs, nas, p), so
+ * multi-GPU code generates 1/N of the molecule blocks per rank and ships each block once over NCCL
+ * (aqml_b200/parallel.py::share_reps) instead of recomputing it N times. */
+#define AQML_REP_LAYOUT_ONLY 1
+int aqml_rep_create_ex(const double *coords, int coords_on_device, const int *zs, const int *nas, int nmol,
+                       const aqml_slatm_params *p, int flags, void *stream, aqml_rep **out);
+/* the representation's single device allocation: pointer (DEVICE) and size in bytes */
+int aqml_rep_slab(const aqml_rep *r, void **ptr, int64_t *bytes);
+/* frees on the creation stream after every kernel that read the representation on another stream has finished */
 void aqml_rep_destroy(aqml_rep *r);
 int64_t aqml_rep_bytes(const aqml_rep *r);
 /* K DEVICE row-major (nsigmas, r1.nmol, r2.nmol), element matched; sigmas HOST (nsigmas, zmax).
@@ -203,6 +215,10 @@ int64_t aqml_launch_count(void);
  * over all tiles since the last reset (all-zero k-tiles are skipped exactly);
  * synchronises the device. */
 int aqml_pair_stats(int64_t *executed_ktiles, int64_t *dense_ktiles, int reset);
+/* Peak rate of the int8 tensor pipe (tcgen05.mma kind::i8, M 128, N 256, K 32, operands resident in shared
+ * memory), measured now on the current device: int8 multiply-add operations (2 per product) per second.
+ * bench.py divides the pair kernel's executed int8 operations by this for `roofline.frac`.  Blocks ~10 ms. */
+int aqml_measure_i8_peak(double *ops_per_s, void *stream);
 /* CTA tile of the pair kernels: bm x bn atom pairs, bk columns per k-tile (2*bm*bn*bk flops each) */
 void aqml_tile_shape(int *bm, int *bn, int *bk);
 

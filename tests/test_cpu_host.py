@@ -138,40 +138,56 @@ def test_block_driver_job_ids():
     assert ms.nzs.tolist() == [[2, 0, 1], [4, 1, 0]] and len(ms.nas1) == 1 and len(ms.nas2) == 1
 
 
+def _digit_planes(X):
+    """i8_rowexp_kernel + i8_slice_kernel (aqml_b200/csrc/i8pair.cuh) in NumPy: six signed 8-bit digits per element."""
+    m = np.abs(X).max(axis=1)
+    f, e0 = np.frexp(m)
+    e = np.where(m > 0, e0 + np.where(f < 0.996, 1, 2), 0)          # |x| 2^-e < 0.498
+    t = X * np.exp2(-e.astype(float))[:, None]
+    qs = []
+    for _ in range(6):
+        u = t * 256.0
+        q = np.clip(np.floor(u + 128.0 / 255.0), -128, 127)
+        t = u - q                                                    # exact, in [-128/255, 127/255)
+        qs.append(q.astype(np.int64))
+    return qs, e, t
+
+
+def _digit_dot(qa, ea, qb, eb, full6=False):
+    """The 22 (26) plane products, exact integer accumulation per level, the epilogue's hi / lo recombination."""
+    keep = (lambda i, j: i + j <= 6) if full6 else (lambda i, j: i + j <= 5 or (i == 3 and j == 3))
+    P = [sum(qa[i] @ qb[g - i].T for i in range(6) if 0 <= g - i < 6 and keep(i, g - i)) for g in range(7)]
+    assert all(np.abs(p).max() < 2 ** 31 for p in P)
+    hi = (P[0] << 16) + (P[1] << 8) + P[2]
+    lo = (P[3] << 24) + (P[4] << 16) + (P[5] << 8) + P[6]
+    d = lo.astype(np.float64) * 2.0 ** -32 + hi.astype(np.float64)
+    return d * np.exp2((ea[:, None] + eb[None, :] - 32).astype(float))
+
+
 def test_digit_plane_algebra():
-    """The arithmetic behind the int8 tensor engine (aqml_b200/csrc/i8pair.cuh), restated in NumPy: 7 signed 7-bit digit
-    planes per row, 28 plane products, exact integer accumulation, Horner recombination -- against the FP64 dot product."""
+    """The arithmetic behind the int8 tensor engine (aqml_b200/csrc/i8pair.cuh), restated in NumPy: 6 signed 8-bit digit
+    planes per row, 22 plane products (levels i + j <= 5 and the square (3,3)), exact integer accumulation, hi / lo
+    recombination -- against the FP64 dot product; every digit must fit an int8."""
     rng = np.random.default_rng(11)
     n, D = 40, 1500
     X = rng.normal(size=(n, D)) * 10.0 ** rng.integers(-6, 2, size=(n, D))
     X[:, ::5] = 0.0
     X[3] = 0.0
-
-    def planes(X):
-        m = np.abs(X).max(axis=1)
-        e = np.where(m > 0, np.frexp(m)[1] + 1, 0)                 # |x| 2^-e <= 1/2
-        t = X * np.exp2(-e.astype(float))[:, None]
-        qs = []
-        for _ in range(7):
-            u = t * 128.0
-            q = np.rint(u)
-            t = u - q                                              # exact, |t| <= 1/2
-            qs.append(q.astype(np.int64))
-        return qs, e, t
-
-    qs, e, resid = planes(X)
-    assert all(np.abs(q).max() <= 64 for q in qs)                   # fits int8 with room to spare
-    recon = sum(q * 128.0 ** -(s + 1) for s, q in enumerate(qs)) * np.exp2(e.astype(float))[:, None]
-    assert np.all(np.abs(recon - X) <= np.exp2(e.astype(float) - 50)[:, None])
-    # P_g = sum_{i+j=g} q_i q_j^T, exact in int32 for rows of this length
-    P = [sum(qs[i] @ qs[g - i].T for i in range(g + 1)) for g in range(7)]
-    assert all(np.abs(p).max() < 2 ** 31 for p in P)
-    hi = (P[0] << 14) + (P[1] << 7) + P[2]
-    lo = (P[3] << 21) + (P[4] << 14) + (P[5] << 7) + P[6]
-    dot = (hi * 2.0 ** -14 + lo * 2.0 ** -42) * np.exp2((e[:, None] + e[None, :] - 14).astype(float))
+    X[4, :64] = (rng.integers(-128, 128, size=64) + 0.5) / 256.0 * 3.9   # ties at digit boundaries
+    X[5] = X[6] * (1 + 1e-9)                                              # a ~ b: the level-6 square does not average out
+    qs, e, resid = _digit_planes(X)
+    assert all(q.min() >= -128 and q.max() <= 127 for q in qs)
+    assert np.all(resid >= -128.0 / 255.0 - 1e-12) and np.all(resid < 127.0 / 255.0 + 1e-12)
+    recon = sum(q * 256.0 ** -(s + 1) for s, q in enumerate(qs)) * np.exp2(e.astype(float))[:, None]
+    assert np.all(np.abs(recon - X) <= 0.503 * np.exp2(e.astype(float) - 48)[:, None])
     exact = X @ X.T
     scale = np.sqrt(np.outer((X * X).sum(1), (X * X).sum(1)))       # |a||b|
-    assert np.all(np.abs(dot - exact) <= 1e-13 * np.maximum(scale, 1e-300))
+    err22 = np.abs(_digit_dot(qs, e, qs, e) - exact) / np.maximum(scale, 1e-300)
+    err26 = np.abs(_digit_dot(qs, e, qs, e, full6=True) - exact) / np.maximum(scale, 1e-300)
+    assert err22.max() <= 2e-13 and err26.max() <= 2e-14, (err22.max(), err26.max())
+    # without the (3,3) product the diagonal (a = b) is biased: that is why it is kept
+    P33 = (qs[3] * qs[3]).sum(axis=1) * 256.0 ** -8 * np.exp2(2.0 * e)
+    assert np.median(P33[scale.diagonal() > 0] / scale.diagonal()[scale.diagonal() > 0]) > 1e-14
 
 
 def test_krr_driver_object_reproduces_readme_rows(demo):

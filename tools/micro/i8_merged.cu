@@ -1,0 +1,242 @@
+// Micro-benchmark for the stacked-N schedule of aqml_b200/csrc/i8pair.cuh (round 2):
+//   (1) correctness of ONE UTCIMMA whose B operand is several digit planes stacked along N (N = 256: four planes of 64
+//       rows one behind the other), output slices = consecutive accumulators, against a CPU product;
+//   (2) rate of the 22- / 26-product schedule (8 / 9 MMAs per 32-column stage, M 128, N 64..256) with the operands
+//       resident in shared memory;
+//   (3) the same inside the real main loop: a producer thread refills a 4-stage ring with cp.async.bulk (36 KB per
+//       stage, L2 resident source), the MMA thread consumes it -- what shared-memory bandwidth and the L2 leave of (2).
+//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o i8_merged tools/micro/i8_merged.cu && ./i8_merged
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
+#include <cuda_runtime.h>
+
+#define CK(x) do { cudaError_t e = (x); if (e != cudaSuccess) { printf("CUDA error %s at %d\n", cudaGetErrorString(e), __LINE__); exit(1); } } while (0)
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *b, int count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(b)), "r"(count)); }
+__device__ __forceinline__ bool mbar_try_wait(uint64_t *b, uint32_t phase) {
+    uint32_t ok;
+    asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}" : "=r"(ok) : "r"(smem_u32(b)), "r"(phase) : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *b, uint32_t phase) {
+    for (long long it = 0; !mbar_try_wait(b, phase); it++)
+        if (it > 200000000ll) { printf("mbarrier timeout\n"); __trap(); }
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *b, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(b)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ uint64_t smem_desc(uint32_t addr, uint32_t lbo, uint32_t sbo) {
+    return (uint64_t)((addr & 0x3FFFF) >> 4) | ((uint64_t)(lbo >> 4) << 16) | ((uint64_t)(sbo >> 4) << 32) | (1ull << 46);
+}
+__device__ __forceinline__ void umma_i8(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+    asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n}" ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t *bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__host__ __device__ constexpr uint32_t make_idesc(int M, int N) { return (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24); }
+
+constexpr int S = 6, A_CHUNK = S * 2048, B_CHUNK = S * 1024, STAGE = 2 * (A_CHUNK + B_CHUNK);
+
+// the kernel's stage layout: [k-chunk c][plane p][row][16 B] for A (128 rows) then for B (64 rows)
+__device__ __host__ inline int offA(int c, int p, int row, int kb) { return c * A_CHUNK + p * 2048 + row * 16 + kb; }
+__device__ __host__ inline int offB(int c, int p, int row, int kb) { return 2 * A_CHUNK + c * B_CHUNK + p * 1024 + row * 16 + kb; }
+
+template <int VAR>
+__device__ __forceinline__ void issue_stage(uint32_t tb, uint32_t st, uint32_t first) {
+    constexpr int NMMA = VAR ? 9 : 8;
+    constexpr int mi[9] = {0, 0, 1, 1, 2, VAR ? 2 : 3, VAR ? 3 : 4, VAR ? 4 : 5, 5};
+    constexpr int mj[9] = {0, 4, 0, VAR ? 4 : 3, 0, VAR ? 3 : 0, 0, 0, 0};
+    constexpr int mn[9] = {4, 2, VAR ? 4 : 3, 2, VAR ? 3 : 4, VAR ? 2 : 4, VAR ? 4 : 2, VAR ? 3 : 1, 2};
+    const uint64_t da = smem_desc(st, A_CHUNK, 128), db = smem_desc(st + 2 * A_CHUNK, B_CHUNK, 128);
+#pragma unroll
+    for (int m = 0; m < NMMA; m++)
+        umma_i8(tb + (mi[m] + mj[m]) * 64, da + (uint64_t)(mi[m] * 2048 >> 4), db + (uint64_t)(mj[m] * 1024 >> 4), make_idesc(128, 64 * mn[m]),
+                (first && mi[m] == 0) ? 0u : 1u);
+}
+
+// (1) one stage of the schedule on real data; C[g][row][col] = level sums P_g
+template <int VAR>
+__global__ void __launch_bounds__(128) check_kernel(const int8_t *stage_img, int32_t *C) {
+    extern __shared__ __align__(1024) int8_t sm[];
+    __shared__ __align__(8) uint64_t bar;
+    __shared__ uint32_t tmem_base;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    for (int i = tid; i < STAGE; i += 128) sm[i] = stage_img[i];
+    if (tid == 0) { mbar_init(&bar, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base)), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tb = tmem_base;
+    {   // accumulator 6 is not cleared by plane 0: zero it like the kernel's epilogue does
+        const uint32_t taddr = tb + ((uint32_t)(warp * 32) << 16) + 6 * 64;
+        for (int c0 = 0; c0 < 64; c0 += 8) {
+            asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%1,%1,%1,%1,%1,%1,%1};" ::"r"(taddr + c0), "r"(0u) : "memory");
+        }
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    if (tid == 0) {
+        issue_stage<VAR>(tb, smem_u32(sm), 1u);
+        umma_commit(&bar);
+    }
+    mbar_wait(&bar, 0);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    for (int c0 = 0; c0 < 7 * 64; c0 += 8) {
+        uint32_t v[8];
+        const uint32_t taddr = tb + ((uint32_t)(warp * 32) << 16) + c0;
+        asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                     : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]) : "r"(taddr));
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        for (int j = 0; j < 8; j++) C[((c0 + j) / 64 * 128 + tid) * 64 + (c0 + j) % 64] = (int32_t)v[j];
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tb), "r"(512u) : "memory");
+}
+
+// (2) / (3): warp 0 lane 0 = producer (if fill), warp 1 lane 0 = MMA issuer
+template <int VAR>
+__global__ void __launch_bounds__(128) rate_kernel(int rounds, int fill, const int8_t *src, long long src_bytes, long long *cycles) {
+    extern __shared__ __align__(1024) int8_t sm[];
+    __shared__ __align__(8) uint64_t full[4], empty[4], done;
+    __shared__ uint32_t tmem_base;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    for (int i = tid; i < 4 * STAGE; i += 128) sm[i] = (int8_t)((i * 37 + 11) % 255 - 127);
+    if (tid == 0) {
+        for (int s = 0; s < 4; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        mbar_init(&done, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base)), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tb = tmem_base;
+    const long long t0 = clock64();
+    if (warp == 0 && (tid & 31) == 0 && fill) {
+        // every CTA walks its own window of the source (like the kernel: tiles of different rows), L2 resident
+        long long pos = ((long long)blockIdx.x * 7919 * STAGE) % (src_bytes - STAGE);
+        for (int r = 0; r < rounds; r++) {
+            const int s = r & 3;
+            if (r >= 4) mbar_wait(&empty[s], ((r >> 2) - 1) & 1);
+            mbar_expect_tx(&full[s], STAGE);
+            int8_t *st = sm + s * STAGE;
+            for (int c = 0; c < 2; c++) {  // the kernel's copies: A chunk 12 KB, B chunk as 6 x 1 KB
+                bulk_g2s(st + c * A_CHUNK, src + pos + c * A_CHUNK, A_CHUNK, &full[s]);
+                for (int p = 0; p < S; p++) bulk_g2s(st + 2 * A_CHUNK + c * B_CHUNK + p * 1024, src + pos + 2 * A_CHUNK + c * B_CHUNK + p * 1024, 1024, &full[s]);
+            }
+            pos += STAGE;
+            if (pos + STAGE > src_bytes) pos = 0;
+        }
+    } else if (warp == 1 && (tid & 31) == 0) {
+        for (int r = 0; r < rounds; r++) {
+            const int s = r & 3;
+            if (fill) {
+                mbar_wait(&full[s], (r >> 2) & 1);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            }
+            issue_stage<VAR>(tb, smem_u32(sm + s * STAGE), 0u);
+            if (fill) umma_commit(&empty[s]);
+        }
+        umma_commit(&done);
+        mbar_wait(&done, 0);
+        cycles[blockIdx.x] = clock64() - t0;
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tb), "r"(512u) : "memory");
+}
+
+template <int VAR>
+static void run_check() {
+    std::vector<int8_t> img(STAGE);
+    srand(7 + VAR);
+    for (auto &v : img) v = (int8_t)(rand() % 256 - 128);
+    int8_t *dimg; int32_t *dC;
+    CK(cudaMalloc(&dimg, STAGE)); CK(cudaMalloc(&dC, 7 * 128 * 64 * 4));
+    CK(cudaMemcpy(dimg, img.data(), STAGE, cudaMemcpyHostToDevice));
+    CK(cudaFuncSetAttribute(check_kernel<VAR>, cudaFuncAttributeMaxDynamicSharedMemorySize, STAGE));
+    check_kernel<VAR><<<1, 128, STAGE>>>(dimg, dC);
+    CK(cudaDeviceSynchronize());
+    std::vector<int32_t> C(7 * 128 * 64);
+    CK(cudaMemcpy(C.data(), dC, C.size() * 4, cudaMemcpyDeviceToHost));
+    long long bad = 0;
+    for (int g = 0; g < 7; g++)
+        for (int r = 0; r < 128; r++)
+            for (int c = 0; c < 64; c++) {
+                long long ref = 0;
+                for (int i = 0; i < 6; i++) {
+                    const int j = g - i;
+                    if (j < 0 || j >= 6) continue;
+                    if (!(VAR ? (i + j <= 6) : (i + j <= 5 || (i == 3 && j == 3)))) continue;
+                    for (int k = 0; k < 32; k++) ref += (long long)img[offA(k >> 4, i, r, k & 15)] * img[offB(k >> 4, j, c, k & 15)];
+                }
+                if (ref != C[(g * 128 + r) * 64 + c]) bad++;
+            }
+    printf("check stacked-N schedule, %d products (%d MMAs): %s (%lld mismatches of %d)\n", VAR ? 26 : 22, VAR ? 9 : 8, bad ? "FAILED" : "OK", bad, 7 * 128 * 64);
+    cudaFree(dimg); cudaFree(dC);
+}
+
+template <int VAR>
+static void run_rate(int fill, const int8_t *src, long long src_bytes) {
+    int dev = 0, sms = 0;
+    CK(cudaGetDevice(&dev));
+    CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    long long *dcy;
+    CK(cudaMalloc(&dcy, sms * 8));
+    CK(cudaFuncSetAttribute(rate_kernel<VAR>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * STAGE));
+    const int rounds = 20000;
+    rate_kernel<VAR><<<sms, 128, 4 * STAGE>>>(200, fill, src, src_bytes, dcy);
+    CK(cudaDeviceSynchronize());
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+    CK(cudaEventRecord(e0));
+    rate_kernel<VAR><<<sms, 128, 4 * STAGE>>>(rounds, fill, src, src_bytes, dcy);
+    CK(cudaEventRecord(e1));
+    CK(cudaDeviceSynchronize());
+    float ms = 0;
+    CK(cudaEventElapsedTime(&ms, e0, e1));
+    std::vector<long long> cy(sms);
+    CK(cudaMemcpy(cy.data(), dcy, sms * 8, cudaMemcpyDeviceToHost));
+    const int nprod = VAR ? 26 : 22;
+    const double ops = 2.0 * 128 * 64 * 32 * nprod * (double)rounds * sms;
+    printf("%d products, %s: %.3f ms, %.2f POPS (int8), %.1f clk per 32-column stage (SM0), FP64-equivalent %.1f TF%s\n", nprod,
+           fill ? "4-stage ring refilled by cp.async.bulk (36 KB per stage)" : "operands resident in shared memory", ms, ops / (ms * 1e-3) / 1e15,
+           (double)cy[0] / rounds, ops / nprod / (ms * 1e-3) / 1e12,
+           fill ? "" : "");
+    if (fill) printf("    L2 -> SM traffic %.2f TB/s\n", (double)STAGE * rounds * sms / (ms * 1e-3) / 1e12);
+    cudaFree(dcy);
+}
+
+int main() {
+    run_check<0>();
+    run_check<1>();
+    const long long src_bytes = 64ll << 20;  // 64 MB: L2 resident (126 MB)
+    int8_t *src;
+    CK(cudaMalloc(&src, src_bytes));
+    CK(cudaMemset(src, 1, src_bytes));
+    run_rate<0>(0, src, src_bytes);
+    run_rate<1>(0, src, src_bytes);
+    run_rate<0>(1, src, src_bytes);
+    run_rate<1>(1, src, src_bytes);
+    cudaFree(src);
+    return 0;
+}
