@@ -94,7 +94,8 @@ struct I8Meta {  // everything the roles need to know about one tile
     int segA[I8_BM], expA[I8_BM];
     double normA[I8_BM];
     int segB[I8_BN + 1];
-    double normB[I8_BN], m2sB[I8_BN];  // |b|^2, -2 * 2^(e_b - 8)
+    double normB[I8_BN];               // |b|^2
+    int expB[I8_BN];                   // e_b
     unsigned short kt[KT_LIST_MAX + 2];
 };
 
@@ -153,9 +154,34 @@ __device__ __forceinline__ double pow2(int e) {  // 2^e, clamped to the normal r
 }
 }  // namespace i8
 
-// exp: the table-based exp_tab of slatm_units.cuh (9 FP64 instructions).  On this chip FP64 arithmetic and the tensor pipe
-// exclude each other (profiles/r01_micro_i8_umma.txt), so every FP64 instruction of the epilogue is time taken from the MMAs.
-__device__ __forceinline__ double i8_exp(double x, const double *tab) { return exp_tab(x, tab); }
+// exp(v), v <= 0 (or -inf, NaN): the table-based exp_tab of slatm_units.cuh with every special case and the final scaling
+// done on the bit patterns -- 9 FP64 instructions.  While UTCIMMA stream through the tensor pipe the FP64 pipe delivers only
+// ~0.3 warp-instructions per clock and SM (2 when the tensor pipe idles; profiles/r02_micro_contention.txt), i.e. every FP64
+// instruction of the epilogue costs ~4 clk per tile and warp: the epilogue is written for few FP64 instructions.
+__device__ __forceinline__ double i8_exp(double v, const double *tab) {
+    const double magic = 6755399441055744.0;
+    double t = fma(v, 23637.115549924776 /* 2^14 log2(e) */, magic);
+    const int n = __double2loint(t);
+    t -= magic;
+    double r = fma(t, -4.2306346131226746e-05 /* ln2 / 2^14, upper 27 bits: t * hi is exact */, v);
+    r = fma(t, -3.384964780863074e-13, r);
+    double p = fma(r, 1.0 / 6.0, 0.5);
+    p = fma(p, r, 1.0);
+    p = fma(p, r, 1.0);
+    const double res = (tab[(n >> 7) & 127] * tab[128 + (n & 127)]) * p;   // in [1, 2.02)
+    int hi = __double2hiint(res) + ((n >> 14) << 20);                     // * 2^(n >> 14): exponent field, n >> 14 >= -1022 below
+    int lo = __double2loint(res);
+    const unsigned vh = (unsigned)__double2hiint(v);
+    if ((vh & 0x7ff00000u) == 0x7ff00000u) {              // -inf -> 0, NaN -> NaN
+        const bool isnan = ((vh & 0xfffffu) | (unsigned)__double2loint(v)) != 0u;
+        hi = isnan ? 0x7ff80000 : 0;
+        lo = 0;
+    } else if (vh > 0xC0862000u) {                         // v < -708: 0 (the reference's exp gives a denormal down to -745)
+        hi = 0;
+        lo = 0;
+    }
+    return __hiloint2double(hi, lo);
+}
 
 // sum the lanes of each A molecule (contiguous lanes, last lane run_end) and add the heads' totals into K
 __device__ __noinline__ void i8_flush(double r, int lane, int run_end, bool head, double *dst) {
@@ -337,7 +363,7 @@ __global__ void __launch_bounds__(I8_THREADS, 1) i8_pair_kernel(const I8Params P
                     const int c = i - I8_BM, r = tn * I8_BN + c;
                     M.segB[c] = (r < G.nrB) ? G.segB[r] : -1;
                     M.normB[c] = (r < G.nrB) ? G.normB[r] : 0.0;
-                    M.m2sB[c] = -2.0 * i8::pow2(((r < G.nrB) ? G.expB[r] : 0) - 8);
+                    M.expB[c] = (r < G.nrB) ? G.expB[r] : 0;
                 }
             }
             if (!__any_sync(0xffffffffu, any)) continue;  // no wanted row in this tile (row-block sharding)
@@ -484,7 +510,7 @@ __global__ void __launch_bounds__(I8_THREADS, 1) i8_pair_kernel(const I8Params P
             const unsigned above = (lane == 31) ? 0u : (heads >> (lane + 1));
             const int run_end = above ? (lane + __ffs(above) - 1) : 31;
             const double na = M.normA[row];
-            const double sa = i8::pow2(M.expA[row] - 24);  // 2^(e_a - 8) * 2^-16 (the scale of `hi` below)
+            const int ea = M.expA[row];
             const int growA = M.tm * I8_BM + row;
             const unsigned lastmask = __ballot_sync(0xffffffffu, lane < EC && (lane == EC - 1 || M.segB[cbase + lane + 1] != M.segB[cbase + lane]));
             const long long e0 = clock64();
@@ -524,17 +550,21 @@ __global__ void __launch_bounds__(I8_THREADS, 1) i8_pair_kernel(const I8Params P
                 if (lane == 0) i8::mbar_arrive(&S.meta_empty[b]);
                 continue;
             }
-            // d^2 of my 16 pairs
+            // d^2 of my 16 pairs: a.b = 2^(ea + eb - 64) V, V = hi 2^32 + lo; W = V >> 16 has <= 62 bits, ONE conversion to double
+            // (rounding 2^-53 of a.b, as in an FP64 dot product), one FMA with the power of two built from the exponents
             double x[EC];
 #pragma unroll
             for (int j = 0; j < EC; j++) {
                 const int col = cbase + j;
-                const double d = fma((double)lo[j], 2.3283064365386963e-10 /* 2^-32 */, (double)hi[j]);  // 2^16 sum_g P_g 256^-g
-                double xx = fma(d * sa, M.m2sB[col], na + M.normB[col]);  // |a|^2 + |b|^2 - 2 a.b
-                xx = (xx < 0.0) ? 0.0 : xx;                                   // clamp rounding noise, keep NaN
+                const long long W = (hi[j] << 16) + (lo[j] >> 16);
+                const int e2 = max(-1022, min(1023, ea + M.expB[col] - 47));                 // -2 a.b = W * -2^(ea + eb - 47)
+                const double sc = __hiloint2double((int)(0x80000000u | ((unsigned)(e2 + 1023) << 20)), 0);
+                double xx = fma((double)W, sc, na + M.normB[col]);                           // |a|^2 + |b|^2 - 2 a.b
+                int xh = __double2hiint(xx), xl = __double2loint(xx);
+                if (xh < 0 && (xh & 0x7ff00000) != 0x7ff00000) { xh = 0; xl = 0; }           // clamp rounding noise, keep NaN
                 // pairs that do not count: on / below the diagonal of a symmetric kernel, padding rows / columns
-                if ((M.sym && M.tn * I8_BN + col <= growA) || sr < 0 || M.segB[col] < 0) xx = __longlong_as_double(0x7ff0000000000000LL);
-                x[j] = xx;
+                if ((M.sym && M.tn * I8_BN + col <= growA) || sr < 0 || M.segB[col] < 0) { xh = 0x7ff00000; xl = 0; }
+                x[j] = __hiloint2double(xh, xl);
             }
             // phase 2: per sigma exp (chain: squarings of the previous sigma's values, in place), then the sums over
             // molecule pairs: column runs sequentially in registers, row runs by a segmented shuffle reduction, one RED

@@ -226,6 +226,7 @@ unsigned long long *pair_stats_buffer();
 // power-of-two multiples of the widest sigma's row; otherwise every sigma gets its own exp.
 void plan_sigma_chain(PairParams &P, const std::vector<double> &isig) {
     P.chain = 0;
+    P.isig_host = isig.data();
     const int S = P.nsig, Z = P.zstride;
     if (S < 2 || S > 16 || Z < 1 || (int)isig.size() != S * Z) return;
     std::vector<int> ord(S);
@@ -239,12 +240,16 @@ void plan_sigma_chain(PairParams &P, const std::vector<double> &isig) {
             if (!(std::isfinite(a) && std::isfinite(b)) || b == 0.0) return;
             int e = 0;
             double m = std::frexp(a / b, &e);           // a/b = m * 2^e, m in [0.5,1)
-            if (m != 0.5 || e - 1 < 0 || e - 1 > 16) return;  // ratio must be 2^k, k >= 0
+            if (m != 0.5 || e - 1 < 0 || e - 1 > 4) return;   // ratio must be 2^k, 0 <= k <= 4 (the kernels unroll <= 4 squarings per step)
             if (a != std::ldexp(b, e - 1)) return;       // exact
             if (k < 0) k = e - 1; else if (k != e - 1) return;
         }
         nsq[i] = k;  // ratio 2^k: k squarings ( x -> x^(2^k) )
     }
+    // the narrowest sigma's value is the widest one's after sum(k) squarings: its error is 2^sum(k) times that of the exp
+    int total = 0;
+    for (int i = 1; i < S; i++) total += nsq[i];
+    if (total > 8) return;
     P.chain = 1;
     for (int i = 0; i < S; i++) { P.order[i] = ord[i]; P.nsq[i] = nsq[i]; }
 }

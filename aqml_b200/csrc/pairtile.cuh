@@ -90,7 +90,11 @@ struct PairParams {
     unsigned long long *stats;  // [2] executed / dense k-tile counts (summed over tiles), or null
     // Sigma chain: when every sigma is an exact power-of-two multiple of the widest one (the usual
     // coefficient ladder 0.5, 1, 2, 4 ...), exp(v*isig[s]) = exp(v*isig[base])^(4^k) exactly in real
-    // arithmetic: one exp for the widest sigma, then 2k squarings each (<= 64 ulp, 1e-14 relative).
+    // arithmetic: one exp for the widest sigma, then squarings.  Every squaring doubles the relative error of the one exp,
+    // so the chain is used only while the squarings ADD UP to <= 8 over the whole ladder (2^8 ulp = 3e-14 in FP64, ~1e-11
+    // in the int8 engine's FP32-pair arithmetic); wider ladders get one exp per sigma.
+    const double *isig_host;  // host copy of isig, valid during the call (set by plan_sigma_chain; the int8 engine derives its
+                              // fixed-point constants from it)
     int chain;            // 1: use order/nsq below
     int order[16];        // evaluation order: widest sigma first
     int nsq[16];          // squarings that take order[i-1]'s values to order[i]'s

@@ -732,10 +732,10 @@ static void i8_fill_planes(const double *x, long long ld, int nr, cudaStream_t s
     AQML_LAUNCH_CHECK();
 }
 
-static void launch_i8(std::vector<I8Group> &gs, const PairParams &PP, Workspace &ws, int store = 0) {
+static bool launch_i8(std::vector<I8Group> &gs, const PairParams &PP, Workspace &ws, int store = 0) {
     int total = 0;
     for (auto &g : gs) { g.tile_begin = total; total += g.tilesM * g.tilesN; }
-    if (total == 0) return;
+    if (total == 0) return true;
     I8Params P;
     memset(&P, 0, sizeof(P));
     P.groups = ws.upload(gs); P.ngroups = (int)gs.size();
@@ -768,10 +768,11 @@ static void launch_i8(std::vector<I8Group> &gs, const PairParams &PP, Workspace 
         fprintf(stderr, "[i8] epilogue warp per tile: waiting for accumulators %.0f clk, TMEM drain %.0f clk, exp + sums %.0f clk\n", (double)h[5] / total,
                 (double)h[6] / total, (double)h[7] / total);
     }
+    return true;
 }
 
 // fused path: the representations carry their digit planes
-static void run_pairs_i8(const aqml_rep *r1, const aqml_rep *r2, int zmax, int row0, int nrows, bool sym, const PairParams &PP, Workspace &ws) {
+static bool run_pairs_i8(const aqml_rep *r1, const aqml_rep *r2, int zmax, int row0, int nrows, bool sym, const PairParams &PP, Workspace &ws) {
     std::vector<I8Group> gs;
     for (const auto &a : r1->els)
         for (const auto &b : r2->els) {
@@ -789,7 +790,7 @@ static void run_pairs_i8(const aqml_rep *r1, const aqml_rep *r2, int zmax, int r
             g.zcol = z - 1; g.segA_off = row0; g.segA_n = nrows; g.sym = sym ? 1 : 0;
             gs.push_back(g);
         }
-    launch_i8(gs, PP, ws);
+    return launch_i8(gs, PP, ws);
 }
 
 }  // namespace aqml
@@ -818,8 +819,7 @@ bool aqml::i8_local_pairs(const std::vector<I8Pair> &pairs, const PairParams &PP
         g.zcol = pr.zcol; g.segA_off = 0; g.segA_n = 0x7fffffff; g.sym = 0;
         gs.push_back(g);
     }
-    launch_i8(gs, PP, ws);
-    return true;
+    return launch_i8(gs, PP, ws);
 }
 
 bool aqml::i8_global_pair(const I8Side &a, int na, const I8Side &b, int nb, const PairParams &PP, Workspace &ws) {
@@ -845,8 +845,7 @@ bool aqml::i8_global_pair(const I8Side &a, int na, const I8Side &b, int nb, cons
     g.tilesM = (a.nr + I8_BM - 1) / I8_BM; g.tilesN = (b.nr + I8_BN - 1) / I8_BN;
     g.zcol = 0; g.segA_off = 0; g.segA_n = 0x7fffffff; g.sym = 0;
     std::vector<I8Group> gs{g};
-    launch_i8(gs, PP, ws, 1);
-    return true;
+    return launch_i8(gs, PP, ws, 1);
 }
 
 namespace aqml {
@@ -1151,8 +1150,8 @@ int aqml_rep_local_gaussian(const aqml_rep *r1, const aqml_rep *r2, const double
         P.isig = ws.upload(isig); P.nsig = nsigmas; P.zstride = zmax;
         plan_sigma_chain(P, isig);
         P.out = K; P.ldo = r2->nmol; P.slab = (long long)nrows * r2->nmol;
-        if (use_i8(r1, r2, nsigmas)) run_pairs_i8(r1, r2, zmax, row0, nrows, false, P, ws);
-        else run_pairs_public(MODE_DOT, EPI_LOCAL, groups, P, ws);
+        if (!(use_i8(r1, r2, nsigmas) && run_pairs_i8(r1, r2, zmax, row0, nrows, false, P, ws)))
+            run_pairs_public(MODE_DOT, EPI_LOCAL, groups, P, ws);
         mark_use(r1, st);
         mark_use(r2, st);
     });
@@ -1189,8 +1188,8 @@ int aqml_rep_local_gaussian_sym(const aqml_rep *r, const double *sigmas, int nsi
         P.isig = ws.upload(isig); P.nsig = nsigmas; P.zstride = zmax;
         plan_sigma_chain(P, isig);
         P.out = K; P.ldo = n; P.slab = (long long)n * n;
-        if (use_i8(r, r, nsigmas)) run_pairs_i8(r, r, zmax, 0, n, true, P, ws);
-        else run_pairs_public(MODE_DOT, EPI_LOCAL, groups, P, ws);
+        if (!(use_i8(r, r, nsigmas) && run_pairs_i8(r, r, zmax, 0, n, true, P, ws)))
+            run_pairs_public(MODE_DOT, EPI_LOCAL, groups, P, ws);
         dim3 grid((n + 31) / 32, (n + 31) / 32, nsigmas);
         symmetrize_kernel<<<grid, 256, 0, st>>>(K, n, nsigmas, ws.upload(diag));
         AQML_LAUNCH_CHECK();

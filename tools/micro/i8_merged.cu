@@ -226,7 +226,100 @@ static void run_rate(int fill, const int8_t *src, long long src_bytes) {
     cudaFree(dcy);
 }
 
-int main() {
+// (4) how do FP64 instructions progress while UTCIMMA of a given N stream through the tensor pipe?  warp 0 lane 0 issues
+// back-to-back MMAs (M 128, N = n_mma, operands resident); warps 1 .. nw run `chains` independent dependent-DFMA chains
+// of `len` steps each and report clk per chain step.  mode 1: DFMA replaced by FFMA (FP32), mode 2: IMAD.
+template <int MODE>
+__global__ void __launch_bounds__(544) contention_kernel(int n_mma, int mma_rounds, int len, int chains, long long *cyc, double *sink) {
+    extern __shared__ __align__(1024) int8_t sm[];
+    __shared__ __align__(8) uint64_t done;
+    __shared__ uint32_t tmem_base;
+    __shared__ volatile int stop;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    for (int i = tid; i < STAGE; i += blockDim.x) sm[i] = (int8_t)((i * 37 + 11) % 255 - 127);
+    if (tid == 0) { mbar_init(&done, 1); stop = 0; asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base)), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tb = tmem_base;
+    const long long t0 = clock64();
+    if (warp == 0) {
+        if (tid == 0 && n_mma > 0) {
+            const uint64_t da = smem_desc(smem_u32(sm), A_CHUNK, 128), db = smem_desc(smem_u32(sm) + 2 * A_CHUNK, B_CHUNK, 128);
+            const uint32_t id = make_idesc(128, n_mma);
+            for (int r = 0; r < mma_rounds; r++) {
+                umma_i8(tb, da, db, id, 1u);
+                umma_i8(tb + 256, da, db, id, 1u);
+            }
+            umma_commit(&done);
+            mbar_wait(&done, 0);
+            cyc[blockIdx.x * 2] = clock64() - t0;
+        }
+    } else {
+        double a[8];
+        float f[8];
+        int q[8];
+        for (int k = 0; k < 8; k++) { a[k] = (double)(tid + k); f[k] = (float)(tid + k); q[k] = tid + k; }
+        const double m = 1.0000000001, c = 1e-12;
+        const long long s0 = clock64();
+        for (int it = 0; it < len; it++) {
+#pragma unroll
+            for (int k = 0; k < 8; k++)
+                if (k < chains) {
+                    if (MODE == 0) a[k] = fma(a[k], m, c);
+                    else if (MODE == 1) f[k] = fmaf(f[k], 1.0000001f, 1e-9f);
+                    else q[k] = q[k] * 3 + 7;
+                }
+        }
+        const long long s1 = clock64();
+        double t = 0;
+        for (int k = 0; k < 8; k++) t += a[k] + f[k] + q[k];
+        if (t == 12345.678) sink[0] = t;
+        if (tid == 32) cyc[blockIdx.x * 2 + 1] = s1 - s0;
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tb), "r"(512u) : "memory");
+}
+
+template <int MODE>
+static void run_contention() {
+    int dev = 0, sms = 0;
+    CK(cudaGetDevice(&dev));
+    CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    long long *dcy; double *dsink;
+    CK(cudaMalloc(&dcy, sms * 16)); CK(cudaMalloc(&dsink, 64));
+    CK(cudaFuncSetAttribute(contention_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, STAGE));
+    const char *name = MODE == 0 ? "DFMA" : MODE == 1 ? "FFMA" : "IMAD";
+    const int len = 4000;
+    for (int nw : {1, 16})
+        for (int chains : {1, 4})
+            for (int n_mma : {0, 64, 128, 256}) {
+                // enough MMAs to outlast the FP warps: assume <= 200 clk per chain step
+                const int mma_rounds = n_mma ? (int)(200.0 * len * 4 / (n_mma / 2 + 16) / 2) : 0;
+                std::vector<long long> cy(sms * 2, 0);
+                CK(cudaMemset(dcy, 0, sms * 16));
+                contention_kernel<MODE><<<sms, 32 * (1 + nw), STAGE>>>(n_mma, mma_rounds, len, chains, dcy, dsink);
+                CK(cudaDeviceSynchronize());
+                CK(cudaMemcpy(cy.data(), dcy, sms * 16, cudaMemcpyDeviceToHost));
+                printf("%s: %2d warps x %d chains, MMA N=%3d: %.1f clk per chain step (FP warp), MMA %.1f clk each\n", name, nw, chains, n_mma,
+                       (double)cy[1] / len, n_mma ? (double)cy[0] / (2.0 * mma_rounds) : 0.0);
+            }
+    cudaFree(dcy); cudaFree(dsink);
+}
+
+int main(int argc, char **argv) {
+    if (argc > 1 && argv[1][0] == 'c') {
+        run_contention<0>();
+        run_contention<1>();
+        run_contention<2>();
+        return 0;
+    }
     run_check<0>();
     run_check<1>();
     const long long src_bytes = 64ll << 20;  // 64 MB: L2 resident (126 MB)
