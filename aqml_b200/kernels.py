@@ -139,6 +139,8 @@ def get_local_kernels_gaussian(x1, x2, zs1, zs2, nas1, nas2, iab, zmax, sigmas, 
     assert np.sum(nas1) == x1.shape[0], "Error in A input"
     assert np.sum(nas2) == x2.shape[0], "Error in B input"
     assert x1.shape[1] == x2.shape[1], "Error in representation sizes"
+    if len(zs1) != x1.shape[0] or len(zs2) != x2.shape[0]:   # raw pointers below: never let a short zs reach the device
+        raise ValueError(f"zs1 / zs2 have {len(zs1)} / {len(zs2)} entries for {x1.shape[0]} / {x2.shape[0]} atoms")
     sig = L.f64(sigmas)
     nsig = len(sig)
     sig = sig.reshape(nsig, -1)

@@ -34,6 +34,10 @@ def generate_slatm_batch(coordinates, nuclear_charges, nas, mbtypes, izeff=False
         if not L.is_tensor(zs):
             zs = torch.as_tensor(L.i32(zs), device=coords.device)
         zs = zs.to(torch.int32).contiguous()
+        # the C ABI only sees raw pointers: a mismatch would read out of bounds on the device
+        if tuple(coords.shape) != (int(zs.shape[0]), 3) or int(nas.sum()) != int(zs.shape[0]):
+            raise ValueError(f"{coords.shape[0]} coordinates, but {int(zs.shape[0])} atom_types "
+                             f"(nas sums to {int(nas.sum())})!")
         rows = coords.shape[0] if local else len(nas)
         out = torch.empty((rows, D), dtype=torch.float64, device=coords.device)
         with torch.cuda.device(coords.device):

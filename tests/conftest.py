@@ -30,3 +30,13 @@ def rel_err(got, ref, floor=None):
     if floor is None:
         floor = 1e-10 * max(np.max(np.abs(ref)), 1e-300)
     return float(np.max(np.abs(got - ref) / np.maximum(np.abs(ref), floor))) if ref.size else 0.0
+
+
+def kernel_rel_err(got, ref):
+    """Per-element RELATIVE error of a kernel matrix (north_star: "1e-10 relative per kernel element").  No floor
+    tied to the largest element: the only floor is where exp itself leaves the normal double range (|ref| < 1e-290:
+    the reference's libm returns denormals down to exp(-745), the device flushes results below 2^-1022 to zero), there
+    the difference is taken absolutely."""
+    got = np.asarray(got, dtype=np.float64)
+    ref = np.asarray(ref, dtype=np.float64)
+    return float(np.max(np.abs(got - ref) / np.maximum(np.abs(ref), 1e-290))) if ref.size else 0.0

@@ -253,3 +253,15 @@ def test_rkrr_driver_object_matches_function(demo):
     ys = obj.ys[:n1]
     pred = K.multi_fidelity_predict(k1, k2, ys, [16, 16], obj.nzs[:n1].astype(float), obj.nzs[n1:].astype(float), 1e-6)
     assert abs((pred[0] - obj.ys[n1, 1]) - obj.maes[-1]) < 1e-8
+
+
+def test_shape_validation_before_any_device_call():
+    """mismatched coords / zs / nas must raise in Python -- the C ABI only sees raw pointers."""
+    from aqml_b200 import fused, kernels
+    x = np.zeros((5, 8))
+    with pytest.raises(ValueError):
+        kernels.get_local_kernels_gaussian(x, x, [1, 1, 1], [1, 1, 1, 1, 1], [5], [5], False, 1, np.ones((1, 1)))
+    with pytest.raises(ValueError):
+        fused.PackedRep(np.zeros((4, 3)), [1, 1, 1, 1, 1], [5], [[1], [1, 1]])
+    with pytest.raises(ValueError):
+        fused.PackedRep(np.zeros((5, 3)), [1, 1, 1, 1], [5], [[1], [1, 1]])

@@ -82,3 +82,71 @@ def test_gloo_world2(tmp_path):
     port = 29500 + (os.getpid() % 2000)
     mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
     assert all((tmp_path / f"ok{r}").exists() for r in range(2))
+
+
+# ----------------------------------------------------------------------------------------------------------
+# aqml_b200/sharded.py: the KRR feed cut over N ranks (host logic; the kernels are stand-ins on the CPU)
+# ----------------------------------------------------------------------------------------------------------
+def test_folded_blocks_balance_and_cover_the_triangle():
+    from aqml_b200 import sharded
+    for world in (1, 2, 3, 4, 8):
+        nblk = 2 * world
+        tiles = [sharded.my_tiles(r, world) for r in range(world)]
+        # every rank: exactly 2N + 1 tiles, two of them diagonal
+        assert all(len(t) == 2 * world + 1 and sum(b == c for b, c in t) == 2 for t in tiles)
+        allt = sorted(t for ts in tiles for t in ts)
+        assert allt == [(b, c) for b in range(nblk) for c in range(b + 1)]          # the lower block triangle, once
+        assert sorted(sharded.fold_owner(b, world) for b in range(nblk)) == sorted(list(range(world)) * 2)
+    bounds = sharded.block_bounds(20000, 16)
+    assert bounds[0][0] == 0 and bounds[-1][1] == 20000 and all(a[1] == b[0] for a, b in zip(bounds, bounds[1:]))
+
+
+class _FakeRep(object):
+    """Stands in for fused.PackedRep on the CPU: storage = one uint8 tensor, 'computed' only by its owner."""
+
+    def __init__(self, nbytes, fill):
+        self.buf = torch.full((nbytes,), fill, dtype=torch.uint8)
+        self.nmol = nbytes
+
+    def slab_tensor(self):
+        return self.buf
+
+    def close(self):
+        pass
+
+
+def _sharded_worker(rank, world, port, tmp):
+    from aqml_b200 import sharded
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        # share_reps: block b (ragged sizes) is computed by its owner only, every rank ends with every block
+        owners = [sharded.fold_owner(b, world) for b in range(2 * world)]
+        reps = [_FakeRep(1000 + 37 * b, (b + 1) if owners[b] == rank else 0) for b in range(2 * world)]
+        parallel.share_reps(reps, owners)
+        assert all(bool((r.buf == b + 1).all()) for b, r in enumerate(reps))
+        # predict: K_test sharded by my training blocks + all-reduce == the full product
+        nas1, nas2 = np.full(41, 3), np.full(7, 3)
+        sk = sharded.ShardedKernels((nas1, np.ones(123, dtype=int)), (nas2, np.ones(21, dtype=int)), None, 9, rank, world)
+        g = torch.Generator().manual_seed(7)
+        K = torch.rand((2, 7, 41), dtype=torch.float64, generator=g)
+        alpha = torch.rand((2, 41), dtype=torch.float64, generator=g)
+        ks = {b: K[:, :, sk.bounds[b][0]:sk.bounds[b][1]].contiguous() for b in sk.mine}
+        y = sk.predict(ks, alpha)
+        assert torch.allclose(y, torch.einsum("stn,sn->st", K, alpha), rtol=1e-13, atol=0)
+        y1 = sk.predict({b: v[0] for b, v in ks.items()}, alpha[0])
+        assert torch.allclose(y1, K[0] @ alpha[0], rtol=1e-13, atol=0)
+        # bookkeeping: the ranks' unique elements add up to the lower triangle + K_test
+        n = torch.tensor([float(sk.unique_elements(2))], dtype=torch.float64)
+        dist.all_reduce(n)
+        assert int(n.item()) == 2 * (41 * 42 // 2 + 7 * 41)
+        open(os.path.join(tmp, f"sharded_ok{rank}"), "w").write("ok")
+    finally:
+        dist.destroy_process_group()
+
+
+def test_sharded_feed_gloo_world2(tmp_path):
+    port = 31500 + (os.getpid() % 2000)
+    mp.spawn(_sharded_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    assert all((tmp_path / f"sharded_ok{r}").exists() for r in range(2))

@@ -4,7 +4,7 @@ import os
 import numpy as np
 import pytest
 
-from conftest import rel_err
+from conftest import kernel_rel_err, rel_err
 from aqml_b200 import synth
 from aqml_b200.representation.slatm_x import MolSet, slatm
 from oracle import c_oracle as co
@@ -51,8 +51,8 @@ def test_chunked_driver_matches_oracle_and_writes_reference_files(mols, tmp_path
                 use_chunks=[True, NAV1, NAV2])
     assert rel_err(run.dsmax, dso) < 1e-10
     assert run.mk1.shape == k1.shape and run.mk2.shape == k2.shape
-    assert rel_err(run.mk1, k1) < 1e-10
-    assert rel_err(run.mk2, k2) < 1e-10
+    assert kernel_rel_err(run.mk1, k1) < 1e-10
+    assert kernel_rel_err(run.mk2, k2) < 1e-10
     files = set(os.listdir(wd))
     # names and keys of slatm_x.py:308,357,425,522
     for f in ('x_aslatm_c1_b001.npz', 'x_aslatm_c1_b003.npz', 't_x_aslatm_c2_b002.npz', 'k_gaussian_aslatm_c11_blk_001_001.npz',
@@ -63,7 +63,7 @@ def test_chunked_driver_matches_oracle_and_writes_reference_files(mols, tmp_path
     a = int(nas[:NAV1].sum())
     assert rel_err(np.load(os.path.join(wd, 'x_aslatm_c1_b001.npz'))['x'], x[:a]) < 1e-10
     kb = np.load(os.path.join(wd, 't_k_gaussian_aslatm_c21_blk_003_002.npz'))['k']
-    assert rel_err(kb, k2[:, NAV2:2 * NAV2, 2 * NAV1:N1]) < 1e-10
+    assert kernel_rel_err(kb, k2[:, NAV2:2 * NAV2, 2 * NAV1:N1]) < 1e-10
     # resume: every x / k / dsmax is read back, nothing is recomputed (poison one file to prove it is used)
     np.savez(os.path.join(wd, 'k_gaussian_aslatm_c11_blk_002_002.npz'), k=np.full((3, NAV1, NAV1), 7.0))
     again = slatm(obj, ck=True, wd=wd, label='t', param=dict(PARAM, reuses=[True, True, True]), navks=[3, 2],
@@ -82,11 +82,11 @@ def test_subjobs_fill_only_their_blocks(mols, tmp_path):
                  param=dict(PARAM, saves=[False, True, True]), use_chunks=[True, NAV1, NAV2])
     assert not part.mk1.any() and not part.mk2.any()
     kb = np.load(os.path.join(str(tmp_path), 'k_gaussian_aslatm_c11_blk_001_002.npz'))['k']
-    assert rel_err(kb, k1[:, NAV1:2 * NAV1, :NAV1]) < 1e-10
+    assert kernel_rel_err(kb, k1[:, NAV1:2 * NAV1, :NAV1]) < 1e-10
     # this worker derived the widths from ITS first chunk = chunk 1 here, so the numbers agree with the full run;
     kb = np.load(os.path.join(str(tmp_path), 't_k_gaussian_aslatm_c21_blk_002_001.npz'))['k']
     # (second job's first chunk is train chunk 2, but dsmax was already fixed by the first job)
-    assert rel_err(kb, k2[:, :NAV2, NAV1:2 * NAV1]) < 1e-10
+    assert kernel_rel_err(kb, k2[:, :NAV2, NAV1:2 * NAV1]) < 1e-10
 
 
 def test_unchunked_driver(mols, tmp_path):
@@ -94,7 +94,7 @@ def test_unchunked_driver(mols, tmp_path):
     _, dso, k1, k2 = _expected(nas, zs, coords, first_block=N1)
     run = slatm(MolSet(zs, coords, nas, N1), ck=True, wd=str(tmp_path), param=PARAM)
     assert rel_err(run.dsmax, dso) < 1e-10
-    assert rel_err(run.mk1, k1) < 1e-10 and rel_err(run.mk2, k2) < 1e-10
+    assert kernel_rel_err(run.mk1, k1) < 1e-10 and kernel_rel_err(run.mk2, k2) < 1e-10
 
 
 def test_global_slatm_chunks(mols, tmp_path):
@@ -108,5 +108,5 @@ def test_global_slatm_chunks(mols, tmp_path):
     assert rel_err(run.dsmax, np.array([dmax])) < 1e-10
     for k, c in enumerate(PARAM['coeffs']):
         s = c * dmax / np.sqrt(2 * np.log(2))
-        assert rel_err(run.mk1[k], o.gaussian_kernel(x[:N1], x[:N1], s)) < 1e-10
-        assert rel_err(run.mk2[k], o.gaussian_kernel(x[N1:], x[:N1], s)) < 1e-10
+        assert kernel_rel_err(run.mk1[k], o.gaussian_kernel(x[:N1], x[:N1], s)) < 1e-10
+        assert kernel_rel_err(run.mk2[k], o.gaussian_kernel(x[N1:], x[:N1], s)) < 1e-10

@@ -4,7 +4,7 @@ elements recomputed by the CPU oracle, row-block sharding consistency, and rotat
 import numpy as np
 import pytest
 
-from conftest import rel_err
+from conftest import kernel_rel_err, rel_err
 from aqml_b200 import fused, synth
 from aqml_b200.representation import core as rcore
 from oracle import c_oracle as co
@@ -45,7 +45,7 @@ def test_config2_sampled_elements_match_oracle():
     xb = co.generate_slatm_batch(cb_, zb_, nb_, mb, True, **KW)
     ref = co.calc_lk_gaussian(xa, xb, za_, zb_, na_, nb_, ZMAX, False, sig)
     got = K[:, torch.as_tensor(ia, device="cuda")][:, :, torch.as_tensor(ib, device="cuda")].cpu().numpy()
-    assert rel_err(got, ref) < 1e-10
+    assert kernel_rel_err(got, ref) < 1e-10
     # (2) row-block sharding: rows [700, 1200) computed on their own == the same rows of the full K
     Kb = fused.local_gaussian(r2, r1, sig, ZMAX, row0=700, nrows=500)
     assert torch.allclose(Kb, K[:, 700:1200], rtol=1e-13, atol=0)

@@ -2,7 +2,7 @@
 import numpy as np
 import pytest
 
-from conftest import mbtypes_from_array, rel_err
+from conftest import kernel_rel_err, mbtypes_from_array, rel_err
 from aqml_b200 import fused, kernels, synth
 from aqml_b200.algo import aqml as algo
 from aqml_b200.representation import core as rcore
@@ -30,15 +30,15 @@ def test_fused_equals_two_step_and_oracle():
     train = fused.PackedRep(coords[:A1], zs[:A1], nas[:n1], mb, **kw)
     test = fused.PackedRep(torch.as_tensor(coords[A1:], device="cuda"), zs[A1:], nas[n1:], mb, **kw)
     K = fused.local_gaussian(test, train, sig, zmax).cpu().numpy()
-    assert rel_err(K, ref) < TOL
+    assert kernel_rel_err(K, ref) < TOL
     # row-block sharding: rows 5..12 of the test set
     Kb = fused.local_gaussian(test, train, sig, zmax, row0=5, nrows=7).cpu().numpy()
-    assert rel_err(Kb, ref[:, 5:12]) < TOL
+    assert kernel_rel_err(Kb, ref[:, 5:12]) < TOL
     # symmetric K(train, train): half the contraction + mirror == the rectangular route == the oracle
     ref11 = co.calc_lk_gaussian(xl[:A1], xl[:A1], zs[:A1], zs[:A1], nas[:n1], nas[:n1], zmax, False, sig)
     K11 = fused.local_gaussian(train, train, sig, zmax).cpu().numpy()
     K11s = fused.local_gaussian(train, train, sig, zmax, symmetric=True).cpu().numpy()
-    assert rel_err(K11, ref11) < TOL and rel_err(K11s, ref11) < TOL
+    assert kernel_rel_err(K11, ref11) < TOL and kernel_rel_err(K11s, ref11) < TOL
     assert np.array_equal(K11s, np.transpose(K11s, (0, 2, 1)))
     # width heuristic on packed rows == dense get_kernel_width on train+test
     both = fused.PackedRep(coords, zs, nas, mb, **kw)
@@ -47,7 +47,7 @@ def test_fused_equals_two_step_and_oracle():
     xd = rcore.generate_slatm_batch(torch.as_tensor(coords, device="cuda"), zs, nas, mb, local=True,
                                     sigmas=[.05, .05], dgrids=[.04, .04], rcut=4.8)
     K2 = kernels.get_local_kernels_gaussian(xd[A1:], xd[:A1], zs[A1:], zs[:A1], nas[n1:], nas[:n1], False, zmax, sig)
-    assert rel_err(K2.cpu().numpy(), ref) < TOL
+    assert kernel_rel_err(K2.cpu().numpy(), ref) < TOL
 
 
 def test_demo_learning_curve_through_gpu(demo):
@@ -113,9 +113,9 @@ def test_int8_tensor_engine_equals_fp64_engine_and_oracle():
                                fused.local_gaussian(train, train, sig, zmax, symmetric=True).cpu().numpy())
             finally:
                 del os.environ["AQML_PAIR_ENGINE"]
-            assert rel_err(out[engine][0], ref) < TOL
-            assert rel_err(out[engine][1], ref[:, 3:14]) < TOL
-            assert rel_err(out[engine][2], ref11) < TOL
+            assert kernel_rel_err(out[engine][0], ref) < TOL
+            assert kernel_rel_err(out[engine][1], ref[:, 3:14]) < TOL
+            assert kernel_rel_err(out[engine][2], ref11) < TOL
         for a, b in zip(out["i8"], out["dmma"]):
             assert rel_err(a, b) < 1e-11
 
@@ -157,4 +157,4 @@ def test_eight_sigmas_on_the_int8_engine():
         sig = np.array([c * dso / np.sqrt(2 * np.log(2)) for c in coeffs])
         ref = co.calc_lk_gaussian(xl[A1:], xl[:A1], zs[A1:], zs[:A1], nas[n1:], nas[:n1], 9, False, sig)
         K = fused.local_gaussian(test, train, sig, 9).cpu().numpy()
-        assert K.shape == ref.shape and rel_err(K, ref) < TOL
+        assert K.shape == ref.shape and kernel_rel_err(K, ref) < TOL

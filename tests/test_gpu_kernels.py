@@ -3,7 +3,7 @@
 import numpy as np
 import pytest
 
-from conftest import rel_err
+from conftest import kernel_rel_err, rel_err
 from aqml_b200 import distance, kernels, synth
 from aqml_b200.algo import aqml as algo
 from oracle import c_oracle as co
@@ -32,9 +32,9 @@ def test_global_gaussian_random(shape):
     for sigma in (0.3 * np.sqrt(D), 2.0 * np.sqrt(D)):
         K = kernels.gaussian_kernel(A, B, sigma)
         assert K.shape == (n1, n2) and K.flags.f_contiguous
-        assert rel_err(K, co.gaussian_kernel(A, B, sigma)) < TOL
+        assert kernel_rel_err(K, co.gaussian_kernel(A, B, sigma)) < TOL
         Kl = kernels.laplacian_kernel(A, B, sigma * 3)
-        assert rel_err(Kl, co.laplacian_kernel(A, B, sigma * 3)) < TOL
+        assert kernel_rel_err(Kl, co.laplacian_kernel(A, B, sigma * 3)) < TOL
 
 
 def test_global_kernels_on_slatm(slatm_set):
@@ -43,16 +43,16 @@ def test_global_kernels_on_slatm(slatm_set):
     dmax = co.l2_distance(A, A).max()
     for c in (0.25, 1.0, 4.0):  # both ends of a sigma list
         sigma = c * dmax / np.sqrt(2 * np.log(2))
-        assert rel_err(kernels.gaussian_kernel(B, A, sigma), co.gaussian_kernel(B, A, sigma)) < TOL
+        assert kernel_rel_err(kernels.gaussian_kernel(B, A, sigma), co.gaussian_kernel(B, A, sigma)) < TOL
         K = kernels.gaussian_kernel(A, A, sigma)  # symmetric, exact-duplicate rows on the diagonal
-        assert rel_err(K, co.gaussian_kernel(A, A, sigma)) < TOL
+        assert kernel_rel_err(K, co.gaussian_kernel(A, A, sigma)) < TOL
         assert np.allclose(np.diag(K), 1.0, rtol=0, atol=1e-12)
     l1max = co.l1_distance(A, A).max()
-    assert rel_err(kernels.laplacian_kernel(B, A, l1max / np.log(2)), co.laplacian_kernel(B, A, l1max / np.log(2))) < TOL
+    assert kernel_rel_err(kernels.laplacian_kernel(B, A, l1max / np.log(2)), co.laplacian_kernel(B, A, l1max / np.log(2))) < TOL
     # near-duplicate rows
     A2 = A.copy()
     A2[1] = A2[0] * (1 + 1e-9)
-    assert rel_err(kernels.gaussian_kernel(A2, A2, dmax), co.gaussian_kernel(A2, A2, dmax)) < TOL
+    assert kernel_rel_err(kernels.gaussian_kernel(A2, A2, dmax), co.gaussian_kernel(A2, A2, dmax)) < TOL
 
 
 def test_distances(slatm_set):
@@ -83,7 +83,7 @@ def test_multi_sigma_device_path(slatm_set):
         K = kernels.global_kernels(At, Bt, s, kern).cpu().numpy()
         assert K.shape == (4, 45, 15)
         for i in range(4):
-            assert rel_err(K[i], ref(A, B, s[i])) < TOL
+            assert kernel_rel_err(K[i], ref(A, B, s[i])) < TOL
     # row-block sharding == slicing rows of A
     Kb = kernels.global_kernels(At[10:30], Bt, sig, "gaussian").cpu().numpy()
     Kf = kernels.global_kernels(At, Bt, sig, "gaussian").cpu().numpy()
@@ -109,9 +109,9 @@ def test_local_gaussian_synthetic(slatm_set, iab):
         K = kernels.get_local_kernels_gaussian(a, b, za, zb, na, nb, iab, zmax, sig)
         ref = co.calc_lk_gaussian(a, b, za, zb, na, nb, zmax, iab, sig)
         assert K.shape == ref.shape == (4, len(na), len(nb))
-        assert rel_err(K, ref) < TOL
+        assert kernel_rel_err(K, ref) < TOL
         Knc = kernels.get_local_kernels_gaussian(a, b, za, zb, na, nb, iab, zmax, sig, center=False)
-        assert rel_err(Knc, ref) < TOL
+        assert kernel_rel_err(Knc, ref) < TOL
 
 
 def test_local_gaussian_arbitrary_sigmas(slatm_set):
@@ -127,14 +127,14 @@ def test_local_gaussian_arbitrary_sigmas(slatm_set):
     sig = 6.0 + 20.0 * rng.random((5, 9))
     for center in (True, False):
         K = kernels.get_local_kernels_gaussian(x2, x1, zs2, zs1, nas2, nas1, False, 9, sig, center=center)
-        assert rel_err(K, co.calc_lk_gaussian(x2, x1, zs2, zs1, nas2, nas1, 9, False, sig)) < TOL
+        assert kernel_rel_err(K, co.calc_lk_gaussian(x2, x1, zs2, zs1, nas2, nas1, 9, False, sig)) < TOL
     # a ladder with a factor-sqrt(2) step (isig ratio 2: one squaring) and a repeated sigma
     base = 5.0 + rng.random(9)
     sig = np.array([base * 4, base * 2 * np.sqrt(2.0), base * 2, base * 2, base])
     K = kernels.get_local_kernels_gaussian(x2, x1, zs2, zs1, nas2, nas1, False, 9, sig, center=False)
-    assert rel_err(K, co.calc_lk_gaussian(x2, x1, zs2, zs1, nas2, nas1, 9, False, sig)) < TOL
+    assert kernel_rel_err(K, co.calc_lk_gaussian(x2, x1, zs2, zs1, nas2, nas1, 9, False, sig)) < TOL
     Kl = kernels.get_local_kernels_laplacian(x2, x1, nas2, nas1, [300., 777., 1500.])
-    assert rel_err(Kl, co.calc_lk_laplacian(x2, x1, nas2, nas1, [300., 777., 1500.])) < TOL
+    assert kernel_rel_err(Kl, co.calc_lk_laplacian(x2, x1, nas2, nas1, [300., 777., 1500.])) < TOL
 
 
 def test_local_gaussian_wide_sigma_mismatch_term(slatm_set):
@@ -146,7 +146,7 @@ def test_local_gaussian_wide_sigma_mismatch_term(slatm_set):
     sig = np.full((2, 9), 3000.0)
     sig[1] = 9000.0
     K = kernels.get_local_kernels_gaussian(x, x, zs, zs, nas, nas, False, 9, sig)
-    assert rel_err(K, co.calc_lk_gaussian(x, x, zs, zs, nas, nas, 9, False, sig)) < TOL
+    assert kernel_rel_err(K, co.calc_lk_gaussian(x, x, zs, zs, nas, nas, 9, False, sig)) < TOL
 
 
 def test_local_gaussian_golden_demo(demo):
@@ -155,8 +155,8 @@ def test_local_gaussian_golden_demo(demo):
     A1 = int(nas[:n1].sum())
     k1 = kernels.get_local_kernels_gaussian(x[:A1], x[:A1], zs[:A1], zs[:A1], nas[:n1], nas[:n1], False, 8, demo["sigmas"])
     k2 = kernels.get_local_kernels_gaussian(x[A1:], x[:A1], zs[A1:], zs[:A1], nas[n1:], nas[:n1], False, 8, demo["sigmas"])
-    assert rel_err(k1, demo["k1"]) < TOL
-    assert rel_err(k2, demo["k2"]) < TOL
+    assert kernel_rel_err(k1, demo["k1"]) < TOL
+    assert kernel_rel_err(k2, demo["k2"]) < TOL
 
 
 def test_local_laplacian(slatm_set):
@@ -167,7 +167,7 @@ def test_local_laplacian(slatm_set):
     nas1, nas2 = s["nas"][:n1], s["nas"][n1:n1 + 9]
     sig = [200., 800., 3200.]
     K = kernels.get_local_kernels_laplacian(x2, x1, nas2, nas1, sig)
-    assert rel_err(K, co.calc_lk_laplacian(x2, x1, nas2, nas1, sig)) < TOL
+    assert kernel_rel_err(K, co.calc_lk_laplacian(x2, x1, nas2, nas1, sig)) < TOL
 
 
 def test_kernel_width(demo, slatm_set):
@@ -189,7 +189,7 @@ def test_ragged_and_empty(slatm_set):
     nas0 = np.array([nas[0], 0, nas[1] + nas[2]], dtype=np.int32)
     K = kernels.get_local_kernels_gaussian(x, x, zs, zs, nas0, nas, False, 9, sig)
     ref = co.calc_lk_gaussian(x, x, zs, zs, nas0, nas, 9, False, sig)
-    assert rel_err(K, ref) < TOL and np.all(K[0, 1] == 0)
+    assert kernel_rel_err(K, ref) < TOL and np.all(K[0, 1] == 0)
     with pytest.raises(AssertionError):
         kernels.get_local_kernels_gaussian(x, x, zs, zs, nas, nas[:2], False, 9, sig)
     from aqml_b200._lib import AqmlError
@@ -204,18 +204,18 @@ def test_linear_matern_sargan(slatm_set):
     d1, d2 = co.l1_distance(A, B), co.l2_distance(A, B)
     K = kernels.linear_kernel(A, B)
     ref = A @ B.T
-    assert K.shape == (21, 37) and K.flags.f_contiguous and rel_err(K, ref) < 1e-13
+    assert K.shape == (21, 37) and K.flags.f_contiguous and kernel_rel_err(K, ref) < 1e-13
     s2, s1 = d2.max(), d1.max()
     for order in (0, 1, 2):
         c = [1.0, np.sqrt(3.0), np.sqrt(5.0)][order]
         poly2 = [1.0, 1 + c * d2 / s2, 1 + c * d2 / s2 + 5.0 / (3 * s2 * s2) * d2 * d2][order]
-        assert rel_err(kernels.matern_kernel(A, B, s2, order, "l2"), np.exp(-c * d2 / s2) * poly2) < 1e-12
+        assert kernel_rel_err(kernels.matern_kernel(A, B, s2, order, "l2"), np.exp(-c * d2 / s2) * poly2) < 1e-12
         x = c * d1 / s1
         poly1 = [1.0, 1 + x, 1 + x + x * x / 3.0][order]
-        assert rel_err(kernels.matern_kernel(A, B, s1, order, "l1"), np.exp(-x) * poly1) < 1e-12
+        assert kernel_rel_err(kernels.matern_kernel(A, B, s1, order, "l1"), np.exp(-x) * poly1) < 1e-12
     g = [0.3, 0.05, 0.7]
     x = d1 / s1
-    assert rel_err(kernels.sargan_kernel(A, B, s1, g), np.exp(-x) * (1 + g[0] * x + g[1] * x ** 2 + g[2] * x ** 3)) < 1e-12
+    assert kernel_rel_err(kernels.sargan_kernel(A, B, s1, g), np.exp(-x) * (1 + g[0] * x + g[1] * x ** 2 + g[2] * x ** 3)) < 1e-12
     with pytest.raises(SystemExit):
         kernels.matern_kernel(A, B, 1.0, 0, "l3")
 
@@ -239,9 +239,9 @@ def test_vector_kernels_on_padded_arrays(slatm_set):
     Kg = kernels.calc_vector_kernels_gaussian(p1.T, p2.T, nas1, nas2, sig)  # .T = what f2py receives
     z1, z2 = np.ones(len(x1), np.int32), np.ones(len(x2), np.int32)
     ref = co.calc_lk_gaussian(x1, x2, z1, z2, nas1, nas2, 1, True, np.array(sig).reshape(-1, 1))
-    assert rel_err(Kg, ref) < TOL
+    assert kernel_rel_err(Kg, ref) < TOL
     Kl = kernels.calc_vector_kernels_laplacian(p1, p2, nas1, nas2, [500., 900.])
-    assert rel_err(Kl, co.calc_lk_laplacian(x1, x2, nas1, nas2, [500., 900.])) < TOL
+    assert kernel_rel_err(Kl, co.calc_lk_laplacian(x1, x2, nas1, nas2, [500., 900.])) < TOL
 
 
 def test_int8_engine_hostile_rows():
@@ -268,7 +268,7 @@ def test_int8_engine_hostile_rows():
                 K = kernels.gaussian_kernel(A, B, sig)
             finally:
                 del os.environ["AQML_PAIR_ENGINE"]
-            assert rel_err(K, ref) < TOL, (engine, sig)
+            assert kernel_rel_err(K, ref) < TOL, (engine, sig)
     # local kernel on the same rows: 3 "elements", ragged molecules
     zs1 = rng.choice([1, 6, 8], size=n1); zs2 = rng.choice([1, 6, 8], size=n2)
     nas1 = np.array([3, 7, 1, 9, 20, 30]); nas2 = np.array([50, 1, 2, 40, 57])
@@ -281,11 +281,11 @@ def test_int8_engine_hostile_rows():
             K0 = kernels.get_local_kernels_gaussian(A, B, zs1, zs2, nas1, nas2, False, 8, sigmas, center=False)
         finally:
             del os.environ["AQML_PAIR_ENGINE"]
-        assert rel_err(K, ref) < TOL and rel_err(K0, ref) < TOL, engine
+        assert kernel_rel_err(K, ref) < TOL and kernel_rel_err(K0, ref) < TOL, engine
     # more than 8 sigmas: served by the FP64 engine automatically
     many = np.array([[c * dmax] * 8 for c in np.linspace(0.1, 2.0, 11)])
     K = kernels.get_local_kernels_gaussian(A, B, zs1, zs2, nas1, nas2, False, 8, many)
-    assert rel_err(K, co.calc_lk_gaussian(A, B, zs1, zs2, nas1, nas2, 8, False, many)) < TOL
+    assert kernel_rel_err(K, co.calc_lk_gaussian(A, B, zs1, zs2, nas1, nas2, 8, False, many)) < TOL
     # NaN / Inf inputs fall back to the FP64 engine and propagate as in the reference
     A2 = A.copy(); A2[7, 3] = np.nan
     K = kernels.gaussian_kernel(A2, B, dmax)
@@ -297,4 +297,23 @@ def test_global_gaussian_very_long_rows():
     rng = np.random.default_rng(5)
     A, B = rng.random((70, 20011)), rng.random((45, 20011))
     sigma = 0.4 * np.sqrt(20011)
-    assert rel_err(kernels.gaussian_kernel(A, B, sigma), co.gaussian_kernel(A, B, sigma)) < TOL
+    assert kernel_rel_err(kernels.gaussian_kernel(A, B, sigma), co.gaussian_kernel(A, B, sigma)) < TOL
+
+
+def test_wide_power_of_two_sigma_ladder():
+    """sigma = [s, 256 s, 65536 s] are exact power-of-two multiples, but chaining them by squarings would need
+    32 squarings (error 2^32 ulp); plan_sigma_chain must refuse (<= 8 squarings in all) and give every sigma its own exp.
+    Also values so close to 1 that a squaring chain would collapse them to exactly 1."""
+    rng = np.random.default_rng(3)
+    A, B = rng.random((70, 300)), rng.random((90, 300))
+    s0 = 3.0
+    for sig in ([s0, 256 * s0, 65536 * s0], [s0, 4 * s0, 64 * s0, 1024 * s0], [s0, 2 * s0, 4 * s0, 8 * s0, 16 * s0, 32 * s0]):
+        K = kernels.gaussian_kernels(A, B, sig)
+        for i, s in enumerate(sig):
+            assert kernel_rel_err(K[i], co.gaussian_kernel(A, B, s)) < TOL, (sig, i)
+    zs1, zs2 = np.full(70, 6), np.full(90, 6)
+    nas1, nas2 = np.array([30, 40]), np.array([45, 45])
+    for ladder in ([1.0, 256.0, 65536.0], [1.0, 2.0, 4.0, 8.0, 16.0, 32.0, 64.0]):
+        sig = np.array([[c * s0] * 6 for c in ladder])
+        K = kernels.get_local_kernels_gaussian(A, B, zs1, zs2, nas1, nas2, False, 6, sig)
+        assert kernel_rel_err(K, co.calc_lk_gaussian(A, B, zs1, zs2, nas1, nas2, 6, False, sig)) < TOL

@@ -2,7 +2,7 @@
 import numpy as np
 import pytest
 
-from conftest import rel_err
+from conftest import kernel_rel_err, rel_err
 from aqml_b200 import kernels, synth
 from aqml_b200.algo import aqml as algo
 from aqml_b200.algo import krr
@@ -42,15 +42,15 @@ def test_calc_ka_matches_restated_reference():
         ref_ks, ref_ksa = _ref_calc_ka(x[A1:], x[:A1], zs[A1:], zs[:A1], nas[:n1], s, kern)
         ks = algo.calc_ka(x[A1:], x[:A1], zs[A1:], zs[:A1], nas[n1:], nas[:n1], False, zmax, s, kernel=kern)
         assert ks.shape == ref_ks.shape
-        assert rel_err(ks, ref_ks) < 1e-9
+        assert kernel_rel_err(ks, ref_ks) < 1e-10
         kz = algo.calc_ka(x[A1:], x[:A1], zs[A1:], zs[:A1], nas[n1:], nas[:n1], False, zmax, s, zaq=6, kernel=kern)
-        assert rel_err(kz, ref_ksa[:, zs[A1:] == 6][:, :, zs[:A1] == 6]) < 1e-9
+        assert kernel_rel_err(kz, ref_ksa[:, zs[A1:] == 6][:, :, zs[:A1] == 6]) < 1e-10
     # the sum of the atomic contributions over test-molecule atoms is the local kernel (aqml.py:913)
     ks = algo.calc_ka(x[A1:], x[:A1], zs[A1:], zs[:A1], nas[n1:], nas[:n1], False, zmax, sig)
     kl = kernels.get_local_kernels_gaussian(x[A1:], x[:A1], zs[A1:], zs[:A1], nas[n1:], nas[:n1], False, zmax, sig)
     off2 = np.concatenate(([0], np.cumsum(nas[n1:])))
     summed = np.stack([ks[:, off2[i]:off2[i + 1]].sum(axis=1) for i in range(len(nas) - n1)], axis=1)
-    assert rel_err(summed, kl) < 1e-10
+    assert kernel_rel_err(summed, kl) < 1e-10
 
 
 def test_learning_curve_and_multifidelity(demo):
@@ -120,7 +120,7 @@ def test_amons_workflow_per_query_sigmas():
         assert np.allclose(sig, ref_sig, rtol=1e-10, atol=0)
         r1 = co.calc_lk_gaussian(x1, x1, a[1], a[1], a[0], a[0], zmax, False, ref_sig)
         r2 = co.calc_lk_gaussian(x2, x1, t[1], a[1], t[0], a[0], zmax, False, ref_sig)
-        assert rel_err(ks1, r1) < 1e-9 and rel_err(ks2, r2) < 1e-9
+        assert kernel_rel_err(ks1, r1) < 1e-10 and kernel_rel_err(ks2, r2) < 1e-10
 
 
 def test_sharded_krr_single_rank_matches_direct_solve():
@@ -138,12 +138,12 @@ def test_sharded_krr_single_rank_matches_direct_solve():
     rep_train = fused.PackedRep(train[2], train[1], train[0], mb, **kw)
     rep_test = fused.PackedRep(test[2], test[1], test[0], mb, **kw)
     dso = model.kernel_width()
-    assert rel_err(dso, fused.kernel_width(rep_train, rep_train, zmax)) < 1e-12
+    assert kernel_rel_err(dso, fused.kernel_width(rep_train, rep_train, zmax)) < 1e-12
     sig = dso / np.sqrt(2 * np.log(2))
     K_loc = model.assemble(sig)
     K = fused.local_gaussian(rep_train, rep_train, sig[None], zmax)[0]
     low = torch.tril(torch.ones_like(K, dtype=torch.bool))
-    assert rel_err(torch.where(low, K_loc, 0).cpu().numpy(), torch.where(low, K, 0).cpu().numpy()) < 1e-12
+    assert kernel_rel_err(torch.where(low, K_loc, 0).cpu().numpy(), torch.where(low, K, 0).cpu().numpy()) < 1e-12
     y = torch.as_tensor(np.random.default_rng(0).normal(size=150), device=K.device)
     # lambda = 10 keeps cond(K + lambda I) ~ 1e4, so that rounding-order noise in K (FP64 atomics, ~1e-16) stays
     # far below the tolerance in alpha
