@@ -70,6 +70,11 @@ def calc_ka(x2, x1, zs2, zs1, nas2, nas1, cab, zmax, sigmas, zaq=None, kernel='g
     x1t = x1 if L.is_tensor(x1) else torch.as_tensor(L.f64(x1), device=dev)
     x2t = x2 if L.is_tensor(x2) else torch.as_tensor(L.f64(x2), device=dev)
     na1, na2, n1 = len(zs1), len(zs2), len(nas1)
+    if zaq is None and kernel[0] == 'g':
+        # every test atom as a one-atom "molecule": the element-matched local kernel IS the atomic kernel summed over the
+        # atoms of each training molecule -- the pair kernel's segmented epilogue does the sum, nothing is scattered
+        ks = cmlk.get_local_kernels_gaussian(x2t, x1t, zs2, zs1, np.ones(na2, dtype=np.int32), nas1, False, zmax, sig)
+        return ks if L.is_tensor(x1) else ks.cpu().numpy()
     zsu = np.unique(zs2) if zaq is None else [zaq]
     blocks = {}
     for zi in zsu:
@@ -90,11 +95,13 @@ def calc_ka(x2, x1, zs2, zs1, nas2, nas1, cab, zmax, sigmas, zaq=None, kernel='g
     if zaq is not None:
         out = blocks[zaq][2]
         return out if L.is_tensor(x1) else out.cpu().numpy()
-    ksa = torch.zeros((nsg, na2, na1), dtype=torch.float64, device=dev)
+    # sum over the atoms of each training molecule, element block by element block (the (nsigmas, A2, A1) matrix of the
+    # reference, aqml.py:296-305, is never formed)
+    mol1 = np.repeat(np.arange(n1), np.asarray(nas1))
+    ks = torch.zeros((nsg, na2, n1), dtype=torch.float64, device=dev)
     for zi, (i1, i2, k) in blocks.items():
         if len(i1) and len(i2):
-            ksa[:, torch.as_tensor(i2, device=dev)[:, None], torch.as_tensor(i1, device=dev)[None, :]] = k
-    mol1 = torch.as_tensor(np.repeat(np.arange(n1), np.asarray(nas1)), device=dev)
-    ks = torch.zeros((nsg, na2, n1), dtype=torch.float64, device=dev)
-    ks.index_add_(2, mol1, ksa)
+            part = torch.zeros((nsg, len(i2), n1), dtype=torch.float64, device=dev)
+            part.index_add_(2, torch.as_tensor(mol1[i1], device=dev), k)
+            ks[:, torch.as_tensor(i2, device=dev)] = part
     return ks if L.is_tensor(x1) else ks.cpu().numpy()

@@ -67,6 +67,9 @@ struct SlatmJob {
     double *pnorm[MAXEL];
     unsigned *pmask[MAXEL];  // [rows/64][maskw] non-zero k-tile bits of the packed rows (pre-zeroed) or null
     int maskw[MAXEL];
+    // int8 digit planes of the packed rows (i8pair.cuh), written by the work-unit kernel right after the rows; null = not wanted
+    int8_t *psl[MAXEL];
+    int *pexpo[MAXEL];
 };
 
 // geometry with the oracle's operation order and no FMA contraction (decisions / angles are
@@ -380,6 +383,7 @@ __global__ void __launch_bounds__(SL_THREADS) slatm_kernel(const SlatmDev T, con
 }
 
 }  // namespace aqml
+#include "i8digits.cuh"
 #include "slatm_units.cuh"
 #include "i8pair.cuh"
 namespace aqml {
@@ -417,6 +421,18 @@ __global__ void zero_rows_kernel(double *x, long long ld, const int *rows, int n
     int r = rows[blockIdx.x];
     for (long long i = threadIdx.x; i < ld; i += blockDim.x) x[(long long)r * ld + i] = 0.0;
     if (threadIdx.x == 0 && norm) norm[r] = 0.0;
+}
+
+// digit planes of rows that no aSLATM row is written to (padding at the end of an element, the unused half of the last
+// 128-row block): all k-chunks zero, exponent 0
+__global__ void i8_zero_rows_kernel(int8_t *sl, int KT, const int *rows, int nrows, int *expo, int nr) {
+    const int r = rows[blockIdx.x], kt = blockIdx.y * 128 + threadIdx.x;
+    if (kt < KT) {
+        int8_t *dst = sl + (((long long)(r >> 7) * (KT + 1) + kt) * I8_S) * 2048 + (r & 127) * 16;
+#pragma unroll
+        for (int p = 0; p < I8_S; p++) *reinterpret_cast<uint4 *>(dst + p * 2048) = make_uint4(0u, 0u, 0u, 0u);
+    }
+    if (kt == 0 && r < nr) expo[r] = 0;
 }
 
 // =============================================================================================
@@ -621,8 +637,8 @@ static bool launch_units_t(const SlatmTables &t, const SlatmJob &J, const MolInd
     const int na_max = (int)round_up(std::max(mi.na_max, 1), 2);
     nbn_max = (int)round_up(nbn_max, 4);
     ba_max = std::max(ba_max, t.dev.n_el);
-    size_t smem = sizeof(double) * (3 * (size_t)na_max + 4 * (size_t)nbn_max + (size_t)ba_max * uc + 2 * GS * M2 + 2 * GS * M3) +
-                  sizeof(int) * na_max + sizeof(short) * ((size_t)nbn_max + (size_t)ba_max * (MAXEL + 1) + 4) + nbn_max + 16;
+    size_t smem = sizeof(double) * (3 * (size_t)na_max + 4 * (size_t)nbn_max + 2 * (size_t)ba_max * uc + 2 * GS * M2 + 2 * GS * M3) +
+                  sizeof(int) * (na_max + ba_max) + sizeof(short) * ((size_t)nbn_max + (size_t)ba_max * (MAXEL + 1) + 4) + nbn_max + 16;
     if (smem > 160 * 1024 || mi.na_max > 30000) return false;
     AQML_CUDA(cudaFuncSetAttribute(slatm_units_kernel<M2, M3, GS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     slatm_units_kernel<M2, M3, GS><<<(unsigned)batches.size(), SL_THREADS, smem, ws.stream()>>>(
@@ -631,10 +647,11 @@ static bool launch_units_t(const SlatmTables &t, const SlatmJob &J, const MolInd
     return true;
 }
 
-static void launch_slatm(const SlatmTables &t, const SlatmJob &J, const MolIndex &mi, Workspace &ws) {
+// true: the work-unit kernel ran (it also wrote the digit planes J.psl asked for)
+static bool launch_slatm(const SlatmTables &t, const SlatmJob &J, const MolIndex &mi, Workspace &ws) {
     cudaStream_t st = ws.stream();
     int nblocks = J.local ? J.A : J.nmol * t.dev.n_el;
-    if (nblocks <= 0) return;
+    if (nblocks <= 0) return true;
     int na_max = (int)round_up(std::max(mi.na_max, 1), 2);
     const SlatmDev &d = t.dev;
     const int m2 = (d.nx2 + 7) / 8, m3 = (d.nx3 + 7) / 8;
@@ -646,12 +663,13 @@ static void launch_slatm(const SlatmTables &t, const SlatmJob &J, const MolIndex
     static const bool force_legacy = getenv("AQML_SLATM_LEGACY") != nullptr;
     if (!force_legacy) {  // work-unit kernel (aSLATM; SLATM of molecules with <= 36 atoms)
         // 8 threads per unit measured best (4: 10.8e6 atoms/s, 8: 16.8e6, 16: 16.0e6 on the bench workload)
-        if (safe(15, 12)) { if (launch_units_t<15, 12, 8>(t, J, mi, ws)) return; }
-        else if (safe(20, 16)) { if (launch_units_t<20, 16, 8>(t, J, mi, ws)) return; }
-        else if (safe(32, 32)) { if (launch_units_t<32, 32, 8>(t, J, mi, ws)) return; }
+        if (safe(15, 12)) { if (launch_units_t<15, 12, 8>(t, J, mi, ws)) return true; }
+        else if (safe(20, 16)) { if (launch_units_t<20, 16, 8>(t, J, mi, ws)) return true; }
+        else if (safe(32, 32)) { if (launch_units_t<32, 32, 8>(t, J, mi, ws)) return true; }
     }
     // general kernel: global SLATM of large molecules, grids outside the recurrence's safe range
     launch_slatm_general(t, J, nblocks, na_max, st);
+    return false;
 }
 
 static void slatm_batch_dev(const double *coords, const int *zs_dev, const int *nas, int nmol, const aqml_slatm_params *p,
@@ -911,6 +929,9 @@ static void rep_create(const double *coords, int on_dev, const int *zs, const in
         if (planes && !rows[e].empty()) { add((size_t)((nr + 127) / 128) * (ld / 16 + 1) * I8_A_CHUNK, 1); add(nr, 4); }
     }
     keep.reserve(total);
+    // AQML_FUSE_PLANES=0: digit planes by the separate split kernels (a second pass over the packed operand) instead of the
+    // aSLATM kernel's phase 4
+    static const bool fuse = !(getenv("AQML_FUSE_PLANES") && atoi(getenv("AQML_FUSE_PLANES")) == 0);
     // pass 2: carve (same order)
     std::vector<int> atom_prow(mi.A, -1);
     SlatmJob J;
@@ -948,6 +969,19 @@ static void rep_create(const double *coords, int on_dev, const int *zs, const in
             rep->bytes += (int64_t)bytes + 4 * el.nr;
         }
         J.px[e] = el.x; J.pnorm[e] = el.norm; J.pmask[e] = el.mask; J.maskw[e] = el.maskw;
+        J.psl[e] = fuse ? el.sl : nullptr; J.pexpo[e] = fuse ? el.expo : nullptr;
+        if (compute && el.sl && fuse) {
+            // planes nobody else writes: the all-zero k-chunk KT of every row block, and the padding rows at the element's end
+            const int KT = el.ld / 16, rb = (int)((nr + 127) / 128);
+            AQML_CUDA(cudaMemset2DAsync(el.sl + (size_t)KT * I8_A_CHUNK, (size_t)(KT + 1) * I8_A_CHUNK, 0, I8_A_CHUNK, rb, st));
+            std::vector<int> empty_rows = pad;
+            for (int r = (int)nr; r < rb * 128; r++) empty_rows.push_back(r);
+            if (!empty_rows.empty()) {
+                i8_zero_rows_kernel<<<dim3((unsigned)empty_rows.size(), (KT + 127) / 128), 128, 0, st>>>(el.sl, KT, ws.upload(empty_rows),
+                                                                                                   (int)empty_rows.size(), el.expo, (int)nr);
+                AQML_LAUNCH_CHECK();
+            }
+        }
         rep->els.push_back(el);
     }
     rep->ne = ne;
@@ -955,8 +989,8 @@ static void rep_create(const double *coords, int on_dev, const int *zs, const in
         const double *dcoords = on_dev ? coords : ws.upload(coords, (size_t)mi.A * 3);
         J.coords = dcoords; J.zs = ws.upload(zs, mi.A); J.mol_off = ws.upload(mi.off); J.atom_mol = ws.upload(mi.atom_mol);
         J.nmol = nmol; J.A = mi.A; J.local = 1; J.out = nullptr; J.ldo = 0; J.atom_prow = ws.upload(atom_prow);
-        launch_slatm(t, J, mi, ws);
-        if (planes)  // stream ordered, no host synchronisation (NaN rows from coincident atoms travel through |row|^2)
+        const bool fused_planes = launch_slatm(t, J, mi, ws);
+        if (planes && !(fused_planes && fuse))  // the general SLATM kernel does not write digit planes: split the finished rows
             for (auto &el : rep->els)
                 if (el.n) i8_fill_planes(el.x, el.ld, el.nr, st, el.sl, el.expo);
     }

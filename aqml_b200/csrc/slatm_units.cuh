@@ -91,9 +91,11 @@ slatm_units_kernel(const SlatmDev T, const SlatmJob J, const Batch *batches, int
     double *dd = mz + na_max;                          // [ba][na] distance centre -> atom q
     double *ux = dd + nbn_max, *uy = ux + nbn_max, *uz = uy + nbn_max;  // [ba][na] unit vector centre -> q
     double *s_norm = uz + nbn_max;                     // [ba][uc] sum of squares of each written block
-    double *sx2 = s_norm + ba_max * uc, *sinv2 = sx2 + GS * M2, *sx3 = sinv2 + GS * M2, *scos3 = sx3 + GS * M3;
+    double *s_max = s_norm + ba_max * uc;              // [ba][uc] largest finite |value| of each written block
+    double *sx2 = s_max + ba_max * uc, *sinv2 = sx2 + GS * M2, *sx3 = sinv2 + GS * M2, *scos3 = sx3 + GS * M3;
     int *mel = reinterpret_cast<int *>(scos3 + GS * M3);
-    short *nbidx = reinterpret_cast<short *>(mel + na_max);   // [ba][na] neighbours sorted by element
+    int *s_exp = mel + na_max;                         // [ba] digit-plane exponent of each centre's packed row
+    short *nbidx = reinterpret_cast<short *>(s_exp + ba_max);   // [ba][na] neighbours sorted by element
     short *sstart = nbidx + nbn_max;                           // [ba][MAXEL+1]
     unsigned char *fls = reinterpret_cast<unsigned char *>(sstart + ba_max * (MAXEL + 1));  // [ba][na]
     __shared__ double4 s_mbox[SL_THREADS];  // per thread: the geometry of "its" entry, read by its whole group
@@ -127,7 +129,7 @@ slatm_units_kernel(const SlatmDev T, const SlatmJob J, const Batch *batches, int
         mel[i] = e;
     }
     if (tid == 0) { s_next = 0; s_next3 = 0; }
-    if (J.local) for (int i = tid; i < bt.cnt * uc; i += SL_THREADS) s_norm[i] = 0.0;
+    if (J.local) for (int i = tid; i < bt.cnt * uc; i += SL_THREADS) { s_norm[i] = 0.0; s_max[i] = 0.0; }
     // packed output: clear the rows too -- units without a single entry are then never visited
     if (J.local && J.atom_prow) {
         for (int ai = 0; ai < bt.cnt; ai++) {
@@ -216,13 +218,14 @@ slatm_units_kernel(const SlatmDev T, const SlatmJob J, const Batch *batches, int
         const int pr = (loc && J.atom_prow) ? J.atom_prow[o + bt.a0 + ui] : -1;
         const int j0 = ch * m, kt0 = (col + j0) >> 4;
         unsigned bits = 0;
-        double ssq = 0.0;
+        double ssq = 0.0, vmax = 0.0;
         for (int j = 0; j < m; j++) {
             const double v = acc[j];
             if (j0 + j < nx) {
                 if (J.out) J.out[orow * J.ldo + dcol + j0 + j] = v;
                 if (pr >= 0) J.px[ec][(long long)pr * T.pld[ec] + col + j0 + j] = v;
                 ssq += v * v;
+                if (fabs(v) <= 1.7976931348623157e308) vmax = fmax(vmax, fabs(v));
                 if (v != 0.0) bits |= 1u << min(((col + j0 + j) >> 4) - kt0, 2);
             }
         }
@@ -231,11 +234,12 @@ slatm_units_kernel(const SlatmDev T, const SlatmJob J, const Batch *batches, int
             for (int q = 0; q < 3; q++)
                 if (bits & (1u << q)) atomicOr(mw + ((kt0 + q) >> 5), 1u << ((kt0 + q) & 31));
         }
-        ssq += __shfl_xor_sync(gmask, ssq, 1);
-        ssq += __shfl_xor_sync(gmask, ssq, 2);
-        if (GS >= 8) ssq += __shfl_xor_sync(gmask, ssq, 4);
-        if (GS >= 16) ssq += __shfl_xor_sync(gmask, ssq, 8);
-        if (ch == 0 && loc) s_norm[ui * uc + cidx] = ssq;
+#pragma unroll
+        for (int o = 1; o < GS; o <<= 1) {
+            ssq += __shfl_xor_sync(gmask, ssq, o);
+            vmax = fmax(vmax, __shfl_xor_sync(gmask, vmax, o));
+        }
+        if (ch == 0 && loc) { s_norm[ui * uc + cidx] = ssq; s_max[ui * uc + cidx] = vmax; }
     };
 
     // ---------- two-body units: (owner, partner element) ----------
@@ -454,11 +458,40 @@ slatm_units_kernel(const SlatmDev T, const SlatmJob J, const Batch *batches, int
         if (J.atom_prow && ec >= 0) {
             const int pr = J.atom_prow[o + c];
             if (pr >= 0) {
-                double t = 0.0;
-                for (int q = 0; q < uc; q++) t += s_norm[ai * uc + q];
+                double t = 0.0, vmax = 0.0;
+                for (int q = 0; q < uc; q++) { t += s_norm[ai * uc + q]; vmax = fmax(vmax, s_max[ai * uc + q]); }
                 J.pnorm[ec][pr] = t;
+                if (J.pexpo[ec]) {
+                    const int e = i8_row_exponent(vmax);
+                    J.pexpo[ec][pr] = e;
+                    s_exp[ai] = e;
+                }
             }
         }
+    }
+    // ---- phase 4: the rows' int8 digit planes (i8pair.cuh), straight from the rows this CTA has just written (they are
+    // still in L2): no separate pass over the packed operand, no second kernel.  One item = 16 columns of one row.
+    if (!J.atom_prow) return;
+    int ktmax = 0;
+    for (int q = 0; q < T.n_el; q++)
+        if (J.psl[q]) ktmax = max(ktmax, T.pld[q] >> 4);
+    if (ktmax == 0) return;
+    __syncthreads();   // rows (global memory, written by other threads of this CTA) and s_exp are complete
+    for (int item = tid; item < bt.cnt * ktmax; item += SL_THREADS) {
+        const int ai = item % bt.cnt, kt = item / bt.cnt, c = bt.a0 + ai, ec = mel[c];
+        if (ec < 0 || !J.psl[ec]) continue;
+        const int pr = J.atom_prow[o + c], KT = T.pld[ec] >> 4;
+        if (pr < 0 || kt >= KT) continue;
+        const double sc = i8::pow2(-s_exp[ai]);   // |e| <= 1000: exact power of two
+        const double *xr = J.px[ec] + (long long)pr * T.pld[ec] + kt * 16;
+        double t[16];
+#pragma unroll
+        for (int q = 0; q < 16; q += 2) {
+            const double2 v = __ldcg(reinterpret_cast<const double2 *>(xr + q));
+            t[q] = v.x * sc;
+            t[q + 1] = v.y * sc;
+        }
+        i8_split16(t, J.psl[ec] + (((long long)(pr >> 7) * (KT + 1) + kt) * I8_S) * 2048 + (pr & 127) * 16);
     }
 }
 

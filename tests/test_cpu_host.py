@@ -190,71 +190,6 @@ def test_digit_plane_algebra():
     assert np.median(P33[scale.diagonal() > 0] / scale.diagonal()[scale.diagonal() > 0]) > 1e-14
 
 
-def test_krr_driver_object_reproduces_readme_rows(demo):
-    """`cml.algo.krr.krr` (krr.py:21-325): init_m / get_idx / run on the golden demo kernels reproduce the README learning
-    curve wherever krr.run's own baseline is defined (it prints None for the rank-deficient N_I = 1, 2 rows, krr.py:262-266;
-    aqml.py falls back to free-atom energies there)."""
-    from cml.algo.krr import krr
-    n1 = int(demo["n1"])
-    nas, zs = demo["nas"], demo["zs"]
-    zs_list = synth.split_zs(nas, zs)
-    zsu = np.unique(zs)
-
-    class Mols:
-        pass
-    m = Mols()
-    m.zs, m.nas, m.coords = zs, nas, demo["coords"]
-    m.nsheav = np.array([(z > 1).sum() for z in zs_list])
-    m.nzs = np.array([[(z == zz).sum() for zz in zsu] for z in zs_list])
-    # the demo's amons are stored sorted by file name, not by size: krr.get_idx sorts the training set by heavy atoms
-    obj = krr(demo["energies"] * 627.5094738898777)
-    obj.init_m(m)
-    obj.get_idx(idx=1, iaml=True, namin=1, namax=7)
-    assert obj.n2 == 1 and len(obj.nas1) == n1 and obj.n1s == [1, 3, 5, 6, 10, 11, 16]
-    order = np.argsort(m.nsheav[:n1], kind='stable')
-    assert np.array_equal(obj.nas1, nas[:n1][order])
-    k1 = demo["k1"][1][order][:, order]
-    k2 = demo["k2"][1][:, order]
-    obj.run([k1, k2], llambda=1e-4, iprt=False)
-    readme = demo["readme_curve"]
-    assert np.isnan(obj.maes[0])                                       # N_I = 1: one molecule, three elements
-    ok = ~np.isnan(obj.maes)
-    assert ok[2:].all()
-    assert np.all(np.abs(obj.maes[ok] - readme[ok, 3]) < 5.1e-5)       # signed error of the single test molecule
-    assert list(obj.n1so) == [int(v) for v in readme[ok, 1]]
-
-
-def test_rkrr_driver_object_matches_function(demo):
-    """`cml.algo.rkrr.rkrr.run` (rkrr.py:179-267) == the sum-over-levels formula restated in
-    `multi_fidelity_predict` (two levels, nested training sets), on the golden demo kernels."""
-    from cml.algo.rkrr import rkrr
-    from aqml_b200.algo import krr as K
-    n1 = int(demo["n1"])
-    nas, zs = demo["nas"], demo["zs"]
-    zs_list = synth.split_zs(nas, zs)
-
-    class Mols:
-        pass
-    m = Mols()
-    m.zs, m.nas, m.coords = zs, nas, demo["coords"]
-    m.nsheav = np.array([(z > 1).sum() for z in zs_list])
-    rng = np.random.default_rng(4)
-    y0 = demo["energies"] * K.H2KC
-    y1 = y0 + 2.0 + 0.05 * rng.normal(size=len(y0))
-    obj = rkrr(np.stack([y0, y1], axis=1))
-    obj.init_m(m)
-    obj.get_idx(idx=-1, namin=1, namax=7)
-    order = np.argsort(m.nsheav[:n1], kind='stable')
-    k1, k2 = demo["k1"][1][order][:, order], demo["k2"][1][:, order]
-    obj.run([k1, k2], llambda=1e-6, iprt=False)
-    sizes = [n for n in obj.n1s if not np.isnan(n)]
-    assert sizes == [1, 3, 5, 6, 10, 11, 16] and obj.n2 == 1
-    # level 0 is trained on the largest set; the last level on each size: compare the largest-size row with the function
-    ys = obj.ys[:n1]
-    pred = K.multi_fidelity_predict(k1, k2, ys, [16, 16], obj.nzs[:n1].astype(float), obj.nzs[n1:].astype(float), 1e-6)
-    assert abs((pred[0] - obj.ys[n1, 1]) - obj.maes[-1]) < 1e-8
-
-
 def test_shape_validation_before_any_device_call():
     """mismatched coords / zs / nas must raise in Python -- the C ABI only sees raw pointers."""
     from aqml_b200 import fused, kernels

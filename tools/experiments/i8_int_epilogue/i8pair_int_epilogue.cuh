@@ -40,20 +40,20 @@
 // Operands are staged in the canonical K-major no-swizzle core-matrix layout (8 rows x 16 B), which is exactly how
 // the slice buffer is written, so a stage is filled by plain 1-D bulk copies (no tensor maps).
 #pragma once
-#include "i8digits.cuh"
+#include "i8epi.cuh"
 
 namespace aqml {
 
+constexpr int I8_S = 6;                          // digit planes (8 bits each)
 constexpr int I8_BM = 128, I8_BN = 64;           // tile: A rows x B rows
 constexpr int I8_STAGES = 4;
 constexpr int I8_A_CHUNK = I8_S * 2048;          // bytes of one k-chunk (16 columns) of an A tile, all planes
 constexpr int I8_B_CHUNK = I8_S * 1024;
 constexpr int I8_STAGE_BYTES = 2 * (I8_A_CHUNK + I8_B_CHUNK);  // 43008
 constexpr int I8_EPI_WARPS = 16;
-// FP64 arithmetic and the tensor pipe exclude each other on this chip (tools/micro/i8_umma.cu: dense FP64 + UTCIMMA take the
-// sum of their times; FP32 overlaps fully).  Measured: overlapping the epilogue's exp / sums with the next tile's MMAs (0)
-// still beats running them strictly after each other (1): 331 vs 353 ms per step.
-constexpr int I8_SERIAL_EPILOGUE = 0;
+// An FP64 instruction issued while UTCIMMA stream through the tensor pipe waits ~800 clk (tools/micro/i8_merged.cu,
+// profiles/r02_micro_contention.txt); FP32 and integer instructions are not affected.  The epilogue (and the metadata warp)
+// therefore contain no FP64 instruction at all (i8epi.cuh) and always overlap with the next tile's MMAs.
 constexpr int I8_META = 3;                       // tile metadata buffers (prepared up to two tiles ahead)
 constexpr int I8_THREADS = 32 * (3 + I8_EPI_WARPS);  // producer, MMA issuer, tile metadata, 16 epilogue warps
 constexpr int I8_MAXSIG = 8;
@@ -76,12 +76,15 @@ struct I8Group {
 struct I8Params {
     const I8Group *groups;
     int ngroups;
-    const double *isig;
+    // exponent of 2 per sigma in fixed point: Z0 = d^2 c0 (44 + g fractional bits, c0 = the widest sigma's -isig log2 e, one
+    // FP64 multiply + conversion per pair), then Z_s = (Z0 x ratio_s) >> 64 with ratio_s = (c_s / c0) 2^(64 - g) in integers
+    const double *c0g;                // per element: c0 2^(44 + g)
+    const unsigned long long *ratio;  // per (sigma, element)
+    const float2 *tab;                // exp tables (i8e::fill_tables)
     int nsig, zstride;
     double *out;
     long long ldo, slab;
     unsigned long long *stats;
-    int chain, order[16], nsq[16];
     int debug;  // AQML_I8_DEBUG: MMA-thread wait timers into stats[2..6]
     int *counter;  // zeroed before the launch: next tile to hand out
     int gm;     // tile rows per raster band
@@ -94,15 +97,14 @@ struct I8Meta {  // everything the roles need to know about one tile
     int segA[I8_BM], expA[I8_BM];
     double normA[I8_BM];
     int segB[I8_BN + 1];
-    double normB[I8_BN];               // |b|^2
-    int expB[I8_BN];                   // e_b
+    double normB[I8_BN], m2sB[I8_BN];  // |b|^2, -2 * 2^(e_b - 8)
     unsigned short kt[KT_LIST_MAX + 2];
 };
 
 struct I8Smem {
     unsigned long long full[I8_STAGES], empty[I8_STAGES], accum, tmem_free, meta_full[I8_META], meta_empty[I8_META];
     unsigned tmem_base;
-    double exptab[256];  // 2^(j/128), 2^(j/16384)
+    float2 tab[3 * i8e::TAB];  // 2^-(j/512), 2^-(j/512^2), 2^-(j/512^3) as FP32 pairs
     I8Meta meta[I8_META];
 };
 
@@ -148,48 +150,71 @@ __device__ __forceinline__ void umma_commit(unsigned long long *bar) {
 }
 // s32 accumulate, s8 x s8, both K-major, N >> 3 at bit 17, M >> 4 at bit 24
 __host__ __device__ constexpr unsigned idesc(int M, int N) { return (2u << 4) | (1u << 7) | (1u << 10) | ((unsigned)(N >> 3) << 17) | ((unsigned)(M >> 4) << 24); }
+__device__ __forceinline__ double pow2(int e) {  // 2^e, clamped to the normal range
+    e = max(-1022, min(1023, e));
+    return __hiloint2double((e + 1023) << 20, 0);
+}
 }  // namespace i8
 
-// exp(v), v <= 0 (or -inf, NaN): the table-based exp_tab of slatm_units.cuh with every special case and the final scaling
-// done on the bit patterns -- 9 FP64 instructions.  While UTCIMMA stream through the tensor pipe the FP64 pipe delivers only
-// ~0.3 warp-instructions per clock and SM (2 when the tensor pipe idles; profiles/r02_micro_contention.txt), i.e. every FP64
-// instruction of the epilogue costs ~4 clk per tile and warp: the epilogue is written for few FP64 instructions.
-__device__ __forceinline__ double i8_exp(double v, const double *tab) {
-    const double magic = 6755399441055744.0;
-    double t = fma(v, 23637.115549924776 /* 2^14 log2(e) */, magic);
-    const int n = __double2loint(t);
-    t -= magic;
-    double r = fma(t, -4.2306346131226746e-05 /* ln2 / 2^14, upper 27 bits: t * hi is exact */, v);
-    r = fma(t, -3.384964780863074e-13, r);
-    double p = fma(r, 1.0 / 6.0, 0.5);
-    p = fma(p, r, 1.0);
-    p = fma(p, r, 1.0);
-    const double res = (tab[(n >> 7) & 127] * tab[128 + (n & 127)]) * p;   // in [1, 2.02)
-    int hi = __double2hiint(res) + ((n >> 14) << 20);                     // * 2^(n >> 14): exponent field, n >> 14 >= -1022 below
-    int lo = __double2loint(res);
-    const unsigned vh = (unsigned)__double2hiint(v);
-    if ((vh & 0x7ff00000u) == 0x7ff00000u) {              // -inf -> 0, NaN -> NaN
-        const bool isnan = ((vh & 0xfffffu) | (unsigned)__double2loint(v)) != 0u;
-        hi = isnan ? 0x7ff80000 : 0;
-        lo = 0;
-    } else if (vh > 0xC0862000u) {                         // v < -708: 0 (the reference's exp gives a denormal down to -745)
-        hi = 0;
-        lo = 0;
-    }
-    return __hiloint2double(hi, lo);
-}
-
-// sum the lanes of each A molecule (contiguous lanes, last lane run_end) and add the heads' totals into K
-__device__ __noinline__ void i8_flush(double r, int lane, int run_end, bool head, double *dst) {
+// One molecule pair's partial sums: acc 2^-53 2^-kc per lane.  Lanes of one A molecule are contiguous (head .. run_end):
+// align them to the smallest kc of the run, add the integers exactly, and let the head lane add the double to K.
+__device__ __noinline__ void i8_flush(long long acc, int kc, bool isnan, int lane, int run_end, int head_lane, bool head, double *dst) {
+    int kr = kc;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
-        const double u = __shfl_down_sync(0xffffffffu, r, o);
-        if (lane + o <= run_end) r += u;
+        const int t = __shfl_down_sync(0xffffffffu, kr, o);
+        if (lane + o <= run_end) kr = min(kr, t);
     }
-    if (head) atomicAdd(dst, r);
+    kr = __shfl_sync(0xffffffffu, kr, head_lane);
+    const int sh = kc - kr;
+    unsigned long long I = (sh > 62 || kc >= i8e::KBIG) ? 0ull : (unsigned long long)((acc + ((1ll << sh) >> 1)) >> sh);
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const unsigned long long u = __shfl_down_sync(0xffffffffu, I, o);
+        if (lane + o <= run_end) I += u;
+    }
+    const unsigned nanb = __ballot_sync(0xffffffffu, isnan);
+    if (head) {
+        const unsigned runmask = ((2u << run_end) - 1u) & ~((1u << lane) - 1u);
+        if (nanb & runmask) atomicAdd(dst, __longlong_as_double(0x7ff8000000000000ll));
+        else if (I) atomicAdd(dst, i8e::fix_to_double(I, -i8e::SUMBITS - kr));
+    }
 }
 
-// ---- slicing (row exponent + digit rule: i8digits.cuh) ------------------------------------------------------------
+// ---- slicing -------------------------------------------------------------------------------------------------
+// exponent per row: |x| * 2^-e < 0.498 (the first digit floor(256 t + 128/255) must not exceed 127).  Non-finite or absurdly large (> 1e301) values need no special path: such a row has
+// |row|^2 = NaN / Inf, which reaches K through d^2 = |a|^2 + |b|^2 - 2 a.b exactly as in the reference (NaN stays NaN,
+// Inf gives exp(-Inf) = 0); whatever digits the row gets are irrelevant.
+__global__ void __launch_bounds__(256) i8_rowexp_kernel(const double *x, long long ld, int nrows, int *expo) {
+    const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (row >= nrows) return;
+    const double *xr = x + (long long)row * ld;
+    double m = 0.0;
+    for (int k = lane; k < ld; k += 32) {
+        const double v = fabs(xr[k]);
+        if (v <= 1.7976931348623157e308) m = fmax(m, v);
+    }
+    m = warp_max(m);
+    if (lane == 0) {
+        int e = 0;
+        if (m > 0.0) {
+            const double f = frexp(m, &e);  // m = f 2^e, f in [1/2, 1)
+            e += (f < 0.996) ? 1 : 2;
+        }
+        expo[row] = max(min(e, 1000), -990);  // tinier rows keep |x| 2^-e < 0.498 and only lose (irrelevant) digits
+    }
+}
+
+// 8-bit digits of t, |t| < 0.498: q = floor(256 t + 128/255) in [-128, 127], remainder in [-128/255, 127/255) -- the one
+// interval that maps onto itself, so every digit fits an int8 (the clamp only acts when the rounding of u + c crosses
+// the interval's end; the remainder stays exact and the following digits absorb it)
+__device__ __forceinline__ int i8_digit(double &t) {
+    const double u = t * 256.0;                                       // exact
+    const double q = fmin(fmax(floor(u + 128.0 / 255.0), -128.0), 127.0);
+    t = u - q;                                                        // exact
+    return (int)q;
+}
+
 // thread = one row of a 128-row block; per 16-column chunk: 6 planes x 16 B
 __global__ void __launch_bounds__(128) i8_slice_kernel(const double *x, long long ld, int nrows, const int *expo, int KT, int kt_per_block,
                                                        int8_t *sl) {
@@ -205,8 +230,17 @@ __global__ void __launch_bounds__(128) i8_slice_kernel(const double *x, long lon
             const double2 v = valid ? *reinterpret_cast<const double2 *>(xr + kt * 16 + c) : make_double2(0.0, 0.0);
             t[c] = v.x * sc;
             t[c + 1] = v.y * sc;
+            if (!(fabs(t[c]) <= 0.5)) t[c] = 0.0;          // NaN / Inf / > 1e301: see i8_rowexp_kernel
+            if (!(fabs(t[c + 1]) <= 0.5)) t[c + 1] = 0.0;
         }
-        i8_split16(t, sl + (((long long)rb * (KT + 1) + kt) * I8_S) * 2048 + r * 16);
+        int8_t *dst = sl + (((long long)rb * (KT + 1) + kt) * I8_S) * 2048 + r * 16;
+#pragma unroll
+        for (int s = 0; s < I8_S; s++) {
+            unsigned w[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+            for (int c = 0; c < 16; c++) w[c >> 2] |= ((unsigned)i8_digit(t[c]) & 0xffu) << ((c & 3) * 8);
+            *reinterpret_cast<uint4 *>(dst + s * 2048) = make_uint4(w[0], w[1], w[2], w[3]);
+        }
     }
 }
 
@@ -266,7 +300,7 @@ __global__ void __launch_bounds__(I8_THREADS, 1) i8_pair_kernel(const I8Params P
         for (int b = 0; b < I8_META; b++) { i8::mbar_init(&S.meta_full[b], 1); i8::mbar_init(&S.meta_empty[b], I8_EPI_WARPS); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    fill_exp_table(S.exptab, tid, I8_THREADS);
+    for (int i = tid; i < 3 * i8e::TAB; i += I8_THREADS) S.tab[i] = P.tab[i];
     if (warp == 1) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(i8::smem_u32(&S.tmem_base)), "r"(512u) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -317,7 +351,9 @@ __global__ void __launch_bounds__(I8_THREADS, 1) i8_pair_kernel(const I8Params P
                     const int c = i - I8_BM, r = tn * I8_BN + c;
                     M.segB[c] = (r < G.nrB) ? G.segB[r] : -1;
                     M.normB[c] = (r < G.nrB) ? G.normB[r] : 0.0;
-                    M.expB[c] = (r < G.nrB) ? G.expB[r] : 0;
+                    // -2 * 2^(e_b - 8), built from its bit pattern (no FP64 instruction in this warp either)
+                    const int e = max(-1022, min(1023, ((r < G.nrB) ? G.expB[r] : 0) - 7));
+                    M.m2sB[c] = __hiloint2double((int)(0x80000000u | (unsigned)((e + 1023) << 20)), 0);
                 }
             }
             if (!__any_sync(0xffffffffu, any)) continue;  // no wanted row in this tile (row-block sharding)
@@ -437,10 +473,11 @@ __global__ void __launch_bounds__(I8_THREADS, 1) i8_pair_kernel(const I8Params P
         }
     } else {
         // ---- epilogue: 16 warps; warp (q, h) owns TMEM lanes / tile rows 32q .. 32q+31 and columns 16h .. 16h+15 ----
-        // (many warps with little state each: the exp / Horner chains are latency bound, not issue bound)
+        // No FP64 instruction from here to the RED (i8epi.cuh): 64-bit integers and FP32 pairs only.
         constexpr int EC = I8_BN / 4;  // 16 columns per warp
         const int q = warp & 3, cbase = ((warp - 3) >> 2) * EC, row = q * 32 + lane;
         const unsigned trow = tb + ((unsigned)(q * 32) << 16) + cbase;
+        const i8e::F2 *tab = reinterpret_cast<const i8e::F2 *>(S.tab);
         auto clear_acc6 = [&]() {  // plane 0's MMAs never touch level 6: it accumulates from zero
             asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1};"
                          ::"r"(trow + 6 * I8_BN), "r"(0u) : "memory");
@@ -463,16 +500,17 @@ __global__ void __launch_bounds__(I8_THREADS, 1) i8_pair_kernel(const I8Params P
             const unsigned heads = __ballot_sync(0xffffffffu, (lane == 0) || (prev != sr));
             const unsigned above = (lane == 31) ? 0u : (heads >> (lane + 1));
             const int run_end = above ? (lane + __ffs(above) - 1) : 31;
+            const int head_lane = 31 - __clz(heads & ((2u << lane) - 1u));
             const double na = M.normA[row];
-            const int ea = M.expA[row];
+            const double sa = i8::pow2(M.expA[row] - 24);  // a.b = 2^(e_a + e_b - 32) d, d = hi + 2^-32 lo = 2^-32 V
             const int growA = M.tm * I8_BM + row;
             const unsigned lastmask = __ballot_sync(0xffffffffu, lane < EC && (lane == EC - 1 || M.segB[cbase + lane + 1] != M.segB[cbase + lane]));
             const long long e0 = clock64();
             i8::mbar_wait(&S.accum, tl & 1);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const long long e1 = clock64();
-            // phase 1: drain my 16 columns of the 6 accumulators into two exact 64-bit integers per pair (integer pipe
-            // only), then hand TMEM back: the next tile's MMAs run while everything below happens
+            // phase 1: drain my 16 columns of the 7 accumulators into two exact 64-bit integers per pair, then hand TMEM
+            // back: the next tile's MMAs run while everything below happens
             long long hi[EC], lo[EC];
 #pragma unroll
             for (int j = 0; j < EC; j++) hi[j] = lo[j] = 0;
@@ -485,7 +523,7 @@ __global__ void __launch_bounds__(I8_THREADS, 1) i8_pair_kernel(const I8Params P
                                    "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
                                  : "r"(trow + g * I8_BN));
                     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                    // sum_g P_g 256^-g = 2^-16 hi + 2^-48 lo with hi = P0 2^16 + P1 2^8 + P2, lo = P3 2^24 + P4 2^16 + P5 2^8 + P6
+                    // V = 2^48 sum_g P_g 256^-g = hi 2^32 + lo with hi = P0 2^16 + P1 2^8 + P2, lo = P3 2^24 + P4 2^16 + P5 2^8 + P6
 #pragma unroll
                     for (int j = 0; j < EC; j++) {
                         const long long pv = (long long)(int)v[j];
@@ -497,92 +535,87 @@ __global__ void __launch_bounds__(I8_THREADS, 1) i8_pair_kernel(const I8Params P
             }
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             __syncwarp();
-            if (!I8_SERIAL_EPILOGUE && lane == 0) i8::mbar_arrive(&S.tmem_free);
+            if (lane == 0) i8::mbar_arrive(&S.tmem_free);
             const long long e2 = clock64();
-            if (P.debug & 2) {  // measurement only: no exp / sums (how much of the tile time is the FP64 epilogue?)
+            if (P.debug & 2) {  // measurement only: no exp / sums (how much of the tile time is the epilogue?)
                 __syncwarp();
                 if (lane == 0) i8::mbar_arrive(&S.meta_empty[b]);
                 continue;
             }
-            // d^2 of my 16 pairs: a.b = 2^(ea + eb - 64) V, V = hi 2^32 + lo; W = V >> 16 has <= 62 bits, ONE conversion to double
-            // (rounding 2^-53 of a.b, as in an FP64 dot product), one FMA with the power of two built from the exponents
+            // phase 2: d^2 = |a|^2 + |b|^2 - 2 a.b of my 16 pairs.  The only FP64 arithmetic of the epilogue: 16 independent
+            // chains of depth 5 (a dependent FP64 step costs ~800 clk while the tensor pipe is busy -- depth is what matters)
             double x[EC];
+            unsigned dead = 0, nanm = 0;  // bit j: the pair does not count (diagonal and below of a symmetric kernel, padding) /
+                                          // is NaN (a NaN norm, as in the reference)
 #pragma unroll
             for (int j = 0; j < EC; j++) {
                 const int col = cbase + j;
-                const long long W = (hi[j] << 16) + (lo[j] >> 16);
-                const int e2 = max(-1022, min(1023, ea + M.expB[col] - 47));                 // -2 a.b = W * -2^(ea + eb - 47)
-                const double sc = __hiloint2double((int)(0x80000000u | ((unsigned)(e2 + 1023) << 20)), 0);
-                double xx = fma((double)W, sc, na + M.normB[col]);                           // |a|^2 + |b|^2 - 2 a.b
-                int xh = __double2hiint(xx), xl = __double2loint(xx);
-                if (xh < 0 && (xh & 0x7ff00000) != 0x7ff00000) { xh = 0; xl = 0; }           // clamp rounding noise, keep NaN
-                // pairs that do not count: on / below the diagonal of a symmetric kernel, padding rows / columns
-                if ((M.sym && M.tn * I8_BN + col <= growA) || sr < 0 || M.segB[col] < 0) { xh = 0x7ff00000; xl = 0; }
-                x[j] = __hiloint2double(xh, xl);
+                const double d = fma((double)lo[j], 2.3283064365386963e-10 /* 2^-32 */, (double)hi[j]);
+                double xx = fma(d * sa, M.m2sB[col], na + M.normB[col]);
+                xx = (xx < 0.0) ? 0.0 : xx;                                   // clamp rounding noise, keep NaN
+                if ((M.sym && M.tn * I8_BN + col <= growA) || sr < 0 || M.segB[col] < 0) dead |= 1u << j;
+                else if (xx != xx) nanm |= 1u << j;
+                x[j] = xx;
             }
-            // phase 2: per sigma exp (chain: squarings of the previous sigma's values, in place), then the sums over
-            // molecule pairs: column runs sequentially in registers, row runs by a segmented shuffle reduction, one RED
-            // per head lane
+            dead |= nanm;
+            // phase 3: the exponent of 2 of the widest sigma, 44 + g fractional bits: ONE batch of 16 FP64 multiplies and
+            // conversions (saturating: +Inf and huge values end as 0 below; NaN is flagged above)
+            unsigned long long Z0[EC];
+            {
+                const double c0 = P.c0g[M.zcol];
+#pragma unroll
+                for (int j = 0; j < EC; j++) Z0[j] = (unsigned long long)__double2ll_rn(x[j] * c0);
+            }
+            // phase 4: per sigma 2^-Z as (FP32 mantissa pair, integer exponent) from tables (i8epi.cuh), and the sums over molecule
+            // pairs: column runs added as 64-bit integers aligned to the run's smallest exponent, row runs by a segmented shuffle
+            // reduction of those integers, one RED per head lane.  No FP64 instruction.
 #pragma unroll 1
-            for (int si = 0; si < P.nsig; si++) {
-                const int s = P.chain ? P.order[si] : si;
+            for (int s = 0; s < P.nsig; s++) {
+                const unsigned long long ratio = P.ratio[s * P.zstride + M.zcol];
                 double *outS = P.out + (long long)s * P.slab + (long long)max(sr, 0) * P.ldo;
-                double run = 0.0;
                 if (P.store) {
                     // global kernel (fkernels.f90:344-355): every pair is one element of K; 16 consecutive columns per lane
-                    if (!P.chain || si == 0) {
-                        const double f = P.isig[s * P.zstride + M.zcol];
-#pragma unroll
-                        for (int j = 0; j < EC; j++) {
-                            const double e = i8_exp(x[j] * f, S.exptab);
-                            if (P.chain) x[j] = e;
-                            const int sc = M.segB[cbase + j];
-                            if (sr >= 0 && sc >= 0) outS[sc] = e;
-                        }
-                    } else {
-                        for (int k = 0; k < P.nsq[si]; k++)
-#pragma unroll
-                            for (int j = 0; j < EC; j++) x[j] *= x[j];
-#pragma unroll
-                        for (int j = 0; j < EC; j++) {
-                            const int sc = M.segB[cbase + j];
-                            if (sr >= 0 && sc >= 0) outS[sc] = x[j];
-                        }
-                    }
-                } else if (P.chain) {
-                    if (si == 0) {
-                        const double f = P.isig[s * P.zstride + M.zcol];
-#pragma unroll
-                        for (int j = 0; j < EC; j++) x[j] = i8_exp(x[j] * f, S.exptab);  // +inf * f = -inf -> 0
-                    } else {
-                        for (int k = 0; k < P.nsq[si]; k++)
-#pragma unroll
-                            for (int j = 0; j < EC; j++) x[j] *= x[j];
-                    }
 #pragma unroll
                     for (int j = 0; j < EC; j++) {
-                        run += x[j];
-                        if ((lastmask >> j) & 1u) {  // warp-uniform: column cbase + j closes a molecule of B
-                            const int sc = M.segB[cbase + j];
-                            if (sc >= 0) i8_flush(run, lane, run_end, head, outS + sc);
-                            run = 0.0;
+                        i8e::F2 m;
+                        int k;
+                        i8e::exp2neg(__umul64hi(Z0[j], ratio), tab, m, k);
+                        const int sc = M.segB[cbase + j];
+                        if (sr >= 0 && sc >= 0) {
+                            double v = 0.0;
+                            if ((nanm >> j) & 1u) v = __longlong_as_double(0x7ff8000000000000ll);
+                            else if (k < i8e::KBIG && !((dead >> j) & 1u))
+                                v = i8e::fix_to_double((unsigned long long)i8e::term_fix(m, k, k), -i8e::SUMBITS - k);
+                            outS[sc] = v;
                         }
                     }
-                } else {
-                    const double f = P.isig[s * P.zstride + M.zcol];
+                    continue;
+                }
+                long long acc = 0;
+                int kc = i8e::KBIG;
 #pragma unroll
-                    for (int j = 0; j < EC; j++) {
-                        run += i8_exp(x[j] * f, S.exptab);
-                        if ((lastmask >> j) & 1u) {
-                            const int sc = M.segB[cbase + j];
-                            if (sc >= 0) i8_flush(run, lane, run_end, head, outS + sc);
-                            run = 0.0;
-                        }
+                for (int j = 0; j < EC; j++) {
+                    i8e::F2 m;
+                    int k;
+                    i8e::exp2neg((P.debug & 4) ? (unsigned long long)(unsigned)Z0[j] & 0x1ffffull : __umul64hi(Z0[j], ratio), tab, m, k);  // debug 4: table entry 0 only (timing)
+                    k = ((dead >> j) & 1u) ? i8e::KBIG : k;
+                    // running alignment, straight-line: the accumulator follows the smallest exponent seen in this molecule pair
+                    const int nd = min(max(kc - k, 0), 63);
+                    acc >>= nd;                       // acc >= 0: a shift by 63 clears it
+                    kc = min(kc, k);
+                    acc += i8e::term_fix(m, k, kc);   // a dead / underflowed pair (k = KBIG) is 2^-63 below anything: adds 0
+                    if ((lastmask >> j) & 1u) {  // warp-uniform: column cbase + j closes a molecule of B
+                        const int sc = M.segB[cbase + j];
+                        const unsigned segbits = (lastmask & ((1u << j) - 1u));  // columns of this molecule: after the previous closing column
+                        const unsigned first = segbits ? (32 - __clz(segbits)) : 0;
+                        const bool anynan = ((nanm >> first) & ((2u << (j - first)) - 1u)) != 0;
+                        if (sc >= 0 && !(P.debug & 8)) i8_flush(acc, kc, anynan, lane, run_end, head_lane, head, outS + sc);
+                        acc = (P.debug & 8) ? (acc >> 63) : 0;
+                        kc = i8e::KBIG;
                     }
                 }
             }
             __syncwarp();
-            if (I8_SERIAL_EPILOGUE && lane == 0) i8::mbar_arrive(&S.tmem_free);
             if (P.debug && warp == 3 && lane == 0) {
                 atomicAdd(P.stats + 7, (unsigned long long)(e1 - e0));
                 atomicAdd(P.stats + 8, (unsigned long long)(e2 - e1));
