@@ -27,27 +27,36 @@ __device__ __forceinline__ int i8_row_exponent(double m) {
     return max(min(e, 1000), -990);  // tinier rows keep |x| 2^-e < 0.498 and only lose (irrelevant) digits
 }
 
-// 8-bit digits of t, |t| < 0.498: q = floor(256 t + 128/255) in [-128, 127], remainder in [-128/255, 127/255) -- the one
-// interval that maps onto itself, so every digit fits an int8 (the clamp only acts when the rounding of u + c crosses
-// the interval's end; the remainder stays exact and the following digits absorb it)
-__device__ __forceinline__ int i8_digit(double &t) {
-    const double u = t * 256.0;                                       // exact
-    const double q = fmin(fmax(floor(u + 128.0 / 255.0), -128.0), 127.0);
-    t = u - q;                                                        // exact
-    return (int)q;
-}
-
-// 16 consecutive columns of one row (already scaled by 2^-e) -> 6 planes x 16 B at dst, dst + 2048, ...
-__device__ __forceinline__ void i8_split16(double (&t)[16], int8_t *dst) {
+// 8-bit digits of t, |t| < 0.498.  Rule: q = floor(256 t + 128/255) in [-128, 127], remainder in [-128/255, 127/255) -- the
+// one interval that maps onto itself, so every digit fits an int8 -- applied six times.  Done on integers: I = rint(t 2^48)
+// (ONE FP64 multiply + conversion per element), J = I + 0x808080808080 (adds 128 to every base-256 digit, carries included:
+// 0 < J < 2^48 because |t| < 0.498 < 128/255), digit_k = byte_k(J) - 128 = byte_k(J) ^ 0x80.  The six bytes of 16 columns
+// are regrouped into the six planes with byte permutes.  ~150 integer instructions per 16 columns instead of ~600 FP64 ones
+// (floor / min / max / subtract per digit).
+//
+// 16 consecutive columns of one row, scale = 2^(48 - e)  ->  6 planes x 16 B at dst, dst + 2048, ...
+__device__ __forceinline__ void i8_split16(const double (&x)[16], double scale, int8_t *dst) {
+    unsigned lo[16], hi[16];   // J = hi 2^32 + lo, hi < 2^16
 #pragma unroll
-    for (int c = 0; c < 16; c++)
-        if (!(fabs(t[c]) <= 0.5)) t[c] = 0.0;          // NaN / Inf / > 1e301: see i8_row_exponent
+    for (int c = 0; c < 16; c++) {
+        long long I = __double2ll_rn(x[c] * scale);
+        if (I >= (1ll << 47) || I <= -(1ll << 47)) I = 0;          // NaN / Inf / > 1e301 (see i8_row_exponent): digits irrelevant
+        const unsigned long long J = (unsigned long long)(I + 0x808080808080ll);
+        lo[c] = (unsigned)J;
+        hi[c] = (unsigned)(J >> 32);
+    }
 #pragma unroll
-    for (int s = 0; s < I8_S; s++) {
-        unsigned w[4] = {0u, 0u, 0u, 0u};
+    for (int p = 0; p < I8_S; p++) {   // plane p = digit of weight 256^-(p+1) = byte 5 - p of J
+        unsigned w[4];
 #pragma unroll
-        for (int c = 0; c < 16; c++) w[c >> 2] |= ((unsigned)i8_digit(t[c]) & 0xffu) << ((c & 3) * 8);
-        *reinterpret_cast<uint4 *>(dst + s * 2048) = make_uint4(w[0], w[1], w[2], w[3]);
+        for (int g = 0; g < 4; g++) {
+            const unsigned *src = (p < 2) ? hi : lo;
+            const int b = (p < 2) ? (1 - p) : (5 - p);             // byte inside the 32-bit word
+            const unsigned a01 = __byte_perm(src[4 * g], src[4 * g + 1], b | ((4 + b) << 4));        // bytes of columns 0, 1
+            const unsigned a23 = __byte_perm(src[4 * g + 2], src[4 * g + 3], b | ((4 + b) << 4));    // bytes of columns 2, 3
+            w[g] = __byte_perm(a01, a23, 0x5410) ^ 0x80808080u;
+        }
+        *reinterpret_cast<uint4 *>(dst + p * 2048) = make_uint4(w[0], w[1], w[2], w[3]);
     }
 }
 

@@ -196,17 +196,17 @@ __global__ void __launch_bounds__(128) i8_slice_kernel(const double *x, long lon
     const int rb = blockIdx.x, r = threadIdx.x, row = rb * 128 + r;
     const int kt0 = blockIdx.y * kt_per_block, kt1 = min(KT, kt0 + kt_per_block);
     const bool valid = row < nrows;
-    const double sc = valid ? i8::pow2(-expo[row]) : 0.0;  // |e| <= 1000: exact power of two
+    const double sc = valid ? i8::pow2(48 - expo[row]) : 0.0;  // |e| <= 1000: exact power of two
     const double *xr = x + (long long)(valid ? row : 0) * ld;
     for (int kt = kt0; kt < kt1; kt++) {
         double t[16];
 #pragma unroll
         for (int c = 0; c < 16; c += 2) {
             const double2 v = valid ? *reinterpret_cast<const double2 *>(xr + kt * 16 + c) : make_double2(0.0, 0.0);
-            t[c] = v.x * sc;
-            t[c + 1] = v.y * sc;
+            t[c] = v.x;
+            t[c + 1] = v.y;
         }
-        i8_split16(t, sl + (((long long)rb * (KT + 1) + kt) * I8_S) * 2048 + r * 16);
+        i8_split16(t, sc, sl + (((long long)rb * (KT + 1) + kt) * I8_S) * 2048 + r * 16);
     }
 }
 

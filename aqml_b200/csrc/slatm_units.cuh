@@ -482,16 +482,16 @@ slatm_units_kernel(const SlatmDev T, const SlatmJob J, const Batch *batches, int
         if (ec < 0 || !J.psl[ec]) continue;
         const int pr = J.atom_prow[o + c], KT = T.pld[ec] >> 4;
         if (pr < 0 || kt >= KT) continue;
-        const double sc = i8::pow2(-s_exp[ai]);   // |e| <= 1000: exact power of two
+        const double sc = i8::pow2(48 - s_exp[ai]);   // |e| <= 1000: exact power of two
         const double *xr = J.px[ec] + (long long)pr * T.pld[ec] + kt * 16;
         double t[16];
 #pragma unroll
         for (int q = 0; q < 16; q += 2) {
             const double2 v = __ldcg(reinterpret_cast<const double2 *>(xr + q));
-            t[q] = v.x * sc;
-            t[q + 1] = v.y * sc;
+            t[q] = v.x;
+            t[q + 1] = v.y;
         }
-        i8_split16(t, J.psl[ec] + (((long long)(pr >> 7) * (KT + 1) + kt) * I8_S) * 2048 + (pr & 127) * 16);
+        i8_split16(t, sc, J.psl[ec] + (((long long)(pr >> 7) * (KT + 1) + kt) * I8_S) * 2048 + (pr & 127) * 16);
     }
 }
 
