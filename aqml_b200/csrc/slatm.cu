@@ -772,7 +772,7 @@ static bool launch_i8(std::vector<I8Group> &gs, const PairParams &PP, Workspace 
     P.debug = getenv("AQML_I8_DEBUG") ? atoi(getenv("AQML_I8_DEBUG")) : 0;
     P.store = store;
     P.counter = ws.zeros<int>(1);
-    P.gm = getenv("AQML_I8_GM") ? std::max(1, atoi(getenv("AQML_I8_GM"))) : 16;
+    P.gm = getenv("AQML_I8_GM") ? std::max(1, atoi(getenv("AQML_I8_GM"))) : 32;  // 32: lowest DRAM traffic (16: +25 %, 64: +35 %, 96: 4 x; the time does not depend on it)
     if (P.debug) AQML_CUDA(cudaMemsetAsync(P.stats + 2, 0, 64, ws.stream()));
     kern<<<std::min(total, sms), I8_THREADS, smem, ws.stream()>>>(P, total);
     AQML_LAUNCH_CHECK();
@@ -929,9 +929,12 @@ static void rep_create(const double *coords, int on_dev, const int *zs, const in
         if (planes && !rows[e].empty()) { add((size_t)((nr + 127) / 128) * (ld / 16 + 1) * I8_A_CHUNK, 1); add(nr, 4); }
     }
     keep.reserve(total);
-    // AQML_FUSE_PLANES=0: digit planes by the separate split kernels (a second pass over the packed operand) instead of the
-    // aSLATM kernel's phase 4
-    static const bool fuse = !(getenv("AQML_FUSE_PLANES") && atoi(getenv("AQML_FUSE_PLANES")) == 0);
+    // Digit planes: by default two small split kernels after the aSLATM kernel (a second pass over the packed operand).
+    // AQML_FUSE_PLANES=1 lets the aSLATM kernel write them itself (slatm_units.cuh, phase 4).  Measured (10 k molecules,
+    // profiles/r02_slatm_units_kernel_ncu.txt): fused 20.5 ms, separate 18.1 ms -- with ~590 CTAs x 290 KB of rows in flight
+    // (172 MB > the 126 MB L2) the re-read of phase 4 misses L2 half of the time (4.2 GB of DRAM reads), so the fusion
+    // saves neither traffic nor time until the work units are handed out atom-major (rows would complete one by one).
+    const bool fuse = getenv("AQML_FUSE_PLANES") && atoi(getenv("AQML_FUSE_PLANES")) != 0;
     // pass 2: carve (same order)
     std::vector<int> atom_prow(mi.A, -1);
     SlatmJob J;

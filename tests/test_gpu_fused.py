@@ -158,3 +158,21 @@ def test_eight_sigmas_on_the_int8_engine():
         ref = co.calc_lk_gaussian(xl[A1:], xl[:A1], zs[A1:], zs[:A1], nas[n1:], nas[:n1], 9, False, sig)
         K = fused.local_gaussian(test, train, sig, 9).cpu().numpy()
         assert K.shape == ref.shape and kernel_rel_err(K, ref) < TOL
+
+
+def test_digit_planes_written_by_the_aslatm_kernel(monkeypatch):
+    """AQML_FUSE_PLANES=1: the aSLATM kernel writes the int8 digit planes of a row itself (phase 4) instead of the two split
+    kernels: same digits from the same FP64 rows, so K agrees to the order of the REDs."""
+    import torch
+    nas, zs, coords = synth.qm9_like(60, 77)
+    mb = rcore.get_slatm_mbtypes(synth.split_zs(nas, zs))
+    kw = dict(sigmas=(.05, .05), dgrids=(.04, .04), rcut=4.8)
+    out = []
+    for fuse in ("0", "1"):
+        monkeypatch.setenv("AQML_FUSE_PLANES", fuse)
+        r = fused.PackedRep(coords, zs, nas, mb, **kw)
+        dso = fused.kernel_width(r, r, 9)
+        sig = np.array([c * dso / np.sqrt(2 * np.log(2)) for c in (0.5, 1.0, 2.0)])
+        out.append(fused.local_gaussian(r, r, sig, 9).cpu())
+        r.close()
+    assert torch.allclose(out[0], out[1], rtol=1e-13, atol=0)
