@@ -82,6 +82,8 @@ def parse():
     ap.add_argument("--n-cols", type=int, default=100000)
     ap.add_argument("--rows-per-gpu", type=int, default=12500)
     ap.add_argument("--kernel", default="gaussian", choices=["gaussian", "laplacian"])
+    ap.add_argument("--square", action="store_true", help="config3: the n_cols x n_cols problem, rows split over the ranks")
+    ap.add_argument("--no-config3", action="store_true", help="N >= 4: skip the embedded 100k x 100k global-kernel measurement")
     return ap.parse_args()
 
 
@@ -407,6 +409,16 @@ def run_ours(args):
     ph = dict(zip(PH, phases))
     atoms_all = int(train[0].sum() + test[0].sum())
 
+    # ---- N >= 4: BASELINE configs[2] / the north_star's target, driver-measured: the 100k x 100k global SLATM Gaussian kernel,
+    # 4 sigmas, rows split over the ranks (K of one rank: 100k / N x 100k x 4 x 8 B -- it fits from N = 4 on) ----------------
+    config3 = None
+    if world >= 4 and not args.no_config3:
+        sk.close()
+        out.clear()
+        torch.cuda.empty_cache()
+        config3 = config3_measure(args, rank, local_rank, world, steps=2, warmup=2, n_cols=100000, rows_per_gpu=0, kernel="gaussian",
+                                  square=True)
+
     if rank == 0:
         p = L.slatm_params(mb, **{k: SLATM_KW[k] for k in SLATM_KW})
         nel = 5
@@ -513,6 +525,8 @@ def run_ours(args):
         if e2e_ms is not None:
             line["e2e"] = {"value": elems_all / (e2e_max * 1e-3), "unit": "kernel elements/s",
                            "h2d_bytes_per_step": int(h2d_all), "d2h_bytes_per_step": int(d2h_all), "ms_per_step": e2e_max}
+        if config3 is not None:
+            line["config3_100k_x_100k"] = config3
         if world == 1 and not args.no_cpu_baseline:
             r = cpu_sample(args, steps=1, warmup=0)
             line["cpu_baseline"] = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}
@@ -525,46 +539,41 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
-def run_config3(args):
-    """BASELINE.json configs[2]: 100k x 100k global SLATM kernel with 4 sigmas, row-block sharded: every rank
-    builds K[:, rows_r, :] for its own --rows-per-gpu molecules against all --n-cols molecules (no collective).
-    Step = coordinates -> global SLATM (rows + columns) -> K block resident in HBM."""
+def config3_measure(args, rank, local_rank, world, steps, warmup, n_cols, rows_per_gpu, kernel, square):
+    """BASELINE.json configs[2]: global SLATM kernel with 4 sigmas, row-block sharded.  square: THE n_cols x n_cols problem
+    (north_star: "100k x 100k ... row blocks of the training set across the 8xB200 box") -- rank r builds K[:, rows_r, :] for
+    its 1/N of the molecules against all of them; the SLATM rows are generated 1/N per rank and all-gathered once over NCCL
+    (the rank's own rows are a slice of the result).  Otherwise every rank has its own rows_per_gpu query molecules.
+    Step = coordinates -> global SLATM -> K block resident in HBM.  Returns the JSON-able result (all ranks)."""
     import torch
     import torch.distributed as dist
     from aqml_b200 import _lib as L
-    from aqml_b200 import kernels, synth
+    from aqml_b200 import distance, kernels, parallel, synth
     from aqml_b200.representation import core as rcore
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    torch.cuda.set_device(local_rank)
-    if world > 1:
-        init_nccl(local_rank)
     dev = torch.device("cuda", local_rank)
-    cols = synth.qm9_like_fast(args.n_cols, SEED + 7, pool=512)
-    rows = synth.qm9_like_fast(args.rows_per_gpu, SEED + 7 + 1000 * (rank + 1), pool=256)
-    mb = mbtypes_for(cols, rows)
+    cols = synth.qm9_like_fast(n_cols, SEED + 7, pool=512)
+    rows = None if square else synth.qm9_like_fast(rows_per_gpu, SEED + 7 + 1000 * (rank + 1), pool=256)
+    mb = mbtypes_for(cols, cols if square else rows)
     kw = dict(sigmas=[.05, .05], dgrids=[.04, .04], rcut=4.8)
-    cc, cr = torch.as_tensor(cols[2], device=dev), torch.as_tensor(rows[2], device=dev)
-    xs = rcore.generate_slatm_batch(cc[:int(cols[0][:2000].sum())], cols[1][:int(cols[0][:2000].sum())], cols[0][:2000],
-                                    mb, local=False, **kw)
-    from aqml_b200 import distance
-    dmax = distance.max_distance(xs, xs, 2 if args.kernel == "gaussian" else 1)
+    cc = torch.as_tensor(cols[2], device=dev)
+    cr = None if square else torch.as_tensor(rows[2], device=dev)
+    nsub = int(cols[0][:2000].sum())
+    xs = rcore.generate_slatm_batch(cc[:nsub], cols[1][:nsub], cols[0][:2000], mb, local=False, **kw)
+    dmax = distance.max_distance(xs, xs, 2 if kernel == "gaussian" else 1)
     del xs
-    fac = 1.0 / np.sqrt(2 * np.log(2)) if args.kernel == "gaussian" else 1.0 / np.log(2)
+    fac = 1.0 / np.sqrt(2 * np.log(2)) if kernel == "gaussian" else 1.0 / np.log(2)
     sig = np.array([c * dmax * fac for c in COEFFS])
     D = int(L.load().aqml_slatm_dim(L.slatm_params(mb, **SLATM_KW)))
     ev = lambda: torch.cuda.Event(enable_timing=True)  # noqa: E731
-
     # SLATM of the column molecules is sharded by molecules over the ranks, then one all-gather (SURVEY 8e)
-    from aqml_b200 import parallel
     shard = world > 1 and not os.environ.get("AQML_NO_SLATM_SHARD")
+    parts = [parallel.shard_range(n_cols, r, world) for r in range(world)]
+    clo, chi = parts[rank]
     if shard:
-        parts = [parallel.shard_range(args.n_cols, r, world) for r in range(world)]
-        clo, chi = parts[rank]
         coff = np.concatenate(([0], np.cumsum(cols[0])))
         cc_loc, zs_loc, nas_loc = cc[coff[clo]:coff[chi]], cols[1][coff[clo]:coff[chi]], cols[0][clo:chi]
         counts = [h - l for l, h in parts]
+    nrows = (chi - clo) if square else rows_per_gpu
 
     def step(tm=None):
         e = [ev() for _ in range(3)]
@@ -573,15 +582,15 @@ def run_config3(args):
             xc = parallel.allgather_rows(rcore.generate_slatm_batch(cc_loc, zs_loc, nas_loc, mb, local=False, **kw), counts)
         else:
             xc = rcore.generate_slatm_batch(cc, cols[1], cols[0], mb, local=False, **kw)
-        xr = rcore.generate_slatm_batch(cr, rows[1], rows[0], mb, local=False, **kw)
+        xr = xc[clo:chi] if square else rcore.generate_slatm_batch(cr, rows[1], rows[0], mb, local=False, **kw)
         e[1].record()
-        K = kernels.global_kernels(xr, xc, sig, args.kernel)
+        K = kernels.global_kernels(xr, xc, sig, kernel)
         e[2].record()
         if tm is not None:
             tm.append(e)
         return K
 
-    for _ in range(max(args.warmup, 3)):
+    for _ in range(max(warmup, 1)):
         K = step()
         del K
     torch.cuda.synchronize()
@@ -590,7 +599,7 @@ def run_config3(args):
     tm = []
     a, b = ev(), ev()
     a.record()
-    for _ in range(args.steps):
+    for _ in range(steps):
         K = step(tm)
         del K
     b.record()
@@ -600,22 +609,37 @@ def run_config3(args):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     tot, t_sl, t_k = [float(v) for v in t.cpu()]
+    torch.cuda.empty_cache()
+    ms = tot / steps
+    S = len(COEFFS)
+    total_rows = n_cols if square else world * rows_per_gpu
+    return {
+        "metric": "global_%s_kernel_elements_per_sec" % kernel,
+        "value": S * total_rows * n_cols / (ms * 1e-3), "unit": "kernel elements/s",
+        "n_gpus": world, "steps": steps, "warmup": max(warmup, 1), "ms_per_step": ms,
+        "higher_is_better": True, "scaling": "strong" if square else "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "config3: global SLATM %s kernel, 4 sigmas, %s, D=%d; K row-block sharded%s"
+                               % (kernel, ("the %d x %d problem, %d rows per GPU" % (n_cols, n_cols, nrows)) if square
+                                  else ("%d rows per GPU x %d columns" % (rows_per_gpu, n_cols)), D,
+                                  "; SLATM generated 1/N per rank + one NCCL all-gather" if shard else ", no collective")},
+        "phases_ms": {"slatm_incl_allgather": t_sl, "kernel_incl_pack": t_k},
+        "slatm_molecules_per_sec": (n_cols if square else world * (n_cols + rows_per_gpu)) / (t_sl * 1e-3),
+        "kernel_fp64_equiv_tflops_per_gpu": 2.0 * D * nrows * n_cols / (t_k * 1e-3) / 1e12}
+
+
+def run_config3(args):
+    import torch
+    import torch.distributed as dist
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        init_nccl(local_rank)
+    res = config3_measure(args, rank, local_rank, world, args.steps, max(args.warmup, 3), args.n_cols, args.rows_per_gpu, args.kernel,
+                          square=args.square)
     if rank == 0:
-        ms = tot / args.steps
-        S = len(COEFFS)
-        ops = 2.0 * D * args.rows_per_gpu * args.n_cols
-        print(json.dumps({
-            "metric": "global_%s_kernel_elements_per_sec" % args.kernel,
-            "value": world * S * args.rows_per_gpu * args.n_cols / (ms * 1e-3), "unit": "kernel elements/s",
-            "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "config3: global SLATM %s kernel, 4 sigmas, %d rows per GPU x %d columns, D=%d; "
-                                   "K row-block sharded%s" % (args.kernel, args.rows_per_gpu, args.n_cols, D,
-                                                           "; column SLATM generated 1/N per rank + one NCCL all-gather" if shard
-                                                           else ", no collective")},
-            "phases_ms": {"slatm": t_sl, "kernel_incl_pack": t_k},
-            "slatm_molecules_per_sec": world * (args.n_cols + args.rows_per_gpu) / (t_sl * 1e-3),
-            "kernel_tera_ops": ops / (t_k * 1e-3) / 1e12}))
+        print(json.dumps(res))
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
