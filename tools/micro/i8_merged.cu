@@ -165,6 +165,106 @@ __global__ void __launch_bounds__(128) rate_kernel(int rounds, int fill, const i
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tb), "r"(512u) : "memory");
 }
 
+// (5) the main loop of (3) on a 2-CTA cluster that SHARES the A tile: each CTA loads half of the A planes (3 of 6) and multicasts
+// it into both CTAs' stage buffers, its own B tile stays private: 24 KB instead of 36 KB per stage and SM from L2.  A stage
+// may be refilled when BOTH CTAs' MMAs have read it: the MMA threads' commits arrive on both CTAs' `empty` barriers (count 2).
+__device__ __forceinline__ void bulk_g2s_mc(void *dst, const void *src, uint32_t bytes, uint64_t *bar, uint16_t mask) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)), "h"(mask) : "memory");
+}
+__device__ __forceinline__ void umma_commit_mc(uint64_t *bar, uint16_t mask) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)), "h"(mask) : "memory");
+}
+template <int VAR>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128) rate_cluster_kernel(int rounds, const int8_t *src, long long src_bytes, long long *cycles) {
+    extern __shared__ __align__(1024) int8_t sm[];
+    __shared__ __align__(8) uint64_t full[4], empty[4], done;
+    __shared__ uint32_t tmem_base;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    unsigned rank;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
+    for (int i = tid; i < 4 * STAGE; i += 128) sm[i] = (int8_t)((i * 37 + 11) % 255 - 127);
+    if (tid == 0) {
+        for (int s = 0; s < 4; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], 2); }
+        mbar_init(&done, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base)), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tb = tmem_base;
+    const long long t0 = clock64();
+    if (warp == 0 && (tid & 31) == 0) {
+        // both CTAs of a cluster walk the same A window (cluster id), their own B windows
+        const long long cl = blockIdx.x >> 1;
+        long long posA = (cl * 7919 * STAGE) % (src_bytes - STAGE), posB = ((long long)blockIdx.x * 104729 * STAGE) % (src_bytes - STAGE);
+        for (int r = 0; r < rounds; r++) {
+            const int s = r & 3;
+            if (r >= 4) mbar_wait(&empty[s], ((r >> 2) - 1) & 1);
+            mbar_expect_tx(&full[s], STAGE);
+            int8_t *st = sm + s * STAGE;
+            for (int c = 0; c < 2; c++) {
+                // my half of the A chunk (3 planes = 6 KB) into BOTH CTAs; my B chunk (6 x 1 KB) into mine
+                bulk_g2s_mc(st + c * A_CHUNK + rank * (A_CHUNK / 2), src + posA + c * A_CHUNK + rank * (A_CHUNK / 2), A_CHUNK / 2, &full[s], (uint16_t)3);
+                for (int p = 0; p < S; p++) bulk_g2s(st + 2 * A_CHUNK + c * B_CHUNK + p * 1024, src + posB + 2 * A_CHUNK + c * B_CHUNK + p * 1024, 1024, &full[s]);
+            }
+            posA += STAGE; posB += STAGE;
+            if (posA + STAGE > src_bytes) posA = 0;
+            if (posB + STAGE > src_bytes) posB = 0;
+        }
+    } else if (warp == 1 && (tid & 31) == 0) {
+        for (int r = 0; r < rounds; r++) {
+            const int s = r & 3;
+            mbar_wait(&full[s], (r >> 2) & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            issue_stage<VAR>(tb, smem_u32(sm + s * STAGE), 0u);
+            umma_commit_mc(&empty[s], (uint16_t)3);
+        }
+        umma_commit(&done);
+        mbar_wait(&done, 0);
+        cycles[blockIdx.x] = clock64() - t0;
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tb), "r"(512u) : "memory");
+}
+
+template <int VAR>
+static void run_rate_cluster(const int8_t *src, long long src_bytes) {
+    int dev = 0, sms = 0;
+    CK(cudaGetDevice(&dev));
+    CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    sms &= ~1;
+    long long *dcy;
+    CK(cudaMalloc(&dcy, sms * 8));
+    CK(cudaFuncSetAttribute(rate_cluster_kernel<VAR>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * STAGE));
+    const int rounds = 20000;
+    rate_cluster_kernel<VAR><<<sms, 128, 4 * STAGE>>>(200, src, src_bytes, dcy);
+    CK(cudaDeviceSynchronize());
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+    CK(cudaEventRecord(e0));
+    rate_cluster_kernel<VAR><<<sms, 128, 4 * STAGE>>>(rounds, src, src_bytes, dcy);
+    CK(cudaEventRecord(e1));
+    CK(cudaDeviceSynchronize());
+    float ms = 0;
+    CK(cudaEventElapsedTime(&ms, e0, e1));
+    std::vector<long long> cy(sms);
+    CK(cudaMemcpy(cy.data(), dcy, sms * 8, cudaMemcpyDeviceToHost));
+    const int nprod = VAR ? 26 : 22;
+    const double ops = 2.0 * 128 * 64 * 32 * nprod * (double)rounds * sms;
+    printf("%d products, 2-CTA clusters sharing the A tile by multicast (24 KB per stage and SM from L2): %.3f ms, %.2f POPS (int8), %.1f clk per stage (SM0)\n",
+           nprod, ms, ops / (ms * 1e-3) / 1e15, (double)cy[0] / rounds);
+    cudaFree(dcy);
+}
+
 template <int VAR>
 static void run_check() {
     std::vector<int8_t> img(STAGE);
@@ -330,6 +430,8 @@ int main(int argc, char **argv) {
     run_rate<1>(0, src, src_bytes);
     run_rate<0>(1, src, src_bytes);
     run_rate<1>(1, src, src_bytes);
+    run_rate_cluster<0>(src, src_bytes);
+    run_rate_cluster<1>(src, src_bytes);
     cudaFree(src);
     return 0;
 }
