@@ -58,7 +58,11 @@ SIGNATURES = {
     "aqml_generate_slatm_batch_dev": (_I, [_P, _P, _P, _I, C.POINTER(SlatmParams), _I, _P, _L, _P]),
     "aqml_rep_create": (_I, [_P, _I, _P, _P, _I, C.POINTER(SlatmParams), _P, C.POINTER(_P)]),
     "aqml_rep_create_ex": (_I, [_P, _I, _P, _P, _I, C.POINTER(SlatmParams), _I, _P, C.POINTER(_P)]),
-    "aqml_rep_slab": (_I, [_P, C.POINTER(_P), C.POINTER(_L)]),
+    "aqml_rep_slab": (_I, [_P, _I, C.POINTER(_P), C.POINTER(_L)]),
+    "aqml_rep_elements": (_I, [_P]),
+    "aqml_rep_element": (_I, [_P, _I, C.POINTER(_I), C.POINTER(_I), C.POINTER(_I), C.POINTER(_P)]),
+    "aqml_rows_colsum_dev": (_I, [_P, _L, _I, _I, _P, _P]),
+    "aqml_rows_dist_dev": (_I, [_I, _P, _L, _I, _P, _I, _P, _P]),
     "aqml_rep_destroy": (None, [_P]),
     "aqml_rep_bytes": (_L, [_P]),
     "aqml_rep_local_gaussian": (_I, [_P, _P, _P, _I, _I, _I, _I, _P, _P]),

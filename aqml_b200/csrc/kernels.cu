@@ -842,6 +842,27 @@ int aqml_global_kernel_dev(int kind, const double *a, int na, int64_t lda, const
     });
 }
 
+int aqml_rows_colsum_dev(const double *x, int64_t ld, int n, int ncols, double *colsum, void *stream) {
+    return guarded([&] {
+        AQML_REQUIRE(x && colsum && n >= 0 && ncols >= 1 && ld >= ncols, "bad argument");
+        require_device();
+        if (n == 0) return;
+        cudaStream_t st = (cudaStream_t)stream;
+        Workspace ws(st);
+        launch_colstats(x, ld, nullptr, n, ncols, colsum, ws.zeros<unsigned>(ncols), st);
+    });
+}
+
+int aqml_rows_dist_dev(int p, const double *x, int64_t ld, int n, const double *c, int ncols, double *r, void *stream) {
+    return guarded([&] {
+        AQML_REQUIRE((p == 1 || p == 2) && x && c && r && n >= 0 && ncols >= 1 && ld >= ncols, "bad argument");
+        require_device();
+        if (n == 0) return;
+        row_dist_kernel<<<(n + 7) / 8, 256, 0, (cudaStream_t)stream>>>(p, x, ld, n, c, ncols, r);
+        AQML_LAUNCH_CHECK();
+    });
+}
+
 int aqml_max_distance_dev(int p, const double *a, int na, int64_t lda, const double *b, int nb, int64_t ldb, int D,
                           double *dmax, void *stream) {
     return guarded([&] {

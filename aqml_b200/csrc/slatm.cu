@@ -710,8 +710,10 @@ struct aqml_rep {
         int nr = 0;            // packed rows (multiple of 64)
     };
     bool i8_ready = false;     // every element has digit planes
-    unsigned char *slab = nullptr;  // the one allocation everything above lives in
+    unsigned char *slab = nullptr;  // the allocation the pair kernel's operands live in (norms, molecule index, masks, planes, exponents)
     int64_t slab_bytes = 0;
+    unsigned char *xslab = nullptr; // the allocation of the packed FP64 rows; null: built without them (AQML_REP_NO_ROWS)
+    int64_t xslab_bytes = 0;
     mutable std::vector<std::pair<cudaStream_t, cudaEvent_t>> uses;  // last consumer launch per foreign stream (aqml_rep_destroy waits)
     std::vector<El> els;
     std::vector<int> nas;
@@ -889,11 +891,13 @@ static bool use_i8(const aqml_rep *r1, const aqml_rep *r2, int nsigmas) {
 // arrive from the rank that computed them (aqml_rep_slab + a broadcast; the layout depends only on zs / nas / p)
 static void rep_create(const double *coords, int on_dev, const int *zs, const int *nas, int nmol,
                        const aqml_slatm_params *p, int flags, cudaStream_t st, aqml_rep **out) {
-    const bool compute = !(flags & 1);
+    const bool compute = !(flags & 1), with_x = !(flags & 2);
     AQML_REQUIRE((coords || !compute) && zs && nas && out && nmol >= 1, "bad argument");
+    AQML_REQUIRE(with_x || !compute, "AQML_REP_NO_ROWS needs AQML_REP_LAYOUT_ONLY");
     require_device();
     Workspace ws(st);     // temporaries
-    Workspace keep(st);   // becomes the rep's storage
+    Workspace keep(st);   // becomes the rep's storage: |row|^2, molecule index, masks, digit planes, exponents -- what the pair kernel reads
+    Workspace keepx(st);  // ... and the packed FP64 rows (width pass, FP64 engine, source of the digit planes)
     SlatmTables t = build_tables(p, true, ws);
     MolIndex mi = index_molecules(nas, nmol);
     AQML_REQUIRE(mi.A >= 1, "no atoms");
@@ -918,17 +922,19 @@ static void rep_create(const double *coords, int on_dev, const int *zs, const in
     const bool planes = i8_engine_enabled();
     // pass 1: packed row maps and the size of the storage (one slab, so that a rep can travel as one buffer)
     std::vector<std::vector<int>> rms(ne), sgs(ne);
-    size_t total = 0;
-    auto add = [&](size_t n, size_t elem) { total = Workspace::slab_aligned(total) + (n ? n : 1) * elem; };  // = Workspace::alloc
+    size_t total = 0, totalx = 0;
+    auto add = [&](size_t &tot, size_t n, size_t elem) { tot = Workspace::slab_aligned(tot) + (n ? n : 1) * elem; };  // = Workspace::alloc
     for (int e = 0; e < ne; e++) {
         build_tiles(rows[e], mols[e], rms[e], sgs[e]);
         const size_t nr = rms[e].size(), ld = (size_t)t.dev.pld[e];
         const int mw = mask_words((long long)ld);
-        add(nr * ld, 8); add(nr, 8); add(nr, 4);
-        if (mw <= 32 && nr) add(nr / 64 * (size_t)mw, 4);
-        if (planes && !rows[e].empty()) { add((size_t)((nr + 127) / 128) * (ld / 16 + 1) * I8_A_CHUNK, 1); add(nr, 4); }
+        add(totalx, nr * ld, 8);
+        add(total, nr, 8); add(total, nr, 4);
+        if (mw <= 32 && nr) add(total, nr / 64 * (size_t)mw, 4);
+        if (planes && !rows[e].empty()) { add(total, (size_t)((nr + 127) / 128) * (ld / 16 + 1) * I8_A_CHUNK, 1); add(total, nr, 4); }
     }
     keep.reserve(total);
+    if (with_x) keepx.reserve(totalx);
     // Digit planes: by default two small split kernels after the aSLATM kernel (a second pass over the packed operand).
     // AQML_FUSE_PLANES=1 lets the aSLATM kernel write them itself (slatm_units.cuh, phase 4).  Measured (10 k molecules,
     // profiles/r02_slatm_units_kernel_ncu.txt): fused 20.5 ms, separate 18.1 ms -- with ~590 CTAs x 290 KB of rows in flight
@@ -944,7 +950,7 @@ static void rep_create(const double *coords, int on_dev, const int *zs, const in
         aqml_rep::El el;
         el.label = t.labels[e]; el.n = (int)rows[e].size(); el.tiles = (int)rm.size() / BM; el.ld = t.dev.pld[e];
         size_t nr = rm.size();
-        el.x = keep.alloc<double>(nr * (size_t)el.ld);
+        el.x = with_x ? keepx.alloc<double>(nr * (size_t)el.ld) : nullptr;
         el.norm = keep.alloc<double>(nr);
         el.seg = keep.alloc<int>(nr);
         if (compute && nr) AQML_CUDA(cudaMemcpyAsync(el.seg, sg.data(), nr * sizeof(int), cudaMemcpyHostToDevice, st));
@@ -999,8 +1005,11 @@ static void rep_create(const double *coords, int on_dev, const int *zs, const in
     }
     rep->i8_ready = planes;
     rep->slab = keep.slab(); rep->slab_bytes = (int64_t)keep.slab_bytes();
+    rep->xslab = with_x ? keepx.slab() : nullptr; rep->xslab_bytes = with_x ? (int64_t)keepx.slab_bytes() : 0;
     rep->owned = keep.pointers();
+    for (void *q : keepx.pointers()) rep->owned.push_back(q);
     keep.release_all();
+    keepx.release_all();
     *out = rep.release();
 }
 
@@ -1014,7 +1023,7 @@ static void rep_groups(const aqml_rep *r1, const aqml_rep *r2, int zmax, std::ve
             AQML_REQUIRE(z >= 1 && z <= zmax, "element %d outside 1..zmax=%d", z, zmax);
             PairGroup g;
             memset(&g, 0, sizeof(g));
-            g.A = a.x; g.B = b.x; g.normA = a.norm; g.normB = b.norm; g.segA = a.seg; g.segB = b.seg;
+            g.A = a.x; g.B = b.x; g.normA = a.norm; g.normB = b.norm; g.segA = a.seg; g.segB = b.seg;  // null x: checked by the caller if used
             g.ld = a.ld; g.tilesM = a.tiles; g.tilesN = b.tiles * (BM / BN); g.zcol = z - 1; g.segA_off = 0; g.segA_n = 0x7fffffff;
             g.maskA = a.mask; g.maskB = b.mask; g.maskw = a.maskw;
             groups.push_back(g);
@@ -1134,11 +1143,24 @@ int aqml_rep_create_ex(const double *coords, int coords_on_device, const int *zs
     return guarded([&] { rep_create(coords, coords_on_device, zs, nas, nmol, p, flags, (cudaStream_t)stream, out); });
 }
 
-int aqml_rep_slab(const aqml_rep *r, void **ptr, int64_t *bytes) {
+int aqml_rep_slab(const aqml_rep *r, int which, void **ptr, int64_t *bytes) {
     return guarded([&] {
-        AQML_REQUIRE(r && ptr && bytes, "bad argument");
-        *ptr = r->slab;
-        *bytes = r->slab_bytes;
+        AQML_REQUIRE(r && ptr && bytes && (which == 0 || which == 1), "bad argument");
+        *ptr = which ? r->xslab : r->slab;
+        *bytes = which ? r->xslab_bytes : r->slab_bytes;
+    });
+}
+
+int aqml_rep_elements(const aqml_rep *r) { return r ? (int)r->els.size() : 0; }
+
+int aqml_rep_element(const aqml_rep *r, int e, int *label, int *n, int *ld, const double **x) {
+    return guarded([&] {
+        AQML_REQUIRE(r && e >= 0 && e < (int)r->els.size(), "bad argument");
+        const auto &el = r->els[e];
+        if (label) *label = el.label;
+        if (n) *n = el.n;
+        if (ld) *ld = el.ld;
+        if (x) *x = el.x;
     });
 }
 
@@ -1187,8 +1209,10 @@ int aqml_rep_local_gaussian(const aqml_rep *r1, const aqml_rep *r2, const double
         P.isig = ws.upload(isig); P.nsig = nsigmas; P.zstride = zmax;
         plan_sigma_chain(P, isig);
         P.out = K; P.ldo = r2->nmol; P.slab = (long long)nrows * r2->nmol;
-        if (!(use_i8(r1, r2, nsigmas) && run_pairs_i8(r1, r2, zmax, row0, nrows, false, P, ws)))
+        if (!(use_i8(r1, r2, nsigmas) && run_pairs_i8(r1, r2, zmax, row0, nrows, false, P, ws))) {
+            AQML_REQUIRE(r1->xslab && r2->xslab, "the FP64 engine needs the FP64 rows (representation built with AQML_REP_NO_ROWS)");
             run_pairs_public(MODE_DOT, EPI_LOCAL, groups, P, ws);
+        }
         mark_use(r1, st);
         mark_use(r2, st);
     });
@@ -1225,8 +1249,10 @@ int aqml_rep_local_gaussian_sym(const aqml_rep *r, const double *sigmas, int nsi
         P.isig = ws.upload(isig); P.nsig = nsigmas; P.zstride = zmax;
         plan_sigma_chain(P, isig);
         P.out = K; P.ldo = n; P.slab = (long long)n * n;
-        if (!(use_i8(r, r, nsigmas) && run_pairs_i8(r, r, zmax, 0, n, true, P, ws)))
+        if (!(use_i8(r, r, nsigmas) && run_pairs_i8(r, r, zmax, 0, n, true, P, ws))) {
+            AQML_REQUIRE(r->xslab, "the FP64 engine needs the FP64 rows (representation built with AQML_REP_NO_ROWS)");
             run_pairs_public(MODE_DOT, EPI_LOCAL, groups, P, ws);
+        }
         dim3 grid((n + 31) / 32, (n + 31) / 32, nsigmas);
         symmetrize_kernel<<<grid, 256, 0, st>>>(K, n, nsigmas, ws.upload(diag));
         AQML_LAUNCH_CHECK();
@@ -1256,6 +1282,7 @@ int aqml_rep_kernel_width_multi(const aqml_rep *const *reps1, int n1, const aqml
                     auto it = lds.find(e.label);
                     if (it == lds.end()) lds[e.label] = e.ld;
                     else AQML_REQUIRE(it->second == e.ld, "representations were built with different many-body types");
+                    AQML_REQUIRE(e.x, "this representation was built without its FP64 rows (AQML_REP_NO_ROWS)");
                     (second ? segs[e.label].second : segs[e.label].first).push_back(RowSeg{e.x, e.n});
                 }
             }

@@ -15,21 +15,23 @@ import numpy as np
 from . import _lib as L
 
 
-class _DeviceBytes:
+class _DeviceArray:
     """CUDA array interface over a raw device allocation (torch.as_tensor wraps it without a copy)."""
 
-    def __init__(self, ptr, nbytes):
-        self.__cuda_array_interface__ = {"shape": (int(nbytes),), "typestr": "|u1", "data": (int(ptr), False), "version": 2}
+    def __init__(self, ptr, shape, typestr="|u1"):
+        self.__cuda_array_interface__ = {"shape": tuple(int(v) for v in shape), "typestr": typestr, "data": (int(ptr), False),
+                                         "version": 2}
 
 
 class PackedRep:
     """aSLATM of a set of molecules, packed by element on the current CUDA device.
 
     ``compute=False`` only lays out the storage (``coordinates`` may be None): the contents are then received
-    from the rank that computed them (``slab_tensor`` + a broadcast, ``parallel.share_reps``)."""
+    from the rank that computed them (``slab_tensor`` + a broadcast, ``parallel.share_reps``); ``rows=False`` (with
+    ``compute=False``) leaves the packed FP64 rows out -- enough for the int8 tensor engine, which reads the digit planes."""
 
     def __init__(self, coordinates, nuclear_charges, nas, mbtypes, izeff=False, sigmas=(0.05, 0.05),
-                 dgrids=(0.03, 0.03), rcut=4.8, rpower=6, compute=True):
+                 dgrids=(0.03, 0.03), rcut=4.8, rpower=6, compute=True, rows=True):
         import torch
         self._h = C.c_void_p()
         self.nas = L.i32(nas)
@@ -50,14 +52,29 @@ class PackedRep:
         self.device = coords.device if on_dev else torch.device("cuda", torch.cuda.current_device())
         with torch.cuda.device(self.device):
             L.call("aqml_rep_create_ex", L.ptr(coords), int(on_dev), L.ptr(self.zs), L.ptr(self.nas), self.nmol, p,
-                   0 if compute else 1, L.current_stream(), C.byref(self._h))
+                   (0 if compute else 1) | (0 if rows else 2), L.current_stream(), C.byref(self._h))
+        self.has_rows = bool(rows)
 
-    def slab_tensor(self):
-        """The representation's storage as one uint8 CUDA tensor (a view: valid while this object lives)."""
+    def slab_tensor(self, which=0):
+        """The representation's storage as a uint8 CUDA tensor (a view: valid while this object lives): which = 0 what the
+        pair kernel reads (norms, molecule index, masks, digit planes, exponents), which = 1 the packed FP64 rows."""
         import torch
         ptr, nb = C.c_void_p(), C.c_int64()
-        L.call("aqml_rep_slab", self._h, C.byref(ptr), C.byref(nb))
-        return torch.as_tensor(_DeviceBytes(ptr.value, nb.value), device=self.device)
+        L.call("aqml_rep_slab", self._h, int(which), C.byref(ptr), C.byref(nb))
+        if not ptr.value:
+            raise L.AqmlError("this representation was built without its FP64 rows")
+        return torch.as_tensor(_DeviceArray(ptr.value, (nb.value,)), device=self.device)
+
+    def element_rows(self):
+        """{Z: (n, ld) float64 CUDA view of the element's valid packed rows} (views: valid while this object lives)."""
+        import torch
+        out = {}
+        for e in range(int(L.load().aqml_rep_elements(self._h))):
+            label, n, ld, x = C.c_int(), C.c_int(), C.c_int(), C.c_void_p()
+            L.call("aqml_rep_element", self._h, e, C.byref(label), C.byref(n), C.byref(ld), C.byref(x))
+            if n.value > 0 and x.value:
+                out[int(label.value)] = torch.as_tensor(_DeviceArray(x.value, (n.value, ld.value), "<f8"), device=self.device)
+        return out
 
     @property
     def nbytes(self):

@@ -95,7 +95,7 @@ def allgather_rows(x_local, counts, group=None):
     return torch.cat([out[r * nmax:r * nmax + counts[r]] for r in range(world)], dim=0)
 
 
-def share_reps(reps, owners, group=None):
+def share_reps(reps, owners, group=None, rows=False):
     """Packed representations computed 1/N per rank, made complete on every rank ("SLATM: molecules are
     independent -> ranges per GPU, then one all-gather so every GPU holds the full column-side representation").
     reps[b] is a PackedRep on every rank -- computed where owners[b] == rank, laid out only (compute=False) elsewhere;
@@ -105,8 +105,10 @@ def share_reps(reps, owners, group=None):
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
         return
     src = (lambda r: dist.get_global_rank(group, r)) if group is not None else (lambda r: r)
-    views = [r.slab_tensor() for r in reps]   # keep the views alive until the collectives have been waited for
-    works = [dist.broadcast(v, src=src(o), group=group, async_op=True) for v, o in zip(views, owners)]
+    # keep the views alive until the collectives have been waited for; rows=True also ships the packed FP64 rows (needed
+    # only by the FP64 engine and by a width pass over foreign blocks)
+    views = [(r.slab_tensor(w), o) for r, o in zip(reps, owners) for w in ((0, 1) if rows else (0,))]
+    works = [dist.broadcast(v, src=src(o), group=group, async_op=True) for v, o in views]
     for w in works:
         w.wait()
 

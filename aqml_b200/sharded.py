@@ -8,9 +8,15 @@ One process per GPU.  The training set is cut into 2 N blocks of molecules; rank
 
   phase       what a rank does                                                        exchange
   aslatm      packs its two training blocks (+ the test set)                          --
-  allgather   --                                                                      each block's storage once (NCCL broadcast
-                                                                                      of one buffer per block, `parallel.share_reps`)
-  width       max distance per element over (its blocks) x (all blocks + test)        all-reduce(MAX) of (zmax,) doubles
+  allgather   --                                                                      each block's pair-kernel operands (digit planes,
+                                                                                      norms, masks: 6 of the 14 bytes per packed
+                                                                                      element) once: one NCCL broadcast per block
+                                                                                      (`parallel.share_reps`), enqueued BEFORE ...
+  width       ... the max distance per element over all train + test atoms, computed   per element: all-reduce of the column sums,
+              where the FP64 rows are (every rank sweeps only its own rows):           two row broadcasts, small all-gathers
+              distances to the common mean, two farthest-point sweeps for an           (candidates: a few % of the rows)
+              attained lower bound, then only the rows the triangle inequality         -- on a second communicator, so that it
+              leaves are gathered and contracted exactly (same pruning as on one GPU)   overlaps the broadcasts of the blocks
   k_train     tiles (b, c), c <= b, of its block rows; diagonal tiles symmetric       --
   k_test      K(test, its training blocks): K_test sharded by training columns        --
   predict     partial K_test . alpha over its columns                                  all-reduce(SUM) of (nsigmas, n_test)
@@ -57,6 +63,7 @@ class ShardedKernels(object):
         self.mine = [b for b in range(self.nblk) if self.owners[b] == self.rank]
         self.tiles = my_tiles(self.rank, self.world)
         self.reps, self.test = [None] * self.nblk, None
+        self.group2, self._works, self._views = None, [], []
 
     # ---- phases ---------------------------------------------------------------------------------------------
     def _block(self, b):
@@ -70,25 +77,134 @@ class ShardedKernels(object):
         for b in range(self.nblk):
             nas, zs, sl = self._block(b)
             own = self.owners[b] == self.rank
-            self.reps[b] = fused.PackedRep(coords_train[sl] if own else None, zs, nas, self.mbtypes, compute=own, **self.kw)
+            self.reps[b] = fused.PackedRep(coords_train[sl] if own else None, zs, nas, self.mbtypes, compute=own, rows=own, **self.kw)
         self.test = fused.PackedRep(coords_test, self.zs2, self.nas2, self.mbtypes, **self.kw)
 
-    def share(self):
-        """Every training block travels once from its owner to the other ranks."""
+    def share_begin(self):
+        """Enqueue the broadcasts: every training block's pair-kernel operands travel once from their owner to the other
+        ranks (the packed FP64 rows stay where they were computed)."""
+        self._works = []
         if self.world > 1:
-            parallel.share_reps(self.reps, self.owners, group=self.group)
+            import torch.distributed as dist
+            src = (lambda r: dist.get_global_rank(self.group, r)) if self.group is not None else (lambda r: r)
+            self._views = [r.slab_tensor(0) for r in self.reps]
+            self._works = [dist.broadcast(v, src=src(o), group=self.group, async_op=True) for v, o in zip(self._views, self.owners)]
+
+    def share_end(self):
+        for w in self._works:
+            w.wait()
+        self._works, self._views = [], []
+
+    def share(self):
+        self.share_begin()
+        self.share_end()
 
     def width(self):
         """dmax per element over all training + test atoms (get_kernel_width with dmxby='a', aqml.py:744-749)."""
+        if self.world == 1:
+            everything = self.reps + [self.test]
+            return fused.kernel_width(everything, everything, self.zmax)
+        return self._width_distributed()
+
+    def _width_distributed(self):
+        """The pruned max-distance pass of `aqml_rep_kernel_width_multi` over rows that live on different GPUs: nobody ever
+        holds all rows.  Exact: the candidates are contracted by the same EPI_MAX pair kernel."""
+        import ctypes as C
         import torch
         import torch.distributed as dist
-        everything = self.reps + [self.test]
+        from . import _lib as L
+        if self.group2 is None:   # a second communicator: these small collectives must not queue behind the block broadcasts
+            self.group2 = dist.new_group(list(range(self.world))) if self.group is None else self.group
+        g, dev = self.group2, self.test.device
         mine = [self.reps[b] for b in self.mine] + ([self.test] if self.rank == self.world - 1 else [])
-        if self.world == 1:
-            return fused.kernel_width(everything, everything, self.zmax)
-        dso = torch.as_tensor(fused.kernel_width(mine, everything, self.zmax), device=self.test.device)
-        dist.all_reduce(dso, op=dist.ReduceOp.MAX, group=self.group)
-        return dso.cpu().numpy()
+        rows = [r.element_rows() for r in mine]
+        labels = sorted(int(t[0]) for t in self.mbtypes if len(t) == 1)
+        st = L.current_stream(dev)
+        dso = np.full(self.zmax, 1.e-9)
+
+        def sweep(segs, point):   # distance of every local row to one point
+            out = []
+            for x in segs:
+                r = torch.empty(x.shape[0], dtype=torch.float64, device=dev)
+                if x.shape[0]:
+                    L.call("aqml_rows_dist_dev", 2, L.ptr(x), x.stride(0), x.shape[0], L.ptr(point), x.shape[1], L.ptr(r), st)
+                out.append(r)
+            return torch.cat(out) if out else torch.empty(0, dtype=torch.float64, device=dev)
+
+        def global_max(v):   # (max over all ranks, owner rank, local index on the owner); NaN anywhere -> NaN
+            loc = torch.full((3,), -1.0, dtype=torch.float64, device=dev)
+            if v.numel():
+                m, i = torch.max(v, dim=0)
+                loc[0], loc[1] = m, i.to(torch.float64)
+                loc[2] = torch.isnan(v).any().to(torch.float64)
+            allv = [torch.empty_like(loc) for _ in range(self.world)]
+            dist.all_gather(allv, loc, group=g)
+            tab = torch.stack(allv).cpu().numpy()
+            if (tab[:, 2] > 0).any():
+                return float("nan"), 0, 0
+            owner = int(np.argmax(tab[:, 0]))
+            return float(tab[owner, 0]), owner, int(tab[owner, 1])
+
+        def row_from(owner, idx, allrows, ncols):
+            p = torch.empty(ncols, dtype=torch.float64, device=dev)
+            if owner == self.rank:
+                p.copy_(allrows(idx))
+            dist.broadcast(p, src=owner if self.group is None else dist.get_global_rank(g, owner), group=g)
+            return p
+
+        for z in labels:
+            segs = [d[z] for d in rows if z in d]
+            if not segs:
+                raise RuntimeError("internal: element %d missing from a packed block" % z)
+            ncols = int(segs[0].shape[1])
+            nloc = sum(int(x.shape[0]) for x in segs)
+            offs = np.concatenate(([0], np.cumsum([int(x.shape[0]) for x in segs])))
+
+            def local_row(i):
+                k = int(np.searchsorted(offs, i, side="right") - 1)
+                return segs[k][i - offs[k]]
+
+            stat = torch.zeros(ncols + 1, dtype=torch.float64, device=dev)
+            for x in segs:
+                if x.shape[0]:
+                    L.call("aqml_rows_colsum_dev", L.ptr(x), x.stride(0), x.shape[0], ncols, L.ptr(stat), st)
+            stat[ncols] = nloc
+            dist.all_reduce(stat, group=g)
+            ntot = int(round(float(stat[ncols].item())))
+            if ntot == 0:
+                continue
+            centre = (stat[:ncols] / ntot).contiguous()
+            r = sweep(segs, centre)
+            rmax, o1, i1 = global_max(r)
+            if rmax != rmax:
+                dso[z - 1] = float("nan")
+                continue
+            t1 = sweep(segs, row_from(o1, i1, local_row, ncols))
+            l1, o2, i2 = global_max(t1)
+            t2 = sweep(segs, row_from(o2, i2, local_row, ncols))
+            l2, _, _ = global_max(t2)
+            low = max(l1, l2) * (1.0 - 1e-9)    # an attained distance: only rows with r_i + max r >= low can take part in the maximum
+            sel = torch.nonzero(r + rmax >= low).flatten()
+            cand = torch.empty((0, ncols), dtype=torch.float64, device=dev)
+            if nloc and sel.numel():   # gather the survivors segment by segment (never a copy of all local rows)
+                cut = torch.searchsorted(sel, torch.as_tensor(offs, device=dev)).tolist()
+                cand = torch.cat([x[sel[cut[k]:cut[k + 1]] - int(offs[k])] for k, x in enumerate(segs)])
+            cnt = torch.tensor([cand.shape[0]], dtype=torch.int64, device=dev)
+            cnts = [torch.empty_like(cnt) for _ in range(self.world)]
+            dist.all_gather(cnts, cnt, group=g)
+            cnts = [int(c.item()) for c in cnts]
+            kmax = max(cnts)
+            pad = torch.zeros((kmax, ncols), dtype=torch.float64, device=dev)
+            pad[:cand.shape[0]] = cand
+            parts = [torch.empty_like(pad) for _ in range(self.world)]
+            dist.all_gather(parts, pad, group=g)
+            allc = torch.cat([p[:c] for p, c in zip(parts, cnts)]).contiguous()
+            dm = C.c_double(0.0)
+            with torch.cuda.device(dev):
+                L.call("aqml_max_distance_dev", 2, L.ptr(allc), allc.shape[0], allc.stride(0), L.ptr(allc), allc.shape[0], allc.stride(0),
+                       ncols, C.c_void_p(C.addressof(dm)), st)
+            dso[z - 1] = dm.value
+        return dso
 
     def alloc_out(self, nsig):
         """Device buffers for my tiles of K_train and my column blocks of K_test."""

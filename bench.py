@@ -271,7 +271,8 @@ def run_ours(args):
     c2 = torch.as_tensor(test[2], device=dev)
     rng = np.random.Generator(np.random.PCG64(SEED))
     alpha = torch.as_tensor(rng.standard_normal((S, args.n_train)) / args.n_train, device=dev)  # stands in for the solver's output
-    PH = ("aslatm", "allgather", "width", "k_train", "k_test", "predict")
+    PH = ("aslatm", "width", "allgather", "k_train", "k_test", "predict")   # N > 1: the broadcasts are enqueued before the width
+                                                                              # pass and waited for after it ("allgather" = the wait)
     out = {}
 
     def ev():
@@ -285,9 +286,10 @@ def run_ours(args):
         if not out:
             out["kt"], out["ks"] = sk.alloc_out(S)
         mark(1)
-        sk.share()
-        mark(2)
+        sk.share_begin()
         sig = sigmas_from(sk.width())
+        mark(2)
+        sk.share_end()
         mark(3)
         sk.k_train(sig, out["kt"], after)
         mark(4)
@@ -359,7 +361,7 @@ def run_ours(args):
             del os.environ["AQML_PAIR_ENGINE"]
 
     # ---- end to end through the public API with host buffers ----------------------------------------------------
-    e2e_ms, h2d, d2h = None, 0, 0
+    e2e_ms, h2d, d2h, e2e_phases = None, 0, 0, [0.0] * len(PH)
     if not args.no_e2e:
         pc1 = torch.as_tensor(train[2]).pin_memory().numpy()
         pc2 = torch.as_tensor(test[2]).pin_memory().numpy()
@@ -375,9 +377,11 @@ def run_ours(args):
             with torch.cuda.stream(side):
                 host[key].copy_(t, non_blocking=True)
 
-        def e2e_step():
+        e2e_timing = []
+
+        def e2e_step(tm=None):
             cur.wait_stream(side)            # the previous step's copies have left the tile buffers
-            y, _ = step(coords=(pc1, pc2), after=to_host)
+            y, _ = step(tm, coords=(pc1, pc2), after=to_host)
             yh.copy_(y, non_blocking=True)
             cur.wait_stream(side)
         for _ in range(2):
@@ -387,23 +391,24 @@ def run_ours(args):
         n_e2e = max(2, min(args.steps, 3))
         a.record()
         for _ in range(n_e2e):
-            e2e_step()
+            e2e_step(e2e_timing)
         b.record()
         barrier()
         e2e_ms = a.elapsed_time(b) / n_e2e
+        e2e_phases = [float(np.mean([e[i].elapsed_time(e[i + 1]) for e in e2e_timing])) for i in range(len(PH))]
         atoms_mine = sum(int(sk.nas1[lo:hi].sum()) for lo, hi in (sk.bounds[b] for b in sk.mine)) + int(sk.nas2.sum())
         h2d = atoms_mine * (24 + 4) + sig.nbytes
         d2h = sum(int(v.numel()) * 8 for v in host.values()) + yh.numel() * 8
         del host
 
     # ---- reduce over ranks ----------------------------------------------------------------------------------------
-    vals = torch.tensor([t_total_ms, e2e_ms or 0.0] + phases, dtype=torch.float64, device=dev)
+    vals = torch.tensor([t_total_ms, e2e_ms or 0.0] + phases + e2e_phases, dtype=torch.float64, device=dev)
     sums = torch.tensor([float(h2d), float(d2h), float(sk.unique_elements(S)), kt_exec, float(launches)], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(vals, op=dist.ReduceOp.MAX)
         dist.all_reduce(sums, op=dist.ReduceOp.SUM)
     vals = [float(v) for v in vals.cpu()]
-    t_total_ms, e2e_max, phases = vals[0], vals[1], vals[2:]
+    t_total_ms, e2e_max, phases, e2e_phases = vals[0], vals[1], vals[2:2 + len(PH)], vals[2 + len(PH):]
     h2d_all, d2h_all, elems_all, kt_exec_all, launches_all = [float(v) for v in sums.cpu()]
     ms_per_step = t_total_ms / args.steps
     ph = dict(zip(PH, phases))
@@ -524,7 +529,8 @@ def run_ours(args):
                 "note": "the north_star's literal design point (FP64 DMMA tiles), kept as the fallback engine"}
         if e2e_ms is not None:
             line["e2e"] = {"value": elems_all / (e2e_max * 1e-3), "unit": "kernel elements/s",
-                           "h2d_bytes_per_step": int(h2d_all), "d2h_bytes_per_step": int(d2h_all), "ms_per_step": e2e_max}
+                           "h2d_bytes_per_step": int(h2d_all), "d2h_bytes_per_step": int(d2h_all), "ms_per_step": e2e_max,
+                           "phases_ms": dict(zip(PH, e2e_phases))}
         if config3 is not None:
             line["config3_100k_x_100k"] = config3
         if world == 1 and not args.no_cpu_baseline:

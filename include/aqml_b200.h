@@ -83,6 +83,13 @@ int aqml_distance_dev(int p, const double *a, int na, int64_t lda, const double 
 int aqml_global_kernel_dev(int kind, const double *a, int na, int64_t lda, const double *b, int nb, int64_t ldb,
                            int D, const double *sigmas, int nsig, int center, double *K, void *stream);
 
+/* Building blocks of the max-distance pass when the rows are spread over several GPUs (aqml_b200/sharded.py: the
+ * reference's get_kernel_width, aqml.py:204-255, over rows that never meet on one device): column sums of n rows ADDED to
+ * colsum (DEVICE, ncols), and the distance (p = 2: Euclidean, 1: Manhattan) of every row to one point c (DEVICE) -> r (DEVICE, n).
+ * Asynchronous on `stream`. */
+int aqml_rows_colsum_dev(const double *x, int64_t ld, int n, int ncols, double *colsum, void *stream);
+int aqml_rows_dist_dev(int p, const double *x, int64_t ld, int n, const double *c, int ncols, double *r, void *stream);
+
 /* max_{i,j} |a_i - b_j|_p (p = 2 or 1) without materialising the distance matrix: the
  * reduction get_kernel_width needs (algo/aqml.py:204-255: np.max(l2_distance(x_z, x_z))).
  * a, b DEVICE; result written to HOST *dmax (synchronises the stream). */
@@ -185,10 +192,18 @@ int aqml_rep_create(const double *coords, int coords_on_device, const int *zs, c
  * multi-GPU code generates 1/N of the molecule blocks per rank and ships each block once over NCCL
  * (aqml_b200/parallel.py::share_reps) instead of recomputing it N times. */
 #define AQML_REP_LAYOUT_ONLY 1
+/* Bit 1 (AQML_REP_NO_ROWS, only with LAYOUT_ONLY): do not allocate the packed FP64 rows either -- the receiver of a block only
+ * contracts it on the int8 tensor engine, which reads the digit planes; the width pass runs distributed on the owners' rows
+ * (aqml_b200/sharded.py) and the FP64 engine refuses such a representation. */
+#define AQML_REP_NO_ROWS 2
 int aqml_rep_create_ex(const double *coords, int coords_on_device, const int *zs, const int *nas, int nmol,
                        const aqml_slatm_params *p, int flags, void *stream, aqml_rep **out);
-/* the representation's single device allocation: pointer (DEVICE) and size in bytes */
-int aqml_rep_slab(const aqml_rep *r, void **ptr, int64_t *bytes);
+/* the representation's device allocations: which = 0 the pair kernel's operands (|row|^2, molecule index, k-tile masks, digit
+ * planes, exponents), which = 1 the packed FP64 rows (NULL / 0 with AQML_REP_NO_ROWS); pointer (DEVICE) and size in bytes */
+int aqml_rep_slab(const aqml_rep *r, int which, void **ptr, int64_t *bytes);
+/* element groups of a representation: count; label (Z), valid rows n (the first n packed rows), row pitch ld, DEVICE rows */
+int aqml_rep_elements(const aqml_rep *r);
+int aqml_rep_element(const aqml_rep *r, int e, int *label, int *n, int *ld, const double **x);
 /* frees on the creation stream after every kernel that read the representation on another stream has finished */
 void aqml_rep_destroy(aqml_rep *r);
 int64_t aqml_rep_bytes(const aqml_rep *r);

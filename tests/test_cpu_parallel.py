@@ -108,7 +108,7 @@ class _FakeRep(object):
         self.buf = torch.full((nbytes,), fill, dtype=torch.uint8)
         self.nmol = nbytes
 
-    def slab_tensor(self):
+    def slab_tensor(self, which=0):
         return self.buf
 
     def close(self):

@@ -413,7 +413,105 @@ static void run_contention() {
     cudaFree(dcy); cudaFree(dsink);
 }
 
+// (6) what bounds the operand feed?  The main loop of (3) with switches: `mma` 0: the consumer only waits for the stage and frees
+// it (pure L2 -> shared-memory copy rate); `same` 1: every CTA reads the same window (maximal overlap of the requests in L2);
+// `one` 1: a stage is ONE 36 KB bulk copy instead of 2 + 12; grid = number of CTAs (one per SM): fewer SMs -> per-SM or chip-wide limit?
+template <int VAR>
+__global__ void __launch_bounds__(128) feed_kernel(int rounds, int mma, int same, int one, const int8_t *src, long long src_bytes, long long *cycles) {
+    extern __shared__ __align__(1024) int8_t sm[];
+    __shared__ __align__(8) uint64_t full[4], empty[4], done;
+    __shared__ uint32_t tmem_base;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    for (int i = tid; i < 4 * STAGE; i += 128) sm[i] = (int8_t)((i * 37 + 11) % 255 - 127);
+    if (tid == 0) {
+        for (int s = 0; s < 4; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        mbar_init(&done, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base)), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tb = tmem_base;
+    const long long t0 = clock64();
+    if (warp == 0 && (tid & 31) == 0) {
+        long long pos = same ? 0 : ((long long)blockIdx.x * 7919 * STAGE) % (src_bytes - STAGE);
+        for (int r = 0; r < rounds; r++) {
+            const int s = r & 3;
+            if (r >= 4) mbar_wait(&empty[s], ((r >> 2) - 1) & 1);
+            mbar_expect_tx(&full[s], STAGE);
+            int8_t *st = sm + s * STAGE;
+            if (one) bulk_g2s(st, src + pos, STAGE, &full[s]);
+            else
+                for (int c = 0; c < 2; c++) {
+                    bulk_g2s(st + c * A_CHUNK, src + pos + c * A_CHUNK, A_CHUNK, &full[s]);
+                    for (int p = 0; p < S; p++) bulk_g2s(st + 2 * A_CHUNK + c * B_CHUNK + p * 1024, src + pos + 2 * A_CHUNK + c * B_CHUNK + p * 1024, 1024, &full[s]);
+                }
+            pos += STAGE;
+            if (pos + STAGE > src_bytes) pos = 0;
+        }
+    } else if (warp == 1 && (tid & 31) == 0) {
+        for (int r = 0; r < rounds; r++) {
+            const int s = r & 3;
+            mbar_wait(&full[s], (r >> 2) & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            if (mma) { issue_stage<VAR>(tb, smem_u32(sm + s * STAGE), 0u); umma_commit(&empty[s]); }
+            else { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&empty[s])) : "memory"); }
+        }
+        if (mma) { umma_commit(&done); mbar_wait(&done, 0); }
+        cycles[blockIdx.x] = clock64() - t0;
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tb), "r"(512u) : "memory");
+}
+
+static void run_feed(const int8_t *src, long long src_bytes) {
+    int dev = 0, sms = 0;
+    CK(cudaGetDevice(&dev));
+    CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    long long *dcy;
+    CK(cudaMalloc(&dcy, sms * 8));
+    CK(cudaFuncSetAttribute(feed_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * STAGE));
+    const int rounds = 20000;
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+    const int grids[4] = {sms, sms / 2, sms / 4, 8};
+    for (int mma = 0; mma < 2; mma++)
+        for (int same = 0; same < 2; same++)
+            for (int one = 0; one < 2; one++)
+                for (int gi = 0; gi < 4; gi++) {
+                    const int g = grids[gi];
+                    feed_kernel<0><<<g, 128, 4 * STAGE>>>(200, mma, same, one, src, src_bytes, dcy);
+                    CK(cudaDeviceSynchronize());
+                    CK(cudaEventRecord(e0));
+                    feed_kernel<0><<<g, 128, 4 * STAGE>>>(rounds, mma, same, one, src, src_bytes, dcy);
+                    CK(cudaEventRecord(e1));
+                    CK(cudaDeviceSynchronize());
+                    float ms = 0;
+                    CK(cudaEventElapsedTime(&ms, e0, e1));
+                    long long cy0;
+                    CK(cudaMemcpy(&cy0, dcy, 8, cudaMemcpyDeviceToHost));
+                    printf("feed: mma %d same-window %d one-copy %d CTAs %3d: %.1f clk per 36 KB stage (CTA 0), %.2f TB/s L2 -> SM in total, %.1f B/clk per SM\n",
+                           mma, same, one, g, (double)cy0 / rounds, (double)STAGE * rounds * g / (ms * 1e-3) / 1e12, (double)STAGE * rounds / (double)cy0);
+                }
+    cudaFree(dcy);
+}
+
 int main(int argc, char **argv) {
+    if (argc > 1 && argv[1][0] == 'f') {
+        const long long src_bytes = 64ll << 20;
+        int8_t *src;
+        CK(cudaMalloc(&src, src_bytes));
+        CK(cudaMemset(src, 1, src_bytes));
+        run_feed(src, src_bytes);
+        cudaFree(src);
+        return 0;
+    }
     if (argc > 1 && argv[1][0] == 'c') {
         run_contention<0>();
         run_contention<1>();
