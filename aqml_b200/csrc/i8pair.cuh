@@ -41,6 +41,7 @@
 // the slice buffer is written, so a stage is filled by plain 1-D bulk copies (no tensor maps).
 #pragma once
 #include "i8digits.cuh"
+#include <cuda.h>   // CUtensorMap (encoded on the host through cudaGetDriverEntryPoint: no link against libcuda)
 
 namespace aqml {
 
@@ -58,6 +59,7 @@ constexpr int I8_META = 3;                       // tile metadata buffers (prepa
 constexpr int I8_THREADS = 32 * (3 + I8_EPI_WARPS);  // producer, MMA issuer, tile metadata, 16 epilogue warps
 constexpr int I8_MAXSIG = 8;
 constexpr int I8_NACC = 7;                       // accumulators: levels i + j = 0 .. 6
+constexpr int I8_MAXGROUPS = 16;                // element groups per launch (their tensor maps travel as kernel parameters)
 constexpr int I8_MAX_LD = 21840;                 // int32 accumulators: <= 6 products each, 6 * ld * 128^2 < 2^31 (longer rows: FP64 engine)
 
 struct I8Group {
@@ -86,10 +88,15 @@ struct I8Params {
     int *counter;  // zeroed before the launch: next tile to hand out
     int gm;     // tile rows per raster band
     int store;  // 0: sum exp over the atoms of each molecule pair (local kernels); 1: K[s][seg_a][seg_b] = exp (global kernels)
+    // per group: the B operand's slice buffer as a 3-D tensor {2 KB plane of a 128-row block, 6 planes, row block x k-chunk}; the
+    // box {half a plane = 64 rows, 6 planes, 1} is one B k-chunk of a tile in ONE copy instruction (the per-instruction cost of
+    // cp.async.bulk, ~57 clk, bounded the operand ring when the six 1 KB pieces were six copies: profiles/r02_micro_feed.txt)
+    CUtensorMap tmB[I8_MAXGROUPS];
 };
 
 struct I8Meta {  // everything the roles need to know about one tile
     int tm, tn, nact, KT, zcol, sym, dense;  // dense: every k-chunk 0 .. KT-1 is active (no list)
+    int group;
     const int8_t *srcA, *srcB;
     int segA[I8_BM], expA[I8_BM];
     double normA[I8_BM];
@@ -135,6 +142,11 @@ __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, unsigned by
 }
 // K-major, no swizzle: 8 rows x 16 B core matrices; sbo = byte stride between 8-row groups, lbo = between the two
 // 16-byte k-chunks of one MMA (checked bit-exactly by tools/micro/i8_umma.cu)
+// one B k-chunk of a tile: box {128 x 8 B, 6 planes, 1} of the group's tensor map -> [plane][64 rows x 16 B] in shared memory
+__device__ __forceinline__ void tensor_g2s(void *dst, const CUtensorMap *tm, int c0, int c1, int c2, unsigned long long *bar) {
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+                 ::"r"(smem_u32(dst)), "l"(tm), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar)) : "memory");
+}
 __device__ __forceinline__ unsigned long long smem_desc(unsigned addr, unsigned lbo, unsigned sbo) {
     return (unsigned long long)((addr & 0x3FFFF) >> 4) | ((unsigned long long)(lbo >> 4) << 16) |
            ((unsigned long long)(sbo >> 4) << 32) | (1ull << 46);
@@ -253,7 +265,7 @@ __global__ void __launch_bounds__(128) i8_peak_kernel(int rounds) {
 // keeps filling across tile boundaries.
 // VAR 0: 22 products (i + j <= 5 and (3,3)); VAR 1: 26 products (i + j <= 6)
 template <int VAR>
-__global__ void __launch_bounds__(I8_THREADS, 1) i8_pair_kernel(const I8Params P, int total_tiles) {
+__global__ void __launch_bounds__(I8_THREADS, 1) i8_pair_kernel(const __grid_constant__ I8Params P, int total_tiles) {
     extern __shared__ __align__(1024) unsigned char i8_smem[];
     unsigned char *stages = i8_smem;
     I8Smem &S = *reinterpret_cast<I8Smem *>(i8_smem + I8_STAGES * I8_STAGE_BYTES);
@@ -346,7 +358,7 @@ __global__ void __launch_bounds__(I8_THREADS, 1) i8_pair_kernel(const I8Params P
             }
             if (lane == 0) {
                 if (masked && (n & 1)) M.kt[n] = (unsigned short)G.KT;  // pad the last stage with the all-zero chunk
-                M.nact = n; M.tm = tm; M.tn = tn; M.KT = G.KT; M.zcol = G.zcol; M.sym = G.sym; M.dense = masked ? 0 : 1;
+                M.nact = n; M.tm = tm; M.tn = tn; M.KT = G.KT; M.zcol = G.zcol; M.sym = G.sym; M.dense = masked ? 0 : 1; M.group = gi;
                 M.srcA = G.slA + (long long)tm * (G.KT + 1) * I8_A_CHUNK;
                 M.srcB = G.slB + (long long)(tn >> 1) * (G.KT + 1) * I8_A_CHUNK + (tn & 1) * 1024;
                 if (P.stats) {  // in units of 64 x 64 x 16 k-tiles, like the DMMA engine
@@ -368,7 +380,9 @@ __global__ void __launch_bounds__(I8_THREADS, 1) i8_pair_kernel(const I8Params P
                 i8::mbar_wait(&S.meta_full[b], (tl / I8_META) & 1);
                 if (M.tm < 0) break;
                 const int nst = (M.nact + 1) >> 1;
-                const int8_t *srcA = M.srcA, *srcB = M.srcB;
+                const int8_t *srcA = M.srcA;
+                const CUtensorMap *tmB = &P.tmB[M.group];
+                const int bx = (M.tn & 1) * 128, bz = (M.tn >> 1) * (M.KT + 1);
                 for (int k = 0; k < nst; k++, it++) {
                     const int s = it % I8_STAGES;
                     if (it >= I8_STAGES) i8::mbar_wait(&S.empty[s], ((it / I8_STAGES) - 1) & 1);
@@ -378,10 +392,7 @@ __global__ void __launch_bounds__(I8_THREADS, 1) i8_pair_kernel(const I8Params P
                     for (int c = 0; c < 2; c++) {
                         const int kt = M.dense ? min(2 * k + c, M.KT) : (int)M.kt[2 * k + c];
                         i8::bulk_g2s(st + c * I8_A_CHUNK, srcA + (long long)kt * I8_A_CHUNK, I8_A_CHUNK, &S.full[s]);
-                        unsigned char *db = st + 2 * I8_A_CHUNK + c * I8_B_CHUNK;
-                        const int8_t *sb = srcB + (long long)kt * I8_A_CHUNK;
-#pragma unroll
-                        for (int p = 0; p < I8_S; p++) i8::bulk_g2s(db + p * 1024, sb + p * 2048, 1024, &S.full[s]);
+                        i8::tensor_g2s(st + 2 * I8_A_CHUNK + c * I8_B_CHUNK, tmB, bx, 0, bz + kt, &S.full[s]);
                     }
                 }
             }
@@ -583,10 +594,15 @@ __global__ void __launch_bounds__(I8_THREADS, 1) i8_pair_kernel(const I8Params P
             }
             __syncwarp();
             if (I8_SERIAL_EPILOGUE && lane == 0) i8::mbar_arrive(&S.tmem_free);
-            if (P.debug && warp == 3 && lane == 0) {
-                atomicAdd(P.stats + 7, (unsigned long long)(e1 - e0));
-                atomicAdd(P.stats + 8, (unsigned long long)(e2 - e1));
-                atomicAdd(P.stats + 9, (unsigned long long)(clock64() - e2));
+            if (P.debug && lane == 0) {
+                const long long e3 = clock64();
+                if (warp == 3) {
+                    atomicAdd(P.stats + 7, (unsigned long long)(e1 - e0));
+                    atomicAdd(P.stats + 8, (unsigned long long)(e2 - e1));
+                    atomicAdd(P.stats + 9, (unsigned long long)(e3 - e2));
+                }
+                atomicAdd(P.stats + 16 + (warp - 3), (unsigned long long)(e3 - e2));   // per epilogue warp: exp + sums, wait
+                atomicAdd(P.stats + 32 + (warp - 3), (unsigned long long)(e1 - e0));
             }
             if (lane == 0) i8::mbar_arrive(&S.meta_empty[b]);  // this tile's metadata buffer may be refilled
         }

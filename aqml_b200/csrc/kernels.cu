@@ -289,8 +289,8 @@ unsigned long long *pair_stats_buffer() {
     AQML_CUDA(cudaGetDevice(&dev));
     if (dev >= 32) return nullptr;
     if (!buf[dev]) {
-        AQML_CUDA(cudaMalloc((void **)&buf[dev], 128));  // [0..1] k-tile counts, [2..] engine debug timers
-        AQML_CUDA(cudaMemset(buf[dev], 0, 128));
+        AQML_CUDA(cudaMalloc((void **)&buf[dev], 512));  // [0..1] k-tile counts, [2..] engine debug timers
+        AQML_CUDA(cudaMemset(buf[dev], 0, 512));
     }
     return buf[dev];
 }

@@ -752,12 +752,35 @@ static void i8_fill_planes(const double *x, long long ld, int nr, cudaStream_t s
     AQML_LAUNCH_CHECK();
 }
 
+// the B operand of a group as a TMA tensor (I8Params::tmB)
+static void i8_encode_b(CUtensorMap *tm, const I8Group &g) {
+    typedef CUresult (*encode_t)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                 const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                 CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static encode_t encode = [] {
+        void *fn = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        AQML_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q));
+        AQML_REQUIRE(fn && q == cudaDriverEntryPointSuccess, "cuTensorMapEncodeTiled is not available in this driver");
+        return (encode_t)fn;
+    }();
+    const cuuint64_t blocks = (cuuint64_t)((g.nrB + 127) / 128) * (cuuint64_t)(g.KT + 1);
+    const cuuint64_t dims[3] = {256, (cuuint64_t)I8_S, blocks};                 // 8-byte elements: 2 KB = one plane of a 128-row block
+    const cuuint64_t strides[2] = {2048, (cuuint64_t)I8_A_CHUNK};               // bytes: plane, (row block, k-chunk)
+    const cuuint32_t box[3] = {128, (cuuint32_t)I8_S, 1}, estr[3] = {1, 1, 1};  // 64 rows x 16 B of every plane: 6 KB
+    const CUresult r = encode(tm, CU_TENSOR_MAP_DATA_TYPE_UINT64, 3, (void *)g.slB, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                              CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    AQML_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed (%d)", (int)r);
+}
+
 static bool launch_i8(std::vector<I8Group> &gs, const PairParams &PP, Workspace &ws, int store = 0) {
     int total = 0;
     for (auto &g : gs) { g.tile_begin = total; total += g.tilesM * g.tilesN; }
     if (total == 0) return true;
+    if ((int)gs.size() > I8_MAXGROUPS) return false;  // (cannot happen with <= 16 elements) -> FP64 engine
     I8Params P;
     memset(&P, 0, sizeof(P));
+    for (size_t i = 0; i < gs.size(); i++) i8_encode_b(&P.tmB[i], gs[i]);
     P.groups = ws.upload(gs); P.ngroups = (int)gs.size();
     P.isig = PP.isig; P.nsig = PP.nsig; P.zstride = PP.zstride; P.out = PP.out; P.ldo = PP.ldo; P.slab = PP.slab;
     P.stats = pair_stats_buffer();
@@ -775,18 +798,23 @@ static bool launch_i8(std::vector<I8Group> &gs, const PairParams &PP, Workspace 
     P.store = store;
     P.counter = ws.zeros<int>(1);
     P.gm = getenv("AQML_I8_GM") ? std::max(1, atoi(getenv("AQML_I8_GM"))) : 32;  // 32: lowest DRAM traffic (16: +25 %, 64: +35 %, 96: 4 x; the time does not depend on it)
-    if (P.debug) AQML_CUDA(cudaMemsetAsync(P.stats + 2, 0, 64, ws.stream()));
+    if (P.debug) AQML_CUDA(cudaMemsetAsync(P.stats + 2, 0, 496, ws.stream()));
     kern<<<std::min(total, sms), I8_THREADS, smem, ws.stream()>>>(P, total);
     AQML_LAUNCH_CHECK();
     if (P.debug) {
-        unsigned long long h[8];
-        AQML_CUDA(cudaMemcpyAsync(h, P.stats + 2, 64, cudaMemcpyDeviceToHost, ws.stream()));
+        unsigned long long h[62];
+        AQML_CUDA(cudaMemcpyAsync(h, P.stats + 2, 496, cudaMemcpyDeviceToHost, ws.stream()));
         AQML_CUDA(cudaStreamSynchronize(ws.stream()));
         const double n = std::min(total, sms), st = (double)std::max<unsigned long long>(h[4], 1);
         fprintf(stderr, "[i8] %d tiles, %.0f stages; MMA thread per CTA: total %.0f clk = %.0f clk/stage; waiting for metadata %.1f%%, TMEM %.1f%%, operands %.1f%%\n",
                 total, st, h[0] / n, (double)h[0] / st, 100.0 * h[1] / h[0], 100.0 * h[2] / h[0], 100.0 * h[3] / h[0]);
         fprintf(stderr, "[i8] epilogue warp per tile: waiting for accumulators %.0f clk, TMEM drain %.0f clk, exp + sums %.0f clk\n", (double)h[5] / total,
                 (double)h[6] / total, (double)h[7] / total);
+        fprintf(stderr, "[i8] exp + sums per tile, epilogue warps 3..18 (k clk):");
+        for (int w = 0; w < I8_EPI_WARPS; w++) fprintf(stderr, " %.1f", h[14 + w] / 1e3 / total);
+        fprintf(stderr, "\n[i8] waiting for accumulators per tile (k clk):");
+        for (int w = 0; w < I8_EPI_WARPS; w++) fprintf(stderr, " %.1f", h[30 + w] / 1e3 / total);
+        fprintf(stderr, "\n");
     }
     return true;
 }
