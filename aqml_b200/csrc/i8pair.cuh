@@ -41,12 +41,14 @@
 // the slice buffer is written, so a stage is filled by plain 1-D bulk copies (no tensor maps).
 #pragma once
 #include "i8digits.cuh"
+#include "i8exp.cuh"
 #include <cuda.h>   // CUtensorMap (encoded on the host through cudaGetDriverEntryPoint: no link against libcuda)
 
 namespace aqml {
 
 constexpr int I8_BM = 128, I8_BN = 64;           // tile: A rows x B rows
-constexpr int I8_STAGES = 4;
+constexpr int I8_STAGES = 5;                     // operand ring: 4 stages in flight cover the L2 / DRAM latency of the B stream
+constexpr int I8_KT_LIST = 512;                  // active k-chunk list capacity (ld <= 8192; longer rows walk all chunks)
 constexpr int I8_A_CHUNK = I8_S * 2048;          // bytes of one k-chunk (16 columns) of an A tile, all planes
 constexpr int I8_B_CHUNK = I8_S * 1024;
 constexpr int I8_STAGE_BYTES = 2 * (I8_A_CHUNK + I8_B_CHUNK);  // 43008
@@ -55,6 +57,12 @@ constexpr int I8_EPI_WARPS = 16;
 // sum of their times; FP32 overlaps fully).  Measured: overlapping the epilogue's exp / sums with the next tile's MMAs (0)
 // still beats running them strictly after each other (1): 331 vs 353 ms per step.
 constexpr int I8_SERIAL_EPILOGUE = 0;
+// integer epilogue, end of a column run: 1 = every lane converts its own partial sum and issues its own RED.F64 (8 instructions);
+// 0 = the lanes of one A molecule first add their partial sums by segmented shuffle reductions (i8_flush_int, ~100 instructions,
+// 1/6 of the REDs).  The epilogue is issue bound, the L2 atomic units are not the limit (measured: see DESIGN 4.1b).
+#ifndef AQML_I8_LANE_RED
+#define AQML_I8_LANE_RED 1
+#endif
 constexpr int I8_META = 3;                       // tile metadata buffers (prepared up to two tiles ahead)
 constexpr int I8_THREADS = 32 * (3 + I8_EPI_WARPS);  // producer, MMA issuer, tile metadata, 16 epilogue warps
 constexpr int I8_MAXSIG = 8;
@@ -92,24 +100,29 @@ struct I8Params {
     // box {half a plane = 64 rows, 6 planes, 1} is one B k-chunk of a tile in ONE copy instruction (the per-instruction cost of
     // cp.async.bulk, ~57 clk, bounded the operand ring when the six 1 KB pieces were six copies: profiles/r02_micro_feed.txt)
     CUtensorMap tmB[I8_MAXGROUPS];
+    const unsigned long long *exp2tab;  // 2^(-j/4096) as Q53, j = 0 .. 4095 (integer epilogue, i8exp.cuh)
 };
 
 struct I8Meta {  // everything the roles need to know about one tile
     int tm, tn, nact, KT, zcol, sym, dense;  // dense: every k-chunk 0 .. KT-1 is active (no list)
     int group;
+    int special;                       // a row norm of this tile is NaN / Inf: the integer epilogue takes its FP64 side path
     const int8_t *srcA, *srcB;
     int segA[I8_BM], expA[I8_BM];
     double normA[I8_BM];
     int segB[I8_BN + 1];
     double normB[I8_BN];               // |b|^2
     int expB[I8_BN];                   // e_b
-    unsigned short kt[KT_LIST_MAX + 2];
+    unsigned short kt[I8_KT_LIST + 2];
 };
 
 struct I8Smem {
     unsigned long long full[I8_STAGES], empty[I8_STAGES], accum, tmem_free, meta_full[I8_META], meta_empty[I8_META];
     unsigned tmem_base;
-    double exptab[256];  // 2^(j/128), 2^(j/16384)
+    union {
+        double exptab[256];                      // 2^(j/128), 2^(j/16384)  (FP64 epilogue)
+        unsigned long long exp2tab[i8x::TAB_N];  // 2^(-j/4096) 2^53  (integer epilogue)
+    };
     I8Meta meta[I8_META];
 };
 
@@ -201,6 +214,43 @@ __device__ __noinline__ void i8_flush(double r, int lane, int run_end, bool head
     if (head) atomicAdd(dst, r);
 }
 
+// integer epilogue: the lanes of one A molecule (lanes head_lane .. run_end) hold acc 2^-(53 + nacc); agree on the smallest
+// exponent, add the aligned integers, ONE conversion to double per molecule pair, RED into K
+__device__ __noinline__ void i8_flush_int(unsigned long long acc, int nacc, int lane, int run_end, int head_lane, bool head, double *dst) {
+    int nm = nacc;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int u = __shfl_down_sync(0xffffffffu, nm, o);
+        if (lane + o <= run_end) nm = min(nm, u);
+    }
+    nm = __shfl_sync(0xffffffffu, nm, head_lane);
+    const int sh = min(nacc - nm, 63);
+    acc >>= sh;
+    unsigned lo = (unsigned)acc, hi = (unsigned)(acc >> 32);
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const unsigned ul = __shfl_down_sync(0xffffffffu, lo, o), uh = __shfl_down_sync(0xffffffffu, hi, o);
+        if (lane + o <= run_end) {
+            const unsigned long long t = (((unsigned long long)hi << 32) | lo) + (((unsigned long long)uh << 32) | ul);
+            lo = (unsigned)t;
+            hi = (unsigned)(t >> 32);
+        }
+    }
+    const unsigned long long tot = ((unsigned long long)hi << 32) | lo;   // < 2^62: <= 16 x 32 terms of <= 2^53
+    if (head && tot != 0ull && nm < i8x::N_ZERO) {                         // a sum below 2^-1022 is dropped
+        const double d = (double)tot;                                      // tot >= 2^52 - few: exponent field >= 1074
+        atomicAdd(dst, __hiloint2double(__double2hiint(d) - ((53 + nm) << 20), __double2loint(d)));
+    }
+}
+
+// integer epilogue: this lane's partial sum acc 2^-(53 + nacc) straight into K (one conversion, one RED)
+__device__ __forceinline__ void i8_lane_red(unsigned long long acc, int nacc, double *dst) {
+    if (acc != 0ull && nacc < i8x::N_ZERO) {                               // a sum below 2^-1022 is dropped
+        const double d = (double)acc;                                      // acc >= 2^52 - few: exponent field >= 1074
+        atomicAdd(dst, __hiloint2double(__double2hiint(d) - ((53 + nacc) << 20), __double2loint(d)));
+    }
+}
+
 // ---- slicing (row exponent + digit rule: i8digits.cuh) ------------------------------------------------------------
 // thread = one row of a 128-row block; per 16-column chunk: 6 planes x 16 B
 __global__ void __launch_bounds__(128) i8_slice_kernel(const double *x, long long ld, int nrows, const int *expo, int KT, int kt_per_block,
@@ -264,7 +314,8 @@ __global__ void __launch_bounds__(128) i8_peak_kernel(int rounds) {
 // hands TMEM back (the next tile's MMAs start while exp / sums / REDs of this tile run), and the operand ring
 // keeps filling across tile boundaries.
 // VAR 0: 22 products (i + j <= 5 and (3,3)); VAR 1: 26 products (i + j <= 6)
-template <int VAR>
+// EPI 1: exp and sums on integers (i8exp.cuh; default), EPI 0: the FP64 epilogue (AQML_I8_EPILOGUE=fp64)
+template <int VAR, int EPI>
 __global__ void __launch_bounds__(I8_THREADS, 1) i8_pair_kernel(const __grid_constant__ I8Params P, int total_tiles) {
     extern __shared__ __align__(1024) unsigned char i8_smem[];
     unsigned char *stages = i8_smem;
@@ -278,7 +329,9 @@ __global__ void __launch_bounds__(I8_THREADS, 1) i8_pair_kernel(const __grid_con
         for (int b = 0; b < I8_META; b++) { i8::mbar_init(&S.meta_full[b], 1); i8::mbar_init(&S.meta_empty[b], I8_EPI_WARPS); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    fill_exp_table(S.exptab, tid, I8_THREADS);
+    if (EPI == 0) fill_exp_table(S.exptab, tid, I8_THREADS);
+    else
+        for (int i = tid; i < i8x::TAB_N; i += I8_THREADS) S.exp2tab[i] = P.exp2tab[i];
     if (warp == 1) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(i8::smem_u32(&S.tmem_base)), "r"(512u) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -287,8 +340,9 @@ __global__ void __launch_bounds__(I8_THREADS, 1) i8_pair_kernel(const __grid_con
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const unsigned tb = S.tmem_base;
+    const int role = (P.debug & 8) ? (warp == 0 ? 2 : warp == 2 ? 0 : warp) : warp;  // experiment: producer and metadata warps swapped
 
-    if (warp == 2) {
+    if (role == 2) {
         // ---- tile metadata, one tile ahead ----
         // tiles are handed out dynamically (one atomic per tile): the tiles in flight are always consecutive in the raster
         // order, so the CTAs that share a B tile read it within one L2 residency and the tail is balanced
@@ -315,27 +369,30 @@ __global__ void __launch_bounds__(I8_THREADS, 1) i8_pair_kernel(const __grid_con
             const int gm = min(GM, G.tilesM - band * GM);
             const int tm = band * GM + rem % gm, tn = rem / gm;
             if (G.sym && (tn + 1) * I8_BN <= tm * I8_BM) continue;  // entirely below the diagonal
-            int any = 0;
+            int any = 0, special = 0;
             for (int i = lane; i < I8_BM + I8_BN; i += 32) {
+                double nrm;
                 if (i < I8_BM) {
                     const int r = tm * I8_BM + i;
                     int sg = (r < G.nrA) ? G.segA[r] : -1;
                     sg = (sg >= G.segA_off && sg - G.segA_off < G.segA_n) ? sg - G.segA_off : -1;
                     M.segA[i] = sg;
                     any |= (sg >= 0);
-                    M.normA[i] = (r < G.nrA) ? G.normA[r] : 0.0;
+                    M.normA[i] = nrm = (r < G.nrA) ? G.normA[r] : 0.0;
                     M.expA[i] = (r < G.nrA) ? G.expA[r] : 0;
                 } else {
                     const int c = i - I8_BM, r = tn * I8_BN + c;
                     M.segB[c] = (r < G.nrB) ? G.segB[r] : -1;
-                    M.normB[c] = (r < G.nrB) ? G.normB[r] : 0.0;
+                    M.normB[c] = nrm = (r < G.nrB) ? G.normB[r] : 0.0;
                     M.expB[c] = (r < G.nrB) ? G.expB[r] : 0;
                 }
+                special |= ((__double2hiint(nrm) & 0x7ff00000) == 0x7ff00000);
             }
+            special = __any_sync(0xffffffffu, special);
             if (!__any_sync(0xffffffffu, any)) continue;  // no wanted row in this tile (row-block sharding)
             // active 16-column k-chunks: both operands have a non-zero there (exact: a zero chunk adds 0 to a.b)
             int n = 0;
-            const bool masked = G.maskA && G.maskB && G.maskw <= 32 && G.KT <= KT_LIST_MAX;
+            const bool masked = G.maskA && G.maskB && G.maskw <= 32 && G.KT <= I8_KT_LIST;
             if (masked) {
                 unsigned bits = 0;
                 if (lane < G.maskw) {
@@ -358,7 +415,7 @@ __global__ void __launch_bounds__(I8_THREADS, 1) i8_pair_kernel(const __grid_con
             }
             if (lane == 0) {
                 if (masked && (n & 1)) M.kt[n] = (unsigned short)G.KT;  // pad the last stage with the all-zero chunk
-                M.nact = n; M.tm = tm; M.tn = tn; M.KT = G.KT; M.zcol = G.zcol; M.sym = G.sym; M.dense = masked ? 0 : 1; M.group = gi;
+                M.nact = n; M.tm = tm; M.tn = tn; M.KT = G.KT; M.zcol = G.zcol; M.sym = G.sym; M.dense = masked ? 0 : 1; M.group = gi; M.special = special;
                 M.srcA = G.slA + (long long)tm * (G.KT + 1) * I8_A_CHUNK;
                 M.srcB = G.slB + (long long)(tn >> 1) * (G.KT + 1) * I8_A_CHUNK + (tn & 1) * 1024;
                 if (P.stats) {  // in units of 64 x 64 x 16 k-tiles, like the DMMA engine
@@ -370,9 +427,11 @@ __global__ void __launch_bounds__(I8_THREADS, 1) i8_pair_kernel(const __grid_con
             if (lane == 0) i8::mbar_arrive(&S.meta_full[b]);
             tl++;
         }
-    } else if (warp == 0) {
-        // ---- producer ----
-        if (lane == 0) {
+    } else if (role == 0) {
+        // ---- producer ----  (whole warp converged, one elected lane issues the copies: see the MMA issuer)
+        {
+            unsigned leader;
+            asm volatile("{\n.reg .pred p;\nelect.sync _|p, 0xffffffff;\nselp.u32 %0, 1, 0, p;\n}" : "=r"(leader));
             int it = 0;  // position in the stage ring, continues across tiles
             for (int tl = 0;; tl++) {
                 const int b = tl % I8_META;
@@ -382,39 +441,48 @@ __global__ void __launch_bounds__(I8_THREADS, 1) i8_pair_kernel(const __grid_con
                 const int nst = (M.nact + 1) >> 1;
                 const int8_t *srcA = M.srcA;
                 const CUtensorMap *tmB = &P.tmB[M.group];
-                const int bx = (M.tn & 1) * 128, bz = (M.tn >> 1) * (M.KT + 1);
+                const int bx = (M.tn & 1) * 128, bz = (M.tn >> 1) * (M.KT + 1), dense = M.dense, KT = M.KT;
                 for (int k = 0; k < nst; k++, it++) {
                     const int s = it % I8_STAGES;
                     if (it >= I8_STAGES) i8::mbar_wait(&S.empty[s], ((it / I8_STAGES) - 1) & 1);
                     unsigned char *st = stages + s * I8_STAGE_BYTES;
-                    i8::mbar_expect_tx(&S.full[s], I8_STAGE_BYTES);
-#pragma unroll
-                    for (int c = 0; c < 2; c++) {
-                        const int kt = M.dense ? min(2 * k + c, M.KT) : (int)M.kt[2 * k + c];
-                        i8::bulk_g2s(st + c * I8_A_CHUNK, srcA + (long long)kt * I8_A_CHUNK, I8_A_CHUNK, &S.full[s]);
-                        i8::tensor_g2s(st + 2 * I8_A_CHUNK + c * I8_B_CHUNK, tmB, bx, 0, bz + kt, &S.full[s]);
+                    const int kt0 = dense ? min(2 * k, KT) : (int)M.kt[2 * k], kt1 = dense ? min(2 * k + 1, KT) : (int)M.kt[2 * k + 1];
+                    if (leader) {
+                        i8::mbar_expect_tx(&S.full[s], I8_STAGE_BYTES);
+                        i8::bulk_g2s(st, srcA + (long long)kt0 * I8_A_CHUNK, I8_A_CHUNK, &S.full[s]);
+                        i8::tensor_g2s(st + 2 * I8_A_CHUNK, tmB, bx, 0, bz + kt0, &S.full[s]);
+                        i8::bulk_g2s(st + I8_A_CHUNK, srcA + (long long)kt1 * I8_A_CHUNK, I8_A_CHUNK, &S.full[s]);
+                        i8::tensor_g2s(st + 2 * I8_A_CHUNK + I8_B_CHUNK, tmB, bx, 0, bz + kt1, &S.full[s]);
                     }
+                    __syncwarp();
                 }
             }
         }
     } else if (warp == 1) {
         // ---- MMA issuer ----
-        if (lane == 0) {
+        // The whole warp walks the loop converged (descriptors, waits: warp-uniform values the compiler keeps in uniform
+        // registers) and ONE elected lane issues: ~3 instructions per UTCIMMA.  With the loop inside `if (lane == 0)` every MMA
+        // carried a ~15-instruction register-to-uniform-register loop; once the epilogue warps of this scheduler were issue
+        // bound (integer epilogue) the issuer could not keep the tensor pipe fed (1120 instead of 750 clk per stage).
+        {
             // A plane i against the stacked B planes j0 .. j0 + n - 1 (N = 64 n) -> accumulators i + j0 .. i + j0 + n - 1
             constexpr int NMMA = VAR ? 9 : 8;
             constexpr int mi[9] = {0, 0, 1, 1, 2, VAR ? 2 : 3, VAR ? 3 : 4, VAR ? 4 : 5, 5};
             constexpr int mj[9] = {0, 4, 0, VAR ? 4 : 3, 0, VAR ? 3 : 0, 0, 0, 0};
             constexpr int mn[9] = {4, 2, VAR ? 4 : 3, 2, VAR ? 3 : 4, VAR ? 2 : 4, VAR ? 4 : 2, VAR ? 3 : 1, 2};
+            unsigned leader;
+            asm volatile("{\n.reg .pred p;\nelect.sync _|p, 0xffffffff;\nselp.u32 %0, 1, 0, p;\n}" : "=r"(leader));
+            const unsigned stage0 = i8::smem_u32(stages);
             int it = 0;
             long long w_meta = 0, w_tmem = 0, w_full = 0;
             const long long t_begin = clock64();
             for (int tl = 0;; tl++) {
                 const int b = tl % I8_META;
-                long long c0 = clock64();
+                long long c0 = P.debug ? clock64() : 0;
                 i8::mbar_wait(&S.meta_full[b], (tl / I8_META) & 1);
-                w_meta += clock64() - c0;
+                if (P.debug) w_meta += clock64() - c0;
                 if (S.meta[b].tm < 0) {
-                    if (P.debug) {
+                    if (P.debug && leader) {
                         atomicAdd(P.stats + 2, (unsigned long long)(clock64() - t_begin));
                         atomicAdd(P.stats + 3, (unsigned long long)w_meta);
                         atomicAdd(P.stats + 4, (unsigned long long)w_tmem);
@@ -424,26 +492,33 @@ __global__ void __launch_bounds__(I8_THREADS, 1) i8_pair_kernel(const __grid_con
                     break;
                 }
                 const int nst = (S.meta[b].nact + 1) >> 1;
-                c0 = clock64();
+                if (P.debug) c0 = clock64();
                 i8::mbar_wait(&S.tmem_free, tl & 1);  // accumulator 6 cleared (tl = 0) / the previous tile's accumulators are in registers
-                w_tmem += clock64() - c0;
+                if (P.debug) w_tmem += clock64() - c0;
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 for (int k = 0; k < nst; k++, it++) {
                     const int s = it % I8_STAGES;
-                    c0 = clock64();
+                    if ((P.debug & 4) && it >= 2) i8::mbar_wait(&S.empty[(it - 2) % I8_STAGES], ((it - 2) / I8_STAGES) & 1);  // experiment: <= 2 stages of MMAs in flight
+                    if (P.debug) c0 = clock64();
                     i8::mbar_wait(&S.full[s], (it / I8_STAGES) & 1);
-                    w_full += clock64() - c0;
+                    if (P.debug) w_full += clock64() - c0;
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                    const unsigned a0 = i8::smem_u32(stages + s * I8_STAGE_BYTES), b0 = a0 + 2 * I8_A_CHUNK;
+                    const unsigned a0 = stage0 + s * I8_STAGE_BYTES, b0 = a0 + 2 * I8_A_CHUNK;
                     const unsigned long long da = i8::smem_desc(a0, I8_A_CHUNK, 128), db = i8::smem_desc(b0, I8_B_CHUNK, 128);
+                    if (leader) {
 #pragma unroll
-                    for (int m = 0; m < NMMA; m++)  // plane 0 comes first and clears accumulators 0 .. 5 at k = 0 (6: the epilogue)
-                        i8::umma(tb + (mi[m] + mj[m]) * I8_BN, da + (unsigned long long)(mi[m] * 2048 >> 4),
-                                 db + (unsigned long long)(mj[m] * 1024 >> 4), i8::idesc(I8_BM, I8_BN * mn[m]), (k > 0 || mi[m] > 0) ? 1u : 0u);
-                    i8::umma_commit(&S.empty[s]);  // stage reusable once these MMAs have read it
+                        for (int m = 0; m < NMMA; m++)  // plane 0 comes first and clears accumulators 0 .. 5 at k = 0 (6: the epilogue)
+                            i8::umma(tb + (mi[m] + mj[m]) * I8_BN, da + (unsigned long long)(mi[m] * 2048 >> 4),
+                                     db + (unsigned long long)(mj[m] * 1024 >> 4), i8::idesc(I8_BM, I8_BN * mn[m]), (k > 0 || mi[m] > 0) ? 1u : 0u);
+                        i8::umma_commit(&S.empty[s]);  // stage reusable once these MMAs have read it
+                    }
+                    __syncwarp();
                 }
-                if (nst > 0) i8::umma_commit(&S.accum);
-                else i8::mbar_arrive(&S.accum);
+                if (leader) {
+                    if (nst > 0) i8::umma_commit(&S.accum);
+                    else i8::mbar_arrive(&S.accum);
+                }
+                __syncwarp();
             }
         }
     } else {
@@ -474,6 +549,7 @@ __global__ void __launch_bounds__(I8_THREADS, 1) i8_pair_kernel(const __grid_con
             const unsigned heads = __ballot_sync(0xffffffffu, (lane == 0) || (prev != sr));
             const unsigned above = (lane == 31) ? 0u : (heads >> (lane + 1));
             const int run_end = above ? (lane + __ffs(above) - 1) : 31;
+            const int head_lane = 31 - __clz(heads & (0xffffffffu >> (31 - lane)));
             const double na = M.normA[row];
             const int ea = M.expA[row];
             const int growA = M.tm * I8_BM + row;
@@ -531,11 +607,106 @@ __global__ void __launch_bounds__(I8_THREADS, 1) i8_pair_kernel(const __grid_con
                 if ((M.sym && M.tn * I8_BN + col <= growA) || sr < 0 || M.segB[col] < 0) { xh = 0x7ff00000; xl = 0; }
                 x[j] = __hiloint2double(xh, xl);
             }
-            // phase 2: per sigma exp (chain: squarings of the previous sigma's values, in place), then the sums over
-            // molecule pairs: column runs sequentially in registers, row runs by a segmented shuffle reduction, one RED
-            // per head lane
+            if (EPI == 1) {
+                // phase 2 on integers (i8exp.cuh): per sigma a term (M, n) per pair from T = d^2 / (2 sigma^2) log2(e) as Q16.48 --
+                // ladder: T of the widest sigma once, the next sigma is a left shift; otherwise one FP64 multiply per (pair, sigma).
+                // Local kernels: column runs added as aligned 64-bit integers, row runs by i8_flush_int; global kernels: the
+                // double is assembled and stored.  The three cases are separate straight-line loops (no per-pair branches).
+                constexpr double LOG2E = 1.4426950408889634;
+                auto fixT = [](double T) { return i8x::fix_from_bits((unsigned)__double2hiint(T) & 0x7fffffffu, (unsigned)__double2loint(T)); };
+                if (M.special) {
+                    // a NaN / Inf row norm in this tile (non-finite input): plain FP64 per pair, so that NaN and exp(-Inf) = 0 reach K
+                    // exactly as in the reference (fkernels.f90:84,351); the integer path would turn NaN into 0
 #pragma unroll 1
-            for (int si = 0; si < P.nsig; si++) {
+                    for (int s = 0; s < P.nsig; s++) {
+                        double *outS = P.out + (long long)s * P.slab + (long long)max(sr, 0) * P.ldo;
+                        const double f = P.isig[s * P.zstride + M.zcol];
+#pragma unroll
+                        for (int j = 0; j < EC; j++) {
+                            const int sc = M.segB[cbase + j];
+                            if (sr < 0 || sc < 0) continue;
+                            const bool counts = !(M.sym && M.tn * I8_BN + cbase + j <= growA);
+                            const double e = counts ? exp(x[j] * f) : 0.0;
+                            if (P.store) outS[sc] = e;
+                            else if (counts) atomicAdd(outS + sc, e);
+                        }
+                    }
+                } else if (P.store) {
+#pragma unroll 1
+                    for (int si = 0; si < P.nsig; si++) {
+                        const int s = P.chain ? P.order[si] : si;
+                        double *outS = P.out + (long long)s * P.slab + (long long)max(sr, 0) * P.ldo;
+                        // ladder: T = d^2 * c of the widest sigma times 2^(squarings so far) -- exact, so one multiply serves here too
+                        const double cs = -P.isig[s * P.zstride + M.zcol] * LOG2E;
+#pragma unroll
+                        for (int j = 0; j < EC; j++) {
+                            unsigned long long Mt;
+                            int nt;
+                            i8x::exp2neg(fixT(x[j] * cs), S.exp2tab, Mt, nt);
+                            const int sc = M.segB[cbase + j];
+                            if (sr >= 0 && sc >= 0) outS[sc] = __longlong_as_double((long long)i8x::term_bits(Mt, nt));
+                        }
+                    }
+                } else if (P.chain) {
+                    unsigned long long V[EC];
+                    const double c0 = -P.isig[P.order[0] * P.zstride + M.zcol] * LOG2E;
+#pragma unroll
+                    for (int j = 0; j < EC; j++) V[j] = fixT(x[j] * c0);
+#pragma unroll 1
+                    for (int si = 0; si < P.nsig; si++) {
+                        double *outS = P.out + (long long)P.order[si] * P.slab + (long long)max(sr, 0) * P.ldo;
+                        const int sq = si ? P.nsq[si] : 0;
+                        unsigned long long acc = 0ull;
+                        int nacc = 4095;
+#pragma unroll
+                        for (int j = 0; j < EC; j++) {
+                            V[j] = i8x::fix_shl(V[j], sq);
+                            unsigned long long Mt;
+                            int nt;
+                            i8x::exp2neg(V[j], S.exp2tab, Mt, nt);
+                            i8x::add_term(acc, nacc, Mt, nt);
+                            if ((lastmask >> j) & 1u) {  // warp-uniform: column cbase + j closes a molecule of B
+                                const int sc = M.segB[cbase + j];
+                                if (sc >= 0) {
+                                    if (AQML_I8_LANE_RED) { if (sr >= 0) i8_lane_red(acc, nacc, outS + sc); }
+                                    else i8_flush_int(acc, nacc, lane, run_end, head_lane, head, outS + sc);
+                                }
+                                acc = 0ull;
+                                nacc = 4095;
+                            }
+                        }
+                    }
+                } else {
+#pragma unroll 1
+                    for (int si = 0; si < P.nsig; si++) {
+                        double *outS = P.out + (long long)si * P.slab + (long long)max(sr, 0) * P.ldo;
+                        const double cs = -P.isig[si * P.zstride + M.zcol] * LOG2E;
+                        unsigned long long acc = 0ull;
+                        int nacc = 4095;
+#pragma unroll
+                        for (int j = 0; j < EC; j++) {
+                            unsigned long long Mt;
+                            int nt;
+                            i8x::exp2neg(fixT(x[j] * cs), S.exp2tab, Mt, nt);
+                            i8x::add_term(acc, nacc, Mt, nt);
+                            if ((lastmask >> j) & 1u) {
+                                const int sc = M.segB[cbase + j];
+                                if (sc >= 0) {
+                                    if (AQML_I8_LANE_RED) { if (sr >= 0) i8_lane_red(acc, nacc, outS + sc); }
+                                    else i8_flush_int(acc, nacc, lane, run_end, head_lane, head, outS + sc);
+                                }
+                                acc = 0ull;
+                                nacc = 4095;
+                            }
+                        }
+                    }
+                }
+            } else {
+                // phase 2: per sigma exp (chain: squarings of the previous sigma's values, in place), then the sums over
+                // molecule pairs: column runs sequentially in registers, row runs by a segmented shuffle reduction, one RED
+                // per head lane
+#pragma unroll 1
+                for (int si = 0; si < P.nsig; si++) {
                 const int s = P.chain ? P.order[si] : si;
                 double *outS = P.out + (long long)s * P.slab + (long long)max(sr, 0) * P.ldo;
                 double run = 0.0;
@@ -592,6 +763,7 @@ __global__ void __launch_bounds__(I8_THREADS, 1) i8_pair_kernel(const __grid_con
                     }
                 }
             }
+            }  // EPI
             __syncwarp();
             if (I8_SERIAL_EPILOGUE && lane == 0) i8::mbar_arrive(&S.tmem_free);
             if (P.debug && lane == 0) {

@@ -773,6 +773,24 @@ static void i8_encode_b(CUtensorMap *tm, const I8Group &g) {
     AQML_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed (%d)", (int)r);
 }
 
+// 2^(-j/4096) as Q53 for the integer epilogue (i8exp.cuh), computed in extended precision on the host, once per device
+static const unsigned long long *i8_exp2_table() {
+    static const unsigned long long *tab[32] = {nullptr};
+    int dev = 0;
+    AQML_CUDA(cudaGetDevice(&dev));
+    AQML_REQUIRE(dev < 32, "device index %d not supported", dev);
+    if (!tab[dev]) {
+        std::vector<unsigned long long> h(i8x::TAB_N);
+        for (int j = 0; j < i8x::TAB_N; j++)
+            h[j] = j ? (unsigned long long)llroundl(exp2l(-(long double)j / i8x::TAB_N) * 9007199254740992.0L) : (1ull << 53) - 1;  // Q53; 2^53 would wrap exp2neg's 32-bit top word
+        unsigned long long *d = nullptr;
+        AQML_CUDA(cudaMalloc((void **)&d, h.size() * 8));
+        AQML_CUDA(cudaMemcpy(d, h.data(), h.size() * 8, cudaMemcpyHostToDevice));
+        tab[dev] = d;
+    }
+    return tab[dev];
+}
+
 static bool launch_i8(std::vector<I8Group> &gs, const PairParams &PP, Workspace &ws, int store = 0) {
     int total = 0;
     for (auto &g : gs) { g.tile_begin = total; total += g.tilesM * g.tilesN; }
@@ -787,9 +805,13 @@ static bool launch_i8(std::vector<I8Group> &gs, const PairParams &PP, Workspace 
     P.chain = PP.chain;
     for (int i = 0; i < 16; i++) { P.order[i] = PP.order[i]; P.nsq[i] = PP.nsq[i]; }
     const int smem = I8_STAGES * I8_STAGE_BYTES + (int)sizeof(I8Smem);
+    static_assert(I8_STAGES * I8_STAGE_BYTES + sizeof(I8Smem) <= 232448, "i8_pair_kernel: more than 227 KB of shared memory");
     // AQML_I8_PRODUCTS=26: every digit product with i + j <= 6 (10 x lower truncation error, ~15 % more tensor work)
     static const bool full6 = getenv("AQML_I8_PRODUCTS") && atoi(getenv("AQML_I8_PRODUCTS")) >= 26;
-    auto kern = full6 ? i8_pair_kernel<1> : i8_pair_kernel<0>;
+    // AQML_I8_EPILOGUE=fp64: the FP64 epilogue (table exp, squaring chain, FP64 sums); default: integers (i8exp.cuh)
+    static const bool fp64epi = getenv("AQML_I8_EPILOGUE") && !strcmp(getenv("AQML_I8_EPILOGUE"), "fp64");
+    auto kern = full6 ? (fp64epi ? i8_pair_kernel<1, 0> : i8_pair_kernel<1, 1>) : (fp64epi ? i8_pair_kernel<0, 0> : i8_pair_kernel<0, 1>);
+    P.exp2tab = i8_exp2_table();
     AQML_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     int dev = 0, sms = 0;
     AQML_CUDA(cudaGetDevice(&dev));
