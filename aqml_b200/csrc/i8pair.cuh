@@ -138,6 +138,12 @@ __device__ __forceinline__ bool mbar_try_wait(unsigned long long *b, unsigned ph
                  : "=r"(ok) : "r"(smem_u32(b)), "r"(phase) : "memory");
     return ok != 0;
 }
+__device__ __forceinline__ bool mbar_test_wait(unsigned long long *b, unsigned phase) {  // non-blocking
+    unsigned ok;
+    asm volatile("{\n.reg .pred p;\nmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+                 : "=r"(ok) : "r"(smem_u32(b)), "r"(phase) : "memory");
+    return ok != 0;
+}
 // bounded: a protocol bug becomes a launch failure, never a hung GPU
 __device__ __forceinline__ void mbar_wait(unsigned long long *b, unsigned phase) {
     for (long long it = 0; !mbar_try_wait(b, phase); it++)
@@ -432,7 +438,8 @@ __global__ void __launch_bounds__(I8_THREADS, 1) i8_pair_kernel(const __grid_con
         {
             unsigned leader;
             asm volatile("{\n.reg .pred p;\nelect.sync _|p, 0xffffffff;\nselp.u32 %0, 1, 0, p;\n}" : "=r"(leader));
-            int it = 0;  // position in the stage ring, continues across tiles
+            int s = 0;           // ring slot of the next stage (continues across tiles) and the parity its `empty` barrier is waited with
+            unsigned par = 1;    // first round: nothing to wait for (a fresh barrier passes a wait on parity 1)
             for (int tl = 0;; tl++) {
                 const int b = tl % I8_META;
                 const I8Meta &M = S.meta[b];
@@ -442,9 +449,8 @@ __global__ void __launch_bounds__(I8_THREADS, 1) i8_pair_kernel(const __grid_con
                 const int8_t *srcA = M.srcA;
                 const CUtensorMap *tmB = &P.tmB[M.group];
                 const int bx = (M.tn & 1) * 128, bz = (M.tn >> 1) * (M.KT + 1), dense = M.dense, KT = M.KT;
-                for (int k = 0; k < nst; k++, it++) {
-                    const int s = it % I8_STAGES;
-                    if (it >= I8_STAGES) i8::mbar_wait(&S.empty[s], ((it / I8_STAGES) - 1) & 1);
+                for (int k = 0; k < nst; k++) {
+                    i8::mbar_wait(&S.empty[s], par);
                     unsigned char *st = stages + s * I8_STAGE_BYTES;
                     const int kt0 = dense ? min(2 * k, KT) : (int)M.kt[2 * k], kt1 = dense ? min(2 * k + 1, KT) : (int)M.kt[2 * k + 1];
                     if (leader) {
@@ -455,6 +461,7 @@ __global__ void __launch_bounds__(I8_THREADS, 1) i8_pair_kernel(const __grid_con
                         i8::tensor_g2s(st + 2 * I8_A_CHUNK + I8_B_CHUNK, tmB, bx, 0, bz + kt1, &S.full[s]);
                     }
                     __syncwarp();
+                    if (++s == I8_STAGES) { s = 0; par ^= 1u; }
                 }
             }
         }
@@ -473,7 +480,9 @@ __global__ void __launch_bounds__(I8_THREADS, 1) i8_pair_kernel(const __grid_con
             unsigned leader;
             asm volatile("{\n.reg .pred p;\nelect.sync _|p, 0xffffffff;\nselp.u32 %0, 1, 0, p;\n}" : "=r"(leader));
             const unsigned stage0 = i8::smem_u32(stages);
-            int it = 0;
+            int it = 0, s = 0;       // stages issued so far; ring slot and parity of the next one (no division in the loop)
+            unsigned par = 0;
+            bool ready = false;      // the next stage's operands were already seen complete (looked ahead while the previous MMAs ran)
             long long w_meta = 0, w_tmem = 0, w_full = 0;
             const long long t_begin = clock64();
             for (int tl = 0;; tl++) {
@@ -497,20 +506,25 @@ __global__ void __launch_bounds__(I8_THREADS, 1) i8_pair_kernel(const __grid_con
                 if (P.debug) w_tmem += clock64() - c0;
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 for (int k = 0; k < nst; k++, it++) {
-                    const int s = it % I8_STAGES;
-                    if ((P.debug & 4) && it >= 2) i8::mbar_wait(&S.empty[(it - 2) % I8_STAGES], ((it - 2) / I8_STAGES) & 1);  // experiment: <= 2 stages of MMAs in flight
-                    if (P.debug) c0 = clock64();
-                    i8::mbar_wait(&S.full[s], (it / I8_STAGES) & 1);
-                    if (P.debug) w_full += clock64() - c0;
-                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    if (!ready) {
+                        if (P.debug) c0 = clock64();
+                        i8::mbar_wait(&S.full[s], par);
+                        if (P.debug) w_full += clock64() - c0;
+                    }
                     const unsigned a0 = stage0 + s * I8_STAGE_BYTES, b0 = a0 + 2 * I8_A_CHUNK;
                     const unsigned long long da = i8::smem_desc(a0, I8_A_CHUNK, 128), db = i8::smem_desc(b0, I8_B_CHUNK, 128);
+                    const int s0 = s;
+                    if (++s == I8_STAGES) { s = 0; par ^= 1u; }
+                    // look ahead: is the NEXT stage (of this or the next tile: the ring is continuous) already complete?  Then nothing
+                    // but the commit stands between this stage's last MMA and the next stage's first one -- the tensor pipe's queue
+                    // is short, and a wait + descriptor arithmetic between the stages showed up as ~180 idle clk per stage
+                    ready = i8::mbar_test_wait(&S.full[s], par);
                     if (leader) {
 #pragma unroll
                         for (int m = 0; m < NMMA; m++)  // plane 0 comes first and clears accumulators 0 .. 5 at k = 0 (6: the epilogue)
                             i8::umma(tb + (mi[m] + mj[m]) * I8_BN, da + (unsigned long long)(mi[m] * 2048 >> 4),
                                      db + (unsigned long long)(mj[m] * 1024 >> 4), i8::idesc(I8_BM, I8_BN * mn[m]), (k > 0 || mi[m] > 0) ? 1u : 0u);
-                        i8::umma_commit(&S.empty[s]);  // stage reusable once these MMAs have read it
+                        i8::umma_commit(&S.empty[s0]);  // stage reusable once these MMAs have read it
                     }
                     __syncwarp();
                 }

@@ -11,6 +11,7 @@
 #include <cstdlib>
 #include <vector>
 #include <cuda_runtime.h>
+#include <cuda.h>
 
 #define CK(x) do { cudaError_t e = (x); if (e != cudaSuccess) { printf("CUDA error %s at %d\n", cudaGetErrorString(e), __LINE__); exit(1); } } while (0)
 
@@ -416,8 +417,13 @@ static void run_contention() {
 // (6) what bounds the operand feed?  The main loop of (3) with switches: `mma` 0: the consumer only waits for the stage and frees
 // it (pure L2 -> shared-memory copy rate); `same` 1: every CTA reads the same window (maximal overlap of the requests in L2);
 // `one` 1: a stage is ONE 36 KB bulk copy instead of 2 + 12; grid = number of CTAs (one per SM): fewer SMs -> per-SM or chip-wide limit?
+__device__ __forceinline__ void tensor_g2s(void *dst, const CUtensorMap *tm, int c0, int c1, int c2, uint64_t *bar) {
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+                 ::"r"(smem_u32(dst)), "l"(tm), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar)) : "memory");
+}
 template <int VAR>
-__global__ void __launch_bounds__(128) feed_kernel(int rounds, int mma, int same, int one, const int8_t *src, long long src_bytes, long long *cycles) {
+__global__ void __launch_bounds__(128) feed_kernel(int rounds, int mma, int same, int one, const int8_t *src, long long src_bytes, long long *cycles,
+                                                   const __grid_constant__ CUtensorMap tmap) {
     extern __shared__ __align__(1024) int8_t sm[];
     __shared__ __align__(8) uint64_t full[4], empty[4], done;
     __shared__ uint32_t tmem_base;
@@ -445,8 +451,15 @@ __global__ void __launch_bounds__(128) feed_kernel(int rounds, int mma, int same
             if (r >= 4) mbar_wait(&empty[s], ((r >> 2) - 1) & 1);
             mbar_expect_tx(&full[s], STAGE);
             int8_t *st = sm + s * STAGE;
-            if (one) bulk_g2s(st, src + pos, STAGE, &full[s]);
-            else
+            if (one == 1) bulk_g2s(st, src + pos, STAGE, &full[s]);
+            else if (one >= 2) {   // the pair kernel's copies: A chunks 12 KB bulk; B chunks as ONE tensor box of 6 rows x 1 KB (2), or 6 KB bulk (3)
+                const int blk = (int)(pos / (6 * 2048));   // 12 KB units of the source viewed as [block][plane 2 KB]
+                for (int c = 0; c < 2; c++) {
+                    bulk_g2s(st + c * A_CHUNK, src + pos + c * A_CHUNK, A_CHUNK, &full[s]);
+                    if (one == 2) tensor_g2s(st + 2 * A_CHUNK + c * B_CHUNK, &tmap, (blockIdx.x & 1) * 128, 0, blk + c, &full[s]);
+                    else bulk_g2s(st + 2 * A_CHUNK + c * B_CHUNK, src + pos + 2 * A_CHUNK + c * B_CHUNK, B_CHUNK, &full[s]);
+                }
+            } else
                 for (int c = 0; c < 2; c++) {
                     bulk_g2s(st + c * A_CHUNK, src + pos + c * A_CHUNK, A_CHUNK, &full[s]);
                     for (int p = 0; p < S; p++) bulk_g2s(st + 2 * A_CHUNK + c * B_CHUNK + p * 1024, src + pos + 2 * A_CHUNK + c * B_CHUNK + p * 1024, 1024, &full[s]);
@@ -480,24 +493,37 @@ static void run_feed(const int8_t *src, long long src_bytes) {
     const int rounds = 20000;
     cudaEvent_t e0, e1;
     CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+    CUtensorMap tmap;
+    {
+        typedef CUresult (*encode_t)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *, const cuuint32_t *,
+                                     const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+        void *fn = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        CK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q));
+        const cuuint64_t dims[3] = {256, 6, (cuuint64_t)(src_bytes / (6 * 2048))}, strides[2] = {2048, 6 * 2048};
+        const cuuint32_t box[3] = {128, 6, 1}, estr[3] = {1, 1, 1};
+        CUresult r = ((encode_t)fn)(&tmap, CU_TENSOR_MAP_DATA_TYPE_UINT64, 3, (void *)src, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                    CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) { printf("cuTensorMapEncodeTiled failed %d\n", (int)r); exit(1); }
+    }
     const int grids[4] = {sms, sms / 2, sms / 4, 8};
     for (int mma = 0; mma < 2; mma++)
-        for (int same = 0; same < 2; same++)
-            for (int one = 0; one < 2; one++)
-                for (int gi = 0; gi < 4; gi++) {
+        for (int same = 0; same < 1; same++)
+            for (int one = 0; one < 4; one++)
+                for (int gi = 0; gi < 4; gi += 3) {
                     const int g = grids[gi];
-                    feed_kernel<0><<<g, 128, 4 * STAGE>>>(200, mma, same, one, src, src_bytes, dcy);
+                    feed_kernel<0><<<g, 128, 4 * STAGE>>>(200, mma, same, one, src, src_bytes, dcy, tmap);
                     CK(cudaDeviceSynchronize());
                     CK(cudaEventRecord(e0));
-                    feed_kernel<0><<<g, 128, 4 * STAGE>>>(rounds, mma, same, one, src, src_bytes, dcy);
+                    feed_kernel<0><<<g, 128, 4 * STAGE>>>(rounds, mma, same, one, src, src_bytes, dcy, tmap);
                     CK(cudaEventRecord(e1));
                     CK(cudaDeviceSynchronize());
                     float ms = 0;
                     CK(cudaEventElapsedTime(&ms, e0, e1));
                     long long cy0;
                     CK(cudaMemcpy(&cy0, dcy, 8, cudaMemcpyDeviceToHost));
-                    printf("feed: mma %d same-window %d one-copy %d CTAs %3d: %.1f clk per 36 KB stage (CTA 0), %.2f TB/s L2 -> SM in total, %.1f B/clk per SM\n",
-                           mma, same, one, g, (double)cy0 / rounds, (double)STAGE * rounds * g / (ms * 1e-3) / 1e12, (double)STAGE * rounds / (double)cy0);
+                    printf("feed: mma %d same-window %d copies %s CTAs %3d: %.1f clk per 36 KB stage (CTA 0), %.2f TB/s L2 -> SM in total, %.1f B/clk per SM\n",
+                           mma, same, one == 0 ? "2 x 12 KB + 12 x 1 KB" : one == 1 ? "1 x 36 KB" : one == 2 ? "2 x 12 KB + 2 tensor boxes (6 x 1 KB)" : "2 x 12 KB + 2 x 6 KB", g, (double)cy0 / rounds, (double)STAGE * rounds * g / (ms * 1e-3) / 1e12, (double)STAGE * rounds / (double)cy0);
                 }
     cudaFree(dcy);
 }
