@@ -80,17 +80,27 @@ AQML_HD int clamp63(int a) {
 }
 
 // one term 2^-T, T = F 2^-48:  value = M 2^-(53 + n), M in [2^52 - few, 2^53]; n >= N_ZERO: below the normal doubles.
-// tab[j] = 2^(-j/4096) 2^53 (Q53, in (2^52, 2^53]);  M = tab[j] (1 - E 2^-44) with the product's low 22 bits dropped (2^-43)
-AQML_HD void exp2neg(u64 F, const u64 *tab, u64 &M, int &n) {
+// tab[j] = 2^(-j/4096) 2^53 (Q53, in (2^52, 2^53]);  M = tab[j] (1 - E 2^-44) with the product's low 22 bits dropped (2^-43).
+// Two halves so that a caller can issue the table look-up of the next term before the arithmetic of this one.
+struct Lookup { u64 t; u32 R; int n; };
+AQML_HD Lookup exp2neg_lookup(u64 F, const u64 *tab) {
     const u32 hi = (u32)(F >> 32), lo = (u32)F;
-    n = (int)(hi >> 16);
-    const u32 j = (hi >> 4) & (TAB_N - 1);
-    const u32 R = funnel_l(lo, hi, 28);                   // r 2^44,  r < 2^-12 (its top 32 bits)
-    const u32 Y = mulhi(R, LN2_Q32);                      // y 2^44,  y = r ln 2
+    Lookup L;
+    L.n = (int)(hi >> 16);
+    L.R = funnel_l(lo, hi, 28);                           // r 2^44,  r < 2^-12 (its top 32 bits)
+    L.t = tab[(hi >> 4) & (TAB_N - 1)];
+    return L;
+}
+AQML_HD u64 exp2neg_finish(const Lookup &L) {
+    const u32 Y = mulhi(L.R, LN2_Q32);                    // y 2^44,  y = r ln 2
     const u32 E = Y - (mulhi(Y, Y) >> 13);                // (y - y^2 / 2) 2^44
-    const u64 t = tab[j];
-    const u32 p = mulhi(funnel_l((u32)t, (u32)(t >> 32), 11), E);   // top 32 bits of the table value times E, >> 32
-    M = t - ((u64)p << 9);
+    const u32 p = mulhi(funnel_l((u32)L.t, (u32)(L.t >> 32), 11), E);   // top 32 bits of the table value times E, >> 32
+    return L.t - ((u64)p << 9);
+}
+AQML_HD void exp2neg(u64 F, const u64 *tab, u64 &M, int &n) {
+    const Lookup L = exp2neg_lookup(F, tab);
+    n = L.n;
+    M = exp2neg_finish(L);
 }
 
 // bit pattern of the double M 2^-(53 + n)  (M = 0 -> 0.0)

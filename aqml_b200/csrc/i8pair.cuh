@@ -107,6 +107,10 @@ struct I8Meta {  // everything the roles need to know about one tile
     int tm, tn, nact, KT, zcol, sym, dense;  // dense: every k-chunk 0 .. KT-1 is active (no list)
     int group;
     int special;                       // a row norm of this tile is NaN / Inf: the integer epilogue takes its FP64 side path
+    // integer d^2 (ladder of sigmas, local kernel, finite norms in range): normA / normB then hold |row|^2 2^(60 - E) as 64-bit
+    // integers (E: binary exponent of the tile's largest norm), T 2^48 = d^2-in-these-units * K, K = Kq 2^-(64 + kr)
+    int fix, kr, eoff;                 // eoff = 13 - E:  2 a.b in the norms' units = W 2^(ea + eb + eoff)
+    unsigned long long Kq;
     const int8_t *srcA, *srcB;
     int segA[I8_BM], expA[I8_BM];
     double normA[I8_BM];
@@ -395,6 +399,31 @@ __global__ void __launch_bounds__(I8_THREADS, 1) i8_pair_kernel(const __grid_con
                 special |= ((__double2hiint(nrm) & 0x7ff00000) == 0x7ff00000);
             }
             special = __any_sync(0xffffffffu, special);
+            // fixed-point norms for the integer d^2 (see I8Meta::fix): decided per tile, warp-uniform
+            int fix = 0, kr = 0, eoff = 0;
+            unsigned long long Kq = 0ull;
+            if (EPI == 1 && P.chain && !P.store && !special) {
+                // integer instructions only (an FP64 instruction takes ~800 clk while the MMAs stream, and this warp must stay two tiles ahead)
+                __syncwarp();
+                unsigned hmax = 0u;   // norms are >= 0: their high words order like the values
+                for (int i = lane; i < I8_BM + I8_BN; i += 32) hmax = max(hmax, (unsigned)__double2hiint(i < I8_BM ? M.normA[i] : M.normB[i - I8_BM]));
+                hmax = __reduce_max_sync(0xffffffffu, hmax);
+                const int E = (int)(hmax >> 20) - 1022;                                         // largest norm = f 2^E, f in [1/2, 1)
+                const double cz = -P.isig[P.order[0] * P.zstride + G.zcol] * 1.4426950408889634;   // the one FP64 instruction
+                const int eK = ((__double2hiint(cz) >> 20) & 0x7ff) + (E - 12);                 // K = cz 2^(E - 12) = m 2^(eK - 1075)
+                if (E > -900 && E < 900 && cz > 0.0 && cz < 1e300 && eK >= 1022 - 63 && eK <= 1021) {   // 2^-63 <= K < 1/2
+                    fix = 1; kr = 1022 - eK; eoff = 13 - E;
+                    Kq = (((unsigned long long)(((unsigned)__double2hiint(cz) & 0xfffffu) | 0x100000u) << 32) | (unsigned)__double2loint(cz)) << 11;
+                    for (int i = lane; i < I8_BM + I8_BN; i += 32) {
+                        double *q = i < I8_BM ? &M.normA[i] : &M.normB[i - I8_BM];
+                        // |row|^2 = m 2^(e - 1075)  ->  m 2^(e - 1015 - E) units of 2^(E - 60); e - 1023 < E: a left shift of <= 7 or a right shift
+                        const unsigned h = (unsigned)__double2hiint(*q), l = (unsigned)__double2loint(*q);
+                        const int e = (int)(h >> 20), sft = e - 1015 - E;
+                        const unsigned long long m = e ? ((((unsigned long long)((h & 0xfffffu) | 0x100000u)) << 32) | l) : 0ull;   // denormal: 0
+                        *reinterpret_cast<unsigned long long *>(q) = sft >= 0 ? (m << sft) : (m >> min(-sft, 63));
+                    }
+                }
+            }
             if (!__any_sync(0xffffffffu, any)) continue;  // no wanted row in this tile (row-block sharding)
             // active 16-column k-chunks: both operands have a non-zero there (exact: a zero chunk adds 0 to a.b)
             int n = 0;
@@ -421,7 +450,7 @@ __global__ void __launch_bounds__(I8_THREADS, 1) i8_pair_kernel(const __grid_con
             }
             if (lane == 0) {
                 if (masked && (n & 1)) M.kt[n] = (unsigned short)G.KT;  // pad the last stage with the all-zero chunk
-                M.nact = n; M.tm = tm; M.tn = tn; M.KT = G.KT; M.zcol = G.zcol; M.sym = G.sym; M.dense = masked ? 0 : 1; M.group = gi; M.special = special;
+                M.nact = n; M.tm = tm; M.tn = tn; M.KT = G.KT; M.zcol = G.zcol; M.sym = G.sym; M.dense = masked ? 0 : 1; M.group = gi; M.special = special; M.fix = fix; M.kr = kr; M.eoff = eoff; M.Kq = Kq;
                 M.srcA = G.slA + (long long)tm * (G.KT + 1) * I8_A_CHUNK;
                 M.srcB = G.slB + (long long)(tn >> 1) * (G.KT + 1) * I8_A_CHUNK + (tn & 1) * 1024;
                 if (P.stats) {  // in units of 64 x 64 x 16 k-tiles, like the DMMA engine
@@ -605,6 +634,70 @@ __global__ void __launch_bounds__(I8_THREADS, 1) i8_pair_kernel(const __grid_con
                 if (lane == 0) i8::mbar_arrive(&S.meta_empty[b]);
                 continue;
             }
+            // integer epilogue, ladder of sigmas, local kernel: V[j] = T of the widest sigma as Q16.48; per sigma (a left shift of V)
+            // a term (M, n) per pair, column runs added as aligned 64-bit integers, one RED per lane and run
+            auto chain_loop = [&](unsigned long long (&V)[EC]) {
+#pragma unroll 1
+                for (int si = 0; si < P.nsig; si++) {
+                    double *outS = P.out + (long long)P.order[si] * P.slab + (long long)max(sr, 0) * P.ldo;
+                    const int sq = si ? P.nsq[si] : 0;
+                    unsigned long long acc = 0ull;
+                    int nacc = 4095;
+#pragma unroll
+                    for (int j = 0; j < EC; j++) {
+                        V[j] = i8x::fix_shl(V[j], sq);
+                        unsigned long long Mt;
+                        int nt;
+                        i8x::exp2neg(V[j], S.exp2tab, Mt, nt);
+                        i8x::add_term(acc, nacc, Mt, nt);
+                        if ((lastmask >> j) & 1u) {  // warp-uniform: column cbase + j closes a molecule of B
+                            const int sc = M.segB[cbase + j];
+                            if (sc >= 0) {
+                                if (AQML_I8_LANE_RED) { if (sr >= 0) i8_lane_red(acc, nacc, outS + sc); }
+                                else i8_flush_int(acc, nacc, lane, run_end, head_lane, head, outS + sc);
+                            }
+                            acc = 0ull;
+                            nacc = 4095;
+                        }
+                    }
+                }
+            };
+            if (EPI == 1 && M.fix) {
+                // d^2 and T on integers too (no FP64 instruction in this tile's epilogue except the conversions at the REDs): the norms
+                // arrive as 64-bit integers in units of 2^(E - 60), 2 a.b = W 2^(ea + eb - 47) is shifted into the same units, and
+                // T 2^48 = d^2 K by one 64 x 64 -> high multiply (K = Kq 2^-(64 + kr), prepared per tile by the metadata warp)
+                unsigned long long V[EC];
+                const long long NA = reinterpret_cast<const long long *>(M.normA)[row];
+                const int eaE = ea + M.eoff, kr = M.kr;
+                const unsigned long long Kq = M.Kq;
+#pragma unroll
+                for (int j = 0; j < EC; j++) {
+                    const int col = cbase + j;
+                    const long long W = (hi[j] << 16) + (lo[j] >> 16);
+                    const int sh = eaE + M.expB[col];
+                    const long long Ws = (long long)((unsigned long long)W << i8x::clamp63(sh)) >> i8x::clamp63(-sh);
+                    long long D = NA + reinterpret_cast<const long long *>(M.normB)[col] - Ws;
+                    D = D < 0 ? 0 : D;                                                          // rounding noise of a.b for a = b
+                    const unsigned long long F = __umul64hi((unsigned long long)D, Kq) >> kr;
+                    const bool out = (M.sym && M.tn * I8_BN + col <= growA) || sr < 0 || M.segB[col] < 0;   // pairs that do not count
+                    V[j] = out ? ~0ull : F;
+                }
+                chain_loop(V);
+                __syncwarp();
+                if (I8_SERIAL_EPILOGUE && lane == 0) i8::mbar_arrive(&S.tmem_free);
+                if (P.debug && lane == 0) {
+                    const long long e3 = clock64();
+                    if (warp == 3) {
+                        atomicAdd(P.stats + 7, (unsigned long long)(e1 - e0));
+                        atomicAdd(P.stats + 8, (unsigned long long)(e2 - e1));
+                        atomicAdd(P.stats + 9, (unsigned long long)(e3 - e2));
+                    }
+                    atomicAdd(P.stats + 16 + (warp - 3), (unsigned long long)(e3 - e2));
+                    atomicAdd(P.stats + 32 + (warp - 3), (unsigned long long)(e1 - e0));
+                }
+                if (lane == 0) i8::mbar_arrive(&S.meta_empty[b]);
+                continue;
+            }
             // d^2 of my 16 pairs: a.b = 2^(ea + eb - 64) V, V = hi 2^32 + lo; W = V >> 16 has <= 62 bits, ONE conversion to double
             // (rounding 2^-53 of a.b, as in an FP64 dot product), one FMA with the power of two built from the exponents
             double x[EC];
@@ -666,30 +759,7 @@ __global__ void __launch_bounds__(I8_THREADS, 1) i8_pair_kernel(const __grid_con
                     const double c0 = -P.isig[P.order[0] * P.zstride + M.zcol] * LOG2E;
 #pragma unroll
                     for (int j = 0; j < EC; j++) V[j] = fixT(x[j] * c0);
-#pragma unroll 1
-                    for (int si = 0; si < P.nsig; si++) {
-                        double *outS = P.out + (long long)P.order[si] * P.slab + (long long)max(sr, 0) * P.ldo;
-                        const int sq = si ? P.nsq[si] : 0;
-                        unsigned long long acc = 0ull;
-                        int nacc = 4095;
-#pragma unroll
-                        for (int j = 0; j < EC; j++) {
-                            V[j] = i8x::fix_shl(V[j], sq);
-                            unsigned long long Mt;
-                            int nt;
-                            i8x::exp2neg(V[j], S.exp2tab, Mt, nt);
-                            i8x::add_term(acc, nacc, Mt, nt);
-                            if ((lastmask >> j) & 1u) {  // warp-uniform: column cbase + j closes a molecule of B
-                                const int sc = M.segB[cbase + j];
-                                if (sc >= 0) {
-                                    if (AQML_I8_LANE_RED) { if (sr >= 0) i8_lane_red(acc, nacc, outS + sc); }
-                                    else i8_flush_int(acc, nacc, lane, run_end, head_lane, head, outS + sc);
-                                }
-                                acc = 0ull;
-                                nacc = 4095;
-                            }
-                        }
-                    }
+                    chain_loop(V);
                 } else {
 #pragma unroll 1
                     for (int si = 0; si < P.nsig; si++) {
