@@ -16,7 +16,7 @@
 // 6th, 2^-49 of 2^ea per element -- measured on aSLATM rows 1e-13 .. 1e-12 relative per exp term at sigma = dmax/2.4
 // (the 7 x 7-bit / 28-product scheme of round 1: 2e-13 .. 6e-13); 26 products: 1e-14 .. 3e-14.
 //
-// The products are issued as 8 (10) MMAs: A plane i meets the B planes 0 .. n-1, which lie one behind the other in
+// The products are issued as 8 (9) MMAs: A plane i meets the B planes 0 .. n-1, which lie one behind the other in
 // the stage buffer, as ONE instruction with N = 64 n stacked rows (split at 256) whose 64-column output slices are
 // the consecutive accumulators g = i .. i+n-1.  N >= 128 runs at the full UTCIMMA rate (64 clk per 128 columns; a
 // single N = 64 product takes 48 clk, not 32: tools/micro/i8_umma.cu), so a stage costs ~720 (832) clk instead of
@@ -25,20 +25,28 @@
 //
 // Kernel: persistent, one CTA per SM; 128 x 64 tiles of atom pairs (A rows = TMEM lanes) handed out in raster order by an
 // atomic counter; roles synchronised by mbarriers only:
-//   warp 0 (one lane)  producer: per stage two active 16-column k-chunks of all 6 digit planes of A (2 x 12 KB,
-//                      contiguous in the pre-tiled slice buffer) and of B (2 x 6 x 1 KB) by cp.async.bulk onto an
-//                      mbarrier (4 stages x 36 KB);
-//   warp 1 (one lane)  issues the 8 UTCIMMA (M 128, N 64..256, K 32 = two k-chunks via the descriptor's leading
-//                      byte offset, so the exact 16-column block sparsity of the DMMA engine carries over) into 7
-//                      accumulators (7 x 64 = 448 TMEM columns); tcgen05.commit frees the stage / signals the end;
-//   warp 2             tile metadata (segments, norms, exponents, active k-chunk list) two tiles ahead, triple buffered;
-//   warps 3-18         epilogue (4 per TMEM lane quarter, 16 columns each): tcgen05.ld of the 7 accumulators into two exact
-//                      64-bit integers per pair, TMEM handed back (the next tile's MMAs start), then FP64:
-//                      d^2 = |a|^2+|b|^2-2a.b, table-based exp, squaring chain over the sigmas, sum over the atoms of a
-//                      molecule pair (column runs in registers, row runs by segmented shuffles), one RED.F64 per
-//                      (sigma, molecule pair, warp); or K[s][i][j] = exp for the global kernel (store epilogue).
+//   warp 0   producer: per stage two active 16-column k-chunks of all 6 digit planes of A (2 x 12 KB, contiguous in the
+//            pre-tiled slice buffer: cp.async.bulk) and of B (2 boxes of 6 planes x 1 KB through a tensor map: ONE
+//            cp.async.bulk.tensor each -- six 1 KB bulk copies cost ~57 clk apiece and bounded the ring at 1150 clk per stage,
+//            profiles/r02_micro_feed.txt) onto an mbarrier; 5 stages x 36 KB;
+//   warp 1   issues the 8 UTCIMMA (M 128, N 64..256, K 32 = two k-chunks via the descriptor's leading byte offset, so the
+//            exact 16-column block sparsity of the DMMA engine carries over) into 7 accumulators (7 x 64 = 448 TMEM columns);
+//            tcgen05.commit frees the stage / signals the end.  Both role warps run their loops converged and let one
+//            elected lane issue (descriptors stay in uniform registers), and the issuer tests the NEXT stage's barrier before
+//            it issues this stage, so that nothing but the commit separates two stages' MMAs;
+//   warp 2   tile metadata (segments, norms -- as 64-bit fixed point for the integer epilogue --, exponents, active k-chunk
+//            list) two tiles ahead, triple buffered;
+//   warps 3-18  epilogue (4 per TMEM lane quarter, 16 columns each): tcgen05.ld of the 7 accumulators into two exact 64-bit
+//            integers per pair, TMEM handed back (the next tile's MMAs start), then -- on INTEGERS, because an FP64 instruction
+//            takes ~800 clk while UTCIMMA stream (i8exp.cuh) -- d^2 = |a|^2+|b|^2-2a.b in fixed point, T = d^2/(2 sigma^2) log2 e
+//            by one 64 x 64 -> high multiply, 2^-T by table + polynomial, the sigma ladder by shifts of T, the sum over the
+//            atoms of a molecule pair as aligned 64-bit integers per (lane, column run), one conversion + RED.F64 per lane
+//            and run; or K[s][i][j] = the assembled double for the global kernel (store epilogue).  Tiles with a NaN / Inf
+//            norm, sigma sets that are no ladder and AQML_I8_EPILOGUE=fp64 use FP64 arithmetic (the round-1/2 epilogue).
 // Operands are staged in the canonical K-major no-swizzle core-matrix layout (8 rows x 16 B), which is exactly how
-// the slice buffer is written, so a stage is filled by plain 1-D bulk copies (no tensor maps).
+// the slice buffer is written.
+// Measured (K(test, train) 800 x 4000 molecules, 4 sigmas, profiles/r02_pair_kernel_steps.txt): 16.0 ms at the start of
+// round 2 -> 11.6 ms; per 32-column stage 1435 -> 998 clk (716 = the UTCIMMA alone).
 #pragma once
 #include "i8digits.cuh"
 #include "i8exp.cuh"
@@ -350,9 +358,8 @@ __global__ void __launch_bounds__(I8_THREADS, 1) i8_pair_kernel(const __grid_con
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const unsigned tb = S.tmem_base;
-    const int role = (P.debug & 8) ? (warp == 0 ? 2 : warp == 2 ? 0 : warp) : warp;  // experiment: producer and metadata warps swapped
 
-    if (role == 2) {
+    if (warp == 2) {
         // ---- tile metadata, one tile ahead ----
         // tiles are handed out dynamically (one atomic per tile): the tiles in flight are always consecutive in the raster
         // order, so the CTAs that share a B tile read it within one L2 residency and the tail is balanced
@@ -462,7 +469,7 @@ __global__ void __launch_bounds__(I8_THREADS, 1) i8_pair_kernel(const __grid_con
             if (lane == 0) i8::mbar_arrive(&S.meta_full[b]);
             tl++;
         }
-    } else if (role == 0) {
+    } else if (warp == 0) {
         // ---- producer ----  (whole warp converged, one elected lane issues the copies: see the MMA issuer)
         {
             unsigned leader;
@@ -791,62 +798,62 @@ __global__ void __launch_bounds__(I8_THREADS, 1) i8_pair_kernel(const __grid_con
                 // per head lane
 #pragma unroll 1
                 for (int si = 0; si < P.nsig; si++) {
-                const int s = P.chain ? P.order[si] : si;
-                double *outS = P.out + (long long)s * P.slab + (long long)max(sr, 0) * P.ldo;
-                double run = 0.0;
-                if (P.store) {
-                    // global kernel (fkernels.f90:344-355): every pair is one element of K; 16 consecutive columns per lane
-                    if (!P.chain || si == 0) {
+                    const int s = P.chain ? P.order[si] : si;
+                    double *outS = P.out + (long long)s * P.slab + (long long)max(sr, 0) * P.ldo;
+                    double run = 0.0;
+                    if (P.store) {
+                        // global kernel (fkernels.f90:344-355): every pair is one element of K; 16 consecutive columns per lane
+                        if (!P.chain || si == 0) {
+                            const double f = P.isig[s * P.zstride + M.zcol];
+#pragma unroll
+                            for (int j = 0; j < EC; j++) {
+                                const double e = i8_exp(x[j] * f, S.exptab);
+                                if (P.chain) x[j] = e;
+                                const int sc = M.segB[cbase + j];
+                                if (sr >= 0 && sc >= 0) outS[sc] = e;
+                            }
+                        } else {
+                            for (int k = 0; k < P.nsq[si]; k++)
+#pragma unroll
+                                for (int j = 0; j < EC; j++) x[j] *= x[j];
+#pragma unroll
+                            for (int j = 0; j < EC; j++) {
+                                const int sc = M.segB[cbase + j];
+                                if (sr >= 0 && sc >= 0) outS[sc] = x[j];
+                            }
+                        }
+                    } else if (P.chain) {
+                        if (si == 0) {
+                            const double f = P.isig[s * P.zstride + M.zcol];
+#pragma unroll
+                            for (int j = 0; j < EC; j++) x[j] = i8_exp(x[j] * f, S.exptab);  // +inf * f = -inf -> 0
+                        } else {
+                            for (int k = 0; k < P.nsq[si]; k++)
+#pragma unroll
+                                for (int j = 0; j < EC; j++) x[j] *= x[j];
+                        }
+#pragma unroll
+                        for (int j = 0; j < EC; j++) {
+                            run += x[j];
+                            if ((lastmask >> j) & 1u) {  // warp-uniform: column cbase + j closes a molecule of B
+                                const int sc = M.segB[cbase + j];
+                                if (sc >= 0) i8_flush(run, lane, run_end, head, outS + sc);
+                                run = 0.0;
+                            }
+                        }
+                    } else {
                         const double f = P.isig[s * P.zstride + M.zcol];
 #pragma unroll
                         for (int j = 0; j < EC; j++) {
-                            const double e = i8_exp(x[j] * f, S.exptab);
-                            if (P.chain) x[j] = e;
-                            const int sc = M.segB[cbase + j];
-                            if (sr >= 0 && sc >= 0) outS[sc] = e;
-                        }
-                    } else {
-                        for (int k = 0; k < P.nsq[si]; k++)
-#pragma unroll
-                            for (int j = 0; j < EC; j++) x[j] *= x[j];
-#pragma unroll
-                        for (int j = 0; j < EC; j++) {
-                            const int sc = M.segB[cbase + j];
-                            if (sr >= 0 && sc >= 0) outS[sc] = x[j];
-                        }
-                    }
-                } else if (P.chain) {
-                    if (si == 0) {
-                        const double f = P.isig[s * P.zstride + M.zcol];
-#pragma unroll
-                        for (int j = 0; j < EC; j++) x[j] = i8_exp(x[j] * f, S.exptab);  // +inf * f = -inf -> 0
-                    } else {
-                        for (int k = 0; k < P.nsq[si]; k++)
-#pragma unroll
-                            for (int j = 0; j < EC; j++) x[j] *= x[j];
-                    }
-#pragma unroll
-                    for (int j = 0; j < EC; j++) {
-                        run += x[j];
-                        if ((lastmask >> j) & 1u) {  // warp-uniform: column cbase + j closes a molecule of B
-                            const int sc = M.segB[cbase + j];
-                            if (sc >= 0) i8_flush(run, lane, run_end, head, outS + sc);
-                            run = 0.0;
-                        }
-                    }
-                } else {
-                    const double f = P.isig[s * P.zstride + M.zcol];
-#pragma unroll
-                    for (int j = 0; j < EC; j++) {
-                        run += i8_exp(x[j] * f, S.exptab);
-                        if ((lastmask >> j) & 1u) {
-                            const int sc = M.segB[cbase + j];
-                            if (sc >= 0) i8_flush(run, lane, run_end, head, outS + sc);
-                            run = 0.0;
+                            run += i8_exp(x[j] * f, S.exptab);
+                            if ((lastmask >> j) & 1u) {
+                                const int sc = M.segB[cbase + j];
+                                if (sc >= 0) i8_flush(run, lane, run_end, head, outS + sc);
+                                run = 0.0;
+                            }
                         }
                     }
                 }
-            }
             }  // EPI
             __syncwarp();
             if (I8_SERIAL_EPILOGUE && lane == 0) i8::mbar_arrive(&S.tmem_free);
