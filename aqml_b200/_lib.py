@@ -38,6 +38,8 @@ SIGNATURES = {
     "aqml_pair_stats": (_I, [_P, _P, _I]),
     "aqml_tile_shape": (None, [_P, _P, _P]),
     "aqml_measure_i8_peak": (_I, [_P, _P]),
+    "aqml_pairwise_dims": (_I, [_P, _D, _I, _I, _I, _P, _P, _P]),
+    "aqml_pairwise_local_spectrum_dev": (_I, [_P, _P, _P, _I, _P, _I, _P, _I, _P, _I, _P, _I, _P, _D, _D, _D, _D, _D, _D, _P, _P, _P]),
     "aqml_fgaussian_kernel": (_I, [_P, _I, _P, _I, _I, _P, _D]),
     "aqml_flaplacian_kernel": (_I, [_P, _I, _P, _I, _I, _P, _D]),
     "aqml_fl2_distance": (_I, [_P, _P, _I, _I, _I, _P]),

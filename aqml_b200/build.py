@@ -7,7 +7,7 @@ import subprocess
 import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-SRC = [os.path.join(HERE, "csrc", f) for f in ("kernels.cu", "slatm.cu")]
+SRC = [os.path.join(HERE, "csrc", f) for f in ("kernels.cu", "slatm.cu", "pairwise.cu")]
 HDR = sorted(os.path.join(HERE, "csrc", f) for f in os.listdir(os.path.join(HERE, "csrc")) if f.endswith(".cuh")) + \
       [os.path.join(os.path.dirname(HERE), "include", "aqml_b200.h")]
 OUT = os.path.join(HERE, "lib", "libaqml_b200.so")

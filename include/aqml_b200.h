@@ -224,6 +224,21 @@ int aqml_rep_kernel_width(const aqml_rep *r1, const aqml_rep *r2, int zmax, doub
 int aqml_rep_kernel_width_multi(const aqml_rep *const *reps1, int n1, const aqml_rep *const *reps2, int n2, int zmax, double *dso,
                                 void *stream);
 
+/* ---- pair-wise / bond aSLATM ("next" row 8f; coreml/cml/representation/fslatm_pairwise.f90) --------------------------
+ * The file is outside the reference's build and cannot run as shipped (`na` unset in calc_sbop_local, :394); semantics =
+ * its statements with na := size(zs) (oracle/np_pairwise.py, PARITY UNPINNED).
+ * aqml_pairwise_dims: grid sizes nsx[3] = {two-body atoms, two-body bonds, three-body} and the row lengths
+ *   n = n1 + n2 nsx[0] + n3 nsx[2] (atom rows), nu = n1 + n2 nsx[1] + n3 nsx[2] (bond rows)      (calc_mk1 :781-788, xb.py:110-124)
+ * aqml_pairwise_local_spectrum_dev: replaces calc_all_local_spectrum / calc_local_spectrum (:525-673) with ia0 = ib0 = 0:
+ *   coords (A,3), zs (A), nas (nmol), nbrs (A, nbmax; molecule-local indices, -1 padded; NULL with nbmax = 0: no bond rows),
+ *   mbs1 (n1), mbs2 (n2,2), mbs3 (n3,3), rscut = {racut, rbcut}: all HOST.  ys DEVICE (A, n), ys2 DEVICE (A, nbmax, nu).
+ *   Synchronises `stream`. */
+int aqml_pairwise_dims(const double *rscut, double dgrid, int n1, int n2, int n3, int *nsx, int *n, int *nu);
+int aqml_pairwise_local_spectrum_dev(const double *coords, const int *zs, const int *nas, int nmol, const int *nbrs, int nbmax,
+                                     const int *mbs1, int n1, const int *mbs2, int n2, const int *mbs3, int n3, const double *rscut,
+                                     double dgrid, double sigma, double w2, double rpower2, double w3, double rpower3, double *ys,
+                                     double *ys2, void *stream);
+
 /* counters for bench.py: number of device kernels this library launched since load */
 int64_t aqml_launch_count(void);
 /* k-tiles (16 columns x one 128x64 tile) the pair kernels executed vs. a dense sweep would have, summed

@@ -200,3 +200,23 @@ def test_shape_validation_before_any_device_call():
         fused.PackedRep(np.zeros((4, 3)), [1, 1, 1, 1, 1], [5], [[1], [1, 1]])
     with pytest.raises(ValueError):
         fused.PackedRep(np.zeros((5, 3)), [1, 1, 1, 1], [5], [[1], [1, 1]])
+
+
+def test_pairwise_oracle_internal_consistency():
+    """oracle/np_pairwise.py (fslatm_pairwise.f90, parity unpinned): with every atom a listed neighbour and equal cut-offs /
+    grids, an atom's two- and three-body blocks are the sums of its bond rows' blocks -- the relation between
+    calc_sbop_local / calc_sbot_local with ib = 0 and ib = j that the file's two code paths must satisfy."""
+    from aqml_b200 import synth
+    from oracle import np_pairwise as o
+    nas, zs, coords = synth.qm9_like(2, 3)
+    nas, zs, coords = np.asarray(nas), np.asarray(zs), np.asarray(coords)
+    z, c = zs[:nas[0]], coords[:nas[0]]
+    mb = o.get_slatm_mbtypes(zs, nas)
+    rc = 3.0
+    _, nbrs = o.get_neighbors(100.0, c)
+    nsx = o.grid_sizes(rc, rc, 0.05)
+    ys, ys2 = o.calc_local_spectrum(z, c, nbrs, mb[0], mb[1], mb[2], nsx, [rc, rc], 0.05, 0.06, 1.0, 6, 1 / 3, 3)
+    n1 = len(mb[0])
+    assert np.array_equal(ys[:, :n1] != 0, z[:, None] == mb[0][None, :]) and np.all(ys2[:, :, :n1] == 0)
+    assert np.max(np.abs(ys[:, n1:] - ys2[:, :, n1:].sum(axis=1))) <= 1e-14 * np.max(np.abs(ys))
+    assert abs(o.R0 - 0.1) > 1e-9 and abs(o.R0 - 0.1) < 2e-9   # r0 is the single-precision 0.1
