@@ -308,11 +308,13 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     warm = max(args.warmup, 3)
+    # the clock sampler starts BEFORE the warm-up: spawning nvidia-smi (fork of this process + NVML initialisation, which takes
+    # driver locks) stalled the first timed step of every rank by ~0.5 s at N = 4 when it was started right before the timed region
+    sampler = ClockSampler(local_rank) if rank == 0 else None
     for _ in range(warm):
         step()
     barrier()
     rep_bytes = sum(r.nbytes for r in sk.reps) + sk.test.nbytes
-    sampler = ClockSampler(local_rank) if rank == 0 else None
     launches0 = lib.aqml_launch_count()
     timing = []
     w0 = time.time()
@@ -326,6 +328,10 @@ def run_ours(args):
     launches = int(lib.aqml_launch_count() - launches0)
     t_total_ms = e_start.elapsed_time(e_end)
     phases = [float(np.mean([e[i].elapsed_time(e[i + 1]) for e in timing])) for i in range(len(PH))]
+    if os.environ.get("AQML_BENCH_DEBUG"):
+        for k, e in enumerate(timing):
+            print("rank %d step %d phases_ms %s" % (rank, k, " ".join("%s=%.1f" % (PH[i], e[i].elapsed_time(e[i + 1])) for i in range(len(PH)))),
+                  file=sys.stderr, flush=True)
     clocks = sampler.stop(w0, w1) if sampler else None
     y_host = y.cpu().numpy()
 
