@@ -809,7 +809,7 @@ static bool launch_i8(std::vector<I8Group> &gs, const PairParams &PP, Workspace 
     // AQML_I8_PRODUCTS=26: every digit product with i + j <= 6 (10 x lower truncation error, ~15 % more tensor work)
     static const bool full6 = getenv("AQML_I8_PRODUCTS") && atoi(getenv("AQML_I8_PRODUCTS")) >= 26;
     // AQML_I8_EPILOGUE=fp64: the FP64 epilogue (table exp, squaring chain, FP64 sums); default: integers (i8exp.cuh)
-    static const bool fp64epi = getenv("AQML_I8_EPILOGUE") && !strcmp(getenv("AQML_I8_EPILOGUE"), "fp64");
+    const bool fp64epi = getenv("AQML_I8_EPILOGUE") && !strcmp(getenv("AQML_I8_EPILOGUE"), "fp64");   // read per call (tests switch it)
     auto kern = full6 ? (fp64epi ? i8_pair_kernel<1, 0> : i8_pair_kernel<1, 1>) : (fp64epi ? i8_pair_kernel<0, 0> : i8_pair_kernel<0, 1>);
     P.exp2tab = i8_exp2_table();
     AQML_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));

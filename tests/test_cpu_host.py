@@ -220,3 +220,14 @@ def test_pairwise_oracle_internal_consistency():
     assert np.array_equal(ys[:, :n1] != 0, z[:, None] == mb[0][None, :]) and np.all(ys2[:, :, :n1] == 0)
     assert np.max(np.abs(ys[:, n1:] - ys2[:, :, n1:].sum(axis=1))) <= 1e-14 * np.max(np.abs(ys))
     assert abs(o.R0 - 0.1) > 1e-9 and abs(o.R0 - 0.1) < 2e-9   # r0 is the single-precision 0.1
+
+
+def test_integer_exp_of_the_int8_epilogue(tmp_path):
+    """aqml_b200/csrc/i8exp.cuh (host-callable): 2^-T by table + polynomial on integers, the sigma ladder as shifts, aligned
+    64-bit sums -- against exp2l in extended precision (tools/micro/i8exp_check.cpp: worst relative error < 2e-12, specials)."""
+    import subprocess
+    exe = str(tmp_path / "i8exp_check")
+    subprocess.check_call(["g++", "-O2", "-o", exe, os.path.join(ROOT, "tools", "micro", "i8exp_check.cpp")])
+    out = subprocess.run([exe], capture_output=True, text=True)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert "T = inf -> 0" in out.stdout and "T = 0 -> 1" in out.stdout

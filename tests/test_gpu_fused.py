@@ -118,6 +118,16 @@ def test_int8_tensor_engine_equals_fp64_engine_and_oracle():
             assert kernel_rel_err(out[engine][2], ref11) < TOL
         for a, b in zip(out["i8"], out["dmma"]):
             assert rel_err(a, b) < 1e-11
+        # the int8 engine's FP64 epilogue (AQML_I8_EPILOGUE=fp64: table exp, squaring chain, FP64 sums) against its default
+        # integer epilogue (i8exp.cuh) on the same accumulators
+        os.environ["AQML_I8_EPILOGUE"] = "fp64"
+        try:
+            f64 = (fused.local_gaussian(test, train, sig, zmax).cpu().numpy(),
+                   fused.local_gaussian(train, train, sig, zmax, symmetric=True).cpu().numpy())
+        finally:
+            del os.environ["AQML_I8_EPILOGUE"]
+        assert kernel_rel_err(f64[0], ref) < TOL and kernel_rel_err(f64[1], ref11) < TOL
+        assert kernel_rel_err(out["i8"][0], f64[0]) < 2e-11 and kernel_rel_err(out["i8"][2], f64[1]) < 2e-11
 
 
 def test_chunked_host_delivery_equals_one_shot():
