@@ -608,28 +608,41 @@ __global__ void __launch_bounds__(I8_THREADS, 1) i8_pair_kernel(const __grid_con
             i8::mbar_wait(&S.accum, tl & 1);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const long long e1 = clock64();
-            // phase 1: drain my 16 columns of the 6 accumulators into two exact 64-bit integers per pair (integer pipe
-            // only), then hand TMEM back: the next tile's MMAs run while everything below happens
-            long long hi[EC], lo[EC];
+            // phase 1: drain my 16 columns of the 7 accumulators into ONE exact 64-bit integer per pair (integer pipe only), then
+            // hand TMEM back: the next tile's MMAs run while everything below happens.
+            //   sum_g P_g 256^-g = 2^-32 W + (dropped fraction),  W = P0 2^32 + P1 2^24 + P2 2^16 + P3 2^8 + P4 + floor((P5 2^8 + P6) / 2^16):
+            // levels 5 and 6 come first (their sum is floored once, exactly as a 128-bit sum shifted right would be), and the loads
+            // go out two at a time so that one TMEM round trip covers two accumulators.
+            long long Wacc[EC];
 #pragma unroll
-            for (int j = 0; j < EC; j++) hi[j] = lo[j] = 0;
+            for (int j = 0; j < EC; j++) Wacc[j] = 0;
             if (nst > 0) {
-#pragma unroll
-                for (int g = 0; g < I8_NACC; g++) {
-                    unsigned v[EC];
+                auto ld16 = [&](unsigned (&v)[EC], int g) {
                     asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
                                  : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
                                    "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
                                  : "r"(trow + g * I8_BN));
-                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                    // sum_g P_g 256^-g = 2^-16 hi + 2^-48 lo with hi = P0 2^16 + P1 2^8 + P2, lo = P3 2^24 + P4 2^16 + P5 2^8 + P6
+                };
+                unsigned va[EC], vb[EC];
+                ld16(va, 5);
+                ld16(vb, 6);
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-                    for (int j = 0; j < EC; j++) {
-                        const long long pv = (long long)(int)v[j];
-                        if (g < 3) hi[j] += pv << (8 * (2 - g));
-                        else lo[j] += pv << (8 * (6 - g));
-                    }
-                }
+                for (int j = 0; j < EC; j++) Wacc[j] = ((((long long)(int)va[j]) << 8) + (long long)(int)vb[j]) >> 16;
+                ld16(va, 0);
+                ld16(vb, 1);
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                for (int j = 0; j < EC; j++) Wacc[j] += (((long long)(int)va[j]) << 32) + (((long long)(int)vb[j]) << 24);
+                ld16(va, 2);
+                ld16(vb, 3);
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                for (int j = 0; j < EC; j++) Wacc[j] += (((long long)(int)va[j]) << 16) + (((long long)(int)vb[j]) << 8);
+                ld16(va, 4);
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                for (int j = 0; j < EC; j++) Wacc[j] += (long long)(int)va[j];
                 clear_acc6();
             }
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -680,7 +693,7 @@ __global__ void __launch_bounds__(I8_THREADS, 1) i8_pair_kernel(const __grid_con
 #pragma unroll
                 for (int j = 0; j < EC; j++) {
                     const int col = cbase + j;
-                    const long long W = (hi[j] << 16) + (lo[j] >> 16);
+                    const long long W = Wacc[j];
                     const int sh = eaE + M.expB[col];
                     const long long Ws = (long long)((unsigned long long)W << i8x::clamp63(sh)) >> i8x::clamp63(-sh);
                     long long D = NA + reinterpret_cast<const long long *>(M.normB)[col] - Ws;
@@ -711,7 +724,7 @@ __global__ void __launch_bounds__(I8_THREADS, 1) i8_pair_kernel(const __grid_con
 #pragma unroll
             for (int j = 0; j < EC; j++) {
                 const int col = cbase + j;
-                const long long W = (hi[j] << 16) + (lo[j] >> 16);
+                const long long W = Wacc[j];
                 const int e2 = max(-1022, min(1023, ea + M.expB[col] - 47));                 // -2 a.b = W * -2^(ea + eb - 47)
                 const double sc = __hiloint2double((int)(0x80000000u | ((unsigned)(e2 + 1023) << 20)), 0);
                 double xx = fma((double)W, sc, na + M.normB[col]);                           // |a|^2 + |b|^2 - 2 a.b
