@@ -7,7 +7,7 @@ One process per GPU.  The training set is cut into 2 N blocks of molecules; rank
 2 N + 1 tiles, two of them diagonal).
 
   phase       what a rank does                                                        exchange
-  aslatm      packs its two training blocks (+ the test set)                          --
+  aslatm      packs its two training blocks and its 1/N of the test molecules         --
   allgather   --                                                                      each block's pair-kernel operands (digit planes,
                                                                                       norms, masks: 6 of the 14 bytes per packed
                                                                                       element) once: one NCCL broadcast per block
@@ -18,7 +18,8 @@ One process per GPU.  The training set is cut into 2 N blocks of molecules; rank
               attained lower bound, then only the rows the triangle inequality         -- on a second communicator, so that it
               leaves are gathered and contracted exactly (same pruning as on one GPU)   overlaps the broadcasts of the blocks
   k_train     tiles (b, c), c <= b, of its block rows; diagonal tiles symmetric       --
-  k_test      K(test, its training blocks): K_test sharded by training columns        --
+  k_test      K(test block t, its training blocks) for all N test blocks: K_test      --
+              sharded by training columns
   predict     partial K_test . alpha over its columns                                  all-reduce(SUM) of (nsigmas, n_test)
 
 The kernel assembly itself needs no communication (north_star: "each GPU builds its K tile independently, only the
@@ -62,7 +63,11 @@ class ShardedKernels(object):
         self.owners = [fold_owner(b, self.world) for b in range(self.nblk)]
         self.mine = [b for b in range(self.nblk) if self.owners[b] == self.rank]
         self.tiles = my_tiles(self.rank, self.world)
-        self.reps, self.test = [None] * self.nblk, None
+        # the test set is cut into N blocks, block t packed by rank t (at N = 8 the 2 k test molecules would otherwise cost every
+        # rank almost as much aSLATM time as its 2.5 k training molecules)
+        self.tbounds = block_bounds(self.n2, self.world)
+        self.off2 = np.concatenate(([0], np.cumsum(self.nas2)))
+        self.reps, self.tests = [None] * self.nblk, [None] * self.world
         self.group2, self._works, self._views = None, [], []
 
     # ---- phases ---------------------------------------------------------------------------------------------
@@ -71,14 +76,24 @@ class ShardedKernels(object):
         return self.nas1[lo:hi], self.zs1[self.off1[lo]:self.off1[hi]], slice(int(self.off1[lo]), int(self.off1[hi]))
 
     def pack(self, coords_train, coords_test):
-        """aSLATM: my training blocks are computed, the others only laid out; the (small) test set is packed by every
-        rank.  coords_*: (A, 3) host arrays (copied to the device inside) or CUDA tensors."""
+        """aSLATM: my training blocks and my test block are computed, the others only laid out.
+        coords_*: (A, 3) host arrays (copied to the device inside) or CUDA tensors."""
         self.close()
         for b in range(self.nblk):
             nas, zs, sl = self._block(b)
             own = self.owners[b] == self.rank
             self.reps[b] = fused.PackedRep(coords_train[sl] if own else None, zs, nas, self.mbtypes, compute=own, rows=own, **self.kw)
-        self.test = fused.PackedRep(coords_test, self.zs2, self.nas2, self.mbtypes, **self.kw)
+        for t in range(self.world):
+            lo, hi = self.tbounds[t]
+            sl = slice(int(self.off2[lo]), int(self.off2[hi]))
+            own = t == self.rank
+            self.tests[t] = fused.PackedRep(coords_test[sl] if own else None, self.zs2[sl], self.nas2[lo:hi], self.mbtypes, compute=own,
+                                            rows=own, **self.kw)
+
+    @property
+    def test(self):
+        """My block of the test set (the whole test set with one rank)."""
+        return self.tests[self.rank]
 
     def share_begin(self):
         """Enqueue the broadcasts: every training block's pair-kernel operands travel once from their owner to the other
@@ -87,8 +102,9 @@ class ShardedKernels(object):
         if self.world > 1:
             import torch.distributed as dist
             src = (lambda r: dist.get_global_rank(self.group, r)) if self.group is not None else (lambda r: r)
-            self._views = [r.slab_tensor(0) for r in self.reps]
-            self._works = [dist.broadcast(v, src=src(o), group=self.group, async_op=True) for v, o in zip(self._views, self.owners)]
+            blocks = list(zip(self.reps, self.owners)) + [(t, r) for r, t in enumerate(self.tests)]
+            self._views = [r.slab_tensor(0) for r, _ in blocks]
+            self._works = [dist.broadcast(v, src=src(o), group=self.group, async_op=True) for v, (_, o) in zip(self._views, blocks)]
 
     def share_end(self):
         for w in self._works:
@@ -102,117 +118,153 @@ class ShardedKernels(object):
     def width(self):
         """dmax per element over all training + test atoms (get_kernel_width with dmxby='a', aqml.py:744-749)."""
         if self.world == 1:
-            everything = self.reps + [self.test]
+            everything = self.reps + self.tests
             return fused.kernel_width(everything, everything, self.zmax)
         return self._width_distributed()
 
     def _width_distributed(self):
         """The pruned max-distance pass of `aqml_rep_kernel_width_multi` over rows that live on different GPUs: nobody ever
-        holds all rows.  Exact: the candidates are contracted by the same EPI_MAX pair kernel."""
+        holds all rows.  Exact: the candidates are contracted by the same EPI_MAX pair kernel.  All elements go through every
+        round together, so the pass costs six small collectives (not six per element) and as many host synchronisations."""
         import ctypes as C
         import torch
         import torch.distributed as dist
         from . import _lib as L
         if self.group2 is None:   # a second communicator: these small collectives must not queue behind the block broadcasts
             self.group2 = dist.new_group(list(range(self.world))) if self.group is None else self.group
-        g, dev = self.group2, self.test.device
-        mine = [self.reps[b] for b in self.mine] + ([self.test] if self.rank == self.world - 1 else [])
+        g, dev, W = self.group2, self.test.device, self.world
+        mine = [self.reps[b] for b in self.mine] + [self.test]
         rows = [r.element_rows() for r in mine]
         labels = sorted(int(t[0]) for t in self.mbtypes if len(t) == 1)
         st = L.current_stream(dev)
         dso = np.full(self.zmax, 1.e-9)
-
-        def sweep(segs, point):   # distance of every local row to one point
-            out = []
-            for x in segs:
-                r = torch.empty(x.shape[0], dtype=torch.float64, device=dev)
-                if x.shape[0]:
-                    L.call("aqml_rows_dist_dev", 2, L.ptr(x), x.stride(0), x.shape[0], L.ptr(point), x.shape[1], L.ptr(r), st)
-                out.append(r)
-            return torch.cat(out) if out else torch.empty(0, dtype=torch.float64, device=dev)
-
-        def global_max(v):   # (max over all ranks, owner rank, local index on the owner); NaN anywhere -> NaN
-            loc = torch.full((3,), -1.0, dtype=torch.float64, device=dev)
-            if v.numel():
-                m, i = torch.max(v, dim=0)
-                loc[0], loc[1] = m, i.to(torch.float64)
-                loc[2] = torch.isnan(v).any().to(torch.float64)
-            allv = [torch.empty_like(loc) for _ in range(self.world)]
-            dist.all_gather(allv, loc, group=g)
-            tab = torch.stack(allv).cpu().numpy()
-            if (tab[:, 2] > 0).any():
-                return float("nan"), 0, 0
-            owner = int(np.argmax(tab[:, 0]))
-            return float(tab[owner, 0]), owner, int(tab[owner, 1])
-
-        def row_from(owner, idx, allrows, ncols):
-            p = torch.empty(ncols, dtype=torch.float64, device=dev)
-            if owner == self.rank:
-                p.copy_(allrows(idx))
-            dist.broadcast(p, src=owner if self.group is None else dist.get_global_rank(g, owner), group=g)
-            return p
-
+        f64 = dict(dtype=torch.float64, device=dev)
+        segs = {z: [d[z] for d in rows if z in d] for z in labels}           # my row segments per element
         for z in labels:
-            segs = [d[z] for d in rows if z in d]
-            if not segs:
+            if not segs[z]:
                 raise RuntimeError("internal: element %d missing from a packed block" % z)
-            ncols = int(segs[0].shape[1])
-            nloc = sum(int(x.shape[0]) for x in segs)
-            offs = np.concatenate(([0], np.cumsum([int(x.shape[0]) for x in segs])))
+        ncol = {z: int(segs[z][0].shape[1]) for z in labels}
+        nloc = {z: sum(int(x.shape[0]) for x in segs[z]) for z in labels}
+        coff = np.concatenate(([0], np.cumsum([ncol[z] for z in labels])))    # offsets into a concatenated "one row per element"
+        ctot = int(coff[-1])
 
-            def local_row(i):
-                k = int(np.searchsorted(offs, i, side="right") - 1)
-                return segs[k][i - offs[k]]
+        def gather(t):   # all ranks' copies of a small tensor, stacked: (world, ...)
+            out = [torch.empty_like(t) for _ in range(W)]
+            dist.all_gather(out, t.contiguous(), group=g)
+            return torch.stack(out)
 
-            stat = torch.zeros(ncols + 1, dtype=torch.float64, device=dev)
-            for x in segs:
+        def sweep(points):   # distance of every local row of every element to that element's point: {z: (nloc_z,)}
+            res = {}
+            for k, z in enumerate(labels):
+                p = points[coff[k]:coff[k + 1]].contiguous()
+                out = []
+                for x in segs[z]:
+                    r = torch.empty(x.shape[0], **f64)
+                    if x.shape[0]:
+                        L.call("aqml_rows_dist_dev", 2, L.ptr(x), x.stride(0), x.shape[0], L.ptr(p), x.shape[1], L.ptr(r), st)
+                    out.append(r)
+                res[z] = torch.cat(out) if out else torch.empty(0, **f64)
+            return res
+
+        def local_row(z, i):
+            for x in segs[z]:
+                if i < x.shape[0]:
+                    return x[i]
+                i -= x.shape[0]
+            raise IndexError(i)
+
+        def farthest(dists):   # per element: the global maximum of `dists` and the row that attains it, known to every rank
+            msg = torch.zeros(len(labels), 2 + 0, **f64)
+            best = torch.zeros(ctot, **f64)
+            for k, z in enumerate(labels):
+                v = dists[z]
+                if v.numel():
+                    m, i = torch.max(v, dim=0)
+                    msg[k, 0] = m
+                    msg[k, 1] = torch.isnan(v).any().to(torch.float64)
+                    best[coff[k]:coff[k + 1]] = local_row(z, int(i.item()))
+                else:
+                    msg[k, 0] = -1.0
+            allm = gather(msg).cpu().numpy()                                  # (world, nel, 2)
+            allb = gather(best)                                               # (world, ctot)
+            vmax = np.empty(len(labels))
+            point = torch.empty(ctot, **f64)
+            for k in range(len(labels)):
+                if (allm[:, k, 1] > 0).any():
+                    vmax[k] = float("nan")
+                    owner = 0
+                else:
+                    owner = int(np.argmax(allm[:, k, 0]))
+                    vmax[k] = allm[owner, k, 0]
+                point[coff[k]:coff[k + 1]] = allb[owner, coff[k]:coff[k + 1]]
+            return vmax, point
+
+        # round 1: the common mean of every element's rows
+        stat = torch.zeros(ctot + len(labels), **f64)
+        for k, z in enumerate(labels):
+            for x in segs[z]:
                 if x.shape[0]:
-                    L.call("aqml_rows_colsum_dev", L.ptr(x), x.stride(0), x.shape[0], ncols, L.ptr(stat), st)
-            stat[ncols] = nloc
-            dist.all_reduce(stat, group=g)
-            ntot = int(round(float(stat[ncols].item())))
-            if ntot == 0:
+                    L.call("aqml_rows_colsum_dev", L.ptr(x), x.stride(0), x.shape[0], ncol[z], L.ptr(stat[coff[k]:coff[k + 1]]), st)
+            stat[ctot + k] = nloc[z]
+        dist.all_reduce(stat, group=g)
+        ntot = stat[ctot:].cpu().numpy()
+        centre = stat[:ctot].clone()
+        for k in range(len(labels)):
+            if ntot[k] > 0:
+                centre[coff[k]:coff[k + 1]] /= float(ntot[k])
+        # rounds 2-4: distances to the mean, two farthest-point sweeps for an attained pair distance
+        r = sweep(centre)
+        rmax, p1 = farthest(r)
+        l1, p2 = farthest(sweep(p1))
+        l2, _ = farthest(sweep(p2))
+        # rounds 5-6: only rows with r_i + max r >= the attained distance can take part in the maximum: gather and contract them
+        cands, cnt = [], torch.zeros(len(labels), dtype=torch.int64, device=dev)
+        for k, z in enumerate(labels):
+            if ntot[k] == 0 or rmax[k] != rmax[k]:
+                cands.append(torch.empty((0, ncol[z]), **f64))
                 continue
-            centre = (stat[:ncols] / ntot).contiguous()
-            r = sweep(segs, centre)
-            rmax, o1, i1 = global_max(r)
-            if rmax != rmax:
+            low = max(l1[k], l2[k]) * (1.0 - 1e-9)
+            sel = torch.nonzero(r[z] + rmax[k] >= low).flatten()
+            parts, base = [], 0
+            for x in segs[z]:
+                m = sel[(sel >= base) & (sel < base + x.shape[0])] - base
+                if m.numel():
+                    parts.append(x[m])
+                base += x.shape[0]
+            cands.append(torch.cat(parts) if parts else torch.empty((0, ncol[z]), **f64))
+            cnt[k] = cands[-1].shape[0]
+        cnts = gather(cnt).cpu().numpy()                                      # (world, nel)
+        kmax = cnts.max(axis=0)
+        pad = torch.zeros(int(sum(int(kmax[k]) * ncol[z] for k, z in enumerate(labels))), **f64)
+        poff = np.concatenate(([0], np.cumsum([int(kmax[k]) * ncol[z] for k, z in enumerate(labels)])))
+        for k, z in enumerate(labels):
+            if cands[k].shape[0]:
+                pad[poff[k]:poff[k] + cands[k].numel()] = cands[k].reshape(-1)
+        allp = gather(pad)                                                    # (world, sum_k kmax_k ncol_k)
+        for k, z in enumerate(labels):
+            if ntot[k] == 0:
+                continue
+            if rmax[k] != rmax[k]:
                 dso[z - 1] = float("nan")
                 continue
-            t1 = sweep(segs, row_from(o1, i1, local_row, ncols))
-            l1, o2, i2 = global_max(t1)
-            t2 = sweep(segs, row_from(o2, i2, local_row, ncols))
-            l2, _, _ = global_max(t2)
-            low = max(l1, l2) * (1.0 - 1e-9)    # an attained distance: only rows with r_i + max r >= low can take part in the maximum
-            sel = torch.nonzero(r + rmax >= low).flatten()
-            cand = torch.empty((0, ncols), dtype=torch.float64, device=dev)
-            if nloc and sel.numel():   # gather the survivors segment by segment (never a copy of all local rows)
-                cut = torch.searchsorted(sel, torch.as_tensor(offs, device=dev)).tolist()
-                cand = torch.cat([x[sel[cut[k]:cut[k + 1]] - int(offs[k])] for k, x in enumerate(segs)])
-            cnt = torch.tensor([cand.shape[0]], dtype=torch.int64, device=dev)
-            cnts = [torch.empty_like(cnt) for _ in range(self.world)]
-            dist.all_gather(cnts, cnt, group=g)
-            cnts = [int(c.item()) for c in cnts]
-            kmax = max(cnts)
-            pad = torch.zeros((kmax, ncols), dtype=torch.float64, device=dev)
-            pad[:cand.shape[0]] = cand
-            parts = [torch.empty_like(pad) for _ in range(self.world)]
-            dist.all_gather(parts, pad, group=g)
-            allc = torch.cat([p[:c] for p, c in zip(parts, cnts)]).contiguous()
+            blk = allp[:, poff[k]:poff[k + 1]].reshape(W, int(kmax[k]), ncol[z])
+            allc = torch.cat([blk[w, :int(cnts[w, k])] for w in range(W)]).contiguous()
             dm = C.c_double(0.0)
             with torch.cuda.device(dev):
                 L.call("aqml_max_distance_dev", 2, L.ptr(allc), allc.shape[0], allc.stride(0), L.ptr(allc), allc.shape[0], allc.stride(0),
-                       ncols, C.c_void_p(C.addressof(dm)), st)
+                       ncol[z], C.c_void_p(C.addressof(dm)), st)
             dso[z - 1] = dm.value
         return dso
 
     def alloc_out(self, nsig):
         """Device buffers for my tiles of K_train and my column blocks of K_test."""
         import torch
-        dev = self.test.device if self.test is not None else torch.device("cuda", torch.cuda.current_device())
+        dev = self.test.device if self.test is not None else torch.device("cuda", torch.cuda.current_device())  # noqa: E501
         size = lambda b: self.bounds[b][1] - self.bounds[b][0]  # noqa: E731
+        tsize = lambda t: self.tbounds[t][1] - self.tbounds[t][0]  # noqa: E731
         kt = {(b, c): torch.empty((nsig, size(b), size(c)), dtype=torch.float64, device=dev) for b, c in self.tiles}
-        ks = {b: torch.empty((nsig, self.n2, size(b)), dtype=torch.float64, device=dev) for b in self.mine}
+        ks = {("test", t, b): torch.empty((nsig, tsize(t), size(b)), dtype=torch.float64, device=dev)
+              for b in self.mine for t in range(self.world)}
         return kt, ks
 
     def k_train(self, sig, out, after=None):
@@ -227,11 +279,13 @@ class ShardedKernels(object):
         return out
 
     def k_test(self, sig, out, after=None):
-        """K(test, my training blocks): K_test sharded by training columns."""
+        """K(test block t, my training blocks), t = 0 .. N-1: K_test sharded by training columns."""
         for b in self.mine:
-            fused.local_gaussian(self.test, self.reps[b], sig, self.zmax, out=out[b])
-            if after is not None:
-                after(b, out[b])
+            for t in range(self.world):
+                key = ("test", t, b)
+                fused.local_gaussian(self.tests[t], self.reps[b], sig, self.zmax, out=out[key])
+                if after is not None:
+                    after(key, out[key])
         return out
 
     def predict(self, k_test, alpha):
@@ -242,8 +296,13 @@ class ShardedKernels(object):
         for b in self.mine:
             lo, hi = self.bounds[b]
             a = alpha[..., lo:hi]
-            part = torch.matmul(k_test[b], a) if a.dim() == 1 else torch.einsum("stn,sn->st", k_test[b], a)
-            y = part if y is None else y + part
+            for t in range(self.world):
+                k = k_test[("test", t, b)]
+                part = torch.matmul(k, a) if a.dim() == 1 else torch.einsum("stn,sn->st", k, a)
+                if y is None:
+                    y = torch.zeros(tuple(part.shape[:-1]) + (self.n2,), dtype=part.dtype, device=part.device)
+                tlo, thi = self.tbounds[t]
+                y[..., tlo:thi] += part
         if self.world > 1:
             import torch.distributed as dist
             dist.all_reduce(y, op=dist.ReduceOp.SUM, group=self.group)
@@ -253,9 +312,10 @@ class ShardedKernels(object):
         for r in self.reps:
             if r is not None:
                 r.close()
-        if self.test is not None:
-            self.test.close()
-        self.reps, self.test = [None] * self.nblk, None
+        for r in self.tests:
+            if r is not None:
+                r.close()
+        self.reps, self.tests = [None] * self.nblk, [None] * self.world
 
     # ---- bookkeeping for the bench ---------------------------------------------------------------------------
     def unique_elements(self, nsig):

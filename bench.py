@@ -132,6 +132,13 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.samples.append((time.time(), line.strip()))
 
+    def wait_first(self, timeout=8.0):
+        """Block until nvidia-smi has delivered its first sample: its start-up (NVML initialisation over every GPU of the box)
+        takes driver locks and must not fall into the timed region."""
+        t0 = time.time()
+        while self.proc is not None and not self.samples and time.time() - t0 < timeout:
+            time.sleep(0.02)
+
     def stop(self, t0, t1):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
@@ -278,9 +285,18 @@ def run_ours(args):
     def ev():
         return torch.cuda.Event(enable_timing=True)
 
+    dbg = bool(os.environ.get("AQML_BENCH_DEBUG"))
+    host_t = []
+
     def step(timing=None, coords=None, after=None):
         e = [ev() for _ in range(len(PH) + 1)] if timing is not None else None
-        mark = (lambda i: e[i].record()) if e else (lambda i: None)
+        ht = []
+
+        def mark(i):
+            if e:
+                e[i].record()
+            if dbg:
+                ht.append(time.perf_counter())
         mark(0)
         sk.pack(*(coords or (c1, c2)))
         if not out:
@@ -299,6 +315,7 @@ def run_ours(args):
         mark(6)
         if timing is not None:
             timing.append(e)
+            host_t.append(ht)
         return y, sig
 
     def barrier():
@@ -311,10 +328,12 @@ def run_ours(args):
     # the clock sampler starts BEFORE the warm-up: spawning nvidia-smi (fork of this process + NVML initialisation, which takes
     # driver locks) stalled the first timed step of every rank by ~0.5 s at N = 4 when it was started right before the timed region
     sampler = ClockSampler(local_rank) if rank == 0 else None
+    if sampler:
+        sampler.wait_first()
     for _ in range(warm):
         step()
     barrier()
-    rep_bytes = sum(r.nbytes for r in sk.reps) + sk.test.nbytes
+    rep_bytes = sum(r.nbytes for r in sk.reps) + sum(r.nbytes for r in sk.tests)
     launches0 = lib.aqml_launch_count()
     timing = []
     w0 = time.time()
@@ -330,8 +349,9 @@ def run_ours(args):
     phases = [float(np.mean([e[i].elapsed_time(e[i + 1]) for e in timing])) for i in range(len(PH))]
     if os.environ.get("AQML_BENCH_DEBUG"):
         for k, e in enumerate(timing):
-            print("rank %d step %d phases_ms %s" % (rank, k, " ".join("%s=%.1f" % (PH[i], e[i].elapsed_time(e[i + 1])) for i in range(len(PH)))),
-                  file=sys.stderr, flush=True)
+            print("rank %d step %d phases_ms %s | host enqueue ms %s" % (
+                rank, k, " ".join("%s=%.1f" % (PH[i], e[i].elapsed_time(e[i + 1])) for i in range(len(PH))),
+                " ".join("%.1f" % ((host_t[k][i + 1] - host_t[k][i]) * 1e3) for i in range(len(PH)))), file=sys.stderr, flush=True)
     clocks = sampler.stop(w0, w1) if sampler else None
     y_host = y.cpu().numpy()
 
@@ -402,7 +422,7 @@ def run_ours(args):
         barrier()
         e2e_ms = a.elapsed_time(b) / n_e2e
         e2e_phases = [float(np.mean([e[i].elapsed_time(e[i + 1]) for e in e2e_timing])) for i in range(len(PH))]
-        atoms_mine = sum(int(sk.nas1[lo:hi].sum()) for lo, hi in (sk.bounds[b] for b in sk.mine)) + int(sk.nas2.sum())
+        atoms_mine = sum(int(sk.nas1[lo:hi].sum()) for lo, hi in (sk.bounds[b] for b in sk.mine)) + int(sk.nas2[slice(*sk.tbounds[rank])].sum())
         h2d = atoms_mine * (24 + 4) + sig.nbytes
         d2h = sum(int(v.numel()) * 8 for v in host.values()) + yh.numel() * 8
         del host
@@ -507,9 +527,10 @@ def run_ours(args):
                        "elements_per_step": int(elems_all),
                        "elements_counted": "unique elements: lower triangle (incl. diagonal) of K(train,train) + K(test,train), "
                                            "x 4 sigmas; diagonal tiles are delivered mirrored",
-                       "sharding": "2N training blocks, rank r owns blocks r and 2N-1-r: its aSLATM, its block rows of the lower "
-                                   "triangle of K(train,train), its columns of K(test,train); NCCL: one broadcast per block "
-                                   "(packed operands), all-reduce MAX (width), all-reduce SUM (prediction)",
+                       "sharding": "2N training blocks, rank r owns blocks r and 2N-1-r (+ test block r of N): their aSLATM, its block "
+                                   "rows of the lower triangle of K(train,train), its columns of K(test,train); NCCL: one "
+                                   "broadcast per block (pair-kernel operands) overlapped with the distributed width pass (six small "
+                                   "collectives), all-reduce SUM (prediction)",
                        "l2": "inputs larger than L2 (packed operands + digit planes %.1f GB per GPU and step)" % (rep_bytes / 1e9)},
             "aslatm_atoms_per_sec": atoms_all / (ph["aslatm"] * 1e-3),
             "phases_ms": ph,

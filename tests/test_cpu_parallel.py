@@ -132,10 +132,13 @@ def _sharded_worker(rank, world, port, tmp):
         g = torch.Generator().manual_seed(7)
         K = torch.rand((2, 7, 41), dtype=torch.float64, generator=g)
         alpha = torch.rand((2, 41), dtype=torch.float64, generator=g)
-        ks = {b: K[:, :, sk.bounds[b][0]:sk.bounds[b][1]].contiguous() for b in sk.mine}
+        # K_test arrives as tiles (test block t of N, my training block b)
+        assert [hi - lo for lo, hi in sk.tbounds] == [4, 3][:world] or world != 2
+        ks = {("test", t, b): K[:, sk.tbounds[t][0]:sk.tbounds[t][1], sk.bounds[b][0]:sk.bounds[b][1]].contiguous()
+              for b in sk.mine for t in range(world)}
         y = sk.predict(ks, alpha)
         assert torch.allclose(y, torch.einsum("stn,sn->st", K, alpha), rtol=1e-13, atol=0)
-        y1 = sk.predict({b: v[0] for b, v in ks.items()}, alpha[0])
+        y1 = sk.predict({k: v[0] for k, v in ks.items()}, alpha[0])
         assert torch.allclose(y1, K[0] @ alpha[0], rtol=1e-13, atol=0)
         # bookkeeping: the ranks' unique elements add up to the lower triangle + K_test
         n = torch.tensor([float(sk.unique_elements(2))], dtype=torch.float64)

@@ -58,9 +58,10 @@ for (b, c), t in kt.items():
     ref = K1[:, lo:hi, clo:chi]
     e_t = max(e_t, float(((t - ref).abs() / ref.abs()).max()))
 e_s = 0.0
-for b, t in ks.items():
-    lo, hi = sk.bounds[b]
-    e_s = max(e_s, float(((t - K2[:, :, lo:hi]).abs() / K2[:, :, lo:hi].abs()).max()))
+for (_, tb, b), t in ks.items():
+    (lo, hi), (tlo, thi) = sk.bounds[b], sk.tbounds[tb]
+    ref = K2[:, tlo:thi, lo:hi]
+    e_s = max(e_s, float(((t - ref).abs() / ref.abs()).max()))
 e_y = float(((y - y_ref).abs() / y_ref.abs()).max())
 ok = e_w < 1e-12 and e_t < 1e-12 and e_s < 1e-12 and e_y < 1e-11
 flags = torch.tensor([int(ok)], device=dev)
