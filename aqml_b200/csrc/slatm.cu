@@ -462,7 +462,9 @@ static void check_params(const aqml_slatm_params *p) {
 
 // mode_local: layout of element e = every 2-body block containing e + every 3-body block centred on e
 // global: 2-body block owned by the smaller element index, 3-body by its centre
-static SlatmTables build_tables(const aqml_slatm_params *p, bool mode_local, Workspace &ws) {
+// device = false: host-side results only (row pitches, labels) -- a layout-only representation uploads no table
+static SlatmTables build_tables(const aqml_slatm_params *p, bool mode_local, Workspace &ws, bool device = true) {
+    auto up = [&](const auto &v) -> decltype(ws.upload(v)) { return device ? ws.upload(v) : nullptr; };
     check_params(p);
     SlatmTables t;
     t.nmb = p->nmb;
@@ -549,7 +551,7 @@ static SlatmTables build_tables(const aqml_slatm_params *p, bool mode_local, Wor
             }
         d.nblk[ec] = nb;
     }
-    d.blk = ws.upload(blk);
+    d.blk = up(blk);
     // grids on the host (same libm as the CPU reference): utils.f90:29-50, slatm.py:60-62,118-122
     std::vector<double> xs2(p->nx2), xp2(p->nx2), xs3(p->nx3), cx3(p->nx3);
     {
@@ -559,13 +561,13 @@ static SlatmTables build_tables(const aqml_slatm_params *p, bool mode_local, Wor
         double st3 = (a1 - a0) / (p->nx3 - 1);
         for (int i = 0; i < p->nx3; i++) { xs3[i] = a0 + i * st3; cx3[i] = std::cos(xs3[i]); }
     }
-    d.slot_kind = ws.upload(kind); d.slot_col = ws.upload(col); d.slot_e0 = ws.upload(e0);
-    d.bop_slot = ws.upload(bop); d.bot_slot = ws.upload(bot); d.lay_col = ws.upload(lay); d.owner = ws.upload(owner);
-    d.xs2 = ws.upload(xs2); d.xpow2 = ws.upload(xp2); d.xs3 = ws.upload(xs3); d.cosx3 = ws.upload(cx3);
+    d.slot_kind = up(kind); d.slot_col = up(col); d.slot_e0 = up(e0);
+    d.bop_slot = up(bop); d.bot_slot = up(bot); d.lay_col = up(lay); d.owner = up(owner);
+    d.xs2 = up(xs2); d.xpow2 = up(xp2); d.xs3 = up(xs3); d.cosx3 = up(cx3);
     {
         std::vector<double> inv2(p->nx2);
         for (int i = 0; i < p->nx2; i++) inv2[i] = p->dgrid2 / xp2[i];
-        d.inv2 = ws.upload(inv2);
+        d.inv2 = up(inv2);
         const double pi = 4.0 * std::atan(1.0);
         d.h2 = (p->rcut - 0.1) / (p->nx2 - 1);
         d.h3 = (pi + 40.0 * pi / 180.0) / (p->nx3 - 1);
@@ -948,7 +950,7 @@ static void rep_create(const double *coords, int on_dev, const int *zs, const in
     Workspace ws(st);     // temporaries
     Workspace keep(st);   // becomes the rep's storage: |row|^2, molecule index, masks, digit planes, exponents -- what the pair kernel reads
     Workspace keepx(st);  // ... and the packed FP64 rows (width pass, FP64 engine, source of the digit planes)
-    SlatmTables t = build_tables(p, true, ws);
+    SlatmTables t = build_tables(p, true, ws, compute);
     MolIndex mi = index_molecules(nas, nmol);
     AQML_REQUIRE(mi.A >= 1, "no atoms");
     const int ne = t.dev.n_el;

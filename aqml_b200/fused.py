@@ -66,14 +66,17 @@ class PackedRep:
         return torch.as_tensor(_DeviceArray(ptr.value, (nb.value,)), device=self.device)
 
     def element_rows(self):
-        """{Z: (n, ld) float64 CUDA view of the element's valid packed rows} (views: valid while this object lives)."""
+        """{Z: (n, ld) float64 CUDA view of the element's valid packed rows} (views: valid while this object lives; n may be 0)."""
         import torch
         out = {}
         for e in range(int(L.load().aqml_rep_elements(self._h))):
             label, n, ld, x = C.c_int(), C.c_int(), C.c_int(), C.c_void_p()
             L.call("aqml_rep_element", self._h, e, C.byref(label), C.byref(n), C.byref(ld), C.byref(x))
-            if n.value > 0 and x.value:
-                out[int(label.value)] = torch.as_tensor(_DeviceArray(x.value, (n.value, ld.value), "<f8"), device=self.device)
+            if x.value:
+                if n.value > 0:
+                    out[int(label.value)] = torch.as_tensor(_DeviceArray(x.value, (n.value, ld.value), "<f8"), device=self.device)
+                else:   # an element of the many-body types without an atom in this set: an empty view with the right pitch
+                    out[int(label.value)] = torch.empty((0, ld.value), dtype=torch.float64, device=self.device)
         return out
 
     @property

@@ -79,16 +79,29 @@ class ShardedKernels(object):
         """aSLATM: my training blocks and my test block are computed, the others only laid out.
         coords_*: (A, 3) host arrays (copied to the device inside) or CUDA tensors."""
         self.close()
-        for b in range(self.nblk):
+
+        def train(b):
             nas, zs, sl = self._block(b)
             own = self.owners[b] == self.rank
             self.reps[b] = fused.PackedRep(coords_train[sl] if own else None, zs, nas, self.mbtypes, compute=own, rows=own, **self.kw)
-        for t in range(self.world):
+
+        def test(t):
             lo, hi = self.tbounds[t]
             sl = slice(int(self.off2[lo]), int(self.off2[hi]))
             own = t == self.rank
             self.tests[t] = fused.PackedRep(coords_test[sl] if own else None, self.zs2[sl], self.nas2[lo:hi], self.mbtypes, compute=own,
                                             rows=own, **self.kw)
+
+        # my own blocks first: their aSLATM kernels run while the host lays out the 3 N - 3 blocks that will arrive over NCCL
+        for b in self.mine:
+            train(b)
+        test(self.rank)
+        for b in range(self.nblk):
+            if self.reps[b] is None:
+                train(b)
+        for t in range(self.world):
+            if self.tests[t] is None:
+                test(t)
 
     @property
     def test(self):
@@ -125,7 +138,8 @@ class ShardedKernels(object):
     def _width_distributed(self):
         """The pruned max-distance pass of `aqml_rep_kernel_width_multi` over rows that live on different GPUs: nobody ever
         holds all rows.  Exact: the candidates are contracted by the same EPI_MAX pair kernel.  All elements go through every
-        round together, so the pass costs six small collectives (not six per element) and as many host synchronisations."""
+        round together, so the pass costs seven small collectives (not six per element) and as many host synchronisations; the
+        candidate contraction itself is cut over the ranks."""
         import ctypes as C
         import torch
         import torch.distributed as dist
@@ -144,7 +158,6 @@ class ShardedKernels(object):
             if not segs[z]:
                 raise RuntimeError("internal: element %d missing from a packed block" % z)
         ncol = {z: int(segs[z][0].shape[1]) for z in labels}
-        nloc = {z: sum(int(x.shape[0]) for x in segs[z]) for z in labels}
         coff = np.concatenate(([0], np.cumsum([ncol[z] for z in labels])))    # offsets into a concatenated "one row per element"
         ctot = int(coff[-1])
 
@@ -153,7 +166,7 @@ class ShardedKernels(object):
             dist.all_gather(out, t.contiguous(), group=g)
             return torch.stack(out)
 
-        def sweep(points):   # distance of every local row of every element to that element's point: {z: (nloc_z,)}
+        def sweep(points):   # distance of every local row of every element to that element's point: {z: [per segment (n,)]}
             res = {}
             for k, z in enumerate(labels):
                 p = points[coff[k]:coff[k + 1]].contiguous()
@@ -163,80 +176,64 @@ class ShardedKernels(object):
                     if x.shape[0]:
                         L.call("aqml_rows_dist_dev", 2, L.ptr(x), x.stride(0), x.shape[0], L.ptr(p), x.shape[1], L.ptr(r), st)
                     out.append(r)
-                res[z] = torch.cat(out) if out else torch.empty(0, **f64)
+                res[z] = out
             return res
 
-        def local_row(z, i):
-            for x in segs[z]:
-                if i < x.shape[0]:
-                    return x[i]
-                i -= x.shape[0]
-            raise IndexError(i)
-
-        def farthest(dists):   # per element: the global maximum of `dists` and the row that attains it, known to every rank
-            msg = torch.zeros(len(labels), 2 + 0, **f64)
+        def farthest(dists):
+            """Per element: the global maximum of `dists` (device tensor (nel,), NaN if any rank saw a NaN) and the row that attains
+            it, known to every rank -- without a host synchronisation: two all-gathers, everything else stays on the device."""
+            msg = torch.full((len(labels), 2), -1.0, **f64)
             best = torch.zeros(ctot, **f64)
             for k, z in enumerate(labels):
-                v = dists[z]
-                if v.numel():
+                ms, rws, nan = [], [], None
+                for x, v in zip(segs[z], dists[z]):
+                    if not v.numel():
+                        continue
                     m, i = torch.max(v, dim=0)
-                    msg[k, 0] = m
-                    msg[k, 1] = torch.isnan(v).any().to(torch.float64)
-                    best[coff[k]:coff[k + 1]] = local_row(z, int(i.item()))
-                else:
-                    msg[k, 0] = -1.0
-            allm = gather(msg).cpu().numpy()                                  # (world, nel, 2)
-            allb = gather(best)                                               # (world, ctot)
-            vmax = np.empty(len(labels))
-            point = torch.empty(ctot, **f64)
-            for k in range(len(labels)):
-                if (allm[:, k, 1] > 0).any():
-                    vmax[k] = float("nan")
-                    owner = 0
-                else:
-                    owner = int(np.argmax(allm[:, k, 0]))
-                    vmax[k] = allm[owner, k, 0]
-                point[coff[k]:coff[k + 1]] = allb[owner, coff[k]:coff[k + 1]]
+                    ms.append(m)
+                    rws.append(x.index_select(0, i.view(1)))
+                    f = torch.isnan(v).any()
+                    nan = f if nan is None else (nan | f)
+                if ms:
+                    mm = torch.stack(ms)
+                    j = torch.argmax(mm).view(1)
+                    msg[k, 0] = mm.index_select(0, j)[0]
+                    msg[k, 1] = nan.to(torch.float64)
+                    best[coff[k]:coff[k + 1]] = torch.cat(rws).index_select(0, j)[0]
+            allm, allb = gather(msg), gather(best)                            # (world, nel, 2), (world, ctot)
+            owner = torch.argmax(allm[:, :, 0], dim=0)                        # (nel,)
+            vmax = allm[:, :, 0].max(dim=0).values
+            vmax = torch.where(allm[:, :, 1].max(dim=0).values > 0, torch.full_like(vmax, float("nan")), vmax)
+            point = torch.cat([allb.index_select(0, owner[k:k + 1])[0, coff[k]:coff[k + 1]] for k in range(len(labels))])
             return vmax, point
 
-        # round 1: the common mean of every element's rows
-        stat = torch.zeros(ctot + len(labels), **f64)
+        # round 1: the common mean of every element's rows (the row counts of the whole problem are known on the host)
+        ntot = np.array([int((self.zs1 == z).sum() + (self.zs2 == z).sum()) for z in labels])
+        stat = torch.zeros(ctot, **f64)
         for k, z in enumerate(labels):
             for x in segs[z]:
                 if x.shape[0]:
                     L.call("aqml_rows_colsum_dev", L.ptr(x), x.stride(0), x.shape[0], ncol[z], L.ptr(stat[coff[k]:coff[k + 1]]), st)
-            stat[ctot + k] = nloc[z]
         dist.all_reduce(stat, group=g)
-        ntot = stat[ctot:].cpu().numpy()
-        centre = stat[:ctot].clone()
-        for k in range(len(labels)):
-            if ntot[k] > 0:
-                centre[coff[k]:coff[k + 1]] /= float(ntot[k])
+        scale = torch.as_tensor(np.repeat(1.0 / np.maximum(ntot, 1), [ncol[z] for z in labels]), **f64)
+        centre = stat * scale
         # rounds 2-4: distances to the mean, two farthest-point sweeps for an attained pair distance
         r = sweep(centre)
         rmax, p1 = farthest(r)
         l1, p2 = farthest(sweep(p1))
         l2, _ = farthest(sweep(p2))
+        low = torch.maximum(l1, l2) * (1.0 - 1e-9)
         # rounds 5-6: only rows with r_i + max r >= the attained distance can take part in the maximum: gather and contract them
-        cands, cnt = [], torch.zeros(len(labels), dtype=torch.int64, device=dev)
+        cands = []
         for k, z in enumerate(labels):
-            if ntot[k] == 0 or rmax[k] != rmax[k]:
-                cands.append(torch.empty((0, ncol[z]), **f64))
-                continue
-            low = max(l1[k], l2[k]) * (1.0 - 1e-9)
-            sel = torch.nonzero(r[z] + rmax[k] >= low).flatten()
-            parts, base = [], 0
-            for x in segs[z]:
-                m = sel[(sel >= base) & (sel < base + x.shape[0])] - base
-                if m.numel():
-                    parts.append(x[m])
-                base += x.shape[0]
+            parts = [x[(v + rmax[k]) >= low[k]] for x, v in zip(segs[z], r[z]) if v.numel()]   # NaN compares false: no candidates
             cands.append(torch.cat(parts) if parts else torch.empty((0, ncol[z]), **f64))
-            cnt[k] = cands[-1].shape[0]
-        cnts = gather(cnt).cpu().numpy()                                      # (world, nel)
+        cnt = torch.tensor([c.shape[0] for c in cands], dtype=torch.int64, device=dev)
+        info = gather(torch.cat([cnt.to(torch.float64), rmax])).cpu().numpy()   # the one host synchronisation before the contraction
+        cnts, rmax_h = info[:, :len(labels)].astype(np.int64), info[0, len(labels):]
         kmax = cnts.max(axis=0)
-        pad = torch.zeros(int(sum(int(kmax[k]) * ncol[z] for k, z in enumerate(labels))), **f64)
         poff = np.concatenate(([0], np.cumsum([int(kmax[k]) * ncol[z] for k, z in enumerate(labels)])))
+        pad = torch.zeros(int(poff[-1]), **f64)
         for k, z in enumerate(labels):
             if cands[k].shape[0]:
                 pad[poff[k]:poff[k] + cands[k].numel()] = cands[k].reshape(-1)
@@ -244,16 +241,23 @@ class ShardedKernels(object):
         for k, z in enumerate(labels):
             if ntot[k] == 0:
                 continue
-            if rmax[k] != rmax[k]:
+            if rmax_h[k] != rmax_h[k]:
                 dso[z - 1] = float("nan")
                 continue
             blk = allp[:, poff[k]:poff[k + 1]].reshape(W, int(kmax[k]), ncol[z])
             allc = torch.cat([blk[w, :int(cnts[w, k])] for w in range(W)]).contiguous()
+            # every rank contracts its 1/N of the candidate rows against all of them; the maxima meet in one all-reduce below
+            part = allc[self.rank::W].contiguous()
             dm = C.c_double(0.0)
-            with torch.cuda.device(dev):
-                L.call("aqml_max_distance_dev", 2, L.ptr(allc), allc.shape[0], allc.stride(0), L.ptr(allc), allc.shape[0], allc.stride(0),
-                       ncol[z], C.c_void_p(C.addressof(dm)), st)
+            if part.shape[0]:
+                with torch.cuda.device(dev):
+                    L.call("aqml_max_distance_dev", 2, L.ptr(part), part.shape[0], part.stride(0), L.ptr(allc), allc.shape[0], allc.stride(0),
+                           ncol[z], C.c_void_p(C.addressof(dm)), st)
             dso[z - 1] = dm.value
+        red = torch.as_tensor(np.where(np.isnan(dso), np.inf, dso), **f64)    # MAX does not propagate NaN: send it as +inf
+        dist.all_reduce(red, op=dist.ReduceOp.MAX, group=g)
+        dso = red.cpu().numpy()
+        dso[np.isinf(dso)] = np.nan
         return dso
 
     def alloc_out(self, nsig):
