@@ -68,7 +68,7 @@ class ShardedKernels(object):
         self.tbounds = block_bounds(self.n2, self.world)
         self.off2 = np.concatenate(([0], np.cumsum(self.nas2)))
         self.reps, self.tests = [None] * self.nblk, [None] * self.world
-        self.group2, self._works, self._views = None, [], []
+        self.group2, self._works, self._views, self._pool = None, [], [], None
 
     # ---- phases ---------------------------------------------------------------------------------------------
     def _block(self, b):
@@ -96,12 +96,22 @@ class ShardedKernels(object):
         for b in self.mine:
             train(b)
         test(self.rank)
-        for b in range(self.nblk):
-            if self.reps[b] is None:
-                train(b)
-        for t in range(self.world):
-            if self.tests[t] is None:
-                test(t)
+        others = [(train, b) for b in range(self.nblk) if self.reps[b] is None] + [(test, t) for t in range(self.world) if self.tests[t] is None]
+        if len(others) > 4:
+            # pure host work (index building, two stream-ordered allocations each): a few threads, the C side releases the GIL
+            import torch
+            from concurrent.futures import ThreadPoolExecutor
+            dev = self.test.device
+
+            def run(job):
+                with torch.cuda.device(dev):
+                    job[0](job[1])
+            if self._pool is None:
+                self._pool = ThreadPoolExecutor(max_workers=4)
+            list(self._pool.map(run, others))
+        else:
+            for f, i in others:
+                f(i)
 
     @property
     def test(self):
