@@ -36,8 +36,8 @@
 //            it issues this stage, so that nothing but the commit separates two stages' MMAs;
 //   warp 2   tile metadata (segments, norms -- as 64-bit fixed point for the integer epilogue --, exponents, active k-chunk
 //            list) two tiles ahead, triple buffered;
-//   warps 3-18  epilogue (4 per TMEM lane quarter, 16 columns each): tcgen05.ld of the 7 accumulators into two exact 64-bit
-//            integers per pair, TMEM handed back (the next tile's MMAs start), then -- on INTEGERS, because an FP64 instruction
+//   warps 3-18  epilogue (4 per TMEM lane quarter, 16 columns each): tcgen05.ld of the 7 accumulators into one exact 64-bit
+//            integer per pair, TMEM handed back (the next tile's MMAs start), then -- on INTEGERS, because an FP64 instruction
 //            takes ~800 clk while UTCIMMA stream (i8exp.cuh) -- d^2 = |a|^2+|b|^2-2a.b in fixed point, T = d^2/(2 sigma^2) log2 e
 //            by one 64 x 64 -> high multiply, 2^-T by table + polynomial, the sigma ladder by shifts of T, the sum over the
 //            atoms of a molecule pair as aligned 64-bit integers per (lane, column run), one conversion + RED.F64 per lane
@@ -46,7 +46,7 @@
 // Operands are staged in the canonical K-major no-swizzle core-matrix layout (8 rows x 16 B), which is exactly how
 // the slice buffer is written.
 // Measured (K(test, train) 800 x 4000 molecules, 4 sigmas, profiles/r02_pair_kernel_steps.txt): 16.0 ms at the start of
-// round 2 -> 11.6 ms; per 32-column stage 1435 -> 998 clk (716 = the UTCIMMA alone).
+// round 2 -> 11.3 ms; per 32-column stage 1435 -> 969 clk (716 = the UTCIMMA alone).
 #pragma once
 #include "i8digits.cuh"
 #include "i8exp.cuh"
