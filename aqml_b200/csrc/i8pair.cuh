@@ -510,9 +510,11 @@ __global__ void __launch_bounds__(I8_THREADS, 1) i8_pair_kernel(const __grid_con
         {
             // A plane i against the stacked B planes j0 .. j0 + n - 1 (N = 64 n) -> accumulators i + j0 .. i + j0 + n - 1
             constexpr int NMMA = VAR ? 9 : 8;
-            constexpr int mi[9] = {0, 0, 1, 1, 2, VAR ? 2 : 3, VAR ? 3 : 4, VAR ? 4 : 5, 5};
-            constexpr int mj[9] = {0, 4, 0, VAR ? 4 : 3, 0, VAR ? 3 : 0, 0, 0, 0};
-            constexpr int mn[9] = {4, 2, VAR ? 4 : 3, 2, VAR ? 3 : 4, VAR ? 2 : 4, VAR ? 4 : 2, VAR ? 3 : 1, 2};
+            // VAR 0: plane 0 first (it clears the accumulators at k = 0), then the short MMAs, the two N = 256 ones last: the tensor
+            // pipe's queue then holds the most work while the issuer does its bookkeeping between two stages
+            constexpr int mi[9] = {0, 0, VAR ? 1 : 5, VAR ? 1 : 4, VAR ? 2 : 1, VAR ? 2 : 1, VAR ? 3 : 2, VAR ? 4 : 3, 5};
+            constexpr int mj[9] = {0, 4, 0, VAR ? 4 : 0, VAR ? 0 : 3, VAR ? 3 : 0, 0, 0, 0};
+            constexpr int mn[9] = {4, 2, VAR ? 4 : 1, 2, VAR ? 3 : 2, VAR ? 2 : 3, 4, VAR ? 3 : 4, 2};
             unsigned leader;
             asm volatile("{\n.reg .pred p;\nelect.sync _|p, 0xffffffff;\nselp.u32 %0, 1, 0, p;\n}" : "=r"(leader));
             const unsigned stage0 = i8::smem_u32(stages);
