@@ -69,7 +69,7 @@ class ShardedKernels(object):
         self.tbounds = block_bounds(self.n2, self.world)
         self.off2 = np.concatenate(([0], np.cumsum(self.nas2)))
         self.reps, self.tests = [None] * self.nblk, [None] * self.world
-        self.group2, self._works, self._views, self._pool = None, [], [], None
+        self.group2, self._works, self._slots, self._pool = None, [], [], None
 
     # ---- phases ---------------------------------------------------------------------------------------------
     def _block(self, b):
@@ -119,21 +119,68 @@ class ShardedKernels(object):
         """My block of the test set (the whole test set with one rank)."""
         return self.tests[self.rank]
 
+    def _slab_bound(self, zs, like):
+        """Upper bound of the operand storage (aqml_rep_slab(..., 0)) of a block with element numbers `zs`, from the row
+        pitches of a representation `like` built with the same many-body types -- so that the exchange can start before the
+        other ranks' blocks have been laid out here."""
+        import ctypes as C
+        from . import _lib as L
+        total = 4096
+        for e in range(int(L.load().aqml_rep_elements(like._h))):
+            label, n, ld, x = C.c_int(), C.c_int(), C.c_int(), C.c_void_p()
+            L.call("aqml_rep_element", like._h, e, C.byref(label), C.byref(n), C.byref(ld), C.byref(x))
+            nz = int(np.count_nonzero(zs == label.value)) + 128          # packed rows incl. the padding at the element's end
+            total += (nz // 128 + 2) * (ld.value // 16 + 1) * 12288        # digit planes: 6 x 2 KB per 128-row block and 16-column chunk
+            total += nz * 16 + (nz // 64 + 2) * ((ld.value // 16 + 31) // 32) * 4 + 5 * 256
+        return total
+
+    def _exchange_start(self):
+        """Enqueue the exchange: every block's pair-kernel operands travel once from their owner to the other ranks (the packed
+        FP64 rows stay where they were computed).  Three all-gathers -- the ranks' first training blocks, their second ones, their
+        test blocks -- into buffers of N equal slots (a block's operand storage is one buffer whose size depends only on its
+        molecules; the slot size is a bound every rank can compute from the element counts): one all-gather per class instead of
+        3 N broadcasts.  `share_end` waits and copies the slots into the blocks."""
+        self._works, self._slots = [], []
+        if self.world == 1:
+            return
+        import torch
+        import torch.distributed as dist
+        W = self.world
+        tz = lambda t: self.zs2[int(self.off2[self.tbounds[t][0]]):int(self.off2[self.tbounds[t][1]])]  # noqa: E731
+        classes = [([r for r in range(W)], self.reps, lambda b: self._block(b)[1]),                    # block r of rank r
+                   ([2 * W - 1 - r for r in range(W)], self.reps, lambda b: self._block(b)[1]),        # block 2N-1-r of rank r
+                   ([t for t in range(W)], self.tests, tz)]                                              # test block r of rank r
+        for ids, store, zs_of in classes:
+            mine = store[ids[self.rank]]
+            size = max(self._slab_bound(np.asarray(zs_of(i)), mine) for i in ids)
+            size = (size + 255) // 256 * 256
+            view = mine.slab_tensor(0)
+            if view.numel() > size:
+                raise RuntimeError("internal: operand storage larger than its bound")
+            buf = torch.empty((W, size), dtype=torch.uint8, device=view.device)
+            buf[self.rank, :view.numel()].copy_(view)
+            work = dist.all_gather_into_tensor(buf.view(-1), buf[self.rank], group=self.group, async_op=True)
+            self._works.append(work)
+            self._slots.append((buf, ids, store))
+
     def share_begin(self):
-        """Enqueue the broadcasts: every training block's pair-kernel operands travel once from their owner to the other
-        ranks (the packed FP64 rows stay where they were computed)."""
-        self._works = []
-        if self.world > 1:
-            import torch.distributed as dist
-            src = (lambda r: dist.get_global_rank(self.group, r)) if self.group is not None else (lambda r: r)
-            blocks = list(zip(self.reps, self.owners)) + [(t, r) for r, t in enumerate(self.tests)]
-            self._views = [r.slab_tensor(0) for r, _ in blocks]
-            self._works = [dist.broadcast(v, src=src(o), group=self.group, async_op=True) for v, (_, o) in zip(self._views, blocks)]
+        """Enqueue the exchange (after `pack`).  Starting it inside `pack`, right after this rank's own blocks and before the host
+        lays out the others, was measured slower (N = 4: 278 vs 264 ms per step: the width pass's small collectives then queue
+        behind the all-gathers for longer)."""
+        if self.world > 1 and not self._works and not self._slots:
+            self._exchange_start()
 
     def share_end(self):
         for w in self._works:
             w.wait()
-        self._works, self._views = [], []
+        for buf, ids, store in self._slots:
+            for r, i in enumerate(ids):
+                if r != self.rank:
+                    v = store[i].slab_tensor(0)
+                    if v.numel() > buf.shape[1]:
+                        raise RuntimeError("internal: operand storage larger than its bound")
+                    v.copy_(buf[r, :v.numel()])
+        self._works, self._slots = [], []
 
     def share(self):
         self.share_begin()
@@ -218,6 +265,16 @@ class ShardedKernels(object):
             point = torch.cat([allb.index_select(0, owner[k:k + 1])[0, coff[k]:coff[k + 1]] for k in range(len(labels))])
             return vmax, point
 
+        import os
+        import time
+        dbg = bool(os.environ.get("AQML_WIDTH_DEBUG"))
+        tms = []
+
+        def tick(name):
+            if dbg:
+                torch.cuda.synchronize()
+                tms.append((name, time.perf_counter()))
+        tick("start")
         # round 1: the common mean of every element's rows (the row counts of the whole problem are known on the host)
         ntot = np.array([int((self.zs1 == z).sum() + (self.zs2 == z).sum()) for z in labels])
         stat = torch.zeros(ctot, **f64)
@@ -228,12 +285,14 @@ class ShardedKernels(object):
         dist.all_reduce(stat, group=g)
         scale = torch.as_tensor(np.repeat(1.0 / np.maximum(ntot, 1), [ncol[z] for z in labels]), **f64)
         centre = stat * scale
+        tick("mean")
         # rounds 2-4: distances to the mean, two farthest-point sweeps for an attained pair distance
         r = sweep(centre)
         rmax, p1 = farthest(r)
         l1, p2 = farthest(sweep(p1))
         l2, _ = farthest(sweep(p2))
         low = torch.maximum(l1, l2) * (1.0 - 1e-9)
+        tick("sweeps")
         # rounds 5-6: only rows with r_i + max r >= the attained distance can take part in the maximum: gather and contract them
         cands = []
         for k, z in enumerate(labels):
@@ -249,6 +308,7 @@ class ShardedKernels(object):
             if cands[k].shape[0]:
                 pad[poff[k]:poff[k] + cands[k].numel()] = cands[k].reshape(-1)
         allp = gather(pad)                                                    # (world, sum_k kmax_k ncol_k)
+        tick("candidates")
         for k, z in enumerate(labels):
             if ntot[k] == 0:
                 continue
@@ -265,6 +325,10 @@ class ShardedKernels(object):
                     L.call("aqml_max_distance_dev", 2, L.ptr(part), part.shape[0], part.stride(0), L.ptr(allc), allc.shape[0], allc.stride(0),
                            ncol[z], C.c_void_p(C.addressof(dm)), st)
             dso[z - 1] = dm.value
+        tick("contraction")
+        if dbg and self.rank == 0:
+            print("width: " + " ".join("%s=%.2f ms" % (n, (t - tms[i][1]) * 1e3) for i, (n, t) in enumerate(tms[1:])) +
+                  " candidates " + str(cnts.sum(axis=0).tolist()), flush=True)
         red = torch.as_tensor(np.where(np.isnan(dso), np.inf, dso), **f64)    # MAX does not propagate NaN: send it as +inf
         dist.all_reduce(red, op=dist.ReduceOp.MAX, group=g)
         dso = red.cpu().numpy()
