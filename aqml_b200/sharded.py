@@ -9,15 +9,15 @@ One process per GPU.  The training set is cut into 2 N blocks of molecules; rank
   phase       what a rank does                                                        exchange
   aslatm      packs its two training blocks and its 1/N of the test molecules (own     --
               blocks first; the others are only laid out, by a few host threads)
-  allgather   --                                                                      each block's pair-kernel operands (digit planes,
+  allgather   copies the arrived operands into the blocks laid out for them            each block's pair-kernel operands (digit planes,
                                                                                       norms, masks: 6 of the 14 bytes per packed
-                                                                                      element) once: one NCCL broadcast per block,
-                                                                                      enqueued BEFORE ...
+                                                                                      element) once: three NCCL all-gathers into
+                                                                                      equal slots, enqueued BEFORE ...
   width       ... the max distance per element over all train + test atoms, computed   all elements per round together: all-reduce of
               where the FP64 rows are (every rank sweeps only its own rows):           the column sums, two all-gathers per sweep,
               distances to the common mean, two farthest-point sweeps for an           candidate counts and rows, all-reduce MAX of the
               attained lower bound, then only the rows the triangle inequality         results -- on a second communicator, so that it
-              leaves are gathered and contracted exactly, 1/N of them per rank          overlaps the broadcasts of the blocks
+              leaves are gathered and contracted exactly, 1/N of them per rank          overlaps the exchange of the blocks
   k_train     tiles (b, c), c <= b, of its block rows; diagonal tiles symmetric       --
   k_test      K(test block t, its training blocks) for all N test blocks: K_test      --
               sharded by training columns
