@@ -46,7 +46,7 @@
 // Operands are staged in the canonical K-major no-swizzle core-matrix layout (8 rows x 16 B), which is exactly how
 // the slice buffer is written.
 // Measured (K(test, train) 800 x 4000 molecules, 4 sigmas, profiles/r02_pair_kernel_steps.txt): 16.0 ms at the start of
-// round 2 -> 11.3 ms; per 32-column stage 1435 -> 969 clk (716 = the UTCIMMA alone).
+// round 2 -> 11.0 ms; per 32-column stage 1435 -> 950 clk (716 = the UTCIMMA alone).
 #pragma once
 #include "i8digits.cuh"
 #include "i8exp.cuh"
