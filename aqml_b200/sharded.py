@@ -239,7 +239,7 @@ class ShardedKernels(object):
 
         def farthest(dists):
             """Per element: the global maximum of `dists` (device tensor (nel,), NaN if any rank saw a NaN) and the row that attains
-            it, known to every rank -- without a host synchronisation: two all-gathers, everything else stays on the device."""
+            it, known to every rank -- without a host synchronisation: one all-gather, everything else stays on the device."""
             msg = torch.full((len(labels), 2), -1.0, **f64)
             best = torch.zeros(ctot, **f64)
             for k, z in enumerate(labels):
@@ -258,7 +258,8 @@ class ShardedKernels(object):
                     msg[k, 0] = mm.index_select(0, j)[0]
                     msg[k, 1] = nan.to(torch.float64)
                     best[coff[k]:coff[k + 1]] = torch.cat(rws).index_select(0, j)[0]
-            allm, allb = gather(msg), gather(best)                            # (world, nel, 2), (world, ctot)
+            both = gather(torch.cat([msg.view(-1), best]))                   # one collective for the values and the rows
+            allm, allb = both[:, :2 * len(labels)].reshape(W, len(labels), 2), both[:, 2 * len(labels):]
             owner = torch.argmax(allm[:, :, 0], dim=0)                        # (nel,)
             vmax = allm[:, :, 0].max(dim=0).values
             vmax = torch.where(allm[:, :, 1].max(dim=0).values > 0, torch.full_like(vmax, float("nan")), vmax)
