@@ -231,3 +231,60 @@ def test_integer_exp_of_the_int8_epilogue(tmp_path):
     out = subprocess.run([exe], capture_output=True, text=True)
     assert out.returncode == 0, out.stdout + out.stderr
     assert "T = inf -> 0" in out.stdout and "T = 0 -> 1" in out.stdout
+
+
+def test_fixed_point_d2_of_the_int8_epilogue():
+    """The integer d^2 / T arithmetic of i8_pair_kernel's epilogue (i8pair.cuh: metadata warp + `M.fix` path), restated with
+    Python integers: per tile the norms become 64-bit integers in units of 2^(E - 60) (E: exponent of the largest norm),
+    2 a.b = W 2^(ea + eb - 47) is shifted into the same units, d^2 = NA + NB - Ws is clamped at 0, and
+    T 2^48 = mulhi64(d^2, Kq) >> kr with K = c 2^(E - 12) = Kq 2^-(64 + kr).  Checked against float64 d^2 * c for rows of very
+    different scale, identical rows (d^2 = 0 up to the digits' truncation) and the range conditions of the metadata warp."""
+    import struct
+    rng = np.random.default_rng(5)
+
+    def bits(x):
+        return struct.unpack("<Q", struct.pack("<d", float(x)))[0]
+
+    def norm_fix(v, E):          # the metadata warp: m 2^(e - 1075) -> m 2^(e - 1015 - E), truncated
+        b = bits(v)
+        e, m = b >> 52, (b & ((1 << 52) - 1)) | (1 << 52)
+        if e == 0:
+            return 0
+        s = e - 1015 - E
+        return (m << s) if s >= 0 else (m >> min(-s, 63))
+
+    worst = 0.0
+    for trial in range(300):
+        n, D = 6, 40
+        scale = 10.0 ** rng.integers(-3, 4)
+        X = rng.normal(size=(n, D)) * scale * 10.0 ** rng.integers(-2, 2, size=(n, 1))
+        X[1] = X[0]                                   # identical rows
+        na = (X * X).sum(axis=1)
+        # exact integers W = round(a.b 2^(48 - ea - eb)) stand for the digit-plane products (their own truncation is tested elsewhere)
+        ex = [int(np.frexp(np.abs(r).max())[1]) + 1 for r in X]
+        E = ((bits(na.max()) >> 52) & 0x7ff) - 1022
+        c = 1.4426950408889634 / (2.0 * (0.3 * np.sqrt(na.max())) ** 2)
+        K = c * 2.0 ** (E - 12)
+        eK = (bits(c) >> 52) + (E - 12)
+        assert 1022 - 63 <= eK <= 1021 and 0.0 < K < 0.5
+        kr = 1022 - eK
+        Kq = ((bits(c) & ((1 << 52) - 1)) | (1 << 52)) << 11
+        assert abs(Kq * 2.0 ** -(64 + kr) - K) <= K * 2.0 ** -52
+        NA = [norm_fix(v, E) for v in na]
+        for i in range(n):
+            for j in range(n):
+                ab = float(np.dot(X[i], X[j]))
+                W = int(round(ab * 2.0 ** (48 - ex[i] - ex[j])))
+                sh = ex[i] + ex[j] + 13 - E
+                Ws = (W << sh) if sh >= 0 else (W >> min(-sh, 63))
+                Dq = max(NA[i] + NA[j] - Ws, 0)
+                assert Dq < 2 ** 63
+                F = ((Dq * Kq) >> 64) >> kr
+                T = F * 2.0 ** -48
+                d2 = max(na[i] + na[j] - 2.0 * ab, 0.0)
+                ref = d2 * c
+                # error budget: the norms' own rounding (as in the FP64 path) ~ 1e-16 (na + nb) c, the fixed-point units 2^-60 of the largest norm
+                tol = 4e-16 * (na[i] + na[j]) * c + 2.0 ** -47 + 2.0 ** (ex[i] + ex[j] - 47) * c   # + the rounding of W itself
+                assert abs(T - ref) <= tol, (trial, i, j, T, ref)
+                worst = max(worst, abs(T - ref))
+    assert worst < 1e-12
